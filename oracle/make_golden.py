@@ -1,0 +1,209 @@
+"""TEST INFRASTRUCTURE — generate `tests/golden/*.npz` by running the UNMODIFIED reference
+(`/root/reference/Main_Final.py`) in the build container on deterministic synthetic weights and
+inputs (integer-hash generated, see `oracle/robust_unet_ref.py`).  Run:
+
+    python oracle/make_golden.py
+
+The fixtures pin the oracle restatement (and through it the CUDA path) to the reference's own
+outputs; the reference cannot travel to the GPU box, the fixtures do.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+
+from oracle import robust_unet_ref as R            # noqa: E402
+from oracle.load_reference import load_reference   # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+class _MaskQueue:
+    """Replaces nn.Dropout2d.forward so the reference consumes the given channel masks in
+    execution order (inc, down1, down2, down3, bottleneck.2, dec4..dec1)."""
+
+    def __init__(self):
+        self.queue = []
+
+    def install(self):
+        q = self
+
+        def fwd(self_mod, x):
+            if not self_mod.training:
+                return x
+            return x * q.queue.pop(0).to(x.dtype)
+
+        self._orig = nn.Dropout2d.forward
+        nn.Dropout2d.forward = fwd
+
+    def remove(self):
+        nn.Dropout2d.forward = self._orig
+
+
+def grad_summary(t: torch.Tensor) -> np.ndarray:
+    f = t.detach().double().flatten()
+    head = f[:8].numpy()
+    if head.size < 8:
+        head = np.pad(head, (0, 8 - head.size))
+    return np.concatenate([[f.norm().item(), f.sum().item()], head])
+
+
+def model_golden(MF, tag, n_channels, base, batch, h, w, w_dice=0.0):
+    shapes = R.robust_unet_shapes(n_channels, 1, base)
+    torch.manual_seed(0)
+    model = MF.RobustUNet(n_channels, 1, base)
+    ref_sd = model.state_dict()
+    assert list(ref_sd.keys()) == list(shapes.keys()), "state_dict schema drifted"
+    for k, v in ref_sd.items():
+        assert tuple(v.shape) == tuple(shapes[k]), k
+    sd = R.synthetic_state_dict(shapes, seed=0)
+    model.load_state_dict(sd)
+    x, y = R.synthetic_inputs(batch, n_channels, h, w, seed=123, blobby=True)
+    masks = R.synthetic_drop_masks(batch, base, seed=7)
+
+    mq = _MaskQueue()
+    mq.install()
+    try:
+        model.train()
+        mq.queue = [masks[n] for n in R.RESBLOCKS]
+        p = model(x)
+        loss = R.bce_dice_loss(p, y, 1.0, w_dice) if w_dice else nn.BCELoss()(p, y)
+        loss.backward()
+    finally:
+        mq.remove()
+    out = {"probs_train": p.detach().numpy(), "loss_train": np.float64(loss.item())}
+    names = [k for k, _ in model.named_parameters()]
+    out["param_names"] = np.array(names)
+    out["grad_summary"] = np.stack([grad_summary(prm.grad) for _, prm in model.named_parameters()])
+    new_sd = model.state_dict()
+    bnames = [k for k in new_sd if k.endswith("running_mean") or k.endswith("running_var")]
+    out["buffer_names"] = np.array(bnames)
+    out["buffer_summary"] = np.stack([grad_summary(new_sd[k]) for k in bnames])
+    # eval forward with the *original* synthetic weights/buffers
+    model.load_state_dict(sd)
+    model.eval()
+    with torch.no_grad():
+        pe = model(x)
+    out["probs_eval"] = pe.numpy()
+    out["loss_eval"] = np.float64(nn.BCELoss()(pe, y).item())
+    ev = MF.ModelEvaluator(torch.device("cpu"))
+    mets = [ev.calculate_metrics(pe[i, 0], y[i, 0]) for i in range(batch)]
+    keys = ["accuracy", "iou", "precision", "recall", "f1_score"]
+    out["metric_keys"] = np.array(keys)
+    out["metrics_eval"] = np.array([[float(m[k]) for k in keys] for m in mets], dtype=np.float64)
+    out["config"] = np.array([n_channels, base, batch, h, w])
+    out["w_dice"] = np.float64(w_dice)
+    np.savez_compressed(os.path.join(OUT, f"model_{tag}.npz"), **out)
+    print(tag, "loss", loss.item(), "eval loss", out["loss_eval"], "mean p", p.mean().item())
+
+
+def module_goldens(MF):
+    """Full-tensor goldens for single modules (small shapes)."""
+    out = {}
+    torch.manual_seed(0)
+    # ResidualBlock 16 -> 32 with projection shortcut, train mode, dropout mask injected
+    shapes = {}
+    full = R.robust_unet_shapes(3, 1, 16)
+    for k, v in full.items():
+        if k.startswith("down1.1."):
+            shapes[k[len("down1.1."):]] = v
+    sd = R.synthetic_state_dict(shapes, seed=3)
+    blk = MF.ResidualBlock(16, 32, dropout_rate=0.1)
+    blk.load_state_dict(sd)
+    x, _ = R.synthetic_inputs(2, 16, 8, 8, seed=11)
+    x.requires_grad_(True)
+    u = R._hash_uniform(2 * 32, 5)
+    mask = torch.from_numpy(((u >= 0.1).astype(np.float32) / np.float32(0.9)).reshape(2, 32, 1, 1))
+    mq = _MaskQueue()
+    mq.install()
+    try:
+        blk.train()
+        mq.queue = [mask]
+        o = blk(x)
+        go, _ = R.synthetic_inputs(2, 32, 8, 8, seed=12)
+        o.backward(go)
+    finally:
+        mq.remove()
+    out["rb_x"] = x.detach().numpy()
+    out["rb_mask"] = mask.numpy()
+    out["rb_out"] = o.detach().numpy()
+    out["rb_gout"] = go.numpy()
+    out["rb_gx"] = x.grad.numpy()
+    for k, prm in blk.named_parameters():
+        out["rb_g_" + k] = prm.grad.numpy()
+    # AttentionGate(32, 32, 16)
+    shapes = {k[len("att1."):]: v for k, v in R.robust_unet_shapes(3, 1, 32).items() if k.startswith("att1.")}
+    sd = R.synthetic_state_dict(shapes, seed=4)
+    gate = MF.AttentionGate(32, 32, 16)
+    gate.load_state_dict(sd)
+    gate.train()
+    g, _ = R.synthetic_inputs(2, 32, 8, 8, seed=21)
+    xs, _ = R.synthetic_inputs(2, 32, 8, 8, seed=22)
+    g.requires_grad_(True)
+    xs.requires_grad_(True)
+    o = gate(g, xs)
+    go, _ = R.synthetic_inputs(2, 32, 8, 8, seed=23)
+    o.backward(go)
+    out.update(ag_g=g.detach().numpy(), ag_x=xs.detach().numpy(), ag_out=o.detach().numpy(),
+               ag_gout=go.numpy(), ag_gg=g.grad.numpy(), ag_gx=xs.grad.numpy())
+    for k, prm in gate.named_parameters():
+        out["ag_g_" + k] = prm.grad.numpy()
+    # DilatedBlock(32 -> 64)
+    shapes = {k[len("bottleneck.1."):]: v for k, v in R.robust_unet_shapes(3, 1, 4).items()
+              if k.startswith("bottleneck.1.")}
+    sd = R.synthetic_state_dict(shapes, seed=5)
+    db = MF.DilatedBlock(32, 64)
+    db.load_state_dict(sd)
+    db.train()
+    xd, _ = R.synthetic_inputs(2, 32, 8, 8, seed=31)
+    xd.requires_grad_(True)
+    o = db(xd)
+    go, _ = R.synthetic_inputs(2, 64, 8, 8, seed=32)
+    o.backward(go)
+    out.update(db_x=xd.detach().numpy(), db_out=o.detach().numpy(), db_gout=go.numpy(),
+               db_gx=xd.grad.numpy())
+    for k, prm in db.named_parameters():
+        out["db_g_" + k] = prm.grad.numpy()
+    np.savez_compressed(os.path.join(OUT, "modules.npz"), **out)
+
+
+def metric_goldens(MF):
+    """calculate_metrics edge cases (Main_Final.py:519-547): pred == 0.5 exactly, all-empty,
+    all-full, random."""
+    ev = MF.ModelEvaluator(torch.device("cpu"))
+    cases = {}
+    rng = np.random.RandomState(0)
+    p = rng.rand(4, 16, 16).astype(np.float32)
+    p[0, :4] = 0.5                                 # strict threshold: 0.5 is negative
+    t = (rng.rand(4, 16, 16) > 0.5).astype(np.float32)
+    p[2] = 0.0
+    t[2] = 0.0                                     # empty / empty
+    p[3] = 1.0
+    t[3] = 1.0                                     # full / full
+    keys = ["accuracy", "iou", "precision", "recall", "f1_score"]
+    m = [ev.calculate_metrics(torch.from_numpy(p[i]), torch.from_numpy(t[i])) for i in range(4)]
+    cases["pred"] = p
+    cases["target"] = t
+    cases["metric_keys"] = np.array(keys)
+    cases["metrics"] = np.array([[float(mm[k]) for k in keys] for mm in m], dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, "metrics.npz"), **cases)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(8)
+    MF = load_reference()
+    model_golden(MF, "c3_b16_32x32", 3, 16, 2, 32, 32)
+    model_golden(MF, "c4_b16_32x48", 4, 16, 2, 32, 48, w_dice=0.5)
+    module_goldens(MF)
+    metric_goldens(MF)
+    print("wrote", sorted(os.listdir(OUT)))
+
+
+if __name__ == "__main__":
+    main()
