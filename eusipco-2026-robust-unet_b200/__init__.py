@@ -1,0 +1,13 @@
+"""B200-native (sm_100a) Robust U-Net hot path behind the reference's torch.nn.Module API.
+
+Drop-in surface (reference: /root/reference/Main_Final.py):
+  RobustUNet(n_channels=3, n_classes=1, base_channels=64)   Main_Final.py:226-321
+  RobustBCEDiceLoss()  (defaults == nn.BCELoss())           Main_Final.py:551,580
+  calculate_metrics(pred, target, threshold=0.5)            Main_Final.py:519-547
+Everything below that surface is hand-written CUDA in csrc/ reached through the C ABI of
+librbunet.so (include/rbunet.h).  There is no CPU fallback.
+"""
+from . import _lib  # noqa: F401
+from .ops import View  # noqa: F401
+
+__all__ = ["View"]

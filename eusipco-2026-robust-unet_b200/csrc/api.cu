@@ -1,0 +1,89 @@
+// Library-level entry points: version, error reporting, device checks, tensor-map encoding.
+#include <stdarg.h>
+
+#include "rbu_common.cuh"
+#include "tma_host.cuh"
+
+namespace {
+thread_local char g_err[1024] = "";
+int g_sms = 0;
+}  // namespace
+
+void rbu_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int rbu_num_sms() {
+  if (g_sms == 0) {
+    int dev = 0;
+    cudaDeviceProp prop;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess)
+      g_sms = prop.multiProcessorCount;
+    else
+      g_sms = 148;
+  }
+  return g_sms;
+}
+
+extern "C" int rbu_version(void) { return 100; }
+
+extern "C" const char* rbu_last_error(void) { return g_err; }
+
+extern "C" int rbu_sm_count(void) { return rbu_num_sms(); }
+
+extern "C" int rbu_device_check(void) {
+  int dev = 0;
+  RBU_CHECK_CUDA(cudaGetDevice(&dev));
+  int major = 0;
+  RBU_CHECK_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) {
+    rbu_set_error("rbunet needs a compute-capability 10.x (Blackwell, sm_100a) device, found %d.x", major);
+    return RBU_ERR_UNSUPPORTED;
+  }
+  return RBU_OK;
+}
+
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int rbu_encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                         const uint64_t* strides_bytes, const uint32_t* box) {
+  static encode_tiled_fn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !sym) {
+      rbu_set_error("cuTensorMapEncodeTiled is not available from the driver (%s)", cudaGetErrorString(e));
+      return RBU_ERR_CUDA;
+    }
+    fn = reinterpret_cast<encode_tiled_fn>(sym);
+  }
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bdim[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+    if (i + 1 < rank) gstr[i] = strides_bytes[i];
+  }
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    rbu_set_error("cuTensorMapEncodeTiled failed (CUresult %d): rank %d dims [%llu %llu %llu %llu %llu] box [%u %u %u %u %u] "
+                  "stride0 %llu base %p",
+                  (int)r, rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+                  (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0),
+                  (unsigned long long)(rank > 4 ? dims[4] : 0), box[0], rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0,
+                  rank > 3 ? box[3] : 0, rank > 4 ? box[4] : 0, (unsigned long long)(rank > 1 ? strides_bytes[0] : 0), base);
+    return RBU_ERR_CUDA;
+  }
+  return RBU_OK;
+}

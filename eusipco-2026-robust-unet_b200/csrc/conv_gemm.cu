@@ -1,0 +1,381 @@
+// K1 / K10: implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05.mma, fp32 accumulators in
+// TMEM), operands staged by TMA as SWIZZLE_128B tiles of NHWC bf16 activations and packed bf16 weights.
+//
+//   D[pixel, n] = sum_{segment} sum_{tap} sum_{c}  X_seg[pixel + tap, c] * W_seg[n, tap, c]
+//
+// One kernel serves: 3x3 convs with dilation 1/2/4 (padding == dilation comes from TMA out-of-bounds
+// zero fill), 1x1 convs, ConvTranspose2d(2, s=2) forward (GEMM with N = 4*Cout + pixel-shuffle epilogue),
+// the data gradients of all of them (same kernel, re-packed weights; ConvTranspose dgrad gathers the four
+// stride-2 quadrants through a 5-D tensor map) and two-segment accumulation (conv1-dgrad + shortcut-dgrad
+// into one accumulator).  Replaces aten::convolution / convolution_backward(input) of
+// Main_Final.py:157,159,172,126,131,205-208,261-270.
+//
+// Structure (persistent, warp specialised, 192 threads, 1 CTA / SM):
+//   warp 0 / lane 0 : TMA producer   (A tile: 128 pixels x 64 ch, B tile: block_n x 64)   -> full[s]
+//   warp 1 / lane 0 : MMA issuer     (4 x tcgen05.mma K=16 per stage, commit -> empty[s], tmem_full[a])
+//   warps 2..5      : epilogue       (tcgen05.ld 32x32b, bias/addend, bf16 pack, 16 B stores) -> tmem_empty[a]
+// Two TMEM accumulator buffers let the epilogue of tile i overlap the MMAs of tile i+1.
+#include "rbu_common.cuh"
+#include "rbu_ptx.cuh"
+#include "tma_host.cuh"
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+constexpr int NUM_THREADS = 192;
+constexpr int MAX_STAGES = 8;
+constexpr int SMEM_LIMIT = 232448;  // 227 KB
+
+struct KParams {
+  int N, H, W;
+  int TW, TH, TN;  // conv mode: tile = TN images x TH rows x TW cols; gather mode: TH = merged (n,h) rows
+  int tiles_w, tiles_h, tiles_n;
+  int n_blocks, block_n, Ncols;
+  int nseg;
+  int taps[2], C[2], dil[2];
+  int gather;
+  int num_stages, tmem_cols, total_tiles;
+  bf16* y;
+  long long y_ld;
+  int scatter, Cout;
+  const float* bias;
+  const bf16* addend;
+  long long addend_ld;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
+                 const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
+                 const KParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int stage_bytes = A_BYTES + p.block_n * 128;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.num_stages * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + MAX_STAGES;
+  uint64_t* tfull = bars + 2 * MAX_STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA0);
+    ptx::prefetch_tmap(&tmB0);
+    if (p.nseg > 1) {
+      ptx::prefetch_tmap(&tmA1);
+      ptx::prefetch_tmap(&tmB1);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.num_stages; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tfull[a], 1);
+      ptx::mbar_init(&tempty[a], 4);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  int kblocks_total = 0;
+  for (int s = 0; s < p.nseg; ++s) kblocks_total += p.taps[s] * ((p.C[s] + BLOCK_K - 1) / BLOCK_K);
+
+  if (warp == 0) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int nb = tile % p.n_blocks;
+        int sp = tile / p.n_blocks;
+        const int w0 = (sp % p.tiles_w) * p.TW;
+        sp /= p.tiles_w;
+        const int h0 = (sp % p.tiles_h) * p.TH;
+        const int n0 = (sp / p.tiles_h) * p.TN;
+        for (int seg = 0; seg < p.nseg; ++seg) {
+          const CUtensorMap* mA = seg ? &tmA1 : &tmA0;
+          const CUtensorMap* mB = seg ? &tmB1 : &tmB0;
+          const int kch = (p.C[seg] + BLOCK_K - 1) / BLOCK_K;
+          for (int tap = 0; tap < p.taps[seg]; ++tap) {
+            int dh = 0, dw = 0;
+            if (p.taps[seg] == 9) {
+              dh = (tap / 3 - 1) * p.dil[seg];
+              dw = (tap % 3 - 1) * p.dil[seg];
+            }
+            for (int kc = 0; kc < kch; ++kc, ++it) {
+              const int s = it % p.num_stages;
+              const uint32_t ph = (it / p.num_stages) & 1;
+              ptx::mbar_wait(&empty[s], ph ^ 1);
+              ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)stage_bytes);
+              uint8_t* a_dst = smem + s * stage_bytes;
+              uint8_t* b_dst = a_dst + A_BYTES;
+              if (p.gather)
+                ptx::tma_load_5d(a_dst, mA, &full[s], kc * BLOCK_K, tap & 1, w0, tap >> 1, h0);
+              else
+                ptx::tma_load_4d(a_dst, mA, &full[s], kc * BLOCK_K, w0 + dw, h0 + dh, n0);
+              ptx::tma_load_2d(b_dst, mB, &full[s], tap * p.C[seg] + kc * BLOCK_K, nb * p.block_n);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer ==============================
+    if (lane == 0) {
+      const uint32_t idesc = ptx::make_idesc_bf16(BLOCK_M, p.block_n, 0, 0);
+      int it = 0, t = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
+        const int a = t & 1;
+        const uint32_t aph = (t >> 1) & 1;
+        ptx::mbar_wait(&tempty[a], aph ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(a * p.block_n);
+        int kb = 0;
+        for (int seg = 0; seg < p.nseg; ++seg) {
+          const int kch = (p.C[seg] + BLOCK_K - 1) / BLOCK_K;
+          for (int tap = 0; tap < p.taps[seg]; ++tap) {
+            for (int kc = 0; kc < kch; ++kc, ++it, ++kb) {
+              const int s = it % p.num_stages;
+              const uint32_t ph = (it / p.num_stages) & 1;
+              ptx::mbar_wait(&full[s], ph);
+              ptx::tc_fence_after();
+              const uint32_t a_addr = ptx::smem_u32(smem + s * stage_bytes);
+              const uint32_t b_addr = a_addr + A_BYTES;
+              int rem = p.C[seg] - kc * BLOCK_K;
+              const int ksteps = rem >= BLOCK_K ? 4 : (rem + 15) / 16;  // channels past C are TMA zero fill
+              for (int k = 0; k < ksteps; ++k) {
+                const uint64_t da = ptx::make_smem_desc(a_addr + k * 32, 16, 1024);
+                const uint64_t db = ptx::make_smem_desc(b_addr + k * 32, 16, 1024);
+                ptx::umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+              }
+              ptx::umma_commit(&empty[s]);  // frees the smem stage once these MMAs retire
+            }
+          }
+        }
+        ptx::umma_commit(&tfull[a]);  // accumulator complete
+      }
+    }
+  } else {
+    // ============================== epilogue (warps 2..5) ==============================
+    const int lg = warp & 3;  // TMEM lane group this warp may access
+    const int row = lg * 32 + lane;
+    int t = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
+      const int nb = tile % p.n_blocks;
+      int sp = tile / p.n_blocks;
+      const int w0 = (sp % p.tiles_w) * p.TW;
+      sp /= p.tiles_w;
+      const int h0 = (sp % p.tiles_h) * p.TH;
+      const int n0 = (sp / p.tiles_h) * p.TN;
+      // pixel owned by this thread
+      bool valid;
+      int n, h, w;
+      {
+        const int wl = row % p.TW;
+        const int r2 = row / p.TW;
+        w = w0 + wl;
+        if (p.gather) {
+          const int nh = h0 + r2;
+          valid = (w < p.W) && (nh < p.N * p.H);
+          n = nh / p.H;
+          h = nh - n * p.H;
+        } else {
+          h = h0 + (r2 % p.TH);
+          n = n0 + r2 / p.TH;
+          valid = (w < p.W) && (h < p.H) && (n < p.N);
+        }
+      }
+      const long long pix = ((long long)n * p.H + h) * p.W + w;
+
+      const int a = t & 1;
+      const uint32_t aph = (t >> 1) & 1;
+      ptx::mbar_wait(&tfull[a], aph);
+      ptx::tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(a * p.block_n);
+      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(t_addr + (uint32_t)c0, r);
+        ptx::tmem_ld_wait();
+        const int col = nb * p.block_n + c0;
+        if (valid && col < p.Ncols) {
+          bf16* dst;
+          int cb;  // bias channel base
+          if (p.scatter) {
+            const int q = col / p.Cout;
+            cb = col - q * p.Cout;
+            const long long opix = ((long long)n * (2 * p.H) + 2 * h + (q >> 1)) * (2 * p.W) + 2 * w + (q & 1);
+            dst = p.y + opix * p.y_ld + cb;
+          } else {
+            cb = col;
+            dst = p.y + pix * p.y_ld + col;
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (col + g * 8 < p.Ncols) {
+              float f[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(r[g * 8 + e]);
+              if (p.bias) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + cb + g * 8));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + cb + g * 8 + 4));
+                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+              }
+              if (p.addend) {
+                float ad[8];
+                unpack8(ld_bf16x8(p.addend + pix * p.addend_ld + col + g * 8), ad);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] += ad[e];
+              }
+              st_bf16x8(dst + g * 8, pack8(f));
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tempty[a]);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+int pow2ceil(int v) {
+  int r = 1;
+  while (r < v) r <<= 1;
+  return r;
+}
+
+}  // namespace
+
+extern "C" int rbu_conv_gemm(const rbu_conv_gemm_args* a, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  RBU_CHECK_ARG(a != nullptr, "rbu_conv_gemm: null args");
+  RBU_CHECK_ARG(a->N > 0 && a->H > 0 && a->W > 0, "rbu_conv_gemm: bad pixel grid %d x %d x %d", a->N, a->H, a->W);
+  RBU_CHECK_ARG(a->nseg == 1 || a->nseg == 2, "rbu_conv_gemm: nseg must be 1 or 2");
+  RBU_CHECK_ARG(a->Ncols > 0 && a->Ncols % 8 == 0, "rbu_conv_gemm: Ncols=%d must be a positive multiple of 8", a->Ncols);
+  RBU_CHECK_ARG(a->y != nullptr && a->y_ld % 8 == 0 && ((uintptr_t)a->y & 15) == 0,
+                "rbu_conv_gemm: output view must be 16-byte aligned with ld %% 8 == 0");
+  RBU_CHECK_ARG(a->bias == nullptr || ((uintptr_t)a->bias & 15) == 0, "rbu_conv_gemm: bias must be 16-byte aligned");
+  if (a->scatter) {
+    RBU_CHECK_ARG(a->Cout > 0 && a->Ncols == 4 * a->Cout && a->Cout % 32 == 0,
+                  "rbu_conv_gemm: scatter needs Ncols == 4*Cout and Cout %% 32 == 0");
+    RBU_CHECK_ARG(a->addend == nullptr, "rbu_conv_gemm: addend is not supported with scatter");
+  }
+  if (a->addend)
+    RBU_CHECK_ARG(a->addend_ld % 8 == 0 && ((uintptr_t)a->addend & 15) == 0, "rbu_conv_gemm: addend view misaligned");
+  int gather = 0;
+  for (int s = 0; s < a->nseg; ++s) {
+    const rbu_gemm_operand& o = a->seg[s];
+    RBU_CHECK_ARG(o.x && o.w, "rbu_conv_gemm: null operand in segment %d", s);
+    RBU_CHECK_ARG(o.C > 0 && o.C % 8 == 0 && o.x_ld % 8 == 0 && ((uintptr_t)o.x & 15) == 0 && ((uintptr_t)o.w & 15) == 0,
+                  "rbu_conv_gemm: segment %d needs C %% 8 == 0, ld %% 8 == 0 and 16-byte aligned pointers", s);
+    if (o.gather) {
+      RBU_CHECK_ARG(o.taps == 4 && a->nseg == 1, "rbu_conv_gemm: gather needs taps == 4 and a single segment");
+      gather = 1;
+    } else {
+      RBU_CHECK_ARG(o.taps == 1 || o.taps == 9, "rbu_conv_gemm: taps must be 1 or 9 (got %d)", o.taps);
+      RBU_CHECK_ARG(o.taps == 1 || o.dil >= 1, "rbu_conv_gemm: dilation must be >= 1");
+    }
+  }
+
+  KParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = a->N; p.H = a->H; p.W = a->W;
+  p.gather = gather;
+  p.TW = pow2ceil(a->W) < 16 ? pow2ceil(a->W) : 16;
+  if (gather) {
+    p.TH = BLOCK_M / p.TW;  // merged (n,h) rows
+    p.TN = 1;
+    p.tiles_w = rbu_cdiv(a->W, p.TW);
+    p.tiles_h = rbu_cdiv((long)a->N * a->H, p.TH);
+    p.tiles_n = 1;
+  } else {
+    const int th_max = BLOCK_M / p.TW;
+    p.TH = pow2ceil(a->H) < th_max ? pow2ceil(a->H) : th_max;
+    p.TN = BLOCK_M / (p.TW * p.TH);
+    p.tiles_w = rbu_cdiv(a->W, p.TW);
+    p.tiles_h = rbu_cdiv(a->H, p.TH);
+    p.tiles_n = rbu_cdiv(a->N, p.TN);
+  }
+  p.Ncols = a->Ncols;
+  p.block_n = a->Ncols >= 256 ? 256 : ((a->Ncols + 31) / 32) * 32;
+  p.n_blocks = rbu_cdiv(a->Ncols, p.block_n);
+  p.nseg = a->nseg;
+  for (int s = 0; s < a->nseg; ++s) {
+    p.taps[s] = a->seg[s].taps;
+    p.C[s] = a->seg[s].C;
+    p.dil[s] = a->seg[s].taps == 9 ? a->seg[s].dil : 0;
+  }
+  const int stage_bytes = A_BYTES + p.block_n * 128;
+  p.num_stages = (SMEM_LIMIT - 2048) / stage_bytes;
+  if (p.num_stages > MAX_STAGES) p.num_stages = MAX_STAGES;
+  p.tmem_cols = 32;
+  while (p.tmem_cols < 2 * p.block_n) p.tmem_cols <<= 1;
+  p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_blocks;
+  p.y = reinterpret_cast<bf16*>(a->y);
+  p.y_ld = a->y_ld;
+  p.scatter = a->scatter;
+  p.Cout = a->scatter ? a->Cout : a->Ncols;
+  p.bias = a->bias;
+  p.addend = reinterpret_cast<const bf16*>(a->addend);
+  p.addend_ld = a->addend_ld;
+
+  CUtensorMap tmA[2], tmB[2];
+  memset(tmA, 0, sizeof(tmA));
+  memset(tmB, 0, sizeof(tmB));
+  for (int s = 0; s < a->nseg; ++s) {
+    const rbu_gemm_operand& o = a->seg[s];
+    int rc;
+    if (o.gather) {
+      // x is [N, 2H, 2W, ld]; view as (C, j, w, i, n*H + h)
+      const uint64_t dims[5] = {(uint64_t)o.C, 2, (uint64_t)a->W, 2, (uint64_t)a->N * a->H};
+      const uint64_t str[4] = {(uint64_t)o.x_ld * 2, (uint64_t)o.x_ld * 4, (uint64_t)o.x_ld * 2 * (2 * a->W),
+                               (uint64_t)o.x_ld * 4 * (2 * a->W)};
+      const uint32_t box[5] = {BLOCK_K, 1, (uint32_t)p.TW, 1, (uint32_t)p.TH};
+      rc = rbu_encode_tmap_bf16(&tmA[s], o.x, 5, dims, str, box);
+    } else {
+      const uint64_t dims[4] = {(uint64_t)o.C, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->N};
+      const uint64_t str[3] = {(uint64_t)o.x_ld * 2, (uint64_t)o.x_ld * 2 * a->W, (uint64_t)o.x_ld * 2 * a->W * a->H};
+      const uint32_t box[4] = {BLOCK_K, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN};
+      rc = rbu_encode_tmap_bf16(&tmA[s], o.x, 4, dims, str, box);
+    }
+    if (rc) return rc;
+    const uint64_t ktot = (uint64_t)o.taps * o.C;
+    const uint64_t bdims[2] = {ktot, (uint64_t)a->Ncols};
+    const uint64_t bstr[1] = {ktot * 2};
+    const uint32_t bbox[2] = {BLOCK_K, (uint32_t)p.block_n};
+    rc = rbu_encode_tmap_bf16(&tmB[s], o.w, 2, bdims, bstr, bbox);
+    if (rc) return rc;
+  }
+  if (a->nseg == 1) {
+    tmA[1] = tmA[0];
+    tmB[1] = tmB[0];
+  }
+
+  const int smem_bytes = p.num_stages * stage_bytes + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RBU_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    attr_set = true;
+  }
+  int grid = p.total_tiles < rbu_num_sms() ? p.total_tiles : rbu_num_sms();
+  conv_gemm_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(tmA[0], tmB[0], tmA[1], tmB[1], p);
+  RBU_CHECK_LAUNCH();
+  return RBU_OK;
+}

@@ -1,0 +1,11 @@
+// Host-side CUtensorMap construction (cuTensorMapEncodeTiled through the runtime's driver entry point,
+// so the library has no link-time dependency on libcuda).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+// Encode a bf16 tensor map with SWIZZLE_128B. dims/strides innermost first; strides[i] is the byte stride
+// of dimension i+1 (dimension 0 is contiguous). Returns 0 on success (error text via rbu_set_error).
+int rbu_encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                         const uint64_t* strides_bytes, const uint32_t* box);

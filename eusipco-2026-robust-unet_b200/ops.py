@@ -1,0 +1,124 @@
+"""Thin Python wrappers: torch tensors -> C-ABI calls (device pointers + sizes)."""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_void_p
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+from ._lib import ConvGemmArgs, call, stream_ptr
+
+
+@dataclass
+class View:
+    """A channel slice of an NHWC bf16 activation buffer [N,H,W,ld]."""
+    base: torch.Tensor      # contiguous bf16 [N,H,W,ld] (or [P,ld])
+    off: int = 0            # first channel of the slice
+    C: int = -1             # channels in the slice
+
+    def __post_init__(self):
+        if self.C < 0:
+            self.C = self.base.shape[-1] - self.off
+        assert self.base.dtype == torch.bfloat16 and self.base.is_contiguous() and self.base.is_cuda
+        assert self.off % 8 == 0 and self.C % 8 == 0 and self.ld % 8 == 0
+
+    @property
+    def ld(self) -> int:
+        return self.base.shape[-1]
+
+    @property
+    def ptr(self) -> int:
+        return self.base.data_ptr() + 2 * self.off
+
+    def slice(self, off, C):
+        return View(self.base, self.off + off, C)
+
+    def dense(self) -> torch.Tensor:
+        return self.base[..., self.off:self.off + self.C]
+
+
+def _p(t):
+    return c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
+
+
+def pack_weight(w: torch.Tensor, mode: int) -> torch.Tensor:
+    """fp32 torch-layout weight -> bf16 GEMM operand [Ncols][taps][K] (see rbu_pack_weight)."""
+    assert w.is_cuda and w.dtype == torch.float32 and w.is_contiguous()
+    if mode == 0:            # Conv2d [Cout,Cin,kh,kw] forward
+        Nn, K, T, cout = w.shape[0], w.shape[1], w.shape[2] * w.shape[3], 0
+    elif mode == 1:          # Conv2d data gradient
+        Nn, K, T, cout = w.shape[1], w.shape[0], w.shape[2] * w.shape[3], 0
+    elif mode == 2:          # ConvTranspose2d [Cin,Cout,2,2] forward
+        Nn, K, T, cout = 4 * w.shape[1], w.shape[0], 1, w.shape[1]
+    elif mode == 3:          # ConvTranspose2d data gradient
+        Nn, K, T, cout = w.shape[0], w.shape[1], 4, 0
+    else:
+        raise ValueError(mode)
+    out = torch.empty((Nn, T, K), dtype=torch.bfloat16, device=w.device)
+    call("rbu_pack_weight", _p(w), _p(out), Nn, T, K, mode, cout, stream_ptr())
+    return out
+
+
+def conv_gemm(N, H, W, segs, Ncols, y: View, scatter=False, Cout=0, bias=None, addend: View = None):
+    """segs: list of (x: View, w_packed, taps, dil, gather)."""
+    a = ConvGemmArgs()
+    a.N, a.H, a.W, a.nseg = N, H, W, len(segs)
+    keep = []
+    for i, (x, wp, taps, dil, gather) in enumerate(segs):
+        a.seg[i].x = x.ptr
+        a.seg[i].x_ld = x.ld
+        a.seg[i].C = x.C
+        a.seg[i].w = wp.data_ptr()
+        a.seg[i].taps = taps
+        a.seg[i].dil = dil
+        a.seg[i].gather = int(gather)
+        keep.append(wp)
+    a.Ncols = Ncols
+    a.y = y.ptr
+    a.y_ld = y.ld
+    a.scatter = int(scatter)
+    a.Cout = Cout
+    a.bias = bias.data_ptr() if bias is not None else None
+    a.addend = addend.ptr if addend is not None else None
+    a.addend_ld = addend.ld if addend is not None else 0
+    call("rbu_conv_gemm", ctypes.byref(a), stream_ptr())
+
+
+def conv_direct_ref(x: View, N, H, W, w, bias, ksz, dil):
+    cout = w.shape[0]
+    out = torch.empty((N, H, W, cout), dtype=torch.float32, device=w.device)
+    call("rbu_conv_direct_ref", c_void_p(x.ptr), x.ld, N, H, W, x.C, _p(w), _p(bias), cout, ksz, dil, _p(out),
+         stream_ptr())
+    return out
+
+
+def loss_forward(probs, target, threshold=0.5, w_bce=1.0, w_dice=0.0, smooth=1.0):
+    """Returns (loss[1] f32, sums[4] f64, counts[B,4] i64) device tensors."""
+    B = probs.shape[0]
+    HW = probs.numel() // B
+    dev = probs.device
+    ws_bytes = _lib.lib().rbu_loss_workspace_bytes(B, HW)
+    ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev)
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    sums = torch.empty(4, dtype=torch.float64, device=dev)
+    counts = torch.empty((B, 4), dtype=torch.int64, device=dev)
+    call("rbu_loss_forward", _p(probs), _p(target), B, HW, threshold, w_bce, w_dice, smooth, _p(ws), ws_bytes,
+         _p(loss), _p(sums), _p(counts), stream_ptr())
+    return loss, sums, counts
+
+
+def loss_backward(probs, target, grad_out, sums, w_bce=1.0, w_dice=0.0, smooth=1.0):
+    dp = torch.empty_like(probs)
+    call("rbu_loss_backward", _p(probs), _p(target), probs.numel(), _p(grad_out), _p(sums), w_bce, w_dice, smooth,
+         _p(dp), stream_ptr())
+    return dp
+
+
+def confusion_counts(pred, target, threshold=0.5):
+    B = pred.shape[0]
+    HW = pred.numel() // B
+    counts = torch.empty((B, 4), dtype=torch.int64, device=pred.device)
+    call("rbu_confusion_counts", _p(pred), _p(target), B, HW, threshold, _p(counts), stream_ptr())
+    return counts
