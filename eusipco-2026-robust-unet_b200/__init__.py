@@ -8,6 +8,10 @@ Everything below that surface is hand-written CUDA in csrc/ reached through the 
 librbunet.so (include/rbunet.h).  There is no CPU fallback.
 """
 from . import _lib  # noqa: F401
+from .loss import (METRIC_KEYS, RobustBCEDiceLoss, batch_metrics, calculate_metrics,  # noqa: F401
+                   confusion_counts, metrics_from_counts)
+from .model import RobustUNet  # noqa: F401
 from .ops import View  # noqa: F401
 
-__all__ = ["View"]
+__all__ = ["RobustUNet", "RobustBCEDiceLoss", "calculate_metrics", "batch_metrics", "confusion_counts",
+           "metrics_from_counts", "METRIC_KEYS", "View"]

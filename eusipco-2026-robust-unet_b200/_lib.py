@@ -1,14 +1,16 @@
-"""ctypes binding of librbunet.so (the C ABI declared in include/rbunet.h).
+"""ctypes binding of librbunet.so, generated from the C ABI declared in include/rbunet.h.
 
 The product path has NO CPU fallback: if the shared library is missing or an entry point fails,
 this module raises.
 """
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_void_p
+import re
+from ctypes import Structure, c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_void_p
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "librbunet.so")
+HEADER_PATH = os.path.join(os.path.dirname(PKG_DIR), "include", "rbunet.h")
 
 
 class GemmOperand(Structure):
@@ -22,29 +24,45 @@ class ConvGemmArgs(Structure):
                 ("bias", c_void_p), ("addend", c_void_p), ("addend_ld", c_int64)]
 
 
-_SIGS = {
-    "rbu_version": (c_int, []),
-    "rbu_last_error": (c_char_p, []),
-    "rbu_device_check": (c_int, []),
-    "rbu_sm_count": (c_int, []),
-    "rbu_conv_gemm": (c_int, [POINTER(ConvGemmArgs), c_void_p]),
-    "rbu_pack_weight": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
-    "rbu_conv_direct_ref": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
-                                    c_int, c_int, c_void_p, c_void_p]),
-    "rbu_loss_workspace_bytes": (c_size_t, [c_int, c_int64]),
-    "rbu_loss_forward": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_float, c_float, c_float, c_float, c_void_p,
-                                 c_size_t, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "rbu_loss_backward": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_float, c_float, c_float,
-                                  c_void_p, c_void_p]),
-    "rbu_confusion_counts": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_float, c_void_p, c_void_p]),
-}
+class WgradArgs(Structure):
+    _fields_ = [("N", c_int), ("H", c_int), ("W", c_int), ("a", c_void_p), ("a_ld", c_int64), ("Ca", c_int),
+                ("b", c_void_p), ("b_ld", c_int64), ("Cb", c_int), ("taps", c_int), ("dil", c_int),
+                ("gather", c_int), ("out", c_void_p), ("accumulate", c_int)]
+
+
+_SCALARS = {"int": c_int, "int64_t": c_int64, "size_t": c_size_t, "float": c_float, "double": c_double}
+
+
+def _ctype(decl: str):
+    decl = decl.strip()
+    if decl in ("void", ""):
+        return None
+    if "*" in decl:
+        return c_char_p if decl.replace(" ", "") == "constchar*" else c_void_p
+    base = decl.replace("const", "").split()[0]
+    return _SCALARS[base]
+
+
+def parse_header(path: str = HEADER_PATH):
+    """{name: (restype, [argtypes])} for every `rbu_*` prototype in the header."""
+    text = open(path).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    sigs = {}
+    for m in re.finditer(r"([A-Za-z_][\w\s\*]*?)\b(rbu_\w+)\s*\(([^;{}]*?)\)\s*;", text):
+        ret, name, args = m.group(1).strip(), m.group(2), m.group(3)
+        argtypes = []
+        for a in args.split(","):
+            a = a.strip()
+            if a in ("void", ""):
+                continue
+            # drop the parameter name
+            a = re.sub(r"\b\w+\s*(\[\w*\])?$", "", a).strip() if not a.endswith("*") else a
+            argtypes.append(_ctype(a))
+        sigs[name] = (_ctype(ret), argtypes)
+    return sigs
+
 
 _lib = None
-
-
-def exported_symbols():
-    """Names every build of the library must export (checked by the CPU tests against include/rbunet.h)."""
-    return sorted(_SIGS)
 
 
 def lib():
@@ -55,8 +73,8 @@ def lib():
                 f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(there is no CPU fallback for the CUDA hot path)")
         handle = ctypes.CDLL(LIB_PATH)
-        for name, (res, args) in _SIGS.items():
-            fn = getattr(handle, name)
+        for name, (res, args) in parse_header().items():
+            fn = getattr(handle, name)   # AttributeError if the build lacks a declared symbol
             fn.restype = res
             fn.argtypes = args
         _lib = handle

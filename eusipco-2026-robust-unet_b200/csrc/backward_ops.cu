@@ -1,0 +1,933 @@
+// Bandwidth-bound backward kernels (K12 of SURVEY.md §2.1): the fused elementwise/reduction passes of
+// ResidualBlock, AttentionGate, BatchNorm(+ReLU+Dropout2d), MaxPool and the `outc` head.
+//
+// Thread layout ("pattern B"): a block of 256 threads = rows x G, G = C/8 channel groups (power of two),
+// each thread owns 8 channels of one pixel per iteration, so per-channel sums live in registers across the
+// pixel loop and per-pixel sums are a reduction over the G threads of a row.  Grids are (chunks, N): one
+// block covers a pixel chunk of ONE image, which makes per-(n,c) reductions local.  Partials are written
+// per block and combined in a fixed order by a finalize kernel (deterministic, no float atomics).
+#include "rbu_common.cuh"
+
+namespace {
+
+constexpr int NT = 256;
+
+// sum over the G threads that share a pixel.  Contains __syncthreads() when G > 32: every thread of the
+// block must call it the same number of times.
+__device__ __forceinline__ float row_sum(float v, int G, float* red) {
+  if (G <= 32) {
+    for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  }
+  v = warp_sum(v);
+  const int wpr = G >> 5;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  const int row = threadIdx.x / G;
+  float t = 0.f;
+  for (int i = 0; i < wpr; ++i) t += red[row * wpr + i];
+  return t;
+}
+
+// reduce a per-thread 8-vector over the rows of the block and store it at dst[cg*8 .. +8]
+__device__ __forceinline__ void rows_reduce_store(const float* acc, int G, int rows, float (*sv)[8], float* dst) {
+  const int cg = threadIdx.x % G, row = threadIdx.x / G;
+  __syncthreads();
+#pragma unroll
+  for (int e = 0; e < 8; ++e) sv[threadIdx.x][e] = acc[e];
+  __syncthreads();
+  if (row == 0) {
+    float a[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a[e] = sv[cg][e];
+    for (int r = 1; r < rows; ++r)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a[e] += sv[r * G + cg][e];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dst[cg * 8 + e] = a[e];
+  }
+}
+
+// out[k] (+ optional out2) = sum over blocks of part[blk][k], fixed order, double accumulation
+__global__ void colsum_kernel(const float* __restrict__ part, int nblk, int K, long blk_stride, float* __restrict__ out,
+                              float post_scale) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  double s = 0.0;
+  for (int b = 0; b < nblk; ++b) s += (double)part[(long)b * blk_stride + k];
+  out[k] = (float)s * post_scale;
+}
+
+// per-(n,c): out[n][c] = sum over the chunks of image n
+__global__ void colsum_nc_kernel(const float* __restrict__ part, int N, int chunks, int C, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = blockIdx.y;
+  if (c >= C) return;
+  double s = 0.0;
+  for (int k = 0; k < chunks; ++k) s += (double)part[((long)n * chunks + k) * C + c];
+  out[(long)n * C + c] = (float)s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// outc head backward (Main_Final.py:274-277): dz = dprobs * p (1-p); dx = dz * w; dw = sum dz x; db = sum dz
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT)
+head_bwd_kernel(const float* __restrict__ dprobs, const float* __restrict__ probs, const bf16* __restrict__ x, long x_ld,
+                bf16* __restrict__ dx, long dx_ld, long P, int C, const float* __restrict__ w, int px_per_block,
+                float* __restrict__ partials) {
+  const int G = C >> 3, rows = NT / G;
+  const int cg = threadIdx.x % G, row = threadIdx.x / G;
+  const long p0 = (long)blockIdx.x * px_per_block;
+  const long p1 = min(p0 + px_per_block, P);
+  float wv[8], acc[8], accb[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { wv[e] = w[cg * 8 + e]; acc[e] = 0.f; accb[e] = 0.f; }
+  if (row < rows) {
+    for (long p = p0 + row; p < p1; p += rows) {
+      const float pr = probs[p];
+      const float dz = dprobs[p] * pr * (1.f - pr);
+      float v[8], o[8];
+      unpack8(ld_bf16x8_stream(x + p * x_ld + cg * 8), v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { acc[e] += dz * v[e]; o[e] = dz * wv[e]; }
+      if (cg == 0) accb[0] += dz;
+      st_bf16x8(dx + p * dx_ld + cg * 8, pack8(o));
+    }
+  }
+  __shared__ float sv[NT][8];
+  float* dst = partials + (long)blockIdx.x * (C + 8);
+  rows_reduce_store(acc, G, rows, sv, dst);
+  __syncthreads();
+  // bias partial: only cg == 0 threads carry it
+#pragma unroll
+  for (int e = 0; e < 8; ++e) sv[threadIdx.x][e] = accb[e];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float b = 0.f;
+    for (int r = 0; r < rows; ++r) b += sv[r * G][0];
+    dst[C] = b;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// ResidualBlock backward, pass 1: de = dout * [out > 0] (stored, may alias dout);
+// dG[p] = sum_c de * (A2g*y2 + B2g);  projection shortcut: per-channel sum(de), sum(de * xhat_s).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT)
+rb_bwd1_kernel(const bf16* __restrict__ dout, long dout_ld, const bf16* __restrict__ out, long out_ld,
+               const bf16* __restrict__ y2, long y2_ld, bf16* __restrict__ de, long de_ld, const bf16* __restrict__ ys,
+               long ys_ld, int HW, int C, int chunk_px, const float* __restrict__ A2g, const float* __restrict__ B2g,
+               const float* __restrict__ mean_s, const float* __restrict__ rstd_s, float* __restrict__ dG,
+               float* __restrict__ partials) {
+  const int G = C >> 3, rows = NT / G;
+  const int cg = threadIdx.x % G, row = threadIdx.x / G;
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  const int p0 = chunk * chunk_px, p1 = min(p0 + chunk_px, HW);
+  const int iters = (p1 - p0 + rows - 1) / rows;
+  __shared__ float red[NT / 32];
+  float a[8], b[8], ms[8], rs[8], acc1[8], acc2[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = cg * 8 + e;
+    a[e] = A2g[(long)n * C + c];
+    b[e] = B2g[(long)n * C + c];
+    ms[e] = ys ? mean_s[c] : 0.f;
+    rs[e] = ys ? rstd_s[c] : 0.f;
+    acc1[e] = 0.f;
+    acc2[e] = 0.f;
+  }
+  for (int it = 0; it < iters; ++it) {
+    const int pl = p0 + it * rows + row;
+    const bool act = row < rows && pl < p1;
+    const long p = (long)n * HW + pl;
+    float part = 0.f;
+    if (act) {
+      float g[8], o[8], y[8];
+      unpack8(ld_bf16x8_stream(dout + p * dout_ld + cg * 8), g);
+      unpack8(ld_bf16x8_stream(out + p * out_ld + cg * 8), o);
+      unpack8(ld_bf16x8(y2 + p * y2_ld + cg * 8), y);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        g[e] = o[e] > 0.f ? g[e] : 0.f;
+        part += g[e] * (a[e] * y[e] + b[e]);
+      }
+      st_bf16x8(de + p * de_ld + cg * 8, pack8(g));
+      if (ys) {
+        float s[8];
+        unpack8(ld_bf16x8(ys + p * ys_ld + cg * 8), s);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          acc1[e] += g[e];
+          acc2[e] += g[e] * (s[e] - ms[e]) * rs[e];
+        }
+      }
+    }
+    part = row_sum(part, G, red);
+    if (act && cg == 0) dG[p] = part;
+  }
+  if (ys) {
+    __shared__ float sv[NT][8];
+    float* dst = partials + ((long)n * gridDim.x + chunk) * 2 * C;
+    rows_reduce_store(acc1, G, rows, sv, dst);
+    rows_reduce_store(acc2, G, rows, sv, dst + C);
+  }
+}
+
+// SpatialAttention backward (Main_Final.py:112-117): dq = dG * gs (1-gs);
+//   ds[k][h,w] = sum_{r,q} K7[k][r][q] * dq[h-r+3, w-q+3]      (data gradient wrt [s_avg, s_max])
+__global__ void __launch_bounds__(NT)
+sa_bwd_data_kernel(const float* __restrict__ dG, const float* __restrict__ gs, int N, int H, int W,
+                   const float* __restrict__ k7, float2* __restrict__ ds) {
+  __shared__ float wk[98];
+  if (threadIdx.x < 98) wk[threadIdx.x] = k7[threadIdx.x];
+  __syncthreads();
+  const long P = (long)N * H * W;
+  for (long p = blockIdx.x * (long)NT + threadIdx.x; p < P; p += (long)gridDim.x * NT) {
+    const int w = (int)(p % W);
+    const int h = (int)((p / W) % H);
+    const long nb = p - (long)h * W - w;
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int r = 0; r < 7; ++r) {
+      const int hh = h - r + 3;
+      if (hh < 0 || hh >= H) continue;
+#pragma unroll
+      for (int q = 0; q < 7; ++q) {
+        const int ww = w - q + 3;
+        if (ww < 0 || ww >= W) continue;
+        const long o = nb + (long)hh * W + ww;
+        const float g = __ldg(&gs[o]);
+        const float dq = __ldg(&dG[o]) * g * (1.f - g);
+        a0 += wk[r * 7 + q] * dq;
+        a1 += wk[49 + r * 7 + q] * dq;
+      }
+    }
+    ds[p] = make_float2(a0, a1);
+  }
+}
+
+//   dK7[k][r][q] = sum_p dq[p] * s_k[p + (r-3, q-3)]      (98 per-thread accumulators, block partials)
+__global__ void __launch_bounds__(NT)
+sa_bwd_weight_kernel(const float* __restrict__ dG, const float* __restrict__ gs, const float2* __restrict__ s, int N,
+                     int H, int W, float* __restrict__ partials) {
+  float acc[98];
+#pragma unroll
+  for (int i = 0; i < 98; ++i) acc[i] = 0.f;
+  const long P = (long)N * H * W;
+  for (long p = blockIdx.x * (long)NT + threadIdx.x; p < P; p += (long)gridDim.x * NT) {
+    const int w = (int)(p % W);
+    const int h = (int)((p / W) % H);
+    const long nb = p - (long)h * W - w;
+    const float g = gs[p];
+    const float dq = dG[p] * g * (1.f - g);
+#pragma unroll
+    for (int r = 0; r < 7; ++r) {
+      const int hh = h + r - 3;
+#pragma unroll
+      for (int q = 0; q < 7; ++q) {
+        const int ww = w + q - 3;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
+          const float2 v = __ldg(&s[nb + (long)hh * W + ww]);
+          acc[r * 7 + q] += dq * v.x;
+          acc[49 + r * 7 + q] += dq * v.y;
+        }
+      }
+    }
+  }
+  __shared__ float sm[98][NT / 32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < 98; ++i) {
+    const float v = warp_sum(acc[i]);
+    if (lane == 0) sm[i][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 98) {
+    float t = 0.f;
+    for (int wq = 0; wq < NT / 32; ++wq) t += sm[threadIdx.x][wq];
+    partials[(long)blockIdx.x * 98 + threadIdx.x] = t;
+  }
+}
+
+// gradient wrt b = BN2(y2) at (pixel, 8 channels), shared by passes 2-4
+struct RbCtx {
+  const float* gs; const float2* ds; const int* amax_c;       // per pixel
+  const float* g_c; const float* du_avg; const float* du_max; // per (n,c)
+  const int* nc_amax; const int* nc_amin;                      // per (n,c)
+  const float* scale2; const float* shift2; const float* mean2; const float* rstd2;  // per c
+};
+
+// pass 2: dT[n,c] = sum_hw dc * b,  dc = de*gs + ds_avg/C + ds_max*[c == argmax_c],  b = scale2*y2 + shift2
+__global__ void __launch_bounds__(NT)
+rb_bwd2_kernel(const bf16* __restrict__ de, long de_ld, const bf16* __restrict__ y2, long y2_ld, int HW, int C,
+               int chunk_px, RbCtx k, float* __restrict__ partials) {
+  const int G = C >> 3, rows = NT / G;
+  const int cg = threadIdx.x % G, row = threadIdx.x / G;
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  const int p0 = chunk * chunk_px, p1 = min(p0 + chunk_px, HW);
+  float sc[8], sh[8], acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { sc[e] = k.scale2[cg * 8 + e]; sh[e] = k.shift2[cg * 8 + e]; acc[e] = 0.f; }
+  const float invC = 1.f / (float)C;
+  if (row < rows) {
+    for (int pl = p0 + row; pl < p1; pl += rows) {
+      const long p = (long)n * HW + pl;
+      float g[8], y[8];
+      unpack8(ld_bf16x8_stream(de + p * de_ld + cg * 8), g);
+      unpack8(ld_bf16x8_stream(y2 + p * y2_ld + cg * 8), y);
+      const float gsp = k.gs[p];
+      const float2 d = k.ds[p];
+      const int am = k.amax_c[p] - cg * 8;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float dc = g[e] * gsp + d.x * invC + (e == am ? d.y : 0.f);
+        acc[e] += dc * (sc[e] * y[e] + sh[e]);
+      }
+    }
+  }
+  __shared__ float sv[NT][8];
+  rows_reduce_store(acc, G, rows, sv, partials + ((long)n * gridDim.x + chunk) * C);
+}
+
+__device__ __forceinline__ void rb_db(const RbCtx& k, int n, int pl, long p, int cg, int C, float invC, float invHW,
+                                      const float* g, const float* gc, const float* dua, const float* dum,
+                                      const int* pstar, float* db) {
+  const float gsp = k.gs[p];
+  const float2 d = k.ds[p];
+  const int am = k.amax_c[p] - cg * 8;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float dc = g[e] * gsp + d.x * invC + (e == am ? d.y : 0.f);
+    db[e] = dc * gc[e] + dua[e] * invHW + (pl == pstar[e] ? dum[e] : 0.f);
+  }
+}
+
+// pass 3 (MODE 0): per-channel sum(db), sum(db * xhat2).   pass 4 (MODE 1): dy2 = scale2*(db - S1/M - xhat2*S2/M)
+// and, for a projection shortcut, dys = scale_s*(de - T1/M - xhat_s*T2/M).
+template <int MODE>
+__global__ void __launch_bounds__(NT)
+rb_bwd34_kernel(const bf16* __restrict__ de, long de_ld, const bf16* __restrict__ y2, long y2_ld, int HW, int C,
+                int chunk_px, RbCtx k, float* __restrict__ partials, const float* __restrict__ sums, float invM,
+                bf16* __restrict__ dy2, long dy2_ld, const bf16* __restrict__ ys, long ys_ld, bf16* __restrict__ dys,
+                long dys_ld, const float* __restrict__ scale_s, const float* __restrict__ mean_s,
+                const float* __restrict__ rstd_s, const float* __restrict__ sums_s) {
+  const int G = C >> 3, rows = NT / G;
+  const int cg = threadIdx.x % G, row = threadIdx.x / G;
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  const int p0 = chunk * chunk_px, p1 = min(p0 + chunk_px, HW);
+  float gc[8], dua[8], dum[8], mu[8], rs[8], acc1[8], acc2[8];
+  int pstar[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = cg * 8 + e;
+    gc[e] = k.g_c[(long)n * C + c];
+    dua[e] = k.du_avg[(long)n * C + c];
+    dum[e] = k.du_max[(long)n * C + c];
+    pstar[e] = k.scale2[c] >= 0.f ? k.nc_amax[(long)n * C + c] : k.nc_amin[(long)n * C + c];
+    mu[e] = k.mean2[c];
+    rs[e] = k.rstd2[c];
+    acc1[e] = 0.f;
+    acc2[e] = 0.f;
+  }
+  const float invC = 1.f / (float)C, invHW = 1.f / (float)HW;
+  if (row < rows) {
+    for (int pl = p0 + row; pl < p1; pl += rows) {
+      const long p = (long)n * HW + pl;
+      float g[8], y[8], db[8];
+      unpack8(ld_bf16x8_stream(de + p * de_ld + cg * 8), g);
+      unpack8(ld_bf16x8_stream(y2 + p * y2_ld + cg * 8), y);
+      rb_db(k, n, pl, p, cg, C, invC, invHW, g, gc, dua, dum, pstar, db);
+      if (MODE == 0) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          acc1[e] += db[e];
+          acc2[e] += db[e] * (y[e] - mu[e]) * rs[e];
+        }
+      } else {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int c = cg * 8 + e;
+          const float xh = (y[e] - mu[e]) * rs[e];
+          o[e] = k.scale2[c] * (db[e] - sums[c] * invM - xh * sums[C + c] * invM);
+        }
+        st_bf16x8(dy2 + p * dy2_ld + cg * 8, pack8(o));
+        if (ys) {
+          float s[8];
+          unpack8(ld_bf16x8_stream(ys + p * ys_ld + cg * 8), s);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int c = cg * 8 + e;
+            const float xh = (s[e] - mean_s[c]) * rstd_s[c];
+            o[e] = scale_s[c] * (g[e] - sums_s[c] * invM - xh * sums_s[C + c] * invM);
+          }
+          st_bf16x8(dys + p * dys_ld + cg * 8, pack8(o));
+        }
+      }
+    }
+  }
+  if (MODE == 0) {
+    __shared__ float sv[NT][8];
+    float* dst = partials + ((long)n * gridDim.x + chunk) * 2 * C;
+    rows_reduce_store(acc1, G, rows, sv, dst);
+    rows_reduce_store(acc2, G, rows, sv, dst + C);
+  }
+}
+
+// ChannelAttention backward (Main_Final.py:97-101), one block per image
+__global__ void __launch_bounds__(NT)
+ca_bwd_n_kernel(const float* __restrict__ dT, const float* __restrict__ g, const float* __restrict__ h_avg,
+                const float* __restrict__ h_max, const float* __restrict__ V1, const float* __restrict__ V2, int C, int Ch,
+                float* __restrict__ dt_out, float* __restrict__ dh_avg_out, float* __restrict__ dh_max_out,
+                float* __restrict__ du_avg, float* __restrict__ du_max) {
+  extern __shared__ float sm[];
+  float* dt = sm;             // [C]
+  float* dha = sm + C;        // [Ch]
+  float* dhm = dha + Ch;      // [Ch]
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += NT) {
+    const float gg = g[(long)n * C + c];
+    const float v = dT[(long)n * C + c] * gg * (1.f - gg);
+    dt[c] = v;
+    dt_out[(long)n * C + c] = v;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int j = warp; j < Ch; j += NT / 32) {
+    float a = 0.f;
+    for (int c = lane; c < C; c += 32) a += V2[(long)c * Ch + j] * dt[c];
+    a = warp_sum(a);
+    if (lane == 0) {
+      const float da = h_avg[(long)n * Ch + j] > 0.f ? a : 0.f;
+      const float dm = h_max[(long)n * Ch + j] > 0.f ? a : 0.f;
+      dha[j] = da;
+      dhm[j] = dm;
+      dh_avg_out[(long)n * Ch + j] = da;
+      dh_max_out[(long)n * Ch + j] = dm;
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += NT) {
+    float a = 0.f, m = 0.f;
+    for (int j = 0; j < Ch; ++j) {
+      const float w = V1[(long)j * C + c];
+      a += w * dha[j];
+      m += w * dhm[j];
+    }
+    du_avg[(long)n * C + c] = a;
+    du_max[(long)n * C + c] = m;
+  }
+}
+// weight gradients of the shared MLP: thread per weight, sum over images
+__global__ void ca_bwd_w_kernel(const float* __restrict__ dt, const float* __restrict__ dh_avg,
+                                const float* __restrict__ dh_max, const float* __restrict__ h_avg,
+                                const float* __restrict__ h_max, const float* __restrict__ u_avg,
+                                const float* __restrict__ u_max, int N, int C, int Ch, float* __restrict__ dV1,
+                                float* __restrict__ dV2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C * Ch) return;
+  {  // dV1[j][c]
+    const int j = i / C, c = i % C;
+    float s = 0.f;
+    for (int n = 0; n < N; ++n)
+      s += dh_avg[(long)n * Ch + j] * u_avg[(long)n * C + c] + dh_max[(long)n * Ch + j] * u_max[(long)n * C + c];
+    dV1[i] = s;
+  }
+  {  // dV2[c][j]
+    const int c = i / Ch, j = i % Ch;
+    float s = 0.f;
+    for (int n = 0; n < N; ++n)
+      s += dt[(long)n * C + c] * (fmaxf(h_avg[(long)n * Ch + j], 0.f) + fmaxf(h_max[(long)n * Ch + j], 0.f));
+    dV2[i] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Generic BatchNorm(+ReLU)(+Dropout2d) backward: dz = dy * drop[n,c] * [scale*y+shift > 0]
+//   MODE 0: per-channel sum(dz), sum(dz * xhat);   MODE 1: dx = scale*(dz - S1/M - xhat*S2/M)
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(NT)
+bn_bwd_kernel(const bf16* __restrict__ dy, long dy_ld, const bf16* __restrict__ y, long y_ld, int HW, int C, int chunk_px,
+              const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
+              const float* __restrict__ rstd, const float* __restrict__ drop, int relu, float* __restrict__ partials,
+              const float* __restrict__ sums, float invM, bf16* __restrict__ dx, long dx_ld) {
+  const int G = C >> 3, rows = NT / G;
+  const int cg = threadIdx.x % G, row = threadIdx.x / G;
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  const int p0 = chunk * chunk_px, p1 = min(p0 + chunk_px, HW);
+  float sc[8], sh[8], mu[8], rs[8], dr[8], s1[8], s2[8], acc1[8], acc2[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = cg * 8 + e;
+    sc[e] = scale[c]; sh[e] = shift[c]; mu[e] = mean[c]; rs[e] = rstd[c];
+    dr[e] = drop ? drop[(long)n * C + c] : 1.f;
+    s1[e] = MODE ? sums[c] * invM : 0.f;
+    s2[e] = MODE ? sums[C + c] * invM : 0.f;
+    acc1[e] = 0.f; acc2[e] = 0.f;
+  }
+  if (row < rows) {
+    for (int pl = p0 + row; pl < p1; pl += rows) {
+      const long p = (long)n * HW + pl;
+      float g[8], v[8];
+      unpack8(ld_bf16x8_stream(dy + p * dy_ld + cg * 8), g);
+      unpack8(ld_bf16x8_stream(y + p * y_ld + cg * 8), v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float dz = g[e] * dr[e];
+        if (relu && !(sc[e] * v[e] + sh[e] > 0.f)) dz = 0.f;
+        const float xh = (v[e] - mu[e]) * rs[e];
+        if (MODE == 0) { acc1[e] += dz; acc2[e] += dz * xh; }
+        else g[e] = sc[e] * (dz - s1[e] - xh * s2[e]);
+      }
+      if (MODE == 1) st_bf16x8(dx + p * dx_ld + cg * 8, pack8(g));
+    }
+  }
+  if (MODE == 0) {
+    __shared__ float sv[NT][8];
+    float* dst = partials + ((long)n * gridDim.x + chunk) * 2 * C;
+    rows_reduce_store(acc1, G, rows, sv, dst);
+    rows_reduce_store(acc2, G, rows, sv, dst + C);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// AttentionGate backward (Main_Final.py:143-148)
+// pass 1 (over C): dskip = da * psi; dpsi = sum_c da * skip; dq = dpsi psi (1-psi) -> dq[P];
+//                  block partials: sum(dq), sum(dq * qhat)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT)
+ag_bwd1_kernel(const bf16* __restrict__ da, long da_ld, const bf16* __restrict__ skip, long s_ld, bf16* __restrict__ dskip,
+               long ds_ld, int HW, int C, int chunk_px, const float* __restrict__ psi, const float* __restrict__ q0,
+               const float* __restrict__ stats, float* __restrict__ dq_out, float* __restrict__ partials) {
+  const int G = C >> 3, rows = NT / G;
+  const int cg = threadIdx.x % G, row = threadIdx.x / G;
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  const int p0 = chunk * chunk_px, p1 = min(p0 + chunk_px, HW);
+  const int iters = (p1 - p0 + rows - 1) / rows;
+  __shared__ float red[NT / 32];
+  const float mean = stats[2], rstd = stats[3];
+  float l0 = 0.f, l1 = 0.f;
+  for (int it = 0; it < iters; ++it) {
+    const int pl = p0 + it * rows + row;
+    const bool act = row < rows && pl < p1;
+    const long p = (long)n * HW + pl;
+    float part = 0.f, ps = 0.f;
+    if (act) {
+      float g[8], x[8];
+      unpack8(ld_bf16x8_stream(da + p * da_ld + cg * 8), g);
+      unpack8(ld_bf16x8(skip + p * s_ld + cg * 8), x);
+      ps = psi[p];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { part += g[e] * x[e]; g[e] *= ps; }
+      st_bf16x8(dskip + p * ds_ld + cg * 8, pack8(g));
+    }
+    part = row_sum(part, G, red);
+    if (act && cg == 0) {
+      const float dq = part * ps * (1.f - ps);
+      dq_out[p] = dq;
+      l0 += dq;
+      l1 += dq * (q0[p] - mean) * rstd;
+    }
+  }
+  __shared__ float r0[NT / 32], r1[NT / 32];
+  l0 = warp_sum(l0);
+  l1 = warp_sum(l1);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) { r0[threadIdx.x >> 5] = l0; r1[threadIdx.x >> 5] = l1; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+    for (int w = 0; w < NT / 32; ++w) { a += r0[w]; b += r1[w]; }
+    float* dst = partials + ((long)n * gridDim.x + chunk) * 2;
+    dst[0] = a;
+    dst[1] = b;
+  }
+}
+
+// pass 2/3 (over F): dq0 = a_psi*(dq - c1 - qhat*c2); t = relu(Ag yg+Bg+Ax yx+Bx); dt = wpsi*dq0*[t>0]
+//   MODE 0: per-channel sum(t*dq0) [dwpsi], sum(dt), sum(dt*xhat_g), sum(dt*xhat_x)
+//   MODE 1: dyg = Ag*(dt - S1/M - xhat_g*S2g/M), dyx likewise
+template <int MODE>
+__global__ void __launch_bounds__(NT)
+ag_bwd23_kernel(const bf16* __restrict__ yg, long yg_ld, const bf16* __restrict__ yx, long yx_ld, int HW, int F,
+                int chunk_px, const float* __restrict__ Ag, const float* __restrict__ Bg, const float* __restrict__ Ax,
+                const float* __restrict__ Bx, const float* __restrict__ mg, const float* __restrict__ rg,
+                const float* __restrict__ mx, const float* __restrict__ rx, const float* __restrict__ wpsi,
+                const float* __restrict__ dq, const float* __restrict__ q0, const float* __restrict__ stats,
+                const float* __restrict__ csum /* [2]: sum(dq), sum(dq*qhat) */, float invM,
+                float* __restrict__ partials, const float* __restrict__ sums /* [4][F] */, bf16* __restrict__ dyg,
+                long dyg_ld, bf16* __restrict__ dyx, long dyx_ld) {
+  const int G = F >> 3, rows = NT / G;
+  const int cg = threadIdx.x % G, row = threadIdx.x / G;
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  const int p0 = chunk * chunk_px, p1 = min(p0 + chunk_px, HW);
+  const float a_psi = stats[0], mean = stats[2], rstd = stats[3];
+  const float c1 = csum[0] * invM, c2 = csum[1] * invM;
+  float acc[4][8];
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[q][e] = 0.f;
+  if (row < rows) {
+    for (int pl = p0 + row; pl < p1; pl += rows) {
+      const long p = (long)n * HW + pl;
+      float a[8], b[8];
+      unpack8(ld_bf16x8_stream(yg + p * yg_ld + cg * 8), a);
+      unpack8(ld_bf16x8_stream(yx + p * yx_ld + cg * 8), b);
+      const float dq0 = a_psi * (dq[p] - c1 - (q0[p] - mean) * rstd * c2);
+      float og[8], ox[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int c = cg * 8 + e;
+        const float t = Ag[c] * a[e] + Bg[c] + Ax[c] * b[e] + Bx[c];
+        const float dt = t > 0.f ? wpsi[c] * dq0 : 0.f;
+        const float xg = (a[e] - mg[c]) * rg[c];
+        const float xx = (b[e] - mx[c]) * rx[c];
+        if (MODE == 0) {
+          acc[0][e] += fmaxf(t, 0.f) * dq0;
+          acc[1][e] += dt;
+          acc[2][e] += dt * xg;
+          acc[3][e] += dt * xx;
+        } else {
+          const float s1 = sums[F + c] * invM;
+          og[e] = Ag[c] * (dt - s1 - xg * sums[2 * F + c] * invM);
+          ox[e] = Ax[c] * (dt - s1 - xx * sums[3 * F + c] * invM);
+        }
+      }
+      if (MODE == 1) {
+        st_bf16x8(dyg + p * dyg_ld + cg * 8, pack8(og));
+        st_bf16x8(dyx + p * dyx_ld + cg * 8, pack8(ox));
+      }
+    }
+  }
+  if (MODE == 0) {
+    __shared__ float sv[NT][8];
+    float* dst = partials + ((long)n * gridDim.x + chunk) * 4 * F;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) rows_reduce_store(acc[q], G, rows, sv, dst + q * F);
+  }
+}
+
+// 2x2 max-pool backward: route dy to the FIRST maximal input in scan order and ADD it to dx
+__global__ void __launch_bounds__(NT)
+maxpool_bwd_kernel(const bf16* __restrict__ x, long x_ld, const bf16* __restrict__ dy, long dy_ld, bf16* __restrict__ dx,
+                   long dx_ld, int N, int Ho, int Wo, int C, int accumulate) {
+  const int G = C >> 3;
+  const long total = (long)N * Ho * Wo * G;
+  const int W = 2 * Wo;
+  for (long i = blockIdx.x * (long)NT + threadIdx.x; i < total; i += (long)gridDim.x * NT) {
+    const int cg = (int)(i % G);
+    const long po = i / G;
+    const int wo = (int)(po % Wo);
+    const int ho = (int)((po / Wo) % Ho);
+    const int n = (int)(po / ((long)Wo * Ho));
+    const long pi = ((long)n * 2 * Ho + 2 * ho) * W + 2 * wo;
+    const long off[4] = {pi, pi + 1, pi + W, pi + W + 1};
+    float v[4][8], g[8], o[4][8];
+    unpack8(ld_bf16x8_stream(dy + po * dy_ld + cg * 8), g);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      unpack8(ld_bf16x8(x + off[q] * x_ld + cg * 8), v[q]);
+      if (accumulate) unpack8(ld_bf16x8(dx + off[q] * dx_ld + cg * 8), o[q]);
+      else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[q][e] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      int best = 0;
+      float bv = v[0][e];
+#pragma unroll
+      for (int q = 1; q < 4; ++q)
+        if (v[q][e] > bv) { bv = v[q][e]; best = q; }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (q == best) o[q][e] += g[e];
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) st_bf16x8(dx + off[q] * dx_ld + cg * 8, pack8(o[q]));
+  }
+}
+
+// per-channel sum over pixels of a bf16 view (bias gradients)
+__global__ void __launch_bounds__(NT)
+chan_sum_kernel(const bf16* __restrict__ x, long ld, long P, int C, int px_per_block, float* __restrict__ partials) {
+  const int G = C >> 3, rows = NT / G;
+  const int cg = threadIdx.x % G, row = threadIdx.x / G;
+  const long p0 = (long)blockIdx.x * px_per_block;
+  const long p1 = min(p0 + px_per_block, P);
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  if (row < rows)
+    for (long p = p0 + row; p < p1; p += rows) {
+      float v[8];
+      unpack8(ld_bf16x8_stream(x + p * ld + cg * 8), v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += v[e];
+    }
+  __shared__ float sv[NT][8];
+  rows_reduce_store(acc, G, rows, sv, partials + (long)blockIdx.x * C);
+}
+
+// ---------------------------------------------------------------------------------- host helpers
+bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+int bwd_chunks(int N, int HW, int C) {
+  const int rows = NT / (C >> 3);
+  long want = ((long)rbu_num_sms() * 4 + N - 1) / N;
+  long maxc = (HW + (long)rows * 4 - 1) / ((long)rows * 4);
+  if (maxc < 1) maxc = 1;
+  if (want > maxc) want = maxc;
+  if (want < 1) want = 1;
+  return (int)want;
+}
+
+int flat_blocks(long P, int C, int* px_per_block) {
+  const int rows = NT / (C >> 3);
+  long blocks = (long)rbu_num_sms() * 4;
+  long maxb = (P + (long)rows * 4 - 1) / ((long)rows * 4);
+  if (maxb < 1) maxb = 1;
+  if (blocks > maxb) blocks = maxb;
+  *px_per_block = (int)((P + blocks - 1) / blocks);
+  return (int)((P + *px_per_block - 1) / *px_per_block);
+}
+
+int grid1d(long items, int per_block) {
+  long b = (items + per_block - 1) / per_block;
+  const long cap = (long)rbu_num_sms() * 8;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace
+
+#define VIEW_OK(ptr, ld) ((ptr) != nullptr && ((uintptr_t)(ptr) & 15) == 0 && (ld) % 8 == 0)
+#define CH_OK(C) ((C) >= 8 && (C) <= 2048 && pow2(C))
+
+// Workspace (floats) large enough for every backward pass of a [N,HW,C] tensor: max partial layout is
+// [N*chunks][4][C] (AttentionGate pass 2); the head / chan_sum layouts are smaller.
+extern "C" size_t rbu_bwd_workspace_bytes(int N, int HW, int C) {
+  if (!CH_OK(C)) return 0;
+  int ppb;
+  const size_t a = (size_t)N * bwd_chunks(N, HW, C) * 4 * C;
+  const size_t b = (size_t)flat_blocks((long)N * HW, C, &ppb) * (C + 8);
+  const size_t c = (size_t)rbu_num_sms() * 8 * 98;
+  size_t m = a > b ? a : b;
+  if (c > m) m = c;
+  return m * sizeof(float);
+}
+
+extern "C" int rbu_head_backward(const float* dprobs, const float* probs, const void* x, int64_t x_ld, void* dx,
+                                 int64_t dx_ld, int64_t P, int C, const float* w, float* dw, float* db, void* workspace,
+                                 size_t workspace_bytes, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  RBU_CHECK_ARG(dprobs && probs && VIEW_OK(x, x_ld) && VIEW_OK(dx, dx_ld) && w && dw && db && CH_OK(C) && C <= 256,
+                "rbu_head_backward: bad arguments");
+  int ppb;
+  const int blocks = flat_blocks(P, C, &ppb);
+  RBU_CHECK_ARG(workspace && workspace_bytes >= (size_t)blocks * (C + 8) * sizeof(float), "rbu_head_backward: workspace too small");
+  float* part = (float*)workspace;
+  head_bwd_kernel<<<blocks, NT, 0, st>>>(dprobs, probs, (const bf16*)x, x_ld, (bf16*)dx, dx_ld, P, C, w, ppb, part);
+  RBU_CHECK_LAUNCH();
+  colsum_kernel<<<rbu_cdiv(C, 128), 128, 0, st>>>(part, blocks, C, C + 8, dw, 1.f);
+  colsum_kernel<<<1, 32, 0, st>>>(part + C, blocks, 1, C + 8, db, 1.f);
+  RBU_CHECK_LAUNCH();
+  return RBU_OK;
+}
+
+extern "C" int rbu_rb_bwd1(const void* dout, int64_t dout_ld, const void* out, int64_t out_ld, const void* y2,
+                           int64_t y2_ld, void* de, int64_t de_ld, const void* ys, int64_t ys_ld, int N, int HW, int C,
+                           const float* A2g, const float* B2g, const float* mean_s, const float* rstd_s, float* dG,
+                           float* sums_s, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  RBU_CHECK_ARG(VIEW_OK(dout, dout_ld) && VIEW_OK(out, out_ld) && VIEW_OK(y2, y2_ld) && VIEW_OK(de, de_ld) && A2g && B2g &&
+                    dG && CH_OK(C) && N > 0 && N <= 65535 && HW > 0, "rbu_rb_bwd1: bad arguments");
+  RBU_CHECK_ARG(!ys || (VIEW_OK(ys, ys_ld) && mean_s && rstd_s && sums_s), "rbu_rb_bwd1: projection-shortcut arguments missing");
+  const int chunks = bwd_chunks(N, HW, C);
+  RBU_CHECK_ARG(workspace && workspace_bytes >= (size_t)N * chunks * 2 * C * sizeof(float), "rbu_rb_bwd1: workspace too small");
+  rb_bwd1_kernel<<<dim3(chunks, N), NT, 0, st>>>((const bf16*)dout, dout_ld, (const bf16*)out, out_ld, (const bf16*)y2,
+                                                 y2_ld, (bf16*)de, de_ld, (const bf16*)ys, ys_ld, HW, C,
+                                                 rbu_cdiv(HW, chunks), A2g, B2g, mean_s, rstd_s, dG, (float*)workspace);
+  RBU_CHECK_LAUNCH();
+  if (ys) {
+    colsum_kernel<<<rbu_cdiv(2 * C, 128), 128, 0, st>>>((const float*)workspace, N * chunks, 2 * C, 2 * C, sums_s, 1.f);
+    RBU_CHECK_LAUNCH();
+  }
+  return RBU_OK;
+}
+
+extern "C" int rbu_sa_bwd(const float* dG, const float* gs, const float* s, int N, int H, int W, const float* k7,
+                          float* ds, float* dk7, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  RBU_CHECK_ARG(dG && gs && s && k7 && ds && dk7 && N > 0 && H > 0 && W > 0, "rbu_sa_bwd: bad arguments");
+  const long P = (long)N * H * W;
+  sa_bwd_data_kernel<<<grid1d(P, NT), NT, 0, st>>>(dG, gs, N, H, W, k7, (float2*)ds);
+  RBU_CHECK_LAUNCH();
+  const int blocks = grid1d(P, NT * 8);
+  RBU_CHECK_ARG(workspace && workspace_bytes >= (size_t)blocks * 98 * sizeof(float), "rbu_sa_bwd: workspace too small");
+  sa_bwd_weight_kernel<<<blocks, NT, 0, st>>>(dG, gs, (const float2*)s, N, H, W, (float*)workspace);
+  RBU_CHECK_LAUNCH();
+  colsum_kernel<<<1, 128, 0, st>>>((const float*)workspace, blocks, 98, 98, dk7, 1.f);
+  RBU_CHECK_LAUNCH();
+  return RBU_OK;
+}
+
+// pass selector: 2 -> dT[N,C];  3 -> sums2[2C] (= dbeta2, dgamma2);  4 -> dy2 (+ dys)
+extern "C" int rbu_rb_bwd_pass(int pass, const void* de, int64_t de_ld, const void* y2, int64_t y2_ld, int N, int HW, int C,
+                               const float* gs, const float* ds, const int* amax_c, const float* g_c,
+                               const float* du_avg, const float* du_max, const int* nc_amax, const int* nc_amin,
+                               const float* scale2, const float* shift2, const float* mean2, const float* rstd2,
+                               float* dT, float* sums2, void* dy2, int64_t dy2_ld, const void* ys, int64_t ys_ld,
+                               void* dys, int64_t dys_ld, const float* scale_s, const float* mean_s,
+                               const float* rstd_s, const float* sums_s, void* workspace, size_t workspace_bytes,
+                               void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  RBU_CHECK_ARG(pass >= 2 && pass <= 4, "rbu_rb_bwd_pass: pass must be 2, 3 or 4");
+  RBU_CHECK_ARG(VIEW_OK(de, de_ld) && VIEW_OK(y2, y2_ld) && CH_OK(C) && N > 0 && N <= 65535 && HW > 0 && gs && ds && amax_c &&
+                    scale2 && shift2, "rbu_rb_bwd_pass: bad arguments");
+  RbCtx k;
+  k.gs = gs; k.ds = (const float2*)ds; k.amax_c = amax_c; k.g_c = g_c; k.du_avg = du_avg; k.du_max = du_max;
+  k.nc_amax = nc_amax; k.nc_amin = nc_amin; k.scale2 = scale2; k.shift2 = shift2; k.mean2 = mean2; k.rstd2 = rstd2;
+  const int chunks = bwd_chunks(N, HW, C);
+  const int chunk_px = rbu_cdiv(HW, chunks);
+  const float invM = 1.f / ((float)N * (float)HW);
+  float* part = (float*)workspace;
+  if (pass == 2) {
+    RBU_CHECK_ARG(dT && workspace_bytes >= (size_t)N * chunks * C * sizeof(float), "rbu_rb_bwd_pass(2): bad arguments");
+    rb_bwd2_kernel<<<dim3(chunks, N), NT, 0, st>>>((const bf16*)de, de_ld, (const bf16*)y2, y2_ld, HW, C, chunk_px, k, part);
+    RBU_CHECK_LAUNCH();
+    colsum_nc_kernel<<<dim3(rbu_cdiv(C, 128), N), 128, 0, st>>>(part, N, chunks, C, dT);
+    RBU_CHECK_LAUNCH();
+    return RBU_OK;
+  }
+  RBU_CHECK_ARG(g_c && du_avg && du_max && nc_amax && nc_amin && mean2 && rstd2 && sums2, "rbu_rb_bwd_pass: null pointer");
+  if (pass == 3) {
+    RBU_CHECK_ARG(workspace_bytes >= (size_t)N * chunks * 2 * C * sizeof(float), "rbu_rb_bwd_pass(3): workspace too small");
+    rb_bwd34_kernel<0><<<dim3(chunks, N), NT, 0, st>>>((const bf16*)de, de_ld, (const bf16*)y2, y2_ld, HW, C, chunk_px, k,
+                                                      part, nullptr, invM, nullptr, 0, nullptr, 0, nullptr, 0, nullptr,
+                                                      nullptr, nullptr, nullptr);
+    RBU_CHECK_LAUNCH();
+    colsum_kernel<<<rbu_cdiv(2 * C, 128), 128, 0, st>>>(part, N * chunks, 2 * C, 2 * C, sums2, 1.f);
+    RBU_CHECK_LAUNCH();
+    return RBU_OK;
+  }
+  RBU_CHECK_ARG(VIEW_OK(dy2, dy2_ld), "rbu_rb_bwd_pass(4): bad dy2 view");
+  RBU_CHECK_ARG(!ys || (VIEW_OK(ys, ys_ld) && VIEW_OK(dys, dys_ld) && scale_s && mean_s && rstd_s && sums_s),
+                "rbu_rb_bwd_pass(4): projection-shortcut arguments missing");
+  rb_bwd34_kernel<1><<<dim3(chunks, N), NT, 0, st>>>((const bf16*)de, de_ld, (const bf16*)y2, y2_ld, HW, C, chunk_px, k,
+                                                    nullptr, sums2, invM, (bf16*)dy2, dy2_ld, (const bf16*)ys, ys_ld,
+                                                    (bf16*)dys, dys_ld, scale_s, mean_s, rstd_s, sums_s);
+  RBU_CHECK_LAUNCH();
+  return RBU_OK;
+}
+
+extern "C" int rbu_ca_bwd(const float* dT, const float* g, const float* h_avg, const float* h_max, const float* u_avg,
+                          const float* u_max, const float* V1, const float* V2, int N, int C, int Ch, float* dt,
+                          float* dh_avg, float* dh_max, float* du_avg, float* du_max, float* dV1, float* dV2,
+                          void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  RBU_CHECK_ARG(dT && g && h_avg && h_max && u_avg && u_max && V1 && V2 && dt && dh_avg && dh_max && du_avg && du_max &&
+                    dV1 && dV2 && N > 0 && C > 0 && Ch > 0 && (C + 2 * Ch) * 4 <= 48 * 1024, "rbu_ca_bwd: bad arguments");
+  ca_bwd_n_kernel<<<N, NT, (C + 2 * Ch) * sizeof(float), st>>>(dT, g, h_avg, h_max, V1, V2, C, Ch, dt, dh_avg, dh_max,
+                                                               du_avg, du_max);
+  RBU_CHECK_LAUNCH();
+  ca_bwd_w_kernel<<<rbu_cdiv((long)C * Ch, 128), 128, 0, st>>>(dt, dh_avg, dh_max, h_avg, h_max, u_avg, u_max, N, C, Ch,
+                                                               dV1, dV2);
+  RBU_CHECK_LAUNCH();
+  return RBU_OK;
+}
+
+// BatchNorm(+ReLU)(+Dropout2d) backward: writes dx and sums[2C] = (dbeta, dgamma)
+extern "C" int rbu_bn_bwd(const void* dy, int64_t dy_ld, const void* y, int64_t y_ld, void* dx, int64_t dx_ld, int N,
+                          int HW, int C, const float* scale, const float* shift, const float* mean, const float* rstd,
+                          const float* drop, int relu, float* sums, void* workspace, size_t workspace_bytes,
+                          void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  RBU_CHECK_ARG(VIEW_OK(dy, dy_ld) && VIEW_OK(y, y_ld) && VIEW_OK(dx, dx_ld) && CH_OK(C) && N > 0 && N <= 65535 && HW > 0 &&
+                    scale && shift && mean && rstd && sums, "rbu_bn_bwd: bad arguments");
+  const int chunks = bwd_chunks(N, HW, C);
+  const int chunk_px = rbu_cdiv(HW, chunks);
+  RBU_CHECK_ARG(workspace && workspace_bytes >= (size_t)N * chunks * 2 * C * sizeof(float), "rbu_bn_bwd: workspace too small");
+  const float invM = 1.f / ((float)N * (float)HW);
+  bn_bwd_kernel<0><<<dim3(chunks, N), NT, 0, st>>>((const bf16*)dy, dy_ld, (const bf16*)y, y_ld, HW, C, chunk_px, scale,
+                                                  shift, mean, rstd, drop, relu, (float*)workspace, nullptr, invM,
+                                                  nullptr, 0);
+  RBU_CHECK_LAUNCH();
+  colsum_kernel<<<rbu_cdiv(2 * C, 128), 128, 0, st>>>((const float*)workspace, N * chunks, 2 * C, 2 * C, sums, 1.f);
+  RBU_CHECK_LAUNCH();
+  bn_bwd_kernel<1><<<dim3(chunks, N), NT, 0, st>>>((const bf16*)dy, dy_ld, (const bf16*)y, y_ld, HW, C, chunk_px, scale,
+                                                  shift, mean, rstd, drop, relu, nullptr, sums, invM, (bf16*)dx, dx_ld);
+  RBU_CHECK_LAUNCH();
+  return RBU_OK;
+}
+
+// AttentionGate backward.  Outputs: dskip view (= da*psi), dyg/dyx views, sums_f[4][F] (dwpsi, dbeta_g(=dbeta_x),
+// dgamma_g, dgamma_x), sums_psi[2] (dbeta_psi, dgamma_psi).
+extern "C" int rbu_ag_bwd(const void* da, int64_t da_ld, const void* skip, int64_t s_ld, void* dskip, int64_t ds_ld,
+                          const void* yg, int64_t yg_ld, const void* yx, int64_t yx_ld, void* dyg, int64_t dyg_ld,
+                          void* dyx, int64_t dyx_ld, int N, int HW, int C, int F, const float* psi, const float* q0,
+                          const float* stats, const float* Ag, const float* Bg, const float* Ax, const float* Bx,
+                          const float* mg, const float* rg, const float* mx, const float* rx, const float* wpsi,
+                          float* dq, float* sums_psi, float* sums_f, void* workspace, size_t workspace_bytes,
+                          void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  RBU_CHECK_ARG(VIEW_OK(da, da_ld) && VIEW_OK(skip, s_ld) && VIEW_OK(dskip, ds_ld) && VIEW_OK(yg, yg_ld) && VIEW_OK(yx, yx_ld) &&
+                    VIEW_OK(dyg, dyg_ld) && VIEW_OK(dyx, dyx_ld) && CH_OK(C) && CH_OK(F) && N > 0 && N <= 65535 && HW > 0,
+                "rbu_ag_bwd: bad views");
+  RBU_CHECK_ARG(psi && q0 && stats && Ag && Bg && Ax && Bx && mg && rg && mx && rx && wpsi && dq && sums_psi && sums_f,
+                "rbu_ag_bwd: null pointer");
+  const float invM = 1.f / ((float)N * (float)HW);
+  float* part = (float*)workspace;
+  {
+    const int chunks = bwd_chunks(N, HW, C);
+    RBU_CHECK_ARG(workspace && workspace_bytes >= (size_t)N * chunks * 2 * sizeof(float), "rbu_ag_bwd: workspace too small");
+    ag_bwd1_kernel<<<dim3(chunks, N), NT, 0, st>>>((const bf16*)da, da_ld, (const bf16*)skip, s_ld, (bf16*)dskip, ds_ld, HW,
+                                                   C, rbu_cdiv(HW, chunks), psi, q0, stats, dq, part);
+    RBU_CHECK_LAUNCH();
+    colsum_kernel<<<1, 32, 0, st>>>(part, N * chunks, 2, 2, sums_psi, 1.f);
+    RBU_CHECK_LAUNCH();
+  }
+  {
+    const int chunks = bwd_chunks(N, HW, F);
+    const int chunk_px = rbu_cdiv(HW, chunks);
+    RBU_CHECK_ARG(workspace_bytes >= (size_t)N * chunks * 4 * F * sizeof(float), "rbu_ag_bwd: workspace too small");
+    ag_bwd23_kernel<0><<<dim3(chunks, N), NT, 0, st>>>((const bf16*)yg, yg_ld, (const bf16*)yx, yx_ld, HW, F, chunk_px, Ag, Bg,
+                                                      Ax, Bx, mg, rg, mx, rx, wpsi, dq, q0, stats, sums_psi, invM, part,
+                                                      nullptr, nullptr, 0, nullptr, 0);
+    RBU_CHECK_LAUNCH();
+    colsum_kernel<<<rbu_cdiv(4 * F, 128), 128, 0, st>>>(part, N * chunks, 4 * F, 4 * F, sums_f, 1.f);
+    RBU_CHECK_LAUNCH();
+    ag_bwd23_kernel<1><<<dim3(chunks, N), NT, 0, st>>>((const bf16*)yg, yg_ld, (const bf16*)yx, yx_ld, HW, F, chunk_px, Ag, Bg,
+                                                      Ax, Bx, mg, rg, mx, rx, wpsi, dq, q0, stats, sums_psi, invM, nullptr,
+                                                      sums_f, (bf16*)dyg, dyg_ld, (bf16*)dyx, dyx_ld);
+    RBU_CHECK_LAUNCH();
+  }
+  return RBU_OK;
+}
+
+extern "C" int rbu_maxpool2x2_bwd(const void* x, int64_t x_ld, const void* dy, int64_t dy_ld, void* dx, int64_t dx_ld,
+                                  int N, int Ho, int Wo, int C, int accumulate, void* stream_) {
+  RBU_CHECK_ARG(VIEW_OK(x, x_ld) && VIEW_OK(dy, dy_ld) && VIEW_OK(dx, dx_ld) && N > 0 && Ho > 0 && Wo > 0 && C % 8 == 0,
+                "rbu_maxpool2x2_bwd: bad arguments");
+  maxpool_bwd_kernel<<<grid1d((long)N * Ho * Wo * (C >> 3), NT), NT, 0, (cudaStream_t)stream_>>>(
+      (const bf16*)x, x_ld, (const bf16*)dy, dy_ld, (bf16*)dx, dx_ld, N, Ho, Wo, C, accumulate);
+  RBU_CHECK_LAUNCH();
+  return RBU_OK;
+}
+
+extern "C" int rbu_chan_sum(const void* x, int64_t ld, int64_t P, int C, float* out, void* workspace,
+                            size_t workspace_bytes, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  RBU_CHECK_ARG(VIEW_OK(x, ld) && out && CH_OK(C) && P > 0, "rbu_chan_sum: bad arguments");
+  int ppb;
+  const int blocks = flat_blocks(P, C, &ppb);
+  RBU_CHECK_ARG(workspace && workspace_bytes >= (size_t)blocks * C * sizeof(float), "rbu_chan_sum: workspace too small");
+  chan_sum_kernel<<<blocks, NT, 0, st>>>((const bf16*)x, ld, P, C, ppb, (float*)workspace);
+  RBU_CHECK_LAUNCH();
+  colsum_kernel<<<rbu_cdiv(C, 128), 128, 0, st>>>((const float*)workspace, blocks, C, C, out, 1.f);
+  RBU_CHECK_LAUNCH();
+  return RBU_OK;
+}

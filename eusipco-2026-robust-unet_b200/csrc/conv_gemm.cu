@@ -210,36 +210,36 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         ptx::tmem_ld_wait();
         const int col = nb * p.block_n + c0;
         if (valid && col < p.Ncols) {
-          bf16* dst;
-          int cb;  // bias channel base
-          if (p.scatter) {
-            const int q = col / p.Cout;
-            cb = col - q * p.Cout;
-            const long long opix = ((long long)n * (2 * p.H) + 2 * h + (q >> 1)) * (2 * p.W) + 2 * w + (q & 1);
-            dst = p.y + opix * p.y_ld + cb;
-          } else {
-            cb = col;
-            dst = p.y + pix * p.y_ld + col;
-          }
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            if (col + g * 8 < p.Ncols) {
+            const int c8 = col + g * 8;
+            if (c8 < p.Ncols) {
+              bf16* dst;
+              int cb = c8;  // bias channel
+              if (p.scatter) {
+                const int q = c8 / p.Cout;
+                cb = c8 - q * p.Cout;
+                const long long opix = ((long long)n * (2 * p.H) + 2 * h + (q >> 1)) * (2 * p.W) + 2 * w + (q & 1);
+                dst = p.y + opix * p.y_ld + cb;
+              } else {
+                dst = p.y + pix * p.y_ld + c8;
+              }
               float f[8];
 #pragma unroll
               for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(r[g * 8 + e]);
               if (p.bias) {
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + cb + g * 8));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + cb + g * 8 + 4));
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + cb));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + cb + 4));
                 f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
                 f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
               }
               if (p.addend) {
                 float ad[8];
-                unpack8(ld_bf16x8(p.addend + pix * p.addend_ld + col + g * 8), ad);
+                unpack8(ld_bf16x8(p.addend + pix * p.addend_ld + c8), ad);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) f[e] += ad[e];
               }
-              st_bf16x8(dst + g * 8, pack8(f));
+              st_bf16x8(dst, pack8(f));
             }
           }
         }
@@ -273,8 +273,8 @@ extern "C" int rbu_conv_gemm(const rbu_conv_gemm_args* a, void* stream_) {
                 "rbu_conv_gemm: output view must be 16-byte aligned with ld %% 8 == 0");
   RBU_CHECK_ARG(a->bias == nullptr || ((uintptr_t)a->bias & 15) == 0, "rbu_conv_gemm: bias must be 16-byte aligned");
   if (a->scatter) {
-    RBU_CHECK_ARG(a->Cout > 0 && a->Ncols == 4 * a->Cout && a->Cout % 32 == 0,
-                  "rbu_conv_gemm: scatter needs Ncols == 4*Cout and Cout %% 32 == 0");
+    RBU_CHECK_ARG(a->Cout > 0 && a->Ncols == 4 * a->Cout && a->Cout % 8 == 0,
+                  "rbu_conv_gemm: scatter needs Ncols == 4*Cout and Cout %% 8 == 0");
     RBU_CHECK_ARG(a->addend == nullptr, "rbu_conv_gemm: addend is not supported with scatter");
   }
   if (a->addend)

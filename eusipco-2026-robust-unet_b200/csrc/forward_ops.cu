@@ -1,0 +1,699 @@
+// Bandwidth-bound forward kernels of the Robust U-Net blocks (K2-K8 of SURVEY.md §2.1): BatchNorm
+// statistics / finalize / apply(+ReLU+Dropout2d scale), ChannelAttention gate, SpatialAttention
+// reduce + 7x7 gate, residual output, 2x2 max-pool, AttentionGate psi / apply, stem im2col, `outc` head.
+// All activations are NHWC bf16 views (16-byte vector accesses, 8 channels per thread); statistics and
+// gates are fp32; every reduction is two-stage with a fixed order (deterministic, no float atomics).
+#include "rbu_common.cuh"
+
+namespace {
+
+constexpr int NT = 256;
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm statistics (nn.BatchNorm2d train mode, Main_Final.py:158,160,173,127,132,210) and, with
+// pool=1, the per-(n,c) mean / max / min (+ first-index arg) that ChannelAttention's AdaptiveAvg/MaxPool
+// (Main_Final.py:87-88,98-99) need — computed on the raw conv output; BN is a per-channel affine map.
+// grid (chunks, N); thread = (channel group of 8, pixel row)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT)
+bn_stats_kernel(const bf16* __restrict__ x, long ld, int HW, int C, int chunk_px, int pool,
+                float* __restrict__ part_f, int* __restrict__ part_i) {
+  const int G = C >> 3;
+  const int rows = NT / G;
+  const int cg = threadIdx.x % G;
+  const int row = threadIdx.x / G;
+  const int n = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
+  const int p0 = chunk * chunk_px;
+  const int p1 = min(p0 + chunk_px, HW);
+  float sum[8], sq[8], mx[8], mn[8];
+  int amx[8], amn[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    sum[e] = 0.f; sq[e] = 0.f; mx[e] = -INFINITY; mn[e] = INFINITY; amx[e] = 0x7fffffff; amn[e] = 0x7fffffff;
+  }
+  if (row < rows) {
+    const bf16* base = x + (long)n * HW * ld + cg * 8;
+    for (int p = p0 + row; p < p1; p += rows) {
+      float v[8];
+      unpack8(ld_bf16x8(base + (long)p * ld), v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        sum[e] += v[e];
+        sq[e] += v[e] * v[e];
+        if (pool) {
+          if (v[e] > mx[e]) { mx[e] = v[e]; amx[e] = p; }
+          if (v[e] < mn[e]) { mn[e] = v[e]; amn[e] = p; }
+        }
+      }
+    }
+  }
+  __shared__ float sv[NT][8];
+  __shared__ int si[NT][8];
+  const long obase = ((long)n * chunks + chunk);
+  // sum, sumsq
+  for (int q = 0; q < 2; ++q) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) sv[threadIdx.x][e] = q == 0 ? sum[e] : sq[e];
+    __syncthreads();
+    if (row == 0) {
+      float a[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a[e] = sv[cg][e];
+      for (int r = 1; r < rows; ++r)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) a[e] += sv[r * G + cg][e];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) part_f[(obase * 4 + q) * C + cg * 8 + e] = a[e];
+    }
+    __syncthreads();
+  }
+  if (pool) {
+    for (int q = 0; q < 2; ++q) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        sv[threadIdx.x][e] = q == 0 ? mx[e] : -mn[e];   // min handled as max of the negation
+        si[threadIdx.x][e] = q == 0 ? amx[e] : amn[e];
+      }
+      __syncthreads();
+      if (row == 0) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float bv = sv[cg][e];
+          int bi = si[cg][e];
+          for (int r = 1; r < rows; ++r) {
+            const float v = sv[r * G + cg][e];
+            const int i = si[r * G + cg][e];
+            if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+          }
+          part_f[(obase * 4 + 2 + q) * C + cg * 8 + e] = q == 0 ? bv : -bv;
+          part_i[(obase * 2 + q) * C + cg * 8 + e] = bi;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// thread per channel: ordered combine of the partials, BN affine (train: batch stats + running update;
+// eval: running stats), optional per-(n,c) pooled outputs.
+__global__ void bn_finalize_kernel(const float* __restrict__ part_f, const int* __restrict__ part_i, int N, int chunks,
+                                   int HW, int C, int pool, int training, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, float momentum, float eps,
+                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
+                                   float* __restrict__ rstd_out, float* __restrict__ nc_mean, float* __restrict__ nc_max,
+                                   float* __restrict__ nc_min, int* __restrict__ nc_amax, int* __restrict__ nc_amin) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double tsum = 0.0, tsq = 0.0;
+  for (int n = 0; n < N; ++n) {
+    double s = 0.0;
+    float bmx = -INFINITY, bmn = INFINITY;
+    int imx = 0, imn = 0;
+    for (int k = 0; k < chunks; ++k) {
+      const long o = (long)n * chunks + k;
+      s += (double)part_f[(o * 4 + 0) * C + c];
+      tsq += (double)part_f[(o * 4 + 1) * C + c];
+      if (pool) {
+        const float vmx = part_f[(o * 4 + 2) * C + c], vmn = part_f[(o * 4 + 3) * C + c];
+        if (vmx > bmx) { bmx = vmx; imx = part_i[(o * 2 + 0) * C + c]; }   // chunks ascend: strict > keeps the first
+        if (vmn < bmn) { bmn = vmn; imn = part_i[(o * 2 + 1) * C + c]; }
+      }
+    }
+    tsum += s;
+    if (pool) {
+      nc_mean[(long)n * C + c] = (float)(s / (double)HW);
+      nc_max[(long)n * C + c] = bmx;
+      nc_min[(long)n * C + c] = bmn;
+      nc_amax[(long)n * C + c] = imx;
+      nc_amin[(long)n * C + c] = imn;
+    }
+  }
+  float mean, var;
+  if (training) {
+    const double M = (double)N * (double)HW;
+    const double m = tsum / M;
+    double v = tsq / M - m * m;
+    if (v < 0.0) v = 0.0;
+    mean = (float)m;
+    var = (float)v;
+    if (running_mean) {
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+      const float unbiased = M > 1.0 ? (float)(v * M / (M - 1.0)) : var;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+    }
+  } else {
+    mean = running_mean[c];
+    var = running_var[c];
+  }
+  const float rstd = 1.0f / sqrtf(var + eps);
+  const float sc = gamma[c] * rstd;
+  scale[c] = sc;
+  shift[c] = beta[c] - mean * sc;
+  if (mean_out) mean_out[c] = mean;
+  if (rstd_out) rstd_out[c] = rstd;
+}
+
+// y = [relu](scale[c]*x + shift[c]) * drop[n,c]     (BN apply + ReLU + Dropout2d, Main_Final.py:182-184,220-221)
+__global__ void __launch_bounds__(NT)
+affine_act_kernel(const bf16* __restrict__ x, long x_ld, bf16* __restrict__ y, long y_ld, long P, int HW, int C,
+                  const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ drop,
+                  int relu) {
+  const int G = C >> 3;
+  const long total = P * G;
+  for (long i = blockIdx.x * (long)NT + threadIdx.x; i < total; i += (long)gridDim.x * NT) {
+    const long p = i / G;
+    const int cg = (int)(i - p * G);
+    float v[8];
+    unpack8(ld_bf16x8_stream(x + p * x_ld + cg * 8), v);
+    const int n = (int)(p / HW);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = cg * 8 + e;
+      float t = scale[c] * v[e] + shift[c];
+      if (relu) t = fmaxf(t, 0.f);
+      if (drop) t *= drop[(long)n * C + c];
+      v[e] = t;
+    }
+    st_bf16x8(y + p * y_ld + cg * 8, pack8(v));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// ChannelAttention gate (Main_Final.py:97-101): g = sigmoid(V2 relu(V1 u_avg) + V2 relu(V1 u_max)),
+// u = BN2 affine of the pooled raw conv2 output.  One block per image.  Also emits the fused per-(n,c)
+// affine  A2g = scale*g, B2g = shift*g  so that  CA(BN2(y2)) = A2g*y2 + B2g.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT)
+ca_gate_kernel(const float* __restrict__ nc_mean, const float* __restrict__ nc_max, const float* __restrict__ nc_min,
+               const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ V1,
+               const float* __restrict__ V2, int C, int Ch, float* __restrict__ g_out, float* __restrict__ A2g,
+               float* __restrict__ B2g, float* __restrict__ u_avg_out, float* __restrict__ u_max_out,
+               float* __restrict__ h_avg_out, float* __restrict__ h_max_out) {
+  extern __shared__ float sm[];
+  float* u_avg = sm;            // [C]
+  float* u_max = sm + C;        // [C]
+  float* h_avg = sm + 2 * C;    // [Ch]
+  float* h_max = h_avg + Ch;    // [Ch]
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += NT) {
+    const float sc = scale[c], sh = shift[c];
+    const float ua = sc * nc_mean[(long)n * C + c] + sh;
+    const float um = sc * (sc >= 0.f ? nc_max[(long)n * C + c] : nc_min[(long)n * C + c]) + sh;
+    u_avg[c] = ua;
+    u_max[c] = um;
+    u_avg_out[(long)n * C + c] = ua;
+    u_max_out[(long)n * C + c] = um;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int j = warp; j < Ch; j += NT / 32) {
+    float a = 0.f, m = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float w = V1[(long)j * C + c];
+      a += w * u_avg[c];
+      m += w * u_max[c];
+    }
+    a = warp_sum(a);
+    m = warp_sum(m);
+    if (lane == 0) {
+      h_avg[j] = a;
+      h_max[j] = m;
+      h_avg_out[(long)n * Ch + j] = a;
+      h_max_out[(long)n * Ch + j] = m;
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += NT) {
+    float o = 0.f;
+    for (int j = 0; j < Ch; ++j) o += V2[(long)c * Ch + j] * (fmaxf(h_avg[j], 0.f) + fmaxf(h_max[j], 0.f));
+    const float g = sigmoidf_acc(o);
+    g_out[(long)n * C + c] = g;
+    A2g[(long)n * C + c] = scale[c] * g;
+    B2g[(long)n * C + c] = shift[c] * g;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SpatialAttention reduce (Main_Final.py:113-115): per pixel mean_c / max_c (+ first argmax) of
+// c = A2g[n,c]*y2 + B2g[n,c].  TPP lanes cooperate on one pixel.
+// ------------------------------------------------------------------------------------------------
+template <int TPP>
+__global__ void __launch_bounds__(NT)
+sa_reduce_kernel(const bf16* __restrict__ y2, long ld, long P, int HW, int C, const float* __restrict__ A2g,
+                 const float* __restrict__ B2g, float2* __restrict__ s_out, int* __restrict__ amax_out) {
+  const int G = C >> 3;
+  const int li = threadIdx.x % TPP;
+  const int slot = threadIdx.x / TPP;
+  constexpr int SLOTS = NT / TPP;
+  for (long p = blockIdx.x * (long)SLOTS + slot; p < P; p += (long)gridDim.x * SLOTS) {
+    const int n = (int)(p / HW);
+    const float* a = A2g + (long)n * C;
+    const float* b = B2g + (long)n * C;
+    float sum = 0.f, best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int cg = li; cg < G; cg += TPP) {
+      float v[8];
+      unpack8(ld_bf16x8(y2 + p * ld + cg * 8), v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int c = cg * 8 + e;
+        const float t = a[c] * v[e] + b[c];
+        sum += t;
+        if (t > best) { best = t; bi = c; }
+      }
+    }
+#pragma unroll
+    for (int o = TPP / 2; o > 0; o >>= 1) {
+      sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (li == 0) {
+      s_out[p] = make_float2(sum / (float)C, best);
+      amax_out[p] = bi;
+    }
+  }
+}
+
+// g_s = sigmoid(conv7x7([s_avg, s_max]))  (Main_Final.py:109,116-117); weight layout [1][2][7][7]
+__global__ void __launch_bounds__(NT)
+sa_gate_kernel(const float2* __restrict__ s, int N, int H, int W, const float* __restrict__ k7, float* __restrict__ gs) {
+  __shared__ float wk[98];
+  if (threadIdx.x < 98) wk[threadIdx.x] = k7[threadIdx.x];
+  __syncthreads();
+  const long P = (long)N * H * W;
+  for (long p = blockIdx.x * (long)NT + threadIdx.x; p < P; p += (long)gridDim.x * NT) {
+    const int w = (int)(p % W);
+    const int h = (int)((p / W) % H);
+    const long nb = p - (long)h * W - w;
+    float acc = 0.f;
+#pragma unroll
+    for (int r = 0; r < 7; ++r) {
+      const int hh = h + r - 3;
+      if (hh < 0 || hh >= H) continue;
+#pragma unroll
+      for (int q = 0; q < 7; ++q) {
+        const int ww = w + q - 3;
+        if (ww < 0 || ww >= W) continue;
+        const float2 v = __ldg(&s[nb + (long)hh * W + ww]);
+        acc += wk[r * 7 + q] * v.x + wk[49 + r * 7 + q] * v.y;
+      }
+    }
+    gs[p] = sigmoidf_acc(acc);
+  }
+}
+
+// out = relu((A2g*y2 + B2g) * g_s + r),  r = As*ys + Bs (projection shortcut) or r = x (identity)
+// (Main_Final.py:179,190-194)
+__global__ void __launch_bounds__(NT)
+rb_out_kernel(const bf16* __restrict__ y2, long y2_ld, const bf16* __restrict__ rsrc, long r_ld, bf16* __restrict__ out,
+              long out_ld, long P, int HW, int C, const float* __restrict__ A2g, const float* __restrict__ B2g,
+              const float* __restrict__ gs, const float* __restrict__ As, const float* __restrict__ Bs) {
+  const int G = C >> 3;
+  const long total = P * G;
+  for (long i = blockIdx.x * (long)NT + threadIdx.x; i < total; i += (long)gridDim.x * NT) {
+    const long p = i / G;
+    const int cg = (int)(i - p * G);
+    const int n = (int)(p / HW);
+    float v[8], r[8];
+    unpack8(ld_bf16x8_stream(y2 + p * y2_ld + cg * 8), v);
+    unpack8(ld_bf16x8_stream(rsrc + p * r_ld + cg * 8), r);
+    const float g = gs[p];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = cg * 8 + e;
+      const float res = As ? As[c] * r[e] + Bs[c] : r[e];
+      v[e] = fmaxf((A2g[(long)n * C + c] * v[e] + B2g[(long)n * C + c]) * g + res, 0.f);
+    }
+    st_bf16x8(out + p * out_ld + cg * 8, pack8(v));
+  }
+}
+
+// 2x2 stride-2 max pool (nn.MaxPool2d(2), Main_Final.py:235,239,243,249)
+__global__ void __launch_bounds__(NT)
+maxpool_kernel(const bf16* __restrict__ x, long x_ld, bf16* __restrict__ y, long y_ld, int N, int Ho, int Wo, int C) {
+  const int G = C >> 3;
+  const long total = (long)N * Ho * Wo * G;
+  const int W = 2 * Wo;
+  for (long i = blockIdx.x * (long)NT + threadIdx.x; i < total; i += (long)gridDim.x * NT) {
+    const int cg = (int)(i % G);
+    const long po = i / G;
+    const int wo = (int)(po % Wo);
+    const int ho = (int)((po / Wo) % Ho);
+    const int n = (int)(po / ((long)Wo * Ho));
+    const long pi = ((long)n * 2 * Ho + 2 * ho) * W + 2 * wo;
+    float a[8], b[8], c[8], d[8];
+    unpack8(ld_bf16x8(x + pi * x_ld + cg * 8), a);
+    unpack8(ld_bf16x8(x + (pi + 1) * x_ld + cg * 8), b);
+    unpack8(ld_bf16x8(x + (pi + W) * x_ld + cg * 8), c);
+    unpack8(ld_bf16x8(x + (pi + W + 1) * x_ld + cg * 8), d);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a[e] = fmaxf(fmaxf(a[e], b[e]), fmaxf(c[e], d[e]));
+    st_bf16x8(y + po * y_ld + cg * 8, pack8(a));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// AttentionGate (Main_Final.py:143-148)
+//   psi stage : t = relu(Ag*yg+Bg + Ax*yx+Bx); q0 = w_psi . t + b_psi  -> q0[P], block partials (sum, sumsq)
+//   finalize  : BatchNorm2d(1) over all pixels (scalar statistics)
+//   apply     : psi = sigmoid(a*q0+b); out = skip * psi
+// ------------------------------------------------------------------------------------------------
+template <int TPP>
+__global__ void __launch_bounds__(NT)
+ag_psi_kernel(const bf16* __restrict__ yg, long yg_ld, const bf16* __restrict__ yx, long yx_ld, long P, int F,
+              const float* __restrict__ Ag, const float* __restrict__ Bg, const float* __restrict__ Ax,
+              const float* __restrict__ Bx, const float* __restrict__ wpsi, const float* __restrict__ bpsi,
+              float* __restrict__ q0, float* __restrict__ partials) {
+  const int G = F >> 3;
+  const int li = threadIdx.x % TPP;
+  const int slot = threadIdx.x / TPP;
+  constexpr int SLOTS = NT / TPP;
+  float ls = 0.f, lq = 0.f;
+  for (long p = blockIdx.x * (long)SLOTS + slot; p < P; p += (long)gridDim.x * SLOTS) {
+    float acc = 0.f;
+    for (int cg = li; cg < G; cg += TPP) {
+      float a[8], b[8];
+      unpack8(ld_bf16x8_stream(yg + p * yg_ld + cg * 8), a);
+      unpack8(ld_bf16x8_stream(yx + p * yx_ld + cg * 8), b);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int c = cg * 8 + e;
+        const float t = fmaxf(Ag[c] * a[e] + Bg[c] + Ax[c] * b[e] + Bx[c], 0.f);
+        acc += wpsi[c] * t;
+      }
+    }
+#pragma unroll
+    for (int o = TPP / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (li == 0) {
+      const float q = acc + bpsi[0];
+      q0[p] = q;
+      ls += q;
+      lq += q * q;
+    }
+  }
+  __shared__ float r0[NT / 32], r1[NT / 32];
+  ls = warp_sum(ls);
+  lq = warp_sum(lq);
+  if ((threadIdx.x & 31) == 0) { r0[threadIdx.x >> 5] = ls; r1[threadIdx.x >> 5] = lq; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+    for (int w = 0; w < NT / 32; ++w) { a += r0[w]; b += r1[w]; }
+    partials[blockIdx.x * 2] = a;
+    partials[blockIdx.x * 2 + 1] = b;
+  }
+}
+
+// scalar BN finalize: stats[0..3] = scale, shift, mean, rstd
+__global__ void scalar_bn_finalize_kernel(const float* __restrict__ partials, int nblk, long M, int training,
+                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                          float* __restrict__ running_mean, float* __restrict__ running_var,
+                                          float momentum, float eps, float* __restrict__ stats) {
+  if (threadIdx.x != 0) return;
+  float mean, var;
+  if (training) {
+    double s = 0.0, q = 0.0;
+    for (int i = 0; i < nblk; ++i) { s += (double)partials[2 * i]; q += (double)partials[2 * i + 1]; }
+    const double m = s / (double)M;
+    double v = q / (double)M - m * m;
+    if (v < 0.0) v = 0.0;
+    mean = (float)m;
+    var = (float)v;
+    if (running_mean) {
+      running_mean[0] = (1.f - momentum) * running_mean[0] + momentum * mean;
+      running_var[0] = (1.f - momentum) * running_var[0] + momentum * (M > 1 ? (float)(v * (double)M / (double)(M - 1)) : var);
+    }
+  } else {
+    mean = running_mean[0];
+    var = running_var[0];
+  }
+  const float rstd = 1.0f / sqrtf(var + eps);
+  stats[0] = gamma[0] * rstd;
+  stats[1] = beta[0] - mean * gamma[0] * rstd;
+  stats[2] = mean;
+  stats[3] = rstd;
+}
+
+__global__ void __launch_bounds__(NT)
+ag_apply_kernel(const bf16* __restrict__ skip, long s_ld, bf16* __restrict__ out, long o_ld, long P, int C,
+                const float* __restrict__ q0, const float* __restrict__ stats, float* __restrict__ psi_out) {
+  const int G = C >> 3;
+  const long total = P * G;
+  const float a = stats[0], b = stats[1];
+  for (long i = blockIdx.x * (long)NT + threadIdx.x; i < total; i += (long)gridDim.x * NT) {
+    const long p = i / G;
+    const int cg = (int)(i - p * G);
+    const float psi = sigmoidf_acc(a * q0[p] + b);
+    if (cg == 0) psi_out[p] = psi;
+    float v[8];
+    unpack8(ld_bf16x8(skip + p * s_ld + cg * 8), v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] *= psi;
+    st_bf16x8(out + p * o_ld + cg * 8, pack8(v));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stem: fp32 NCHW image -> bf16 3x3 patches [P][Kp], k = tap*nc + c (zero padded), so that inc.conv1
+// (3x3, Cin=3|4) and inc.shortcut (1x1) run as ONE tensor-core GEMM with K = Kp (Main_Final.py:157,172,233).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT)
+stem_im2col_kernel(const float* __restrict__ x, int N, int nc, int H, int W, int Kp, bf16* __restrict__ out) {
+  const long P = (long)N * H * W;
+  const int KG = Kp >> 3;
+  const long total = P * KG;
+  for (long i = blockIdx.x * (long)NT + threadIdx.x; i < total; i += (long)gridDim.x * NT) {
+    const long p = i % P;     // pixel fastest: coalesced fp32 reads
+    const int kg = (int)(i / P);
+    const int w = (int)(p % W);
+    const int h = (int)((p / W) % H);
+    const int n = (int)(p / ((long)W * H));
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = kg * 8 + e;
+      float t = 0.f;
+      if (k < 9 * nc) {
+        const int tap = k / nc, c = k - tap * nc;
+        const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) t = x[(((long)n * nc + c) * H + hh) * W + ww];
+      }
+      v[e] = t;
+    }
+    st_bf16x8(out + p * Kp + kg * 8, pack8(v));
+  }
+}
+
+// outc: probs = sigmoid(w . x + b)   (1x1 conv C->1 + Sigmoid, fp32; Main_Final.py:274-277,321)
+template <int TPP>
+__global__ void __launch_bounds__(NT)
+head_fwd_kernel(const bf16* __restrict__ x, long ld, long P, int C, const float* __restrict__ w,
+                const float* __restrict__ b, float* __restrict__ probs, float* __restrict__ logits) {
+  const int G = C >> 3;
+  const int li = threadIdx.x % TPP;
+  const int slot = threadIdx.x / TPP;
+  constexpr int SLOTS = NT / TPP;
+  for (long p = blockIdx.x * (long)SLOTS + slot; p < P; p += (long)gridDim.x * SLOTS) {
+    float acc = 0.f;
+    for (int cg = li; cg < G; cg += TPP) {
+      float v[8];
+      unpack8(ld_bf16x8_stream(x + p * ld + cg * 8), v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc += w[cg * 8 + e] * v[e];
+    }
+#pragma unroll
+    for (int o = TPP / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (li == 0) {
+      const float z = acc + b[0];
+      probs[p] = sigmoidf_acc(z);
+      if (logits) logits[p] = z;
+    }
+  }
+}
+
+int grid_for(long items, int per_block) {
+  long b = (items + per_block - 1) / per_block;
+  const long cap = (long)rbu_num_sms() * 8;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+int pick_tpp(int C) {
+  const int G = C >> 3;
+  int t = 4;
+  while (t * 2 <= G && t < 32) t <<= 1;
+  return t;
+}
+
+int stats_chunks(int N, int HW, int C) {
+  const int rows = NT / (C >> 3);
+  long want = ((long)rbu_num_sms() * 4 + N - 1) / N;          // ~4 blocks per SM in total
+  long maxc = (HW + (long)rows * 8 - 1) / ((long)rows * 8);   // at least ~8 pixels per thread
+  if (maxc < 1) maxc = 1;
+  if (want > maxc) want = maxc;
+  if (want < 1) want = 1;
+  return (int)want;
+}
+
+}  // namespace
+
+#define VIEW_OK(ptr, ld) ((ptr) != nullptr && ((uintptr_t)(ptr) & 15) == 0 && (ld) % 8 == 0)
+
+extern "C" size_t rbu_bn_stats_workspace_bytes(int N, int HW, int C) {
+  if (C < 8 || C % 8 || C > 2048) return 0;
+  return (size_t)N * stats_chunks(N, HW, C) * 6 * C * sizeof(float);
+}
+
+extern "C" int rbu_bn_stats(const void* x, int64_t ld, int N, int HW, int C, int pool, int training,
+                            const float* gamma, const float* beta, float* running_mean, float* running_var,
+                            float momentum, float eps, float* scale, float* shift, float* mean_out, float* rstd_out,
+                            float* nc_mean, float* nc_max, float* nc_min, int* nc_amax, int* nc_amin, void* workspace,
+                            size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  RBU_CHECK_ARG(VIEW_OK(x, ld), "rbu_bn_stats: misaligned view");
+  RBU_CHECK_ARG(N > 0 && HW > 0 && C >= 8 && C % 8 == 0 && C <= 2048, "rbu_bn_stats: unsupported shape N=%d HW=%d C=%d", N, HW, C);
+  RBU_CHECK_ARG(gamma && beta && scale && shift, "rbu_bn_stats: null parameter pointer");
+  RBU_CHECK_ARG(training || (running_mean && running_var), "rbu_bn_stats: eval mode needs running statistics");
+  RBU_CHECK_ARG(!pool || (nc_mean && nc_max && nc_min && nc_amax && nc_amin), "rbu_bn_stats: pool outputs missing");
+  if (!training && !pool) {  // pure eval affine: no pass over the data
+    bn_finalize_kernel<<<rbu_cdiv(C, 128), 128, 0, stream>>>(nullptr, nullptr, 0, 0, HW, C, 0, 0, gamma, beta,
+                                                              running_mean, running_var, momentum, eps, scale, shift,
+                                                              mean_out, rstd_out, nullptr, nullptr, nullptr, nullptr,
+                                                              nullptr);
+    RBU_CHECK_LAUNCH();
+    return RBU_OK;
+  }
+  RBU_CHECK_ARG(workspace && workspace_bytes >= rbu_bn_stats_workspace_bytes(N, HW, C), "rbu_bn_stats: workspace too small");
+  RBU_CHECK_ARG(N <= 65535, "rbu_bn_stats: batch too large");
+  const int chunks = stats_chunks(N, HW, C);
+  const int chunk_px = rbu_cdiv(HW, chunks);
+  float* part_f = (float*)workspace;
+  int* part_i = (int*)(part_f + (size_t)N * chunks * 4 * C);
+  bn_stats_kernel<<<dim3(chunks, N), NT, 0, stream>>>((const bf16*)x, ld, HW, C, chunk_px, pool, part_f, part_i);
+  RBU_CHECK_LAUNCH();
+  bn_finalize_kernel<<<rbu_cdiv(C, 128), 128, 0, stream>>>(part_f, part_i, N, chunks, HW, C, pool, training, gamma, beta,
+                                                            running_mean, running_var, momentum, eps, scale, shift,
+                                                            mean_out, rstd_out, nc_mean, nc_max, nc_min, nc_amax,
+                                                            nc_amin);
+  RBU_CHECK_LAUNCH();
+  return RBU_OK;
+}
+
+extern "C" int rbu_affine_act(const void* x, int64_t x_ld, void* y, int64_t y_ld, int64_t P, int HW, int C,
+                              const float* scale, const float* shift, const float* drop, int relu, void* stream_) {
+  RBU_CHECK_ARG(VIEW_OK(x, x_ld) && VIEW_OK(y, y_ld) && scale && shift && C % 8 == 0 && P > 0 && HW > 0,
+                "rbu_affine_act: bad arguments");
+  affine_act_kernel<<<grid_for(P * (C >> 3), NT * 4), NT, 0, (cudaStream_t)stream_>>>(
+      (const bf16*)x, x_ld, (bf16*)y, y_ld, P, HW, C, scale, shift, drop, relu);
+  RBU_CHECK_LAUNCH();
+  return RBU_OK;
+}
+
+extern "C" int rbu_ca_gate(const float* nc_mean, const float* nc_max, const float* nc_min, const float* scale,
+                           const float* shift, const float* V1, const float* V2, int N, int C, int Ch, float* g,
+                           float* A2g, float* B2g, float* u_avg, float* u_max, float* h_avg, float* h_max,
+                           void* stream_) {
+  RBU_CHECK_ARG(nc_mean && nc_max && nc_min && scale && shift && V1 && V2 && g && A2g && B2g && u_avg && u_max &&
+                    h_avg && h_max, "rbu_ca_gate: null pointer");
+  RBU_CHECK_ARG(N > 0 && C > 0 && Ch > 0 && (2 * C + 2 * Ch) * 4 <= 48 * 1024, "rbu_ca_gate: unsupported shape");
+  ca_gate_kernel<<<N, NT, (2 * C + 2 * Ch) * sizeof(float), (cudaStream_t)stream_>>>(
+      nc_mean, nc_max, nc_min, scale, shift, V1, V2, C, Ch, g, A2g, B2g, u_avg, u_max, h_avg, h_max);
+  RBU_CHECK_LAUNCH();
+  return RBU_OK;
+}
+
+extern "C" int rbu_sa_reduce(const void* y2, int64_t ld, int64_t P, int HW, int C, const float* A2g, const float* B2g,
+                             float* s_out, int* amax_out, void* stream_) {
+  RBU_CHECK_ARG(VIEW_OK(y2, ld) && A2g && B2g && s_out && amax_out && C >= 8 && C % 8 == 0, "rbu_sa_reduce: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream_;
+  const int tpp = pick_tpp(C);
+  const int grid = grid_for(P, NT / tpp * 4);
+#define LAUNCH(T) sa_reduce_kernel<T><<<grid, NT, 0, st>>>((const bf16*)y2, ld, P, HW, C, A2g, B2g, (float2*)s_out, amax_out)
+  if (tpp == 4) LAUNCH(4); else if (tpp == 8) LAUNCH(8); else if (tpp == 16) LAUNCH(16); else LAUNCH(32);
+#undef LAUNCH
+  RBU_CHECK_LAUNCH();
+  return RBU_OK;
+}
+
+extern "C" int rbu_sa_gate(const float* s, int N, int H, int W, const float* k7, float* gs, void* stream_) {
+  RBU_CHECK_ARG(s && k7 && gs && N > 0 && H > 0 && W > 0, "rbu_sa_gate: bad arguments");
+  sa_gate_kernel<<<grid_for((long)N * H * W, NT), NT, 0, (cudaStream_t)stream_>>>((const float2*)s, N, H, W, k7, gs);
+  RBU_CHECK_LAUNCH();
+  return RBU_OK;
+}
+
+extern "C" int rbu_rb_out(const void* y2, int64_t y2_ld, const void* rsrc, int64_t r_ld, void* out, int64_t out_ld,
+                          int64_t P, int HW, int C, const float* A2g, const float* B2g, const float* gs,
+                          const float* As, const float* Bs, void* stream_) {
+  RBU_CHECK_ARG(VIEW_OK(y2, y2_ld) && VIEW_OK(rsrc, r_ld) && VIEW_OK(out, out_ld) && A2g && B2g && gs && C % 8 == 0,
+                "rbu_rb_out: bad arguments");
+  RBU_CHECK_ARG((As == nullptr) == (Bs == nullptr), "rbu_rb_out: As/Bs must both be set or both NULL");
+  rb_out_kernel<<<grid_for(P * (C >> 3), NT * 4), NT, 0, (cudaStream_t)stream_>>>(
+      (const bf16*)y2, y2_ld, (const bf16*)rsrc, r_ld, (bf16*)out, out_ld, P, HW, C, A2g, B2g, gs, As, Bs);
+  RBU_CHECK_LAUNCH();
+  return RBU_OK;
+}
+
+extern "C" int rbu_maxpool2x2(const void* x, int64_t x_ld, void* y, int64_t y_ld, int N, int Ho, int Wo, int C,
+                              void* stream_) {
+  RBU_CHECK_ARG(VIEW_OK(x, x_ld) && VIEW_OK(y, y_ld) && N > 0 && Ho > 0 && Wo > 0 && C % 8 == 0, "rbu_maxpool2x2: bad arguments");
+  maxpool_kernel<<<grid_for((long)N * Ho * Wo * (C >> 3), NT * 2), NT, 0, (cudaStream_t)stream_>>>(
+      (const bf16*)x, x_ld, (bf16*)y, y_ld, N, Ho, Wo, C);
+  RBU_CHECK_LAUNCH();
+  return RBU_OK;
+}
+
+extern "C" int rbu_ag_psi_blocks(int64_t P, int F) { return grid_for(P, NT / pick_tpp(F) * 4); }
+
+extern "C" int rbu_ag_psi(const void* yg, int64_t yg_ld, const void* yx, int64_t yx_ld, int64_t P, int F,
+                          const float* Ag, const float* Bg, const float* Ax, const float* Bx, const float* wpsi,
+                          const float* bpsi, int training, const float* gamma, const float* beta, float* running_mean,
+                          float* running_var, float momentum, float eps, float* q0, float* stats, float* partials,
+                          void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  RBU_CHECK_ARG(VIEW_OK(yg, yg_ld) && VIEW_OK(yx, yx_ld) && Ag && Bg && Ax && Bx && wpsi && bpsi && q0 && stats &&
+                    partials && gamma && beta && F >= 8 && F % 8 == 0, "rbu_ag_psi: bad arguments");
+  const int tpp = pick_tpp(F);
+  const int grid = rbu_ag_psi_blocks(P, F);
+#define LAUNCH(T) ag_psi_kernel<T><<<grid, NT, 0, st>>>((const bf16*)yg, yg_ld, (const bf16*)yx, yx_ld, P, F, Ag, Bg, Ax, Bx, wpsi, bpsi, q0, partials)
+  if (tpp == 4) LAUNCH(4); else if (tpp == 8) LAUNCH(8); else if (tpp == 16) LAUNCH(16); else LAUNCH(32);
+#undef LAUNCH
+  RBU_CHECK_LAUNCH();
+  scalar_bn_finalize_kernel<<<1, 32, 0, st>>>(partials, grid, P, training, gamma, beta, running_mean, running_var,
+                                              momentum, eps, stats);
+  RBU_CHECK_LAUNCH();
+  return RBU_OK;
+}
+
+extern "C" int rbu_ag_apply(const void* skip, int64_t s_ld, void* out, int64_t o_ld, int64_t P, int C, const float* q0,
+                            const float* stats, float* psi, void* stream_) {
+  RBU_CHECK_ARG(VIEW_OK(skip, s_ld) && VIEW_OK(out, o_ld) && q0 && stats && psi && C % 8 == 0, "rbu_ag_apply: bad arguments");
+  ag_apply_kernel<<<grid_for(P * (C >> 3), NT * 4), NT, 0, (cudaStream_t)stream_>>>((const bf16*)skip, s_ld, (bf16*)out,
+                                                                                   o_ld, P, C, q0, stats, psi);
+  RBU_CHECK_LAUNCH();
+  return RBU_OK;
+}
+
+extern "C" int rbu_stem_im2col(const float* x, int N, int nc, int H, int W, int Kp, void* out, void* stream_) {
+  RBU_CHECK_ARG(x && out && N > 0 && nc > 0 && H > 0 && W > 0 && Kp % 8 == 0 && Kp >= 9 * nc && ((uintptr_t)out & 15) == 0,
+                "rbu_stem_im2col: bad arguments");
+  stem_im2col_kernel<<<grid_for((long)N * H * W * (Kp >> 3), NT * 2), NT, 0, (cudaStream_t)stream_>>>(x, N, nc, H, W, Kp,
+                                                                                                     (bf16*)out);
+  RBU_CHECK_LAUNCH();
+  return RBU_OK;
+}
+
+extern "C" int rbu_head_forward(const void* x, int64_t ld, int64_t P, int C, const float* w, const float* b,
+                                float* probs, float* logits, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  RBU_CHECK_ARG(VIEW_OK(x, ld) && w && b && probs && C >= 8 && C % 8 == 0, "rbu_head_forward: bad arguments");
+  const int tpp = pick_tpp(C);
+  const int grid = grid_for(P, NT / tpp * 4);
+#define LAUNCH(T) head_fwd_kernel<T><<<grid, NT, 0, st>>>((const bf16*)x, ld, P, C, w, b, probs, logits)
+  if (tpp == 4) LAUNCH(4); else if (tpp == 8) LAUNCH(8); else if (tpp == 16) LAUNCH(16); else LAUNCH(32);
+#undef LAUNCH
+  RBU_CHECK_LAUNCH();
+  return RBU_OK;
+}

@@ -1,0 +1,488 @@
+"""Host-side schedule of the Robust U-Net forward / backward on the CUDA kernels (one stream, no
+hidden synchronisation).  Mirrors the data flow of RobustUNet.forward (Main_Final.py:290-321) and the
+backward derivation in SURVEY.md Appendix C; every tensor op is a C-ABI call into librbunet.so.
+
+Layout: activations are NHWC bf16 (`View`s, possibly channel slices of a wider buffer so that
+`torch.cat` never materialises); statistics, gates, probabilities and all parameter gradients are fp32.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_void_p
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import WgradArgs, call, stream_ptr
+from .ops import View, conv_gemm, pack_weight
+
+BN_EPS = 1e-5
+NULL = c_void_p(0)
+
+
+def _p(t):
+    return c_void_p(t.data_ptr()) if t is not None else NULL
+
+
+def _vp(v: View):
+    return c_void_p(v.ptr)
+
+
+class Workspace:
+    """One scratch buffer shared by all kernels of a step (they run back to back on one stream)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.buf = torch.empty(1 << 22, dtype=torch.float32, device=device)
+
+    def get(self, nbytes: int):
+        if nbytes > self.buf.numel() * 4:
+            self.buf = torch.empty((nbytes + 3) // 4 + (1 << 20), dtype=torch.float32, device=self.device)
+        return self.buf
+
+
+class Engine:
+    def __init__(self, model):
+        self.model = model
+        self._packs = {}
+        self._ws = None
+        self.drop_mask_fn = None     # optional callable(name, N, C) -> float32 [N,C] device tensor (tests)
+        self.kernel_launches = 0
+
+    # ------------------------------------------------------------------ helpers
+    def ws(self, nbytes, device):
+        if self._ws is None or self._ws.device != device:
+            self._ws = Workspace(device)
+        return self._ws.get(int(nbytes))
+
+    def pack(self, param: torch.Tensor, mode: int):
+        key = (id(param), mode)
+        ent = self._packs.get(key)
+        if ent is None or ent[0] != param._version or ent[1].device != param.device:
+            ent = (param._version, pack_weight(param.detach().contiguous(), mode))
+            self._packs[key] = ent
+        return ent[1]
+
+    def pack_stem(self, w1, wsc, Kp):
+        key = (id(w1), "stem")
+        ent = self._packs.get(key)
+        ver = (w1._version, wsc._version)
+        if ent is None or ent[0] != ver or ent[1].device != w1.device:
+            C, nc = w1.shape[0], w1.shape[1]
+            m = torch.zeros((2 * C, Kp), dtype=torch.float32, device=w1.device)
+            m[:C, :9 * nc] = w1.detach().permute(0, 2, 3, 1).reshape(C, 9 * nc)
+            m[C:, 4 * nc:5 * nc] = wsc.detach().reshape(C, nc)
+            ent = (ver, m.to(torch.bfloat16).reshape(2 * C, 1, Kp).contiguous())
+            self._packs[key] = ent
+        return ent[1]
+
+    @staticmethod
+    def new(N, H, W, C, device):
+        return View(torch.empty((N, H, W, C), dtype=torch.bfloat16, device=device))
+
+    @staticmethod
+    def f32(*shape, device):
+        return torch.empty(shape, dtype=torch.float32, device=device)
+
+    def bn_stats(self, x: View, N, HW, bn: nn.BatchNorm2d, training, pool=False):
+        C, dev = x.C, x.base.device
+        out = {"scale": self.f32(C, device=dev), "shift": self.f32(C, device=dev),
+               "mean": self.f32(C, device=dev), "rstd": self.f32(C, device=dev)}
+        if pool:
+            out.update(nc_mean=self.f32(N, C, device=dev), nc_max=self.f32(N, C, device=dev),
+                       nc_min=self.f32(N, C, device=dev),
+                       nc_amax=torch.empty((N, C), dtype=torch.int32, device=dev),
+                       nc_amin=torch.empty((N, C), dtype=torch.int32, device=dev))
+        nbytes = _lib.lib().rbu_bn_stats_workspace_bytes(N, HW, C)
+        ws = self.ws(nbytes, dev)
+        call("rbu_bn_stats", _vp(x), x.ld, N, HW, C, int(pool), int(training), _p(bn.weight), _p(bn.bias),
+             _p(bn.running_mean), _p(bn.running_var), float(bn.momentum), float(bn.eps), _p(out["scale"]),
+             _p(out["shift"]), _p(out["mean"]), _p(out["rstd"]), _p(out.get("nc_mean")), _p(out.get("nc_max")),
+             _p(out.get("nc_min")), _p(out.get("nc_amax")), _p(out.get("nc_amin")), _p(ws), ws.numel() * 4,
+             stream_ptr())
+        if training:
+            bn.num_batches_tracked += 1
+        return out
+
+    def wgrad(self, N, H, W, a: View, b: View, taps, dil, gather, out: torch.Tensor):
+        args = WgradArgs()
+        args.N, args.H, args.W = N, H, W
+        args.a, args.a_ld, args.Ca = a.ptr, a.ld, a.C
+        args.b, args.b_ld, args.Cb = b.ptr, b.ld, b.C
+        args.taps, args.dil, args.gather = taps, dil, int(gather)
+        args.out, args.accumulate = out.data_ptr(), 0
+        nbytes = _lib.lib().rbu_wgrad_workspace_bytes(ctypes.byref(args))
+        ws = self.ws(nbytes, out.device)
+        call("rbu_wgrad_gemm", ctypes.byref(args), _p(ws), ws.numel() * 4, stream_ptr())
+
+    def bwd_ws(self, N, HW, C, device):
+        return self.ws(_lib.lib().rbu_bwd_workspace_bytes(N, HW, max(C, 32)), device)
+
+    def drop_mask(self, name, N, C, p, device):
+        if self.drop_mask_fn is not None:
+            m = self.drop_mask_fn(name, N, C)
+            return m.to(device=device, dtype=torch.float32).reshape(N, C).contiguous()
+        # nn.Dropout2d (Main_Final.py:162,184): per-(n,c) Bernoulli(1-p) / (1-p)
+        return torch.empty((N, C), dtype=torch.float32, device=device).bernoulli_(1.0 - p).div_(1.0 - p)
+
+    # ------------------------------------------------------------------ ResidualBlock (Main_Final.py:178-196)
+    def rb_forward(self, name, blk, x: View, N, H, W, training, out: View = None, stem_patches: View = None):
+        dev = x.base.device if x is not None else stem_patches.base.device
+        C = blk.conv2.out_channels
+        HW, P = H * W, N * H * W
+        proj = not isinstance(blk.shortcut, nn.Identity)
+        s = {"name": name, "x": x, "N": N, "H": H, "W": W, "C": C, "proj": proj, "patches": stem_patches}
+        if stem_patches is not None:
+            y12 = self.new(N, H, W, 2 * C, dev)
+            wst = self.pack_stem(blk.conv1.weight, blk.shortcut[0].weight, stem_patches.C)
+            conv_gemm(N, H, W, [(stem_patches, wst, 1, 0, False)], 2 * C, y12)
+            y1, ys = y12.slice(0, C), y12.slice(C, C)
+        else:
+            y1 = self.new(N, H, W, C, dev)
+            conv_gemm(N, H, W, [(x, self.pack(blk.conv1.weight, 0), 9, 1, False)], C, y1)
+            ys = None
+            if proj:
+                ys = self.new(N, H, W, C, dev)
+                conv_gemm(N, H, W, [(x, self.pack(blk.shortcut[0].weight, 0), 1, 0, False)], C, ys)
+        bn1 = self.bn_stats(y1, N, HW, blk.bn1, training)
+        drop = self.drop_mask(name, N, C, blk.dropout.p, dev) if training and blk.dropout.p > 0 else None
+        a1 = self.new(N, H, W, C, dev)
+        call("rbu_affine_act", _vp(y1), y1.ld, _vp(a1), a1.ld, P, HW, C, _p(bn1["scale"]), _p(bn1["shift"]), _p(drop), 1,
+             stream_ptr())
+        y2 = self.new(N, H, W, C, dev)
+        conv_gemm(N, H, W, [(a1, self.pack(blk.conv2.weight, 0), 9, 1, False)], C, y2)
+        bn2 = self.bn_stats(y2, N, HW, blk.bn2, training, pool=True)
+        Ch = blk.ca.fc[0].out_channels
+        ca = {k: self.f32(N, C, device=dev) for k in ("g", "A2g", "B2g", "u_avg", "u_max")}
+        ca["h_avg"], ca["h_max"] = self.f32(N, Ch, device=dev), self.f32(N, Ch, device=dev)
+        call("rbu_ca_gate", _p(bn2["nc_mean"]), _p(bn2["nc_max"]), _p(bn2["nc_min"]), _p(bn2["scale"]), _p(bn2["shift"]),
+             _p(blk.ca.fc[0].weight), _p(blk.ca.fc[2].weight), N, C, Ch, _p(ca["g"]), _p(ca["A2g"]), _p(ca["B2g"]),
+             _p(ca["u_avg"]), _p(ca["u_max"]), _p(ca["h_avg"]), _p(ca["h_max"]), stream_ptr())
+        sa_s = self.f32(P, 2, device=dev)
+        amax_c = torch.empty(P, dtype=torch.int32, device=dev)
+        call("rbu_sa_reduce", _vp(y2), y2.ld, P, HW, C, _p(ca["A2g"]), _p(ca["B2g"]), _p(sa_s), _p(amax_c), stream_ptr())
+        gs = self.f32(P, device=dev)
+        call("rbu_sa_gate", _p(sa_s), N, H, W, _p(blk.sa.conv1.weight), _p(gs), stream_ptr())
+        bns = self.bn_stats(ys, N, HW, blk.shortcut[1], training) if proj else None
+        if out is None:
+            out = self.new(N, H, W, C, dev)
+        rsrc = ys if proj else x
+        call("rbu_rb_out", _vp(y2), y2.ld, _vp(rsrc), rsrc.ld, _vp(out), out.ld, P, HW, C, _p(ca["A2g"]), _p(ca["B2g"]),
+             _p(gs), _p(bns["scale"]) if proj else NULL, _p(bns["shift"]) if proj else NULL, stream_ptr())
+        s.update(y1=y1, ys=ys, a1=a1, y2=y2, out=out, bn1=bn1, bn2=bn2, bns=bns, drop=drop, ca=ca, sa_s=sa_s,
+                 amax_c=amax_c, gs=gs, Ch=Ch)
+        return out, s
+
+    def rb_backward(self, blk, s, dout: View, grads: dict, prefix: str, need_dx=True, dx: View = None):
+        """dout may be overwritten (it becomes de).  Returns the View holding d(input)."""
+        N, H, W, C = s["N"], s["H"], s["W"], s["C"]
+        HW, P = H * W, N * H * W
+        dev = dout.base.device
+        proj, ys, y2, ca, bn2, bns = s["proj"], s["ys"], s["y2"], s["ca"], s["bn2"], s["bns"]
+        ws = self.bwd_ws(N, HW, C, dev)
+        wsb = ws.numel() * 4
+        st = stream_ptr()
+        de = dout
+        dG = self.f32(P, device=dev)
+        sums_s = self.f32(2 * C, device=dev) if proj else None
+        call("rbu_rb_bwd1", _vp(dout), dout.ld, _vp(s["out"]), s["out"].ld, _vp(y2), y2.ld, _vp(de), de.ld,
+             _vp(ys) if proj else NULL, ys.ld if proj else 0, N, HW, C, _p(ca["A2g"]), _p(ca["B2g"]),
+             _p(bns["mean"]) if proj else NULL, _p(bns["rstd"]) if proj else NULL, _p(dG), _p(sums_s), _p(ws), wsb, st)
+        ds = self.f32(P, 2, device=dev)
+        dk7 = self.f32(98, device=dev)
+        call("rbu_sa_bwd", _p(dG), _p(s["gs"]), _p(s["sa_s"]), N, H, W, _p(blk.sa.conv1.weight), _p(ds), _p(dk7), _p(ws),
+             wsb, st)
+        grads[prefix + ".sa.conv1.weight"] = dk7.view(1, 2, 7, 7)
+
+        def rb_pass(k, dT=None, sums2=None, dy2=None, dys=None):
+            call("rbu_rb_bwd_pass", k, _vp(de), de.ld, _vp(y2), y2.ld, N, HW, C, _p(s["gs"]), _p(ds), _p(s["amax_c"]),
+                 _p(ca["g"]), _p(du_avg), _p(du_max), _p(bn2["nc_amax"]), _p(bn2["nc_amin"]), _p(bn2["scale"]),
+                 _p(bn2["shift"]), _p(bn2["mean"]), _p(bn2["rstd"]), _p(dT), _p(sums2),
+                 _vp(dy2) if dy2 is not None else NULL, dy2.ld if dy2 is not None else 0,
+                 _vp(ys) if (proj and dys is not None) else NULL, ys.ld if (proj and dys is not None) else 0,
+                 _vp(dys) if dys is not None else NULL, dys.ld if dys is not None else 0,
+                 _p(bns["scale"]) if proj else NULL, _p(bns["mean"]) if proj else NULL,
+                 _p(bns["rstd"]) if proj else NULL, _p(sums_s), _p(ws), wsb, st)
+
+        du_avg = du_max = None
+        dT = self.f32(N, C, device=dev)
+        rb_pass(2, dT=dT)
+        Ch = s["Ch"]
+        dt, du_avg, du_max = (self.f32(N, C, device=dev) for _ in range(3))
+        dh_avg, dh_max = self.f32(N, Ch, device=dev), self.f32(N, Ch, device=dev)
+        dV1, dV2 = self.f32(Ch, C, 1, 1, device=dev), self.f32(C, Ch, 1, 1, device=dev)
+        call("rbu_ca_bwd", _p(dT), _p(ca["g"]), _p(ca["h_avg"]), _p(ca["h_max"]), _p(ca["u_avg"]), _p(ca["u_max"]),
+             _p(blk.ca.fc[0].weight), _p(blk.ca.fc[2].weight), N, C, Ch, _p(dt), _p(dh_avg), _p(dh_max), _p(du_avg),
+             _p(du_max), _p(dV1), _p(dV2), st)
+        grads[prefix + ".ca.fc.0.weight"] = dV1
+        grads[prefix + ".ca.fc.2.weight"] = dV2
+        sums2 = self.f32(2 * C, device=dev)
+        rb_pass(3, sums2=sums2)
+        grads[prefix + ".bn2.bias"], grads[prefix + ".bn2.weight"] = sums2[:C], sums2[C:]
+        # dy1 | dys share one buffer so the stem's fused GEMM sees them as one operand
+        dy12 = self.new(N, H, W, 2 * C if proj else C, dev)
+        dy1 = dy12.slice(0, C)
+        dys = dy12.slice(C, C) if proj else None
+        dy2 = self.new(N, H, W, C, dev)
+        rb_pass(4, sums2=sums2, dy2=dy2, dys=dys)
+        if proj:
+            grads[prefix + ".shortcut.1.bias"], grads[prefix + ".shortcut.1.weight"] = sums_s[:C], sums_s[C:]
+        # conv2
+        a1 = s["a1"]
+        da1 = self.new(N, H, W, C, dev)
+        conv_gemm(N, H, W, [(dy2, self.pack(blk.conv2.weight, 1), 9, 1, False)], C, da1)
+        gW2 = torch.empty_like(blk.conv2.weight)
+        self.wgrad(N, H, W, dy2, a1, 9, 1, False, gW2)
+        grads[prefix + ".conv2.weight"] = gW2
+        # bn1 + relu + dropout
+        bn1 = s["bn1"]
+        sums1 = self.f32(2 * C, device=dev)
+        call("rbu_bn_bwd", _vp(da1), da1.ld, _vp(s["y1"]), s["y1"].ld, _vp(dy1), dy1.ld, N, HW, C, _p(bn1["scale"]),
+             _p(bn1["shift"]), _p(bn1["mean"]), _p(bn1["rstd"]), _p(s["drop"]), 1, _p(sums1), _p(ws), wsb, st)
+        grads[prefix + ".bn1.bias"], grads[prefix + ".bn1.weight"] = sums1[:C], sums1[C:]
+        # conv1 / shortcut
+        if s["patches"] is not None:
+            pt = s["patches"]
+            nc = blk.conv1.in_channels
+            gst = self.f32(2 * C, pt.C, device=dev)
+            self.wgrad(N, H, W, dy12, pt, 1, 0, False, gst)
+            grads[prefix + ".conv1.weight"] = gst[:C, :9 * nc].reshape(C, 3, 3, nc).permute(0, 3, 1, 2).contiguous()
+            grads[prefix + ".shortcut.0.weight"] = gst[C:, 4 * nc:5 * nc].reshape(C, nc, 1, 1).contiguous()
+            return None
+        x = s["x"]
+        gW1 = torch.empty_like(blk.conv1.weight)
+        self.wgrad(N, H, W, dy1, x, 9, 1, False, gW1)
+        grads[prefix + ".conv1.weight"] = gW1
+        if proj:
+            gWs = torch.empty_like(blk.shortcut[0].weight)
+            self.wgrad(N, H, W, dys, x, 1, 0, False, gWs)
+            grads[prefix + ".shortcut.0.weight"] = gWs
+        if not need_dx:
+            return None
+        if dx is None:
+            dx = self.new(N, H, W, x.C, dev)
+        segs = [(dy1, self.pack(blk.conv1.weight, 1), 9, 1, False)]
+        if proj:
+            segs.append((dys, self.pack(blk.shortcut[0].weight, 1), 1, 0, False))
+        conv_gemm(N, H, W, segs, x.C, dx, addend=None if proj else de)
+        return dx
+
+    # ------------------------------------------------------------------ AttentionGate (Main_Final.py:143-148)
+    def ag_forward(self, gate, g: View, skip: View, out: View, N, H, W, training):
+        dev = g.base.device
+        C, F = skip.C, gate.W_g[0].out_channels
+        HW, P = H * W, N * H * W
+        yg, yx = self.new(N, H, W, F, dev), self.new(N, H, W, F, dev)
+        conv_gemm(N, H, W, [(g, self.pack(gate.W_g[0].weight, 0), 1, 0, False)], F, yg, bias=gate.W_g[0].bias)
+        conv_gemm(N, H, W, [(skip, self.pack(gate.W_x[0].weight, 0), 1, 0, False)], F, yx, bias=gate.W_x[0].bias)
+        bg = self.bn_stats(yg, N, HW, gate.W_g[1], training)
+        bx = self.bn_stats(yx, N, HW, gate.W_x[1], training)
+        q0 = self.f32(P, device=dev)
+        stats = self.f32(4, device=dev)
+        nblk = _lib.lib().rbu_ag_psi_blocks(P, F)
+        part = self.ws(nblk * 8, dev)
+        bnp = gate.psi[1]
+        call("rbu_ag_psi", _vp(yg), yg.ld, _vp(yx), yx.ld, P, F, _p(bg["scale"]), _p(bg["shift"]), _p(bx["scale"]),
+             _p(bx["shift"]), _p(gate.psi[0].weight), _p(gate.psi[0].bias), int(training), _p(bnp.weight), _p(bnp.bias),
+             _p(bnp.running_mean), _p(bnp.running_var), float(bnp.momentum), float(bnp.eps), _p(q0), _p(stats), _p(part),
+             stream_ptr())
+        if training:
+            bnp.num_batches_tracked += 1
+        psi = self.f32(P, device=dev)
+        call("rbu_ag_apply", _vp(skip), skip.ld, _vp(out), out.ld, P, C, _p(q0), _p(stats), _p(psi), stream_ptr())
+        return {"g": g, "skip": skip, "yg": yg, "yx": yx, "bg": bg, "bx": bx, "q0": q0, "stats": stats, "psi": psi,
+                "N": N, "H": H, "W": W, "C": C, "F": F}
+
+    def ag_backward(self, gate, s, da: View, dskip: View, dgup: View, grads: dict, prefix: str):
+        N, H, W, C, F = s["N"], s["H"], s["W"], s["C"], s["F"]
+        HW, P = H * W, N * H * W
+        dev = da.base.device
+        ws = self.bwd_ws(N, HW, max(C, F), dev)
+        dyg, dyx = self.new(N, H, W, F, dev), self.new(N, H, W, F, dev)
+        dq = self.f32(P, device=dev)
+        sums_psi, sums_f = self.f32(2, device=dev), self.f32(4 * F, device=dev)
+        bg, bx = s["bg"], s["bx"]
+        call("rbu_ag_bwd", _vp(da), da.ld, _vp(s["skip"]), s["skip"].ld, _vp(dskip), dskip.ld, _vp(s["yg"]), s["yg"].ld,
+             _vp(s["yx"]), s["yx"].ld, _vp(dyg), dyg.ld, _vp(dyx), dyx.ld, N, HW, C, F, _p(s["psi"]), _p(s["q0"]),
+             _p(s["stats"]), _p(bg["scale"]), _p(bg["shift"]), _p(bx["scale"]), _p(bx["shift"]), _p(bg["mean"]),
+             _p(bg["rstd"]), _p(bx["mean"]), _p(bx["rstd"]), _p(gate.psi[0].weight), _p(dq), _p(sums_psi), _p(sums_f),
+             _p(ws), ws.numel() * 4, stream_ptr())
+        grads[prefix + ".psi.0.weight"] = sums_f[0:F].reshape(1, F, 1, 1)
+        grads[prefix + ".psi.0.bias"] = torch.zeros(1, device=dev)          # BN removes the mean: exactly zero
+        grads[prefix + ".psi.1.bias"], grads[prefix + ".psi.1.weight"] = sums_psi[0:1], sums_psi[1:2]
+        grads[prefix + ".W_g.1.bias"], grads[prefix + ".W_g.1.weight"] = sums_f[F:2 * F], sums_f[2 * F:3 * F]
+        grads[prefix + ".W_x.1.bias"], grads[prefix + ".W_x.1.weight"] = sums_f[F:2 * F], sums_f[3 * F:4 * F]
+        grads[prefix + ".W_g.0.bias"] = torch.zeros(F, device=dev)
+        grads[prefix + ".W_x.0.bias"] = torch.zeros(F, device=dev)
+        gWg, gWx = torch.empty_like(gate.W_g[0].weight), torch.empty_like(gate.W_x[0].weight)
+        self.wgrad(N, H, W, dyg, s["g"], 1, 0, False, gWg)
+        self.wgrad(N, H, W, dyx, s["skip"], 1, 0, False, gWx)
+        grads[prefix + ".W_g.0.weight"], grads[prefix + ".W_x.0.weight"] = gWg, gWx
+        conv_gemm(N, H, W, [(dyg, self.pack(gate.W_g[0].weight, 1), 1, 0, False)], C, dgup, addend=dgup)
+        conv_gemm(N, H, W, [(dyx, self.pack(gate.W_x[0].weight, 1), 1, 0, False)], C, dskip, addend=dskip)
+
+    # ------------------------------------------------------------------ DilatedBlock (Main_Final.py:213-223)
+    def dil_forward(self, blk, x: View, N, H, W, training):
+        dev = x.base.device
+        Cq = blk.conv1.out_channels
+        C = 4 * Cq
+        HW, P = H * W, N * H * W
+        ycat = self.new(N, H, W, C, dev)
+        convs = (blk.conv1, blk.conv2, blk.conv3, blk.conv4)
+        for i, cv in enumerate(convs):
+            taps = 1 if i == 0 else 9
+            conv_gemm(N, H, W, [(x, self.pack(cv.weight, 0), taps, cv.dilation[0], False)], Cq, ycat.slice(i * Cq, Cq),
+                      bias=cv.bias)
+        bn = self.bn_stats(ycat, N, HW, blk.bn, training)
+        out = self.new(N, H, W, C, dev)
+        call("rbu_affine_act", _vp(ycat), ycat.ld, _vp(out), out.ld, P, HW, C, _p(bn["scale"]), _p(bn["shift"]), NULL, 1,
+             stream_ptr())
+        return out, {"x": x, "ycat": ycat, "bn": bn, "N": N, "H": H, "W": W, "C": C, "Cq": Cq}
+
+    def dil_backward(self, blk, s, dout: View, grads: dict, prefix: str):
+        N, H, W, C, Cq = s["N"], s["H"], s["W"], s["C"], s["Cq"]
+        HW = H * W
+        dev = dout.base.device
+        x, ycat, bn = s["x"], s["ycat"], s["bn"]
+        ws = self.bwd_ws(N, HW, C, dev)
+        dycat = self.new(N, H, W, C, dev)
+        sums = self.f32(2 * C, device=dev)
+        call("rbu_bn_bwd", _vp(dout), dout.ld, _vp(ycat), ycat.ld, _vp(dycat), dycat.ld, N, HW, C, _p(bn["scale"]),
+             _p(bn["shift"]), _p(bn["mean"]), _p(bn["rstd"]), NULL, 1, _p(sums), _p(ws), ws.numel() * 4, stream_ptr())
+        grads[prefix + ".bn.bias"], grads[prefix + ".bn.weight"] = sums[:C], sums[C:]
+        convs = (blk.conv1, blk.conv2, blk.conv3, blk.conv4)
+        segs = []
+        for i, cv in enumerate(convs):
+            taps = 1 if i == 0 else 9
+            d = dycat.slice(i * Cq, Cq)
+            g = torch.empty_like(cv.weight)
+            self.wgrad(N, H, W, d, x, taps, cv.dilation[0], False, g)
+            grads[f"{prefix}.conv{i + 1}.weight"] = g
+            grads[f"{prefix}.conv{i + 1}.bias"] = torch.zeros(Cq, device=dev)   # a bias before a train-mode BN
+            segs.append((d, self.pack(cv.weight, 1), taps, cv.dilation[0], False))
+        dx = self.new(N, H, W, x.C, dev)
+        conv_gemm(N, H, W, segs[:2], x.C, dx)
+        conv_gemm(N, H, W, segs[2:], x.C, dx, addend=dx)
+        return dx
+
+    # ------------------------------------------------------------------ whole model
+    def forward(self, x: torch.Tensor, training: bool, save: bool):
+        m = self.model
+        _lib.check(0)
+        if not x.is_cuda:
+            raise RuntimeError("rbunet.RobustUNet runs on CUDA tensors only (no CPU fallback)")
+        N, nc, H, W = x.shape
+        if H % 16 or W % 16:
+            raise RuntimeError(f"input H,W must be multiples of 16, got {H}x{W}")
+        if nc != m.inc.conv1.in_channels:
+            raise RuntimeError(f"expected {m.inc.conv1.in_channels} input channels, got {nc}")
+        dev = x.device
+        x = x.contiguous().float()
+        S = {"N": N, "H": H, "W": W}
+        Kp = ((9 * nc + 7) // 8) * 8
+        patches = View(torch.empty((N, H, W, Kp), dtype=torch.bfloat16, device=dev))
+        call("rbu_stem_im2col", _p(x), N, nc, H, W, Kp, _vp(patches), stream_ptr())
+        b = m.inc.conv2.out_channels
+        enc = []
+        cur, s_inc = self.rb_forward("inc", m.inc, None, N, H, W, training, stem_patches=patches)
+        S["inc"] = s_inc
+        enc.append(cur)
+        h, w = H, W
+        pools = []
+        for i, name in enumerate(("down1", "down2", "down3")):
+            h, w = h // 2, w // 2
+            pooled = self.new(N, h, w, cur.C, dev)
+            call("rbu_maxpool2x2", _vp(cur), cur.ld, _vp(pooled), pooled.ld, N, h, w, cur.C, stream_ptr())
+            pools.append(pooled)
+            cur, S[name] = self.rb_forward(name + ".1", getattr(m, name)[1], pooled, N, h, w, training)
+            enc.append(cur)
+        h, w = h // 2, w // 2
+        pooled = self.new(N, h, w, cur.C, dev)
+        call("rbu_maxpool2x2", _vp(cur), cur.ld, _vp(pooled), pooled.ld, N, h, w, cur.C, stream_ptr())
+        pools.append(pooled)
+        x5a, S["dil"] = self.dil_forward(m.bottleneck[1], pooled, N, h, w, training)
+        cur, S["bott"] = self.rb_forward("bottleneck.2", m.bottleneck[2], x5a, N, h, w, training)
+        S["pools"] = pools
+        S["enc"] = enc
+        for k in (4, 3, 2, 1):
+            up = getattr(m, f"up{k}")
+            C = up.out_channels
+            skip = enc[k - 1]
+            cat = self.new(N, 2 * h, 2 * w, 2 * C, dev)
+            conv_gemm(N, h, w, [(cur, self.pack(up.weight, 2), 1, 0, False)], 4 * C, cat.slice(C, C), scatter=True,
+                      Cout=C, bias=up.bias)
+            S[f"up{k}"] = {"x": cur, "N": N, "H": h, "W": w, "C": C}
+            h, w = 2 * h, 2 * w
+            S[f"att{k}"] = self.ag_forward(getattr(m, f"att{k}"), cat.slice(C, C), skip, cat.slice(0, C), N, h, w, training)
+            cur, S[f"dec{k}"] = self.rb_forward(f"dec{k}", getattr(m, f"dec{k}"), cat, N, h, w, training)
+        P = N * H * W
+        probs = torch.empty((N, 1, H, W), dtype=torch.float32, device=dev)
+        hc = m.outc[0]
+        call("rbu_head_forward", _vp(cur), cur.ld, P, cur.C, _p(hc.weight), _p(hc.bias), _p(probs), NULL, stream_ptr())
+        S["head_x"] = cur
+        S["probs"] = probs
+        return probs, (S if save else None)
+
+    def backward(self, S, dprobs: torch.Tensor, allreduce_hook=None):
+        """Returns {param_name: fp32 gradient}.  `allreduce_hook(names)` is called as soon as the gradients of a
+        top-level child are complete (reverse execution order) so data-parallel buckets can overlap."""
+        m = self.model
+        grads = {}
+        N, H, W = S["N"], S["H"], S["W"]
+        dev = dprobs.device
+        P = N * H * W
+        hx = S["head_x"]
+        hc = m.outc[0]
+        d = self.new(N, H, W, hx.C, dev)
+        gw, gb = torch.empty_like(hc.weight), torch.empty_like(hc.bias)
+        ws = self.bwd_ws(N, H * W, hx.C, dev)
+        call("rbu_head_backward", _p(dprobs.contiguous()), _p(S["probs"]), _vp(hx), hx.ld, _vp(d), d.ld, P, hx.C,
+             _p(hc.weight), _p(gw), _p(gb), _p(ws), ws.numel() * 4, stream_ptr())
+        grads["outc.0.weight"], grads["outc.0.bias"] = gw, gb
+
+        def done(*prefixes):
+            if allreduce_hook is not None:
+                allreduce_hook([k for k in grads if any(k == p or k.startswith(p + ".") for p in prefixes)])
+
+        done("outc")
+        enc = S["enc"]
+        denc = [None] * 4
+        for k in (1, 2, 3, 4):
+            sd = S[f"dec{k}"]
+            dcat = self.rb_backward(getattr(m, f"dec{k}"), sd, d, grads, f"dec{k}")
+            C = sd["C"]
+            hk, wk = sd["H"], sd["W"]
+            denc[k - 1] = self.new(N, hk, wk, C, dev)
+            self.ag_backward(getattr(m, f"att{k}"), S[f"att{k}"], dcat.slice(0, C), denc[k - 1], dcat.slice(C, C), grads,
+                             f"att{k}")
+            up = getattr(m, f"up{k}")
+            su = S[f"up{k}"]
+            dup = dcat.slice(C, C)
+            gub = torch.empty_like(up.bias)
+            ws = self.bwd_ws(N, hk * wk, C, dev)
+            call("rbu_chan_sum", _vp(dup), dup.ld, N * hk * wk, C, _p(gub), _p(ws), ws.numel() * 4, stream_ptr())
+            guw = torch.empty_like(up.weight)
+            self.wgrad(N, su["H"], su["W"], su["x"], dup, 4, 0, True, guw)
+            grads[f"up{k}.bias"], grads[f"up{k}.weight"] = gub, guw
+            d = self.new(N, su["H"], su["W"], su["x"].C, dev)
+            conv_gemm(N, su["H"], su["W"], [(dup, self.pack(up.weight, 3), 4, 0, True)], su["x"].C, d)
+            done(f"dec{k}", f"att{k}", f"up{k}")
+        d = self.rb_backward(m.bottleneck[2], S["bott"], d, grads, "bottleneck.2")
+        d = self.dil_backward(m.bottleneck[1], S["dil"], d, grads, "bottleneck.1")
+        done("bottleneck")
+        pools = S["pools"]
+        for lvl in (3, 2, 1, 0):
+            src = enc[lvl]                      # x_{lvl+1}: input of the pool
+            pl = pools[lvl]
+            n_, ho, wo, _ = pl.base.shape
+            call("rbu_maxpool2x2_bwd", _vp(src), src.ld, _vp(d), d.ld, _vp(denc[lvl]), denc[lvl].ld, N, ho, wo, src.C, 1,
+                 stream_ptr())
+            if lvl > 0:
+                name = f"down{lvl}"
+                d = self.rb_backward(getattr(m, name)[1], S[name], denc[lvl], grads, name + ".1")
+                done(name)
+            else:
+                self.rb_backward(m.inc, S["inc"], denc[0], grads, "inc", need_dx=False)
+                done("inc")
+        return grads

@@ -102,6 +102,109 @@ int rbu_loss_backward(const float* probs, const float* target, int64_t total, co
 int rbu_confusion_counts(const float* pred, const float* target, int B, int64_t HW, float threshold,
                          int64_t* counts, void* stream);
 
+/* ------------------------------------------------------------------ weight-gradient GEMM (K11)
+ * out[(m*Cb + n)*taps + t] (+)= sum_pixels A[p, m] * B[p (+) tap t, n]   (fp32, torch parameter layout)
+ *   Conv2d:            A = dy (Ca = Cout), B = x (Cb = Cin), taps 1|9, dilation dil -> weight.grad [Cout,Cin,kh,kw]
+ *   ConvTranspose2d:   A = x  (Ca = Cin),  B = dout [N,2H,2W] gathered per quadrant (gather=1, taps=4)
+ *                                                                          -> weight.grad [Cin,Cout,2,2]
+ * Replaces aten::convolution_backward (weight) of Main_Final.py:157,159,172,126,131,205-208,261-270.
+ * Split-K partials live in the caller's workspace; the reduction order is fixed (deterministic). */
+typedef struct {
+  int N, H, W;      /* pixel grid of A (gather: the low-resolution grid)           */
+  const void* a;    /* bf16 NHWC view, M = Ca channels                             */
+  int64_t a_ld;
+  int Ca;
+  const void* b;    /* bf16 NHWC view, N = Cb channels (gather: the [N,2H,2W] map) */
+  int64_t b_ld;
+  int Cb;
+  int taps, dil, gather;
+  float* out;
+  int accumulate;   /* 1: add to out, 0: overwrite                                 */
+} rbu_wgrad_args;
+size_t rbu_wgrad_workspace_bytes(const rbu_wgrad_args* args);
+int rbu_wgrad_gemm(const rbu_wgrad_args* args, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ forward block kernels (K2-K8)
+ * BatchNorm2d statistics + affine (Main_Final.py:158,160,173,127,132,210): scale = gamma*rstd,
+ * shift = beta - mean*scale; training=1 uses batch statistics (biased variance) and updates the running
+ * buffers (momentum, unbiased variance); training=0 uses the running buffers.  pool=1 additionally emits
+ * per-(n,c) mean/max/min and first-index argmax/argmin over H*W of the raw input — the
+ * AdaptiveAvg/MaxPool2d of ChannelAttention (Main_Final.py:87-88,98-99). */
+size_t rbu_bn_stats_workspace_bytes(int N, int HW, int C);
+int rbu_bn_stats(const void* x, int64_t ld, int N, int HW, int C, int pool, int training, const float* gamma,
+                 const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                 float* scale, float* shift, float* mean_out, float* rstd_out, float* nc_mean, float* nc_max,
+                 float* nc_min, int* nc_amax, int* nc_amin, void* workspace, size_t workspace_bytes, void* stream);
+/* y = [relu](scale[c]*x + shift[c]) * drop[n,c]   (BN apply + ReLU + Dropout2d; Main_Final.py:182-184,220-221) */
+int rbu_affine_act(const void* x, int64_t x_ld, void* y, int64_t y_ld, int64_t P, int HW, int C, const float* scale,
+                   const float* shift, const float* drop, int relu, void* stream);
+/* ChannelAttention gate (Main_Final.py:97-101) from the pooled statistics; also A2g = scale*g, B2g = shift*g. */
+int rbu_ca_gate(const float* nc_mean, const float* nc_max, const float* nc_min, const float* scale,
+                const float* shift, const float* V1, const float* V2, int N, int C, int Ch, float* g, float* A2g,
+                float* B2g, float* u_avg, float* u_max, float* h_avg, float* h_max, void* stream);
+/* SpatialAttention (Main_Final.py:112-117): channel mean/max (+argmax) of A2g*y2+B2g, then the 7x7 gate. */
+int rbu_sa_reduce(const void* y2, int64_t ld, int64_t P, int HW, int C, const float* A2g, const float* B2g,
+                  float* s_out /* [P][2] */, int* amax_out, void* stream);
+int rbu_sa_gate(const float* s, int N, int H, int W, const float* k7, float* gs, void* stream);
+/* out = relu((A2g*y2+B2g)*gs + r), r = As*ys+Bs (projection) or the identity input (Main_Final.py:179,190-194) */
+int rbu_rb_out(const void* y2, int64_t y2_ld, const void* rsrc, int64_t r_ld, void* out, int64_t out_ld, int64_t P,
+               int HW, int C, const float* A2g, const float* B2g, const float* gs, const float* As, const float* Bs,
+               void* stream);
+/* nn.MaxPool2d(2) (Main_Final.py:235,239,243,249) */
+int rbu_maxpool2x2(const void* x, int64_t x_ld, void* y, int64_t y_ld, int N, int Ho, int Wo, int C, void* stream);
+/* AttentionGate (Main_Final.py:143-148): q0 = w_psi . relu(BN_g(yg) + BN_x(yx)) + b_psi, BatchNorm2d(1)
+ * statistics -> stats[4] = {scale, shift, mean, rstd}; then out = skip * sigmoid(scale*q0 + shift). */
+int rbu_ag_psi_blocks(int64_t P, int F);  /* partials needs 2*blocks floats */
+int rbu_ag_psi(const void* yg, int64_t yg_ld, const void* yx, int64_t yx_ld, int64_t P, int F, const float* Ag,
+               const float* Bg, const float* Ax, const float* Bx, const float* wpsi, const float* bpsi, int training,
+               const float* gamma, const float* beta, float* running_mean, float* running_var, float momentum,
+               float eps, float* q0, float* stats, float* partials, void* stream);
+int rbu_ag_apply(const void* skip, int64_t s_ld, void* out, int64_t o_ld, int64_t P, int C, const float* q0,
+                 const float* stats, float* psi, void* stream);
+/* Stem: fp32 NCHW image -> bf16 3x3 patches [P][Kp] (k = tap*nc + c) so inc.conv1 + inc.shortcut
+ * (Main_Final.py:157,172,233) run as one tensor-core GEMM. */
+int rbu_stem_im2col(const float* x, int N, int nc, int H, int W, int Kp, void* out, void* stream);
+/* outc (Main_Final.py:274-277,321): probs = sigmoid(w.x + b) in fp32; logits optional. */
+int rbu_head_forward(const void* x, int64_t ld, int64_t P, int C, const float* w, const float* b, float* probs,
+                     float* logits, void* stream);
+
+/* ------------------------------------------------------------------ backward block kernels (K12)
+ * Replace the autograd nodes of the same reference lines (native_batch_norm_backward, threshold_backward,
+ * sigmoid_backward, mul/add/sum, adaptive_max_pool2d_backward, max_pool2d_with_indices_backward). */
+size_t rbu_bwd_workspace_bytes(int N, int HW, int C);
+int rbu_head_backward(const float* dprobs, const float* probs, const void* x, int64_t x_ld, void* dx, int64_t dx_ld,
+                      int64_t P, int C, const float* w, float* dw, float* db, void* workspace, size_t workspace_bytes,
+                      void* stream);
+int rbu_rb_bwd1(const void* dout, int64_t dout_ld, const void* out, int64_t out_ld, const void* y2, int64_t y2_ld,
+                void* de, int64_t de_ld, const void* ys, int64_t ys_ld, int N, int HW, int C, const float* A2g,
+                const float* B2g, const float* mean_s, const float* rstd_s, float* dG, float* sums_s, void* workspace,
+                size_t workspace_bytes, void* stream);
+int rbu_sa_bwd(const float* dG, const float* gs, const float* s, int N, int H, int W, const float* k7, float* ds,
+               float* dk7, void* workspace, size_t workspace_bytes, void* stream);
+int rbu_rb_bwd_pass(int pass, const void* de, int64_t de_ld, const void* y2, int64_t y2_ld, int N, int HW, int C,
+                    const float* gs, const float* ds, const int* amax_c, const float* g_c, const float* du_avg,
+                    const float* du_max, const int* nc_amax, const int* nc_amin, const float* scale2,
+                    const float* shift2, const float* mean2, const float* rstd2, float* dT, float* sums2, void* dy2,
+                    int64_t dy2_ld, const void* ys, int64_t ys_ld, void* dys, int64_t dys_ld, const float* scale_s,
+                    const float* mean_s, const float* rstd_s, const float* sums_s, void* workspace,
+                    size_t workspace_bytes, void* stream);
+int rbu_ca_bwd(const float* dT, const float* g, const float* h_avg, const float* h_max, const float* u_avg,
+               const float* u_max, const float* V1, const float* V2, int N, int C, int Ch, float* dt, float* dh_avg,
+               float* dh_max, float* du_avg, float* du_max, float* dV1, float* dV2, void* stream);
+int rbu_bn_bwd(const void* dy, int64_t dy_ld, const void* y, int64_t y_ld, void* dx, int64_t dx_ld, int N, int HW,
+               int C, const float* scale, const float* shift, const float* mean, const float* rstd, const float* drop,
+               int relu, float* sums /* [2C]: dbeta, dgamma */, void* workspace, size_t workspace_bytes, void* stream);
+int rbu_ag_bwd(const void* da, int64_t da_ld, const void* skip, int64_t s_ld, void* dskip, int64_t ds_ld,
+               const void* yg, int64_t yg_ld, const void* yx, int64_t yx_ld, void* dyg, int64_t dyg_ld, void* dyx,
+               int64_t dyx_ld, int N, int HW, int C, int F, const float* psi, const float* q0, const float* stats,
+               const float* Ag, const float* Bg, const float* Ax, const float* Bx, const float* mg, const float* rg,
+               const float* mx, const float* rx, const float* wpsi, float* dq, float* sums_psi, float* sums_f,
+               void* workspace, size_t workspace_bytes, void* stream);
+int rbu_maxpool2x2_bwd(const void* x, int64_t x_ld, const void* dy, int64_t dy_ld, void* dx, int64_t dx_ld, int N,
+                       int Ho, int Wo, int C, int accumulate, void* stream);
+int rbu_chan_sum(const void* x, int64_t ld, int64_t P, int C, float* out, void* workspace, size_t workspace_bytes,
+                 void* stream);
+
 #ifdef __cplusplus
 }
 #endif

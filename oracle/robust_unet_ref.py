@@ -35,6 +35,77 @@ IMAGENET_STD = (0.229, 0.224, 0.225)
 
 
 # --------------------------------------------------------------------------------------
+# storage model
+# --------------------------------------------------------------------------------------
+class _RoundBoth(torch.autograd.Function):
+    """value rounded to bf16 on the way forward, gradient rounded to bf16 on the way back."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).float()
+
+
+class _RoundGrad(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).float()
+
+
+class _RoundValue(torch.autograd.Function):
+    """straight-through: the fp32 master weight receives the gradient of its bf16 copy."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+class Fp32Storage:
+    """The reference's numerics: every tensor stays fp32 (identity hooks)."""
+    name = "fp32"
+
+    def act(self, x):      # an activation that the device path keeps in HBM
+        return x
+
+    def grad(self, x):     # a point where only the gradient is stored
+        return x
+
+    def weight(self, w):   # a tensor-core GEMM weight operand
+        return w
+
+
+class Bf16Storage(Fp32Storage):
+    """Same algorithm, but rounding to bf16 exactly where the CUDA path stores bf16 in HBM (conv / ConvTranspose
+    outputs, the BN1+ReLU+dropout output, block and gate outputs, their gradients, and the GEMM weight operands);
+    statistics, gates, the head and the loss stay fp32.  Used to separate logic errors from storage rounding."""
+    name = "bf16"
+
+    def act(self, x):
+        return _RoundBoth.apply(x)
+
+    def grad(self, x):
+        return _RoundGrad.apply(x)
+
+    def weight(self, w):
+        return _RoundValue.apply(w)
+
+
+FP32 = Fp32Storage()
+BF16 = Bf16Storage()
+
+
+# --------------------------------------------------------------------------------------
 # building blocks
 # --------------------------------------------------------------------------------------
 def batch_norm(sd: Dict[str, torch.Tensor], prefix: str, x: torch.Tensor, training: bool,
@@ -76,69 +147,72 @@ def spatial_attention(sd, prefix, x):
     return x * torch.sigmoid(att)
 
 
-def residual_block(sd, prefix, x, training, drop_mask=None, new_buffers=None):
+def residual_block(sd, prefix, x, training, drop_mask=None, new_buffers=None, st=FP32):
     """ResidualBlock.forward (Main_Final.py:178-196).  `drop_mask` is the Dropout2d channel mask
     [B,C,1,1] with values in {0, 1/(1-p)} (train mode only; None = identity)."""
     if (prefix + ".shortcut.0.weight") in sd:
-        r = F.conv2d(x, sd[prefix + ".shortcut.0.weight"])
+        r = st.act(F.conv2d(x, st.weight(sd[prefix + ".shortcut.0.weight"])))
         r = batch_norm(sd, prefix + ".shortcut.1", r, training, new_buffers)
     else:
         r = x
-    out = F.conv2d(x, sd[prefix + ".conv1.weight"], padding=1)
+    out = st.act(F.conv2d(x, st.weight(sd[prefix + ".conv1.weight"]), padding=1))
     out = F.relu(batch_norm(sd, prefix + ".bn1", out, training, new_buffers))
     if training and drop_mask is not None:
         out = out * drop_mask
-    out = F.conv2d(out, sd[prefix + ".conv2.weight"], padding=1)
+    out = st.act(out)
+    out = st.act(F.conv2d(out, st.weight(sd[prefix + ".conv2.weight"]), padding=1))
     out = batch_norm(sd, prefix + ".bn2", out, training, new_buffers)
     out = channel_attention(sd, prefix + ".ca", out)
     out = spatial_attention(sd, prefix + ".sa", out)
-    return F.relu(out + r)
+    return st.act(F.relu(st.grad(out + r)))
 
 
-def dilated_block(sd, prefix, x, training, new_buffers=None):
+def dilated_block(sd, prefix, x, training, new_buffers=None, st=FP32):
     """DilatedBlock.forward (Main_Final.py:213-223): cat(1x1, 3x3 d1, 3x3 d2, 3x3 d4) -> BN -> ReLU."""
-    x1 = F.conv2d(x, sd[prefix + ".conv1.weight"], sd[prefix + ".conv1.bias"])
-    x2 = F.conv2d(x, sd[prefix + ".conv2.weight"], sd[prefix + ".conv2.bias"], padding=1, dilation=1)
-    x3 = F.conv2d(x, sd[prefix + ".conv3.weight"], sd[prefix + ".conv3.bias"], padding=2, dilation=2)
-    x4 = F.conv2d(x, sd[prefix + ".conv4.weight"], sd[prefix + ".conv4.bias"], padding=4, dilation=4)
-    out = torch.cat([x1, x2, x3, x4], dim=1)
-    return F.relu(batch_norm(sd, prefix + ".bn", out, training, new_buffers))
+    def w(i):
+        return st.weight(sd[f"{prefix}.conv{i}.weight"])
+    x1 = F.conv2d(x, w(1), sd[prefix + ".conv1.bias"])
+    x2 = F.conv2d(x, w(2), sd[prefix + ".conv2.bias"], padding=1, dilation=1)
+    x3 = F.conv2d(x, w(3), sd[prefix + ".conv3.bias"], padding=2, dilation=2)
+    x4 = F.conv2d(x, w(4), sd[prefix + ".conv4.bias"], padding=4, dilation=4)
+    out = st.act(torch.cat([x1, x2, x3, x4], dim=1))
+    return st.act(F.relu(batch_norm(sd, prefix + ".bn", out, training, new_buffers)))
 
 
-def attention_gate(sd, prefix, g, x, training, new_buffers=None):
+def attention_gate(sd, prefix, g, x, training, new_buffers=None, st=FP32):
     """AttentionGate.forward (Main_Final.py:143-148)."""
     g1 = batch_norm(sd, prefix + ".W_g.1",
-                    F.conv2d(g, sd[prefix + ".W_g.0.weight"], sd[prefix + ".W_g.0.bias"]),
+                    st.act(F.conv2d(g, st.weight(sd[prefix + ".W_g.0.weight"]), sd[prefix + ".W_g.0.bias"])),
                     training, new_buffers)
     x1 = batch_norm(sd, prefix + ".W_x.1",
-                    F.conv2d(x, sd[prefix + ".W_x.0.weight"], sd[prefix + ".W_x.0.bias"]),
+                    st.act(F.conv2d(x, st.weight(sd[prefix + ".W_x.0.weight"]), sd[prefix + ".W_x.0.bias"])),
                     training, new_buffers)
     t = F.relu(g1 + x1)
     q = batch_norm(sd, prefix + ".psi.1",
                    F.conv2d(t, sd[prefix + ".psi.0.weight"], sd[prefix + ".psi.0.bias"]),
                    training, new_buffers)
-    return x * torch.sigmoid(q)
+    return st.act(x * torch.sigmoid(q))
 
 
 def robust_unet_forward(sd, x, training=False, drop_masks: Optional[dict] = None,
-                        new_buffers: Optional[dict] = None, return_logits=False):
+                        new_buffers: Optional[dict] = None, return_logits=False, st=FP32):
     """RobustUNet.forward (Main_Final.py:290-321).  Concat order is [gated skip, upsampled]
     (:303,308,313,318).  Returns probabilities [B,1,H,W] (sigmoid inside `outc`, :274-277)."""
     dm = drop_masks or {}
 
     def rb(prefix, t):
-        return residual_block(sd, prefix, t, training, dm.get(prefix), new_buffers)
+        return residual_block(sd, prefix, t, training, dm.get(prefix), new_buffers, st)
 
-    x1 = rb("inc", x)
+    x1 = rb("inc", st.act(x))
     x2 = rb("down1.1", F.max_pool2d(x1, 2))
     x3 = rb("down2.1", F.max_pool2d(x2, 2))
     x4 = rb("down3.1", F.max_pool2d(x3, 2))
-    x5 = dilated_block(sd, "bottleneck.1", F.max_pool2d(x4, 2), training, new_buffers)
+    x5 = dilated_block(sd, "bottleneck.1", F.max_pool2d(x4, 2), training, new_buffers, st)
     x5 = rb("bottleneck.2", x5)
     t = x5
     for k, skip in ((4, x4), (3, x3), (2, x2), (1, x1)):
-        t = F.conv_transpose2d(t, sd[f"up{k}.weight"], sd[f"up{k}.bias"], stride=2)
-        att = attention_gate(sd, f"att{k}", t, skip, training, new_buffers)
+        t = st.act(F.conv_transpose2d(t, st.weight(sd[f"up{k}.weight"]), sd[f"up{k}.bias"], stride=2))
+        att = attention_gate(sd, f"att{k}", t, skip, training, new_buffers, st)
         t = rb(f"dec{k}", torch.cat([att, t], dim=1))
     z = F.conv2d(t, sd["outc.0.weight"], sd["outc.0.bias"])
     return z if return_logits else torch.sigmoid(z)
@@ -148,7 +222,15 @@ def robust_unet_forward(sd, x, training=False, drop_masks: Optional[dict] = None
 # loss and metrics
 # --------------------------------------------------------------------------------------
 def bce_loss(p: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
-    """nn.BCELoss() on probabilities (Main_Final.py:551,580): logs clamped at -100, mean."""
+    """nn.BCELoss() on probabilities (Main_Final.py:551,580).  Forward: mean(-(y*max(ln p,-100) +
+    (1-y)*max(ln(1-p),-100))); backward (torch's binary_cross_entropy_backward):
+    (p-y)/max(p(1-p),1e-12)/N — which is NOT the autograd of the clamped-log form at p in {0,1}, so the
+    reference's own functional is called here."""
+    return F.binary_cross_entropy(p, y)
+
+
+def bce_loss_restated(p: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """Forward-only literal restatement of nn.BCELoss (checked against bce_loss in the CPU tests)."""
     lp = torch.clamp(torch.log(p), min=-100.0)
     l1p = torch.clamp(torch.log(1.0 - p), min=-100.0)
     return -(y * lp + (1.0 - y) * l1p).mean()
