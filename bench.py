@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py -- Robust U-Net hot-path benchmark (contract: see DESIGN.md "Measurement").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's sm_100a path
+  python bench.py --impl reference [--gpus N] [--steps K] ...    # the reference arithmetic on the host cores
+
+Own arm.  A step is one pass of the training hot path over one synthetic batch: forward, BCE loss (+ confusion
+counts), backward, (N > 1: bucketed gradient all-reduce overlapped with the backward) and the Adam update of
+Main_Final.py:552,573-582.  Workload at every N: BASELINE.json configs[1] per GPU -- bf16 storage / fp32 accumulate,
+batch 64 at 256x256, 3 channels (weak scaling).  `value` is images/s with the batch resident in HBM; `e2e` is the same
+loop fed from pinned host memory (H2D of images + masks and D2H of the loss inside the timed region) through the public
+nn.Module API.  `--workload infer` times config 4 (eval forward + thresholded counts) instead.
+
+Reference arm.  The oracle port of the reference (oracle/robust_unet_ref.py, fp32 torch CPU ops = the reference's own
+CPU path) on all host threads, same metric/unit, on a bounded sample of the workload.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+TRAIN_GFLOP_PER_IMG_256 = 323.6      # SURVEY.md §2.2 / BASELINE.md: fwd + dgrad + wgrad conv FLOPs per image at 256x256
+FWD_GFLOP_PER_IMG_256 = 107.9
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p["bf16_tflops_sustained"],
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {nv.nvmlClocksEventReasonHwSlowdown: "hw_slowdown",
+                     nv.nvmlClocksEventReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                     nv.nvmlClocksEventReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                     nv.nvmlClocksEventReasonSwPowerCap: "sw_power_cap"}
+            while not self.stop_flag:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+                time.sleep(0.05)
+        except Exception as e:   # NVML missing: report that instead of failing the bench
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def result(self):
+        self.stop_flag = True
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------ own arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import rbunet
+    from rbunet import _lib
+    from oracle import robust_unet_ref as R          # synthetic input generator + cpu_baseline leg only
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.check(_lib.lib().rbu_device_check(), "rbu_device_check")
+
+    infer = args.workload == "infer"
+    B = args.batch or (32 if infer else 64)
+    S = args.size or (1024 if infer else 256)
+    nc = args.channels
+    torch.manual_seed(0)
+    model = rbunet.RobustUNet(nc, 1, 64).to(dev)
+    crit = rbunet.RobustBCEDiceLoss()
+    net = model
+    if infer:
+        model.eval()
+    else:
+        model.train()
+        if world > 1:
+            net = rbunet.DataParallel(model)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=1e-4, fused=True)      # Main_Final.py:552
+    x_cpu, y_cpu = R.synthetic_inputs(B, nc, S, S, seed=123 + rank, blobby=True)
+    x_pin, y_pin = x_cpu.pin_memory(), y_cpu.pin_memory()
+    x_dev, y_dev = x_cpu.to(dev), y_cpu.to(dev)
+    x_stage, y_stage = torch.empty_like(x_dev), torch.empty_like(y_dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    def step(x, y):
+        if infer:
+            with torch.no_grad():
+                p = net(x)
+                counts = rbunet.confusion_counts(p, y)
+            return counts
+        opt.zero_grad(set_to_none=True)
+        loss = crit(net(x), y)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def step_e2e():
+        x_stage.copy_(x_pin, non_blocking=True)
+        y_stage.copy_(y_pin, non_blocking=True)
+        out = step(x_stage, y_stage)
+        return out.cpu() if infer else out.item()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        sampler = ClockSampler(local)
+        sampler.start()
+        l0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            flush.zero_()                   # L2 flush between timed iterations (the batch itself is also > L2)
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = _lib.launch_count() - l0
+        clocks = sampler.result()
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms, launches, clocks
+
+    ms, launches, clocks = timed(lambda: step(x_dev, y_dev), args.steps, args.warmup)
+    ms_e2e, _, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+
+    # per-kernel-class device times of one extra step (CUDA events around every C-ABI call on the launching stream)
+    prof = _lib.Profiler()
+    _lib.PROFILER = prof
+    step(x_dev, y_dev)
+    _lib.PROFILER = None
+    summ = prof.summary()
+    peaks = load_peaks()
+    gemm = {k: v for k, v in summ.items() if v["flops"] > 0}
+    gemm_ms = sum(v["ms"] for v in gemm.values())
+    gemm_flops = sum(v["flops"] for v in gemm.values())
+    lib_ms = sum(v["ms"] for v in summ.values())
+    top = max(gemm.items(), key=lambda kv: kv[1]["ms"])
+    peak_tf = peaks["bf16_tflops_sustained"]
+    roof = {"bound": "tensor", "kernel": top[0], "achieved": top[1]["flops"] / top[1]["ms"] / 1e9 if top[1]["ms"] else None,
+            "peak": peak_tf, "unit": "TFLOP/s", "frac": None, "traffic": None, "peak_source": peaks["source"] + " (sustained)",
+            "launches_per_step": top[1]["calls"], "avg_launch_ms": top[1]["ms"] / max(1, top[1]["calls"]),
+            "share_of_step": top[1]["ms"] / lib_ms if lib_ms else None,
+            "all_gemm_tflops": gemm_flops / gemm_ms / 1e9 if gemm_ms else None}
+    if roof["achieved"]:
+        roof["frac"] = roof["achieved"] / peak_tf
+    classes = {k: {"calls": v["calls"], "ms": round(v["ms"], 3), "share": round(v["ms"] / lib_ms, 4) if lib_ms else None,
+                   **({"tflops": round(v["flops"] / v["ms"] / 1e9, 1)} if v["flops"] and v["ms"] else {})}
+               for k, v in sorted(summ.items(), key=lambda kv: -kv[1]["ms"])}
+
+    out = None
+    if rank == 0:
+        imgs = B * world * args.steps
+        gflop_img = (FWD_GFLOP_PER_IMG_256 if infer else TRAIN_GFLOP_PER_IMG_256) * (S * S) / (256 * 256)
+        value = imgs / (ms / 1e3)
+        h2d = x_pin.numel() * 4 + y_pin.numel() * 4
+        d2h = (B * 4 * 8) if infer else 4
+        out = {"metric": "infer_images_per_sec" if infer else "train_images_per_sec", "value": round(value, 2), "unit": "img/s",
+               "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+               "config": {"workload": (f"Robust U-Net inference {S}x{S} batch {B}/GPU, thresholded counts" if infer else
+                                       f"Robust U-Net bf16 training step (fwd+BCE+bwd+Adam), batch {B}/GPU at {S}x{S}, "
+                                       f"{nc} channels, base 64"),
+                          "global_batch": B * world, "image": [nc, S, S], "parallelism": f"dp{world}",
+                          "l2": "256 MiB flush buffer written between timed steps; per-step activations exceed L2",
+                          "weights": "reference init (seed 0), random", "optimizer": "torch.optim.Adam(fused) lr 1e-4 wd 1e-4"},
+               "clocks": clocks,
+               "e2e": {"value": round(imgs / (ms_e2e / 1e3), 2), "unit": "img/s", "h2d_bytes_per_step": h2d,
+                       "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_e2e / args.steps, 3)},
+               "gpu_launches": int(launches),
+               "model_tflops": round(value * gflop_img / 1e3, 1),
+               "model_frac_of_sustained_peak": round(value * gflop_img / 1e3 / peak_tf, 4),
+               "roofline": roof, "kernel_classes": classes}
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_port(R, infer, nc, S, budget_s=20.0)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ CPU port
+def cpu_port(R, infer, nc, S, budget_s, steps=None, warmup=1, batch=None):
+    """Times the oracle port (fp32 torch CPU ops, all host threads) on a bounded sample of the workload."""
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = R.synthetic_state_dict(R.robust_unet_shapes(nc, 1, 64), seed=0)
+    names = [k for k, v in sd.items() if v.is_floating_point() and "running" not in k]
+    params = [sd[n].requires_grad_(not infer) for n in names]
+    opt = None if infer else torch.optim.Adam(params, lr=1e-4, weight_decay=1e-4)
+    b = batch or 2
+    masks = R.synthetic_drop_masks(64, 64, seed=7)
+
+    def one(bs):
+        x, y = R.synthetic_inputs(bs, nc, S, S, seed=5, blobby=True)
+        t0 = time.perf_counter()
+        if infer:
+            with torch.no_grad():
+                p = R.robust_unet_forward(sd, x, training=False)
+            R.confusion_counts(p.numpy(), y.numpy())
+        else:
+            opt.zero_grad()
+            dm = {k: v[:bs] for k, v in masks.items()}
+            p = R.robust_unet_forward(sd, x, training=True, drop_masks=dm, new_buffers={})
+            loss = R.bce_loss(p, y)
+            loss.backward()
+            opt.step()
+        return time.perf_counter() - t0
+
+    t_probe = one(b)                                   # also the warm-up
+    if batch is None:                                  # size the sample to the time budget
+        n_steps = steps or 2
+        per_img = t_probe / b
+        b = int(max(1, min(8, budget_s / max(per_img * (n_steps + warmup), 1e-9))))
+    for _ in range(max(0, warmup - 1)):
+        one(b)
+    n_steps = steps or 2
+    times = [one(b) for _ in range(n_steps)]
+    total = sum(times)
+    return {"value": round(b * n_steps / total, 4), "unit": "img/s", "cores": cores, "kind": "port",
+            "sample": f"{n_steps} steps of batch {b} at {S}x{S} ({'eval forward + counts' if infer else 'fwd+BCE+bwd+Adam'}), "
+                      f"fp32 torch CPU ops ({torch.__version__}), {cores} threads",
+            "ms_per_step": round(1e3 * total / n_steps, 1), "batch": b}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import robust_unet_ref as R
+    infer = args.workload == "infer"
+    S = args.size or (1024 if infer else 256)
+    nc = args.channels
+    steps, warmup = args.steps, max(1, args.warmup)
+    budget = 150.0
+    r = cpu_port(R, infer, nc, S, budget_s=budget, steps=steps, warmup=warmup)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    out = {"impl": "reference", "metric": "infer_images_per_sec" if infer else "train_images_per_sec", "value": r["value"],
+           "unit": "img/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"],
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": (f"Robust U-Net inference {S}x{S}" if infer else
+                                   f"Robust U-Net training step (fwd+BCE+bwd+Adam) at {S}x{S}, {nc} channels, base 64")
+                      + f"; bounded sample: batch {r['batch']} per step on the host CPU", "parallelism": "cpu"},
+           "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+           "e2e": {"value": r["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="train", choices=["train", "infer"])
+    ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--size", type=int, default=0)
+    ap.add_argument("--channels", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

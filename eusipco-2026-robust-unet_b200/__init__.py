@@ -12,6 +12,7 @@ from .loss import (METRIC_KEYS, RobustBCEDiceLoss, batch_metrics, calculate_metr
                    confusion_counts, metrics_from_counts)
 from .model import RobustUNet  # noqa: F401
 from .ops import View  # noqa: F401
+from .parallel import DataParallel, GradBucketer  # noqa: F401
 
 __all__ = ["RobustUNet", "RobustBCEDiceLoss", "calculate_metrics", "batch_metrics", "confusion_counts",
-           "metrics_from_counts", "METRIC_KEYS", "View"]
+           "metrics_from_counts", "METRIC_KEYS", "View", "DataParallel", "GradBucketer"]

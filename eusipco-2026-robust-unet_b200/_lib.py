@@ -6,7 +6,7 @@ this module raises.
 import ctypes
 import os
 import re
-from ctypes import Structure, c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_void_p
+from ctypes import Structure, c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_ulonglong, c_void_p
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "librbunet.so")
@@ -39,6 +39,8 @@ def _ctype(decl: str):
         return None
     if "*" in decl:
         return c_char_p if decl.replace(" ", "") == "constchar*" else c_void_p
+    if decl.replace("const", "").split() == ["unsigned", "long", "long"]:
+        return c_ulonglong
     base = decl.replace("const", "").split()[0]
     return _SCALARS[base]
 
@@ -87,9 +89,46 @@ def check(rc: int, what: str = ""):
         raise RuntimeError(f"librbunet {what} failed (code {rc}): {msg.decode() if msg else ''}")
 
 
-def call(name: str, *args):
+class Profiler:
+    """Optional per-call device timing (CUDA events on the launching stream) used by bench.py for the roofline
+    numbers: every C-ABI call made while a profiler is installed is bracketed by two events and tagged with its
+    algorithmic work (`flops` for the tensor-core GEMMs, `bytes` for the bandwidth-bound kernels)."""
+
+    def __init__(self):
+        self.records = []      # (entry point, tag, flops, bytes, start event, stop event)
+
+    def summary(self):
+        import torch
+        torch.cuda.synchronize()
+        out = {}
+        for name, tag, flops, nbytes, e0, e1 in self.records:
+            d = out.setdefault(tag or name, {"calls": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+            d["calls"] += 1
+            d["ms"] += e0.elapsed_time(e1)
+            d["flops"] += flops
+            d["bytes"] += nbytes
+        return out
+
+
+PROFILER = None
+
+
+def call(name: str, *args, tag=None, flops=0.0, nbytes=0.0):
     """Call an int-returning entry point and raise RuntimeError with rbu_last_error() on failure."""
+    prof = PROFILER
+    if prof is None:
+        check(getattr(lib(), name)(*args), name)
+        return
+    import torch
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     check(getattr(lib(), name)(*args), name)
+    e1.record()
+    prof.records.append((name, tag, flops, nbytes, e0, e1))
+
+
+def launch_count() -> int:
+    return int(lib().rbu_launch_count())
 
 
 def stream_ptr():

@@ -9,6 +9,10 @@ thread_local char g_err[1024] = "";
 int g_sms = 0;
 }  // namespace
 
+unsigned long long g_rbu_launches = 0;
+
+extern "C" unsigned long long rbu_launch_count(void) { return g_rbu_launches; }
+
 void rbu_set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);

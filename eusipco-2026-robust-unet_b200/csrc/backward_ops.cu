@@ -733,6 +733,7 @@ extern "C" int rbu_head_backward(const float* dprobs, const float* probs, const 
   head_bwd_kernel<<<blocks, NT, 0, st>>>(dprobs, probs, (const bf16*)x, x_ld, (bf16*)dx, dx_ld, P, C, w, ppb, part);
   RBU_CHECK_LAUNCH();
   colsum_kernel<<<rbu_cdiv(C, 128), 128, 0, st>>>(part, blocks, C, C + 8, dw, 1.f);
+  RBU_CHECK_LAUNCH();
   colsum_kernel<<<1, 32, 0, st>>>(part + C, blocks, 1, C + 8, db, 1.f);
   RBU_CHECK_LAUNCH();
   return RBU_OK;

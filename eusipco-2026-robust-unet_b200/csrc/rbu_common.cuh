@@ -33,7 +33,13 @@ void rbu_set_error(const char* fmt, ...);
     }                                                                                     \
   } while (0)
 
-#define RBU_CHECK_LAUNCH() RBU_CHECK_CUDA(cudaGetLastError())
+// every kernel launch of the library goes through this macro: it also feeds rbu_launch_count()
+extern unsigned long long g_rbu_launches;
+#define RBU_CHECK_LAUNCH()                  \
+  do {                                      \
+    ++g_rbu_launches;                       \
+    RBU_CHECK_CUDA(cudaGetLastError());     \
+  } while (0)
 
 int rbu_num_sms();
 

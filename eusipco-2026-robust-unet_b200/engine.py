@@ -114,7 +114,8 @@ class Engine:
         args.out, args.accumulate = out.data_ptr(), 0
         nbytes = _lib.lib().rbu_wgrad_workspace_bytes(ctypes.byref(args))
         ws = self.ws(nbytes, out.device)
-        call("rbu_wgrad_gemm", ctypes.byref(args), _p(ws), ws.numel() * 4, stream_ptr())
+        call("rbu_wgrad_gemm", ctypes.byref(args), _p(ws), ws.numel() * 4, stream_ptr(), tag="wgrad_gemm",
+             flops=2.0 * N * H * W * a.C * b.C * taps)
 
     def bwd_ws(self, N, HW, C, device):
         return self.ws(_lib.lib().rbu_bwd_workspace_bytes(N, HW, max(C, 32)), device)
@@ -136,7 +137,8 @@ class Engine:
         if stem_patches is not None:
             y12 = self.new(N, H, W, 2 * C, dev)
             wst = self.pack_stem(blk.conv1.weight, blk.shortcut[0].weight, stem_patches.C)
-            conv_gemm(N, H, W, [(stem_patches, wst, 1, 0, False)], 2 * C, y12)
+            conv_gemm(N, H, W, [(stem_patches, wst, 1, 0, False)], 2 * C, y12,
+                      flops=2.0 * N * H * W * C * 10 * blk.conv1.in_channels)
             y1, ys = y12.slice(0, C), y12.slice(C, C)
         else:
             y1 = self.new(N, H, W, C, dev)
@@ -425,8 +427,8 @@ class Engine:
         return probs, (S if save else None)
 
     def backward(self, S, dprobs: torch.Tensor, allreduce_hook=None):
-        """Returns {param_name: fp32 gradient}.  `allreduce_hook(names)` is called as soon as the gradients of a
-        top-level child are complete (reverse execution order) so data-parallel buckets can overlap."""
+        """Returns {param_name: fp32 gradient}.  `allreduce_hook(names, grads)` is called as soon as the gradients
+        of a top-level child are complete (reverse execution order) so data-parallel buckets can overlap."""
         m = self.model
         grads = {}
         N, H, W = S["N"], S["H"], S["W"]
@@ -443,7 +445,7 @@ class Engine:
 
         def done(*prefixes):
             if allreduce_hook is not None:
-                allreduce_hook([k for k in grads if any(k == p or k.startswith(p + ".") for p in prefixes)])
+                allreduce_hook([k for k in grads if any(k == p or k.startswith(p + ".") for p in prefixes)], grads)
 
         done("outc")
         enc = S["enc"]

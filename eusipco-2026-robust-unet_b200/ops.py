@@ -61,8 +61,10 @@ def pack_weight(w: torch.Tensor, mode: int) -> torch.Tensor:
     return out
 
 
-def conv_gemm(N, H, W, segs, Ncols, y: View, scatter=False, Cout=0, bias=None, addend: View = None):
-    """segs: list of (x: View, w_packed, taps, dil, gather)."""
+def conv_gemm(N, H, W, segs, Ncols, y: View, scatter=False, Cout=0, bias=None, addend: View = None, tag="conv_gemm",
+              flops=None):
+    """segs: list of (x: View, w_packed, taps, dil, gather).  `flops`: algorithmic FLOPs of the call when they
+    differ from the GEMM's own 2*M*N*K (e.g. the zero-padded stem)."""
     a = ConvGemmArgs()
     a.N, a.H, a.W, a.nseg = N, H, W, len(segs)
     keep = []
@@ -83,7 +85,9 @@ def conv_gemm(N, H, W, segs, Ncols, y: View, scatter=False, Cout=0, bias=None, a
     a.bias = bias.data_ptr() if bias is not None else None
     a.addend = addend.ptr if addend is not None else None
     a.addend_ld = addend.ld if addend is not None else 0
-    call("rbu_conv_gemm", ctypes.byref(a), stream_ptr())
+    if flops is None:
+        flops = 2.0 * N * H * W * Ncols * sum(t * x.C for (x, _, t, _, _) in segs)
+    call("rbu_conv_gemm", ctypes.byref(a), stream_ptr(), tag=tag, flops=flops)
 
 
 def conv_direct_ref(x: View, N, H, W, w, bias, ksz, dil):

@@ -38,6 +38,8 @@ const char* rbu_last_error(void);
 /* 0 if the current device is compute capability 10.x (tcgen05/TMEM/TMA available). */
 int rbu_device_check(void);
 int rbu_sm_count(void);
+/* Number of CUDA kernels this library has launched in the calling process (bench.py's gpu_launches). */
+unsigned long long rbu_launch_count(void);
 
 /* ------------------------------------------------------------------ tensor-core implicit GEMM
  * Replaces aten::convolution for 3x3 (dilation 1/2/4), 1x1 and ConvTranspose2d(2, stride 2)
