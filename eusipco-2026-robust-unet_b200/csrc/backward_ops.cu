@@ -50,13 +50,22 @@ __device__ __forceinline__ void rows_reduce_store(const float* acc, int G, int r
 }
 
 // out[k] (+ optional out2) = sum over blocks of part[blk][k], fixed order, double accumulation
-__global__ void colsum_kernel(const float* __restrict__ part, int nblk, int K, long blk_stride, float* __restrict__ out,
-                              float post_scale) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= K) return;
+// block = 32 columns x 8 lanes (launch with 256 threads, grid = ceil(K / 32))
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float* __restrict__ part, int nblk, int K, long blk_stride, float* __restrict__ out, float post_scale) {
+  __shared__ double sh[8][32];
+  const int kx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  const int k = blockIdx.x * 32 + kx;
   double s = 0.0;
-  for (int b = 0; b < nblk; ++b) s += (double)part[(long)b * blk_stride + k];
-  out[k] = (float)s * post_scale;
+  if (k < K)
+    for (int b = ly; b < nblk; b += 8) s += (double)part[(long)b * blk_stride + k];
+  sh[ly][kx] = s;
+  __syncthreads();
+  if (ly == 0 && k < K) {
+    double t = 0.0;
+    for (int j = 0; j < 8; ++j) t += sh[j][kx];
+    out[k] = (float)t * post_scale;
+  }
 }
 
 // per-(n,c): out[n][c] = sum over the chunks of image n
@@ -271,6 +280,7 @@ rb_bwd2_kernel(const bf16* __restrict__ de, long de_ld, const bf16* __restrict__
   for (int e = 0; e < 8; ++e) { sc[e] = k.scale2[cg * 8 + e]; sh[e] = k.shift2[cg * 8 + e]; acc[e] = 0.f; }
   const float invC = 1.f / (float)C;
   if (row < rows) {
+#pragma unroll 2
     for (int pl = p0 + row; pl < p1; pl += rows) {
       const long p = (long)n * HW + pl;
       float g[8], y[8];
@@ -332,6 +342,7 @@ rb_bwd34_kernel(const bf16* __restrict__ de, long de_ld, const bf16* __restrict_
   }
   const float invC = 1.f / (float)C, invHW = 1.f / (float)HW;
   if (row < rows) {
+#pragma unroll 2
     for (int pl = p0 + row; pl < p1; pl += rows) {
       const long p = (long)n * HW + pl;
       float g[8], y[8], db[8];
@@ -468,6 +479,7 @@ bn_bwd_kernel(const bf16* __restrict__ dy, long dy_ld, const bf16* __restrict__ 
     acc1[e] = 0.f; acc2[e] = 0.f;
   }
   if (row < rows) {
+#pragma unroll 2
     for (int pl = p0 + row; pl < p1; pl += rows) {
       const long p = (long)n * HW + pl;
       float g[8], v[8];
@@ -571,6 +583,7 @@ ag_bwd23_kernel(const bf16* __restrict__ yg, long yg_ld, const bf16* __restrict_
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[q][e] = 0.f;
   if (row < rows) {
+#pragma unroll 2
     for (int pl = p0 + row; pl < p1; pl += rows) {
       const long p = (long)n * HW + pl;
       float a[8], b[8];
@@ -678,7 +691,7 @@ bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 int bwd_chunks(int N, int HW, int C) {
   const int rows = NT / (C >> 3);
-  long want = ((long)rbu_num_sms() * 4 + N - 1) / N;
+  long want = ((long)rbu_num_sms() * 16 + N - 1) / N;    // ~16 blocks per SM in total: small tail wave
   long maxc = (HW + (long)rows * 4 - 1) / ((long)rows * 4);
   if (maxc < 1) maxc = 1;
   if (want > maxc) want = maxc;
@@ -688,7 +701,7 @@ int bwd_chunks(int N, int HW, int C) {
 
 int flat_blocks(long P, int C, int* px_per_block) {
   const int rows = NT / (C >> 3);
-  long blocks = (long)rbu_num_sms() * 4;
+  long blocks = (long)rbu_num_sms() * 16;
   long maxb = (P + (long)rows * 4 - 1) / ((long)rows * 4);
   if (maxb < 1) maxb = 1;
   if (blocks > maxb) blocks = maxb;
@@ -732,9 +745,9 @@ extern "C" int rbu_head_backward(const float* dprobs, const float* probs, const 
   float* part = (float*)workspace;
   head_bwd_kernel<<<blocks, NT, 0, st>>>(dprobs, probs, (const bf16*)x, x_ld, (bf16*)dx, dx_ld, P, C, w, ppb, part);
   RBU_CHECK_LAUNCH();
-  colsum_kernel<<<rbu_cdiv(C, 128), 128, 0, st>>>(part, blocks, C, C + 8, dw, 1.f);
+  colsum_kernel<<<rbu_cdiv(C, 32), 256, 0, st>>>(part, blocks, C, C + 8, dw, 1.f);
   RBU_CHECK_LAUNCH();
-  colsum_kernel<<<1, 32, 0, st>>>(part + C, blocks, 1, C + 8, db, 1.f);
+  colsum_kernel<<<1, 256, 0, st>>>(part + C, blocks, 1, C + 8, db, 1.f);
   RBU_CHECK_LAUNCH();
   return RBU_OK;
 }
@@ -754,7 +767,7 @@ extern "C" int rbu_rb_bwd1(const void* dout, int64_t dout_ld, const void* out, i
                                                  rbu_cdiv(HW, chunks), A2g, B2g, mean_s, rstd_s, dG, (float*)workspace);
   RBU_CHECK_LAUNCH();
   if (ys) {
-    colsum_kernel<<<rbu_cdiv(2 * C, 128), 128, 0, st>>>((const float*)workspace, N * chunks, 2 * C, 2 * C, sums_s, 1.f);
+    colsum_kernel<<<rbu_cdiv(2 * C, 32), 256, 0, st>>>((const float*)workspace, N * chunks, 2 * C, 2 * C, sums_s, 1.f);
     RBU_CHECK_LAUNCH();
   }
   return RBU_OK;
@@ -771,7 +784,7 @@ extern "C" int rbu_sa_bwd(const float* dG, const float* gs, const float* s, int 
   RBU_CHECK_ARG(workspace && workspace_bytes >= (size_t)blocks * 98 * sizeof(float), "rbu_sa_bwd: workspace too small");
   sa_bwd_weight_kernel<<<blocks, NT, 0, st>>>(dG, gs, (const float2*)s, N, H, W, (float*)workspace);
   RBU_CHECK_LAUNCH();
-  colsum_kernel<<<1, 128, 0, st>>>((const float*)workspace, blocks, 98, 98, dk7, 1.f);
+  colsum_kernel<<<rbu_cdiv(98, 32), 256, 0, st>>>((const float*)workspace, blocks, 98, 98, dk7, 1.f);
   RBU_CHECK_LAUNCH();
   return RBU_OK;
 }
@@ -811,7 +824,7 @@ extern "C" int rbu_rb_bwd_pass(int pass, const void* de, int64_t de_ld, const vo
                                                       part, nullptr, invM, nullptr, 0, nullptr, 0, nullptr, 0, nullptr,
                                                       nullptr, nullptr, nullptr);
     RBU_CHECK_LAUNCH();
-    colsum_kernel<<<rbu_cdiv(2 * C, 128), 128, 0, st>>>(part, N * chunks, 2 * C, 2 * C, sums2, 1.f);
+    colsum_kernel<<<rbu_cdiv(2 * C, 32), 256, 0, st>>>(part, N * chunks, 2 * C, 2 * C, sums2, 1.f);
     RBU_CHECK_LAUNCH();
     return RBU_OK;
   }
@@ -857,7 +870,7 @@ extern "C" int rbu_bn_bwd(const void* dy, int64_t dy_ld, const void* y, int64_t 
                                                   shift, mean, rstd, drop, relu, (float*)workspace, nullptr, invM,
                                                   nullptr, 0);
   RBU_CHECK_LAUNCH();
-  colsum_kernel<<<rbu_cdiv(2 * C, 128), 128, 0, st>>>((const float*)workspace, N * chunks, 2 * C, 2 * C, sums, 1.f);
+  colsum_kernel<<<rbu_cdiv(2 * C, 32), 256, 0, st>>>((const float*)workspace, N * chunks, 2 * C, 2 * C, sums, 1.f);
   RBU_CHECK_LAUNCH();
   bn_bwd_kernel<1><<<dim3(chunks, N), NT, 0, st>>>((const bf16*)dy, dy_ld, (const bf16*)y, y_ld, HW, C, chunk_px, scale,
                                                   shift, mean, rstd, drop, relu, nullptr, sums, invM, (bf16*)dx, dx_ld);
@@ -888,7 +901,7 @@ extern "C" int rbu_ag_bwd(const void* da, int64_t da_ld, const void* skip, int64
     ag_bwd1_kernel<<<dim3(chunks, N), NT, 0, st>>>((const bf16*)da, da_ld, (const bf16*)skip, s_ld, (bf16*)dskip, ds_ld, HW,
                                                    C, rbu_cdiv(HW, chunks), psi, q0, stats, dq, part);
     RBU_CHECK_LAUNCH();
-    colsum_kernel<<<1, 32, 0, st>>>(part, N * chunks, 2, 2, sums_psi, 1.f);
+    colsum_kernel<<<1, 256, 0, st>>>(part, N * chunks, 2, 2, sums_psi, 1.f);
     RBU_CHECK_LAUNCH();
   }
   {
@@ -899,7 +912,7 @@ extern "C" int rbu_ag_bwd(const void* da, int64_t da_ld, const void* skip, int64
                                                       Ax, Bx, mg, rg, mx, rx, wpsi, dq, q0, stats, sums_psi, invM, part,
                                                       nullptr, nullptr, 0, nullptr, 0);
     RBU_CHECK_LAUNCH();
-    colsum_kernel<<<rbu_cdiv(4 * F, 128), 128, 0, st>>>(part, N * chunks, 4 * F, 4 * F, sums_f, 1.f);
+    colsum_kernel<<<rbu_cdiv(4 * F, 32), 256, 0, st>>>(part, N * chunks, 4 * F, 4 * F, sums_f, 1.f);
     RBU_CHECK_LAUNCH();
     ag_bwd23_kernel<1><<<dim3(chunks, N), NT, 0, st>>>((const bf16*)yg, yg_ld, (const bf16*)yx, yx_ld, HW, F, chunk_px, Ag, Bg,
                                                       Ax, Bx, mg, rg, mx, rx, wpsi, dq, q0, stats, sums_psi, invM, nullptr,
@@ -928,7 +941,7 @@ extern "C" int rbu_chan_sum(const void* x, int64_t ld, int64_t P, int C, float* 
   RBU_CHECK_ARG(workspace && workspace_bytes >= (size_t)blocks * C * sizeof(float), "rbu_chan_sum: workspace too small");
   chan_sum_kernel<<<blocks, NT, 0, st>>>((const bf16*)x, ld, P, C, ppb, (float*)workspace);
   RBU_CHECK_LAUNCH();
-  colsum_kernel<<<rbu_cdiv(C, 128), 128, 0, st>>>((const float*)workspace, blocks, C, C, out, 1.f);
+  colsum_kernel<<<rbu_cdiv(C, 32), 256, 0, st>>>((const float*)workspace, blocks, C, C, out, 1.f);
   RBU_CHECK_LAUNCH();
   return RBU_OK;
 }

@@ -33,6 +33,7 @@ bn_stats_kernel(const bf16* __restrict__ x, long ld, int HW, int C, int chunk_px
   }
   if (row < rows) {
     const bf16* base = x + (long)n * HW * ld + cg * 8;
+#pragma unroll 4
     for (int p = p0 + row; p < p1; p += rows) {
       float v[8];
       unpack8(ld_bf16x8(base + (long)p * ld), v);
@@ -94,43 +95,63 @@ bn_stats_kernel(const bf16* __restrict__ x, long ld, int HW, int C, int chunk_px
   }
 }
 
-// thread per channel: ordered combine of the partials, BN affine (train: batch stats + running update;
-// eval: running stats), optional per-(n,c) pooled outputs.
-__global__ void bn_finalize_kernel(const float* __restrict__ part_f, const int* __restrict__ part_i, int N, int chunks,
-                                   int HW, int C, int pool, int training, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float* __restrict__ running_mean,
-                                   float* __restrict__ running_var, float momentum, float eps,
-                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
-                                   float* __restrict__ rstd_out, float* __restrict__ nc_mean, float* __restrict__ nc_max,
-                                   float* __restrict__ nc_min, int* __restrict__ nc_amax, int* __restrict__ nc_amin) {
+// Stage 2 of the statistics: thread per (n, c) combines the chunk partials of image n in chunk order (strict
+// comparisons keep the first index on ties) -> per-(n,c) sum / sumsq (double, workspace) and the pooled outputs.
+__global__ void bn_reduce_nc_kernel(const float* __restrict__ part_f, const int* __restrict__ part_i, int chunks, int HW,
+                                    int C, int pool, double* __restrict__ nsum /* [N][2][C] */,
+                                    float* __restrict__ nc_mean, float* __restrict__ nc_max, float* __restrict__ nc_min,
+                                    int* __restrict__ nc_amax, int* __restrict__ nc_amin) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = blockIdx.y;
   if (c >= C) return;
-  double tsum = 0.0, tsq = 0.0;
-  for (int n = 0; n < N; ++n) {
-    double s = 0.0;
-    float bmx = -INFINITY, bmn = INFINITY;
-    int imx = 0, imn = 0;
-    for (int k = 0; k < chunks; ++k) {
-      const long o = (long)n * chunks + k;
-      s += (double)part_f[(o * 4 + 0) * C + c];
-      tsq += (double)part_f[(o * 4 + 1) * C + c];
-      if (pool) {
-        const float vmx = part_f[(o * 4 + 2) * C + c], vmn = part_f[(o * 4 + 3) * C + c];
-        if (vmx > bmx) { bmx = vmx; imx = part_i[(o * 2 + 0) * C + c]; }   // chunks ascend: strict > keeps the first
-        if (vmn < bmn) { bmn = vmn; imn = part_i[(o * 2 + 1) * C + c]; }
-      }
-    }
-    tsum += s;
+  double s = 0.0, q = 0.0;
+  float bmx = -INFINITY, bmn = INFINITY;
+  int imx = 0, imn = 0;
+  for (int k = 0; k < chunks; ++k) {
+    const long o = (long)n * chunks + k;
+    s += (double)part_f[(o * 4 + 0) * C + c];
+    q += (double)part_f[(o * 4 + 1) * C + c];
     if (pool) {
-      nc_mean[(long)n * C + c] = (float)(s / (double)HW);
-      nc_max[(long)n * C + c] = bmx;
-      nc_min[(long)n * C + c] = bmn;
-      nc_amax[(long)n * C + c] = imx;
-      nc_amin[(long)n * C + c] = imn;
+      const float vmx = part_f[(o * 4 + 2) * C + c], vmn = part_f[(o * 4 + 3) * C + c];
+      if (vmx > bmx) { bmx = vmx; imx = part_i[(o * 2 + 0) * C + c]; }
+      if (vmn < bmn) { bmn = vmn; imn = part_i[(o * 2 + 1) * C + c]; }
     }
   }
+  nsum[((long)n * 2 + 0) * C + c] = s;
+  nsum[((long)n * 2 + 1) * C + c] = q;
+  if (pool) {
+    nc_mean[(long)n * C + c] = (float)(s / (double)HW);
+    nc_max[(long)n * C + c] = bmx;
+    nc_min[(long)n * C + c] = bmn;
+    nc_amax[(long)n * C + c] = imx;
+    nc_amin[(long)n * C + c] = imn;
+  }
+}
+
+// Stage 3: block = 32 channels x 8 lanes; lane j adds images j, j+8, ... and the 8 lane sums are combined in lane
+// order (fixed order -> deterministic).  BN affine (train: batch statistics + running update; eval: running stats).
+__global__ void __launch_bounds__(256)
+bn_finalize_kernel(const double* __restrict__ nsum, int N, int HW, int C, int training, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, float* __restrict__ running_mean, float* __restrict__ running_var,
+                   float momentum, float eps, float* __restrict__ scale, float* __restrict__ shift,
+                   float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  __shared__ double sh[2][8][32];
+  const int cx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  double s = 0.0, q = 0.0;
+  if (training && c < C)
+    for (int n = ly; n < N; n += 8) {
+      s += nsum[((long)n * 2 + 0) * C + c];
+      q += nsum[((long)n * 2 + 1) * C + c];
+    }
+  sh[0][ly][cx] = s;
+  sh[1][ly][cx] = q;
+  __syncthreads();
+  if (ly != 0 || c >= C) return;
   float mean, var;
   if (training) {
+    double tsum = 0.0, tsq = 0.0;
+    for (int j = 0; j < 8; ++j) { tsum += sh[0][j][cx]; tsq += sh[1][j][cx]; }
     const double M = (double)N * (double)HW;
     const double m = tsum / M;
     double v = tsq / M - m * m;
@@ -529,7 +550,7 @@ int pick_tpp(int C) {
 
 int stats_chunks(int N, int HW, int C) {
   const int rows = NT / (C >> 3);
-  long want = ((long)rbu_num_sms() * 4 + N - 1) / N;          // ~4 blocks per SM in total
+  long want = ((long)rbu_num_sms() * 16 + N - 1) / N;         // ~16 blocks per SM in total: small tail wave
   long maxc = (HW + (long)rows * 8 - 1) / ((long)rows * 8);   // at least ~8 pixels per thread
   if (maxc < 1) maxc = 1;
   if (want > maxc) want = maxc;
@@ -543,7 +564,7 @@ int stats_chunks(int N, int HW, int C) {
 
 extern "C" size_t rbu_bn_stats_workspace_bytes(int N, int HW, int C) {
   if (C < 8 || C % 8 || C > 2048) return 0;
-  return (size_t)N * stats_chunks(N, HW, C) * 6 * C * sizeof(float);
+  return (size_t)N * stats_chunks(N, HW, C) * 6 * C * sizeof(float) + (size_t)N * 2 * C * sizeof(double) + 16;
 }
 
 extern "C" int rbu_bn_stats(const void* x, int64_t ld, int N, int HW, int C, int pool, int training,
@@ -558,10 +579,8 @@ extern "C" int rbu_bn_stats(const void* x, int64_t ld, int N, int HW, int C, int
   RBU_CHECK_ARG(training || (running_mean && running_var), "rbu_bn_stats: eval mode needs running statistics");
   RBU_CHECK_ARG(!pool || (nc_mean && nc_max && nc_min && nc_amax && nc_amin), "rbu_bn_stats: pool outputs missing");
   if (!training && !pool) {  // pure eval affine: no pass over the data
-    bn_finalize_kernel<<<rbu_cdiv(C, 128), 128, 0, stream>>>(nullptr, nullptr, 0, 0, HW, C, 0, 0, gamma, beta,
-                                                              running_mean, running_var, momentum, eps, scale, shift,
-                                                              mean_out, rstd_out, nullptr, nullptr, nullptr, nullptr,
-                                                              nullptr);
+    bn_finalize_kernel<<<rbu_cdiv(C, 32), 256, 0, stream>>>(nullptr, 0, HW, C, 0, gamma, beta, running_mean, running_var,
+                                                             momentum, eps, scale, shift, mean_out, rstd_out);
     RBU_CHECK_LAUNCH();
     return RBU_OK;
   }
@@ -573,10 +592,12 @@ extern "C" int rbu_bn_stats(const void* x, int64_t ld, int N, int HW, int C, int
   int* part_i = (int*)(part_f + (size_t)N * chunks * 4 * C);
   bn_stats_kernel<<<dim3(chunks, N), NT, 0, stream>>>((const bf16*)x, ld, HW, C, chunk_px, pool, part_f, part_i);
   RBU_CHECK_LAUNCH();
-  bn_finalize_kernel<<<rbu_cdiv(C, 128), 128, 0, stream>>>(part_f, part_i, N, chunks, HW, C, pool, training, gamma, beta,
-                                                            running_mean, running_var, momentum, eps, scale, shift,
-                                                            mean_out, rstd_out, nc_mean, nc_max, nc_min, nc_amax,
-                                                            nc_amin);
+  double* nsum = (double*)(((uintptr_t)(part_i + (size_t)N * chunks * 2 * C) + 15) & ~(uintptr_t)15);
+  bn_reduce_nc_kernel<<<dim3(rbu_cdiv(C, 128), N), 128, 0, stream>>>(part_f, part_i, chunks, HW, C, pool, nsum, nc_mean,
+                                                                      nc_max, nc_min, nc_amax, nc_amin);
+  RBU_CHECK_LAUNCH();
+  bn_finalize_kernel<<<rbu_cdiv(C, 32), 256, 0, stream>>>(nsum, N, HW, C, training, gamma, beta, running_mean, running_var,
+                                                           momentum, eps, scale, shift, mean_out, rstd_out);
   RBU_CHECK_LAUNCH();
   return RBU_OK;
 }
