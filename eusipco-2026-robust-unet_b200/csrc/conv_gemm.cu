@@ -18,6 +18,7 @@
 #include "rbu_common.cuh"
 #include "rbu_ptx.cuh"
 #include "tma_host.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -96,7 +97,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   if (warp == 0) {
     // ============================== TMA producer ==============================
     if (lane == 0) {
-      int it = 0;
+      int s = 0;
+      uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int nb = tile % p.n_blocks;
         int sp = tile / p.n_blocks;
@@ -114,9 +116,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
               dh = (tap / 3 - 1) * p.dil[seg];
               dw = (tap % 3 - 1) * p.dil[seg];
             }
-            for (int kc = 0; kc < kch; ++kc, ++it) {
-              const int s = it % p.num_stages;
-              const uint32_t ph = (it / p.num_stages) & 1;
+            for (int kc = 0; kc < kch; ++kc) {
               ptx::mbar_wait(&empty[s], ph ^ 1);
               ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)stage_bytes);
               uint8_t* a_dst = smem + s * stage_bytes;
@@ -126,6 +126,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
               else
                 ptx::tma_load_4d(a_dst, mA, &full[s], kc * BLOCK_K, w0 + dw, h0 + dh, n0);
               ptx::tma_load_2d(b_dst, mB, &full[s], tap * p.C[seg] + kc * BLOCK_K, nb * p.block_n);
+              if (++s == p.num_stages) { s = 0; ph ^= 1; }
             }
           }
         }
@@ -133,39 +134,48 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
-    if (lane == 0) {
-      const uint32_t idesc = ptx::make_idesc_bf16(BLOCK_M, p.block_n, 0, 0);
-      int it = 0, t = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
-        const int a = t & 1;
-        const uint32_t aph = (t >> 1) & 1;
-        ptx::mbar_wait(&tempty[a], aph ^ 1);
-        ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(a * p.block_n);
-        int kb = 0;
-        for (int seg = 0; seg < p.nseg; ++seg) {
-          const int kch = (p.C[seg] + BLOCK_K - 1) / BLOCK_K;
-          for (int tap = 0; tap < p.taps[seg]; ++tap) {
-            for (int kc = 0; kc < kch; ++kc, ++it, ++kb) {
-              const int s = it % p.num_stages;
-              const uint32_t ph = (it / p.num_stages) & 1;
-              ptx::mbar_wait(&full[s], ph);
-              ptx::tc_fence_after();
-              const uint32_t a_addr = ptx::smem_u32(smem + s * stage_bytes);
-              const uint32_t b_addr = a_addr + A_BYTES;
-              int rem = p.C[seg] - kc * BLOCK_K;
-              const int ksteps = rem >= BLOCK_K ? 4 : (rem + 15) / 16;  // channels past C are TMA zero fill
-              for (int k = 0; k < ksteps; ++k) {
-                const uint64_t da = ptx::make_smem_desc(a_addr + k * 32, 16, 1024);
-                const uint64_t db = ptx::make_smem_desc(b_addr + k * 32, 16, 1024);
-                ptx::umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+    // Whole warp walks the schedule, one elected lane issues; lean per-stage body (see conv_halo.cu).
+    const uint32_t idesc = ptx::make_idesc_bf16(BLOCK_M, p.block_n, 0, 0);
+    const uint32_t full_s = ptx::smem_u32(full), empty_s = ptx::smem_u32(empty);
+    const uint32_t hi = ptx::desc_hi(1024);
+    const uint32_t a_lo0 = ptx::desc_lo(ptx::smem_u32(smem), 16);
+    const uint32_t st_step = (uint32_t)stage_bytes >> 4;
+    int s = 0, t = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
+      const int a = t & 1;
+      ptx::mbar_wait(&tempty[a], ((t >> 1) & 1) ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(a * p.block_n);
+      uint32_t accumulate = 0;
+      for (int seg = 0; seg < p.nseg; ++seg) {
+        const int kch = (p.C[seg] + BLOCK_K - 1) / BLOCK_K;
+        for (int tap = 0; tap < p.taps[seg]; ++tap) {
+          for (int kc = 0; kc < kch; ++kc) {
+            ptx::mbar_wait_s(full_s + s * 8, ph);
+            ptx::tc_fence_after();
+            const int rem = p.C[seg] - kc * BLOCK_K;
+            const int ksteps = rem >= BLOCK_K ? 4 : (rem + 15) / 16;  // channels past C are TMA zero fill
+            if (ptx::elect_one()) {
+              const uint32_t a_lo = a_lo0 + s * st_step;
+              const uint32_t b_lo = a_lo + (A_BYTES >> 4);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (k < ksteps) {
+                  ptx::umma_bf16(d_tmem, ptx::pack_desc(a_lo + 2 * k, hi), ptx::pack_desc(b_lo + 2 * k, hi), idesc, accumulate);
+                  accumulate = 1;
+                }
               }
-              ptx::umma_commit(&empty[s]);  // frees the smem stage once these MMAs retire
+              ptx::umma_commit_s(empty_s + s * 8);  // frees the smem stage once these MMAs retire
             }
+            accumulate = 1;
+            __syncwarp();
+            if (++s == p.num_stages) { s = 0; ph ^= 1; }
           }
         }
-        ptx::umma_commit(&tfull[a]);  // accumulator complete
       }
+      if (ptx::elect_one()) ptx::umma_commit(&tfull[a]);  // accumulator complete
+      __syncwarp();
     }
   } else {
     // ============================== epilogue (warps 2..5) ==============================
@@ -292,6 +302,12 @@ extern "C" int rbu_conv_gemm(const rbu_conv_gemm_args* a, void* stream_) {
       RBU_CHECK_ARG(o.taps == 1 || o.taps == 9, "rbu_conv_gemm: taps must be 1 or 9 (got %d)", o.taps);
       RBU_CHECK_ARG(o.taps == 1 || o.dil >= 1, "rbu_conv_gemm: dilation must be >= 1");
     }
+  }
+
+  {
+    static int no_halo = -1;   // RBU_NO_HALO=1 forces the generic per-tap kernel (A/B comparisons in the tests)
+    if (no_halo < 0) no_halo = getenv("RBU_NO_HALO") ? 1 : 0;
+    if (!no_halo && rbu_conv_halo_supported(a)) return rbu_conv_halo_launch(a, stream);
   }
 
   KParams p;

@@ -1,0 +1,375 @@
+// K1 / K10, halo variant: 3x3 (dilation 1) and 1x1 convolutions and their data gradients as an implicit GEMM on
+// tcgen05 tensor cores where every activation tile is fetched from L2 ONCE and reused by all nine taps.
+//
+// The generic kernel (conv_gemm.cu) issues one TMA load of the 128-pixel x 64-channel A tile per tap, i.e. nine
+// loads of (almost) the same pixels per 64-channel slab: 24-48 KB of L2->SM traffic per k-block, 44-87 FLOP per
+// byte, which caps the 64/128-channel layers at 540-810 TFLOP/s on the ~12 TB/s L2 (measured 553 on inc.conv2,
+// profiles/r01_a_*).  Here the output tile is 16 rows x 8 columns of one image and the A operand is its
+// 18 x 16(10 used) x 64-channel halo, loaded by ONE 4-D TMA box into a SWIZZLE_128B buffer with a 2048-byte row
+// pitch.  Tap (dy,dx) is then just a different START ADDRESS of the same buffer: the UMMA shared-memory descriptor
+// (K-major, 8-pixel row groups, stride-byte-offset = 2048 = one halo row) starts at pixel (dy, dx) of the halo; the
+// start is a multiple of 128 B, not of 1024 B.  Measured on B200: the tensor core applies the 128-byte swizzle XOR
+// from the ABSOLUTE shared-memory address bits [7:9] of every row it fetches -- exactly what TMA did when it wrote
+// the rows -- so the descriptor's matrix-base-offset field stays 0 (setting it to (start >> 7) & 7 double-counts
+// the phase: every 3x3 parity test failed with it, all pass without).
+// L2->SM traffic per 64-channel slab drops from 9 x 16 KB to 36 KB for A; B (weights) still streams per tap.
+//
+// Structure (persistent, warp specialised, 192 threads, 1 CTA / SM), as conv_gemm.cu:
+//   warp 0 lane 0 : TMA producer -- A ring (halo tiles, 2-3 stages) and B ring (one weight tile per tap)
+//   warp 1 lane 0 : MMA issuer   -- per slab 9 taps x 4 tcgen05.mma (K = 16) into one of two TMEM accumulators
+//   warps 2..5    : epilogue     -- tcgen05.ld, bias / addend, bf16 pack, 16-byte stores
+// Two accumulated segments are supported (conv1 3x3 dgrad + shortcut 1x1 dgrad; 1x1 segments use a plain
+// 16 x 8-pixel box with a 1024-byte pitch).
+// Replaces aten::convolution / convolution_backward(input) of Main_Final.py:157,159,172,126,131.
+#include "rbu_common.cuh"
+#include "rbu_ptx.cuh"
+#include "tma_host.cuh"
+#include <stdlib.h>
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;
+constexpr int TILE_W = 8, TILE_H = 16;
+constexpr int HALO_W = 16, HALO_H = 18;               // 16 column slots (10 used): row pitch 2048 B = 2 swizzle atoms
+constexpr int A_HALO_BYTES = HALO_H * HALO_W * 128;   // 36864
+constexpr int A_PLAIN_BYTES = BLOCK_M * 128;          // 16384
+constexpr int NUM_THREADS = 192;
+constexpr int MAX_B_STAGES = 8;
+constexpr int SMEM_LIMIT = 232448;
+constexpr int LOOKAHEAD_TAP = 4;                      // the next slab's A tile is requested after this tap's B tile
+
+struct HParams {
+  int N, H, W;
+  int tiles_w, tiles_h;
+  int n_blocks, block_n, Ncols;
+  int nseg;
+  int taps[2], C[2];
+  int a_stages, b_stages, tmem_cols, total_tiles;
+  bf16* y;
+  long long y_ld;
+  const float* bias;
+  const bf16* addend;
+  long long addend_ld;
+};
+
+// Enumerates the (tile, segment, 64-channel slab) sequence of this CTA; producer and MMA issuer walk it in lockstep.
+struct SlabIter {
+  int tile, seg, kc;
+  bool valid;
+  __device__ __forceinline__ void init(const HParams& p) {
+    tile = blockIdx.x; seg = 0; kc = 0;
+    valid = tile < p.total_tiles;
+  }
+  __device__ __forceinline__ void next(const HParams& p) {
+    if (++kc < (p.C[seg] + BLOCK_K - 1) / BLOCK_K) return;
+    kc = 0;
+    if (++seg < p.nseg) return;
+    seg = 0;
+    tile += gridDim.x;
+    valid = tile < p.total_tiles;
+  }
+};
+
+__device__ __forceinline__ void tile_coords(const HParams& p, int tile, int& nb, int& w0, int& h0, int& n) {
+  nb = tile % p.n_blocks;
+  int sp = tile / p.n_blocks;
+  w0 = (sp % p.tiles_w) * TILE_W;
+  sp /= p.tiles_w;
+  h0 = (sp % p.tiles_h) * TILE_H;
+  n = sp / p.tiles_h;
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
+                 const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1, const HParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int b_bytes = p.block_n * 128;
+  uint8_t* smA = smem;
+  uint8_t* smB = smem + p.a_stages * A_HALO_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smB + p.b_stages * b_bytes);
+  uint64_t* fullA = bars;                      // [4]
+  uint64_t* emptyA = bars + 4;                 // [4]
+  uint64_t* fullB = bars + 8;                  // [MAX_B_STAGES]
+  uint64_t* emptyB = bars + 8 + MAX_B_STAGES;  // [MAX_B_STAGES]
+  uint64_t* tfull = bars + 8 + 2 * MAX_B_STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA0);
+    ptx::prefetch_tmap(&tmB0);
+    if (p.nseg > 1) {
+      ptx::prefetch_tmap(&tmA1);
+      ptx::prefetch_tmap(&tmB1);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.a_stages; ++s) {
+      ptx::mbar_init(&fullA[s], 1);
+      ptx::mbar_init(&emptyA[s], 1);
+    }
+    for (int s = 0; s < p.b_stages; ++s) {
+      ptx::mbar_init(&fullB[s], 1);
+      ptx::mbar_init(&emptyB[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tfull[a], 1);
+      ptx::mbar_init(&tempty[a], 4);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      SlabIter ia, ib;
+      ia.init(p);
+      ib.init(p);
+      int sa = 0, sb = 0;
+      uint32_t pha = 0, phb = 0;
+      auto issue_a = [&]() {
+        const int s = sa;
+        const uint32_t ph = pha;
+        if (++sa == p.a_stages) { sa = 0; pha ^= 1; }
+        int nb, w0, h0, n;
+        tile_coords(p, ia.tile, nb, w0, h0, n);
+        const bool halo = p.taps[ia.seg] == 9;
+        ptx::mbar_wait(&emptyA[s], ph ^ 1);
+        ptx::mbar_arrive_expect_tx(&fullA[s], halo ? A_HALO_BYTES : A_PLAIN_BYTES);
+        const CUtensorMap* mA = ia.seg ? &tmA1 : &tmA0;
+        if (halo)
+          ptx::tma_load_4d(smA + s * A_HALO_BYTES, mA, &fullA[s], ia.kc * BLOCK_K, w0 - 1, h0 - 1, n);
+        else
+          ptx::tma_load_4d(smA + s * A_HALO_BYTES, mA, &fullA[s], ia.kc * BLOCK_K, w0, h0, n);
+        ia.next(p);
+      };
+      if (ia.valid) issue_a();
+      while (ib.valid) {
+        int nb, w0, h0, n;
+        tile_coords(p, ib.tile, nb, w0, h0, n);
+        const int taps = p.taps[ib.seg];
+        const int look = taps - 1 < LOOKAHEAD_TAP ? taps - 1 : LOOKAHEAD_TAP;
+        const CUtensorMap* mB = ib.seg ? &tmB1 : &tmB0;
+        for (int tap = 0; tap < taps; ++tap) {
+          const int s = sb;
+          const uint32_t ph = phb;
+          if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
+          ptx::mbar_wait(&emptyB[s], ph ^ 1);
+          ptx::mbar_arrive_expect_tx(&fullB[s], (uint32_t)b_bytes);
+          ptx::tma_load_2d(smB + s * b_bytes, mB, &fullB[s], tap * p.C[ib.seg] + ib.kc * BLOCK_K, nb * p.block_n);
+          if (tap == look && ia.valid) issue_a();
+        }
+        ib.next(p);
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer ==============================
+    // The whole warp walks the schedule (uniform control flow, barrier waits by all lanes); one elected lane issues
+    // the tcgen05 instructions.  The per-tap body is kept to a few dozen instructions: descriptor halves are
+    // precomputed, ring indices wrap by compare instead of modulo -- the issuing thread, not the tensor pipe, was the
+    // bottleneck of the first version (ncu: ~1190 cycles of scalar code per tap, profiles/r01_b_*).
+    const uint32_t idesc = ptx::make_idesc_bf16(BLOCK_M, p.block_n, 0, 0);
+    const uint32_t fullA_s = ptx::smem_u32(fullA), emptyA_s = ptx::smem_u32(emptyA);
+    const uint32_t fullB_s = ptx::smem_u32(fullB), emptyB_s = ptx::smem_u32(emptyB);
+    const uint32_t smA_s = ptx::smem_u32(smA), smB_s = ptx::smem_u32(smB);
+    const uint32_t b_hi = ptx::desc_hi(1024);
+    const uint32_t b_step = (uint32_t)b_bytes >> 4;
+    SlabIter it;
+    it.init(p);
+    int sa = 0, sb = 0, t = 0;
+    uint32_t pha = 0, phb = 0;
+    while (it.valid) {
+      const int a = t & 1;
+      ptx::mbar_wait(&tempty[a], ((t >> 1) & 1) ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(a * p.block_n);
+      const int cur_tile = it.tile;
+      uint32_t accumulate = 0;
+      while (it.valid && it.tile == cur_tile) {
+        ptx::mbar_wait_s(fullA_s + sa * 8, pha);
+        ptx::tc_fence_after();
+        const int taps = p.taps[it.seg];
+        const bool halo = taps == 9;
+        const uint32_t a_hi = ptx::desc_hi(halo ? HALO_W * 128 : TILE_W * 128);
+        const uint32_t a_lo0 = ptx::desc_lo(smA_s + sa * A_HALO_BYTES, 16);
+        const int rem = p.C[it.seg] - it.kc * BLOCK_K;
+        const int ksteps = rem >= BLOCK_K ? 4 : (rem + 15) / 16;   // channels past C are TMA zero fill
+        // halo origin is pixel (h0-1, w0-1): tap (dy,dx) starts dy halo rows (2048 B) down and dx pixels (128 B) right
+        uint32_t a_row = a_lo0, a_lo = a_lo0;
+        int dx = 0;
+        for (int tap = 0; tap < taps; ++tap) {
+          ptx::mbar_wait_s(fullB_s + sb * 8, phb);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            const uint32_t b_lo = ptx::desc_lo(smB_s, 16) + sb * b_step;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (k < ksteps) {
+                ptx::umma_bf16(d_tmem, ptx::pack_desc(a_lo + 2 * k, a_hi), ptx::pack_desc(b_lo + 2 * k, b_hi), idesc,
+                               accumulate);
+                accumulate = 1;
+              }
+            }
+            ptx::umma_commit_s(emptyB_s + sb * 8);
+          }
+          accumulate = 1;
+          __syncwarp();
+          if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
+          if (++dx == 3) { dx = 0; a_row += (HALO_W * 128) >> 4; a_lo = a_row; } else { a_lo += 128 >> 4; }
+        }
+        if (ptx::elect_one()) ptx::umma_commit_s(emptyA_s + sa * 8);
+        __syncwarp();
+        if (++sa == p.a_stages) { sa = 0; pha ^= 1; }
+        it.next(p);
+      }
+      if (ptx::elect_one()) ptx::umma_commit(&tfull[a]);
+      __syncwarp();
+      ++t;
+    }
+  } else {
+    // ============================== epilogue (warps 2..5) ==============================
+    const int lg = warp & 3;
+    const int row = lg * 32 + lane;
+    int t = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
+      int nb, w0, h0, n;
+      tile_coords(p, tile, nb, w0, h0, n);
+      const int h = h0 + row / TILE_W, w = w0 + row % TILE_W;
+      const bool valid = h < p.H && w < p.W;
+      const long long pix = ((long long)n * p.H + h) * p.W + w;
+      const int a = t & 1;
+      const uint32_t aph = (t >> 1) & 1;
+      ptx::mbar_wait(&tfull[a], aph);
+      ptx::tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(a * p.block_n);
+      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(t_addr + (uint32_t)c0, r);
+        ptx::tmem_ld_wait();
+        const int col = nb * p.block_n + c0;
+        if (valid && col < p.Ncols) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int c8 = col + g * 8;
+            if (c8 < p.Ncols) {
+              float f[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(r[g * 8 + e]);
+              if (p.bias) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c8));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + c8 + 4));
+                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+              }
+              if (p.addend) {
+                float ad[8];
+                unpack8(ld_bf16x8(p.addend + pix * p.addend_ld + c8), ad);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] += ad[e];
+              }
+              st_bf16x8(p.y + pix * p.y_ld + c8, pack8(f));
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tempty[a]);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+}  // namespace
+
+// Returns 1 if the halo kernel can run these arguments (3x3 dilation-1 and 1x1 segments on images of at least
+// 16 x 8 pixels, no gather / scatter), else 0.
+int rbu_conv_halo_supported(const rbu_conv_gemm_args* a) {
+  if (a->scatter || a->H < TILE_H || a->W < TILE_W) return 0;
+  int any3x3 = 0;
+  for (int s = 0; s < a->nseg; ++s) {
+    const rbu_gemm_operand& o = a->seg[s];
+    if (o.gather) return 0;
+    if (!(o.taps == 1 || (o.taps == 9 && o.dil == 1))) return 0;
+    any3x3 |= o.taps == 9;
+  }
+  return any3x3;   // pure 1x1 GEMMs have no halo to reuse: the generic kernel's deeper A+B ring is faster for them
+}
+
+// Argument validation is done by the caller (rbu_conv_gemm).
+int rbu_conv_halo_launch(const rbu_conv_gemm_args* a, cudaStream_t stream) {
+  HParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = a->N; p.H = a->H; p.W = a->W;
+  p.tiles_w = rbu_cdiv(a->W, TILE_W);
+  p.tiles_h = rbu_cdiv(a->H, TILE_H);
+  p.Ncols = a->Ncols;
+  p.block_n = a->Ncols >= 256 ? 256 : ((a->Ncols + 31) / 32) * 32;
+  p.n_blocks = rbu_cdiv(a->Ncols, p.block_n);
+  p.nseg = a->nseg;
+  for (int s = 0; s < a->nseg; ++s) {
+    p.taps[s] = a->seg[s].taps;
+    p.C[s] = a->seg[s].C;
+  }
+  const int b_bytes = p.block_n * 128;
+  p.a_stages = p.block_n >= 256 ? 2 : 3;
+  p.b_stages = (SMEM_LIMIT - 2048 - p.a_stages * A_HALO_BYTES) / b_bytes;
+  if (p.b_stages > MAX_B_STAGES) p.b_stages = MAX_B_STAGES;
+  p.tmem_cols = 32;
+  while (p.tmem_cols < 2 * p.block_n) p.tmem_cols <<= 1;
+  p.total_tiles = p.tiles_w * p.tiles_h * a->N * p.n_blocks;
+  p.y = reinterpret_cast<bf16*>(a->y);
+  p.y_ld = a->y_ld;
+  p.bias = a->bias;
+  p.addend = reinterpret_cast<const bf16*>(a->addend);
+  p.addend_ld = a->addend_ld;
+
+  CUtensorMap tmA[2], tmB[2];
+  memset(tmA, 0, sizeof(tmA));
+  memset(tmB, 0, sizeof(tmB));
+  for (int s = 0; s < a->nseg; ++s) {
+    const rbu_gemm_operand& o = a->seg[s];
+    const bool halo = o.taps == 9;
+    const uint64_t dims[4] = {(uint64_t)o.C, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->N};
+    const uint64_t str[3] = {(uint64_t)o.x_ld * 2, (uint64_t)o.x_ld * 2 * a->W, (uint64_t)o.x_ld * 2 * a->W * a->H};
+    const uint32_t box[4] = {BLOCK_K, (uint32_t)(halo ? HALO_W : TILE_W), (uint32_t)(halo ? HALO_H : TILE_H), 1};
+    int rc = rbu_encode_tmap_bf16(&tmA[s], o.x, 4, dims, str, box);
+    if (rc) return rc;
+    const uint64_t ktot = (uint64_t)o.taps * o.C;
+    const uint64_t bdims[2] = {ktot, (uint64_t)a->Ncols};
+    const uint64_t bstr[1] = {ktot * 2};
+    const uint32_t bbox[2] = {BLOCK_K, (uint32_t)p.block_n};
+    rc = rbu_encode_tmap_bf16(&tmB[s], o.w, 2, bdims, bstr, bbox);
+    if (rc) return rc;
+  }
+  if (a->nseg == 1) {
+    tmA[1] = tmA[0];
+    tmB[1] = tmB[0];
+  }
+  const int smem_bytes = p.a_stages * A_HALO_BYTES + p.b_stages * b_bytes + 1024 + 512;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RBU_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    attr_set = true;
+  }
+  const int grid = p.total_tiles < rbu_num_sms() ? p.total_tiles : rbu_num_sms();
+  conv_halo_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(tmA[0], tmB[0], tmA[1], tmB[1], p);
+  RBU_CHECK_LAUNCH();
+  return RBU_OK;
+}

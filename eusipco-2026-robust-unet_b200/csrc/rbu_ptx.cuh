@@ -49,14 +49,48 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
   return ok;
 }
 // Bounded wait: a protocol bug must trap (sticky CUDA error on the host) instead of hanging the GPU.
+static __device__ __noinline__ void mbar_timeout() {
+  printf("rbunet: mbarrier wait timeout (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) {
-      printf("rbunet: mbarrier wait timeout (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
-      __trap();
-    }
+    if (++spins > (1u << 26)) mbar_timeout();
   }
+}
+// same, addressed by a 32-bit shared address (no generic->shared conversion in hot loops)
+__device__ __forceinline__ uint32_t mbar_try_wait_s(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait_s(bar, parity)) return;
+  uint32_t spins = 0;
+  while (!mbar_try_wait_s(bar, parity)) {
+    if (++spins > (1u << 26)) mbar_timeout();
+  }
+}
+__device__ __forceinline__ void umma_commit_s(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint64_t pack_desc(uint32_t lo, uint32_t hi) {
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+// upper / lower 32 bits of a SWIZZLE_128B shared-memory matrix descriptor (see make_smem_desc below)
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+}
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
 }
 
 // ----------------------------------------------------------------------------- TMA

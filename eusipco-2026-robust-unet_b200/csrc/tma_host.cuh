@@ -5,7 +5,13 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "../../include/rbunet.h"
+
 // Encode a bf16 tensor map with SWIZZLE_128B. dims/strides innermost first; strides[i] is the byte stride
 // of dimension i+1 (dimension 0 is contiguous). Returns 0 on success (error text via rbu_set_error).
 int rbu_encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                          const uint64_t* strides_bytes, const uint32_t* box);
+
+// conv_halo.cu: halo-reuse variant of the implicit-GEMM convolution (3x3 dilation 1 / 1x1 segments).
+int rbu_conv_halo_supported(const rbu_conv_gemm_args* a);
+int rbu_conv_halo_launch(const rbu_conv_gemm_args* a, cudaStream_t stream);

@@ -91,7 +91,8 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   if (warp == 0) {
     if (lane == 0) {
-      int ia = 0, ib = 0;
+      int sa = 0, sb = 0;
+      uint32_t pha = 0, phb = 0;
       for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
         int mb, nb, tg, ks;
         decode_item(p, item, mb, nb, tg, ks);
@@ -103,18 +104,18 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           int w0, h0, n0;
           tile_origin(p, tile, w0, h0, n0);
           {
-            const int s = ia % A_STAGES;
-            const uint32_t ph = (ia / A_STAGES) & 1;
-            ++ia;
+            const int s = sa;
+            const uint32_t ph = pha;
+            if (++sa == A_STAGES) { sa = 0; pha ^= 1; }
             ptx::mbar_wait(&emptyA[s], ph ^ 1);
             ptx::mbar_arrive_expect_tx(&fullA[s], (uint32_t)a_bytes);
             for (int bx = 0; bx < a_boxes; ++bx)
               ptx::tma_load_4d(smA + s * a_bytes + bx * BOX_BYTES, &tmA, &fullA[s], mb * p.BM + bx * 64, w0, h0, n0);
           }
           for (int t = t_begin; t < t_end; ++t) {
-            const int s = ib % p.b_stages;
-            const uint32_t ph = (ib / p.b_stages) & 1;
-            ++ib;
+            const int s = sb;
+            const uint32_t ph = phb;
+            if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
             ptx::mbar_wait(&emptyB[s], ph ^ 1);
             ptx::mbar_arrive_expect_tx(&fullB[s], (uint32_t)b_bytes);
             for (int bx = 0; bx < b_boxes; ++bx) {
@@ -133,45 +134,52 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = ptx::make_idesc_bf16(p.BM, p.BN, 1, 1);
-      int ia = 0, ib = 0, it = 0;
-      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
-        int mb, nb, tg, ks;
-        decode_item(p, item, mb, nb, tg, ks);
-        const int t_begin = tg * p.T;
-        const int t_end = min(t_begin + p.T, p.taps);
-        const int tile0 = (int)((long)ks * p.tiles_total / p.ksplit);
-        const int tile1 = (int)((long)(ks + 1) * p.tiles_total / p.ksplit);
-        ptx::mbar_wait(tempty, (it & 1) ^ 1);
+    // MMA issuer: the whole warp walks the schedule (uniform control flow), one elected lane issues; descriptor
+    // halves are precomputed and the ring indices wrap by compare (the issuing thread must stay well below the
+    // 8 x 64-cycle MMA time of a tap).
+    const uint32_t idesc = ptx::make_idesc_bf16(p.BM, p.BN, 1, 1);
+    const uint32_t fullA_s = ptx::smem_u32(fullA), emptyA_s = ptx::smem_u32(emptyA);
+    const uint32_t fullB_s = ptx::smem_u32(fullB), emptyB_s = ptx::smem_u32(emptyB);
+    const uint32_t hi = ptx::desc_hi(1024);
+    const uint32_t a_lo0 = ptx::desc_lo(ptx::smem_u32(smA), BOX_BYTES), b_lo0 = ptx::desc_lo(ptx::smem_u32(smB), BOX_BYTES);
+    const uint32_t a_step = (uint32_t)a_bytes >> 4, b_step = (uint32_t)b_bytes >> 4;
+    int sa = 0, sb = 0, it = 0;
+    uint32_t pha = 0, phb = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+      int mb, nb, tg, ks;
+      decode_item(p, item, mb, nb, tg, ks);
+      const int ntap = min(tg * p.T + p.T, p.taps) - tg * p.T;
+      const int tile0 = (int)((long)ks * p.tiles_total / p.ksplit);
+      const int tile1 = (int)((long)(ks + 1) * p.tiles_total / p.ksplit);
+      ptx::mbar_wait(tempty, (it & 1) ^ 1);
+      ptx::tc_fence_after();
+      uint32_t accumulate = 0;
+      for (int tile = tile0; tile < tile1; ++tile) {
+        ptx::mbar_wait_s(fullA_s + sa * 8, pha);
         ptx::tc_fence_after();
-        for (int tile = tile0; tile < tile1; ++tile) {
-          const int sa = ia % A_STAGES;
-          const uint32_t pha = (ia / A_STAGES) & 1;
-          ++ia;
-          ptx::mbar_wait(&fullA[sa], pha);
+        const uint32_t a_lo = a_lo0 + sa * a_step;
+        for (int t = 0; t < ntap; ++t) {
+          ptx::mbar_wait_s(fullB_s + sb * 8, phb);
           ptx::tc_fence_after();
-          const uint32_t a_addr = ptx::smem_u32(smA + sa * a_bytes);
-          for (int t = t_begin; t < t_end; ++t) {
-            const int sb = ib % p.b_stages;
-            const uint32_t phb = (ib / p.b_stages) & 1;
-            ++ib;
-            ptx::mbar_wait(&fullB[sb], phb);
-            ptx::tc_fence_after();
-            const uint32_t b_addr = ptx::smem_u32(smB + sb * b_bytes);
-            const uint32_t d_tmem = tmem_base + (uint32_t)((t - t_begin) * p.BN);
+          if (ptx::elect_one()) {
+            const uint32_t b_lo = b_lo0 + sb * b_step;
+            const uint32_t d_tmem = tmem_base + (uint32_t)(t * p.BN);
 #pragma unroll
-            for (int k = 0; k < TILE_PX / 16; ++k) {
-              const uint64_t da = ptx::make_smem_desc(a_addr + k * 2048, BOX_BYTES, 1024);
-              const uint64_t db = ptx::make_smem_desc(b_addr + k * 2048, BOX_BYTES, 1024);
-              ptx::umma_bf16(d_tmem, da, db, idesc, (tile > tile0 || k > 0) ? 1u : 0u);
-            }
-            ptx::umma_commit(&emptyB[sb]);
+            for (int k = 0; k < TILE_PX / 16; ++k)
+              ptx::umma_bf16(d_tmem, ptx::pack_desc(a_lo + k * (2048 >> 4), hi), ptx::pack_desc(b_lo + k * (2048 >> 4), hi),
+                             idesc, (k > 0) ? 1u : accumulate);
+            ptx::umma_commit_s(emptyB_s + sb * 8);
           }
-          ptx::umma_commit(&emptyA[sa]);
+          __syncwarp();
+          if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
         }
-        ptx::umma_commit(tfull);
+        accumulate = 1;
+        if (ptx::elect_one()) ptx::umma_commit_s(emptyA_s + sa * 8);
+        __syncwarp();
+        if (++sa == A_STAGES) { sa = 0; pha ^= 1; }
       }
+      if (ptx::elect_one()) ptx::umma_commit(tfull);
+      __syncwarp();
     }
   } else {
     const int lg = warp & 3;
