@@ -170,6 +170,10 @@ def run_ours(args):
     step(x_dev, y_dev)
     _lib.PROFILER = None
     summ = prof.summary()
+    if args.detail and rank == 0:
+        with open(args.detail, "w") as f:
+            for lab, ms_, fl, nb_ in prof.detail():
+                f.write(f"{ms_:8.3f} ms  {fl / ms_ / 1e9 if fl and ms_ else 0:8.1f} TF/s  {lab}\n")
     peaks = load_peaks()
     gemm = {k: v for k, v in summ.items() if v["flops"] > 0}
     gemm_ms = sum(v["ms"] for v in gemm.values())
@@ -300,6 +304,7 @@ def main():
     ap.add_argument("--size", type=int, default=0)
     ap.add_argument("--channels", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--detail", default="", help="write the per-call device times of one profiled step to this file")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

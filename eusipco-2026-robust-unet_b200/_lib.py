@@ -97,11 +97,18 @@ class Profiler:
     def __init__(self):
         self.records = []      # (entry point, tag, flops, bytes, start event, stop event)
 
+    def detail(self):
+        """Per-call rows (label, ms, flops, bytes), slowest first."""
+        import torch
+        torch.cuda.synchronize()
+        rows = [(lab or tag or name, e0.elapsed_time(e1), flops, nbytes) for name, tag, flops, nbytes, e0, e1, lab in self.records]
+        return sorted(rows, key=lambda r: -r[1])
+
     def summary(self):
         import torch
         torch.cuda.synchronize()
         out = {}
-        for name, tag, flops, nbytes, e0, e1 in self.records:
+        for name, tag, flops, nbytes, e0, e1, _ in self.records:
             d = out.setdefault(tag or name, {"calls": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
             d["calls"] += 1
             d["ms"] += e0.elapsed_time(e1)
@@ -113,7 +120,7 @@ class Profiler:
 PROFILER = None
 
 
-def call(name: str, *args, tag=None, flops=0.0, nbytes=0.0):
+def call(name: str, *args, tag=None, flops=0.0, nbytes=0.0, label=None):
     """Call an int-returning entry point and raise RuntimeError with rbu_last_error() on failure."""
     prof = PROFILER
     if prof is None:
@@ -124,7 +131,7 @@ def call(name: str, *args, tag=None, flops=0.0, nbytes=0.0):
     e0.record()
     check(getattr(lib(), name)(*args), name)
     e1.record()
-    prof.records.append((name, tag, flops, nbytes, e0, e1))
+    prof.records.append((name, tag, flops, nbytes, e0, e1, label))
 
 
 def launch_count() -> int:

@@ -82,7 +82,8 @@ __device__ __forceinline__ void tile_coords(const HParams& p, int tile, int& nb,
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
-                 const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1, const HParams p) {
+                 const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
+                 const __grid_constant__ HParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int b_bytes = p.block_n * 128;

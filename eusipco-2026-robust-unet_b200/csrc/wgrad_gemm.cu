@@ -50,7 +50,8 @@ __device__ __forceinline__ void tile_origin(const WParams& p, int tile, int& w0,
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const WParams p) {
+wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ WParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int a_boxes = p.BM / 64 > 0 ? (p.BM + 63) / 64 : 1;

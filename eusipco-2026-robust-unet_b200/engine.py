@@ -115,7 +115,8 @@ class Engine:
         nbytes = _lib.lib().rbu_wgrad_workspace_bytes(ctypes.byref(args))
         ws = self.ws(nbytes, out.device)
         call("rbu_wgrad_gemm", ctypes.byref(args), _p(ws), ws.numel() * 4, stream_ptr(), tag="wgrad_gemm",
-             flops=2.0 * N * H * W * a.C * b.C * taps)
+             flops=2.0 * N * H * W * a.C * b.C * taps,
+             label=f"wgrad {N}x{H}x{W} {a.C}x{b.C} t{taps}{'g' if gather else ''}d{dil}")
 
     def bwd_ws(self, N, HW, C, device):
         return self.ws(_lib.lib().rbu_bwd_workspace_bytes(N, HW, max(C, 32)), device)

@@ -87,7 +87,11 @@ def conv_gemm(N, H, W, segs, Ncols, y: View, scatter=False, Cout=0, bias=None, a
     a.addend_ld = addend.ld if addend is not None else 0
     if flops is None:
         flops = 2.0 * N * H * W * Ncols * sum(t * x.C for (x, _, t, _, _) in segs)
-    call("rbu_conv_gemm", ctypes.byref(a), stream_ptr(), tag=tag, flops=flops)
+    label = None
+    if _lib.PROFILER is not None:
+        label = f"conv {N}x{H}x{W} " + "+".join(f"{x.C}t{t}{'g' if g else ''}d{d}" for (x, _, t, d, g) in segs) + \
+            f"->{Ncols}{' scatter' if scatter else ''}"
+    call("rbu_conv_gemm", ctypes.byref(a), stream_ptr(), tag=tag, flops=flops, label=label)
 
 
 def conv_direct_ref(x: View, N, H, W, w, bias, ksz, dil):
