@@ -120,60 +120,80 @@ head_bwd_kernel(const float* __restrict__ dprobs, const float* __restrict__ prob
 }
 
 // ------------------------------------------------------------------------------------------------
-// ResidualBlock backward, pass 1: de = dout * [out > 0] (stored, may alias dout);
-// dG[p] = sum_c de * (A2g*y2 + B2g);  projection shortcut: per-channel sum(de), sum(de * xhat_s).
+// ResidualBlock backward in three passes over the activations:
+//   pass 1  de = dout * [out > 0] (stored, may alias dout);  dG[p] = sum_c de * (A2g*y2 + B2g);
+//           projection shortcut: per-channel sum(de), sum(de * ys)                       [-> SpatialAttention bwd]
+//   pass 2  per (n,c):  D0 = sum_hw dc,  D1 = sum_hw dc * y2,
+//           dc = de*gs + ds_avg/C + ds_max*[c == argmax_c]                               [-> rbu_rb_mid]
+//   pass 3  dy2 = c1*dc + c0 + cy*y2 + cm*[pixel == argmax_hw];  dys = es*de + e0 + ey*ys
+// Everything BatchNorm2 / ChannelAttention need between passes 2 and 3 (dT, the BN sums S1/S2, the gate MLP
+// gradients) follows algebraically from D0/D1 and forward statistics, so no further pass over the data is needed.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NT)
 rb_bwd1_kernel(const bf16* __restrict__ dout, long dout_ld, const bf16* __restrict__ out, long out_ld,
                const bf16* __restrict__ y2, long y2_ld, bf16* __restrict__ de, long de_ld, const bf16* __restrict__ ys,
                long ys_ld, int HW, int C, int chunk_px, const float* __restrict__ A2g, const float* __restrict__ B2g,
-               const float* __restrict__ mean_s, const float* __restrict__ rstd_s, float* __restrict__ dG,
-               float* __restrict__ partials) {
+               float* __restrict__ dG, float* __restrict__ partials) {
   const int G = C >> 3, rows = NT / G;
   const int cg = threadIdx.x % G, row = threadIdx.x / G;
   const int n = blockIdx.y, chunk = blockIdx.x;
   const int p0 = chunk * chunk_px, p1 = min(p0 + chunk_px, HW);
-  const int iters = (p1 - p0 + rows - 1) / rows;
+  constexpr int U = 2;
+  const int iters = (p1 - p0 + rows * U - 1) / (rows * U);
   __shared__ float red[NT / 32];
-  float a[8], b[8], ms[8], rs[8], acc1[8], acc2[8];
+  float a[8], b[8], acc1[8], acc2[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const int c = cg * 8 + e;
     a[e] = A2g[(long)n * C + c];
     b[e] = B2g[(long)n * C + c];
-    ms[e] = ys ? mean_s[c] : 0.f;
-    rs[e] = ys ? rstd_s[c] : 0.f;
     acc1[e] = 0.f;
     acc2[e] = 0.f;
   }
   for (int it = 0; it < iters; ++it) {
-    const int pl = p0 + it * rows + row;
-    const bool act = row < rows && pl < p1;
-    const long p = (long)n * HW + pl;
-    float part = 0.f;
-    if (act) {
-      float g[8], o[8], y[8];
-      unpack8(ld_bf16x8_stream(dout + p * dout_ld + cg * 8), g);
-      unpack8(ld_bf16x8_stream(out + p * out_ld + cg * 8), o);
-      unpack8(ld_bf16x8(y2 + p * y2_ld + cg * 8), y);
+    bf16x8 rg[U], ro[U], ry[U], rs[U];
+    bool act[U];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        g[e] = o[e] > 0.f ? g[e] : 0.f;
-        part += g[e] * (a[e] * y[e] + b[e]);
-      }
-      st_bf16x8(de + p * de_ld + cg * 8, pack8(g));
-      if (ys) {
-        float s[8];
-        unpack8(ld_bf16x8(ys + p * ys_ld + cg * 8), s);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          acc1[e] += g[e];
-          acc2[e] += g[e] * (s[e] - ms[e]) * rs[e];
-        }
+    for (int u = 0; u < U; ++u) {
+      const int pl = p0 + (it * U + u) * rows + row;
+      act[u] = row < rows && pl < p1;
+      if (act[u]) {
+        const long p = (long)n * HW + pl;
+        rg[u] = ld_bf16x8_stream(dout + p * dout_ld + cg * 8);
+        ro[u] = ld_bf16x8_stream(out + p * out_ld + cg * 8);
+        ry[u] = ld_bf16x8(y2 + p * y2_ld + cg * 8);
+        if (ys) rs[u] = ld_bf16x8(ys + p * ys_ld + cg * 8);
       }
     }
-    part = row_sum(part, G, red);
-    if (act && cg == 0) dG[p] = part;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int pl = p0 + (it * U + u) * rows + row;
+      const long p = (long)n * HW + pl;
+      float part = 0.f;
+      if (act[u]) {
+        float g[8], o[8], y[8];
+        unpack8(rg[u], g);
+        unpack8(ro[u], o);
+        unpack8(ry[u], y);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          g[e] = o[e] > 0.f ? g[e] : 0.f;
+          part += g[e] * (a[e] * y[e] + b[e]);
+        }
+        st_bf16x8(de + p * de_ld + cg * 8, pack8(g));
+        if (ys) {
+          float sv8[8];
+          unpack8(rs[u], sv8);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            acc1[e] += g[e];
+            acc2[e] += g[e] * sv8[e];
+          }
+        }
+      }
+      part = row_sum(part, G, red);
+      if (act[u] && cg == 0) dG[p] = part;
+    }
   }
   if (ys) {
     __shared__ float sv[NT][8];
@@ -259,136 +279,145 @@ sa_bwd_weight_kernel(const float* __restrict__ dG, const float* __restrict__ gs,
   }
 }
 
-// gradient wrt b = BN2(y2) at (pixel, 8 channels), shared by passes 2-4
-struct RbCtx {
-  const float* gs; const float2* ds; const int* amax_c;       // per pixel
-  const float* g_c; const float* du_avg; const float* du_max; // per (n,c)
-  const int* nc_amax; const int* nc_amin;                      // per (n,c)
-  const float* scale2; const float* shift2; const float* mean2; const float* rstd2;  // per c
-};
-
-// pass 2: dT[n,c] = sum_hw dc * b,  dc = de*gs + ds_avg/C + ds_max*[c == argmax_c],  b = scale2*y2 + shift2
+// pass 2: per-(n, chunk, c) partials of D0 = sum dc and D1 = sum dc * y2
 __global__ void __launch_bounds__(NT)
 rb_bwd2_kernel(const bf16* __restrict__ de, long de_ld, const bf16* __restrict__ y2, long y2_ld, int HW, int C,
-               int chunk_px, RbCtx k, float* __restrict__ partials) {
+               int chunk_px, const float* __restrict__ gs, const float2* __restrict__ ds, const int* __restrict__ amax_c,
+               float* __restrict__ partials) {
   const int G = C >> 3, rows = NT / G;
   const int cg = threadIdx.x % G, row = threadIdx.x / G;
   const int n = blockIdx.y, chunk = blockIdx.x;
   const int p0 = chunk * chunk_px, p1 = min(p0 + chunk_px, HW);
-  float sc[8], sh[8], acc[8];
+  float acc0[8], acc1[8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) { sc[e] = k.scale2[cg * 8 + e]; sh[e] = k.shift2[cg * 8 + e]; acc[e] = 0.f; }
+  for (int e = 0; e < 8; ++e) { acc0[e] = 0.f; acc1[e] = 0.f; }
   const float invC = 1.f / (float)C;
+  constexpr int U = 4;
   if (row < rows) {
-#pragma unroll 2
-    for (int pl = p0 + row; pl < p1; pl += rows) {
-      const long p = (long)n * HW + pl;
-      float g[8], y[8];
-      unpack8(ld_bf16x8_stream(de + p * de_ld + cg * 8), g);
-      unpack8(ld_bf16x8_stream(y2 + p * y2_ld + cg * 8), y);
-      const float gsp = k.gs[p];
-      const float2 d = k.ds[p];
-      const int am = k.amax_c[p] - cg * 8;
+    for (int pl0 = p0 + row; pl0 < p1; pl0 += rows * U) {
+      bf16x8 rg[U], ry[U];
+      float gsp[U];
+      float2 d[U];
+      int am[U];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float dc = g[e] * gsp + d.x * invC + (e == am ? d.y : 0.f);
-        acc[e] += dc * (sc[e] * y[e] + sh[e]);
+      for (int u = 0; u < U; ++u) {
+        const int pl = pl0 + u * rows;
+        if (pl < p1) {
+          const long p = (long)n * HW + pl;
+          rg[u] = ld_bf16x8_stream(de + p * de_ld + cg * 8);
+          ry[u] = ld_bf16x8_stream(y2 + p * y2_ld + cg * 8);
+          gsp[u] = __ldg(gs + p);
+          d[u] = __ldg(ds + p);
+          am[u] = __ldg(amax_c + p) - cg * 8;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (pl0 + u * rows < p1) {
+          float g[8], y[8];
+          unpack8(rg[u], g);
+          unpack8(ry[u], y);
+          const float base = d[u].x * invC;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float dc = g[e] * gsp[u] + base + (e == am[u] ? d[u].y : 0.f);
+            acc0[e] += dc;
+            acc1[e] += dc * y[e];
+          }
+        }
       }
     }
   }
   __shared__ float sv[NT][8];
-  rows_reduce_store(acc, G, rows, sv, partials + ((long)n * gridDim.x + chunk) * C);
+  float* dst = partials + ((long)n * gridDim.x + chunk) * 2 * C;
+  rows_reduce_store(acc0, G, rows, sv, dst);
+  rows_reduce_store(acc1, G, rows, sv, dst + C);
 }
 
-__device__ __forceinline__ void rb_db(const RbCtx& k, int n, int pl, long p, int cg, int C, float invC, float invHW,
-                                      const float* g, const float* gc, const float* dua, const float* dum,
-                                      const int* pstar, float* db) {
-  const float gsp = k.gs[p];
-  const float2 d = k.ds[p];
-  const int am = k.amax_c[p] - cg * 8;
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const float dc = g[e] * gsp + d.x * invC + (e == am ? d.y : 0.f);
-    db[e] = dc * gc[e] + dua[e] * invHW + (pl == pstar[e] ? dum[e] : 0.f);
-  }
+// D[n][q][c] (double) = sum over the chunks of image n, chunk order
+__global__ void rb_d_reduce_kernel(const float* __restrict__ part, int chunks, int C, double* __restrict__ D) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;   // over 2C
+  const int n = blockIdx.y;
+  if (k >= 2 * C) return;
+  double s = 0.0;
+  for (int j = 0; j < chunks; ++j) s += (double)part[((long)n * chunks + j) * 2 * C + k];
+  D[(long)n * 2 * C + k] = s;
 }
 
-// pass 3 (MODE 0): per-channel sum(db), sum(db * xhat2).   pass 4 (MODE 1): dy2 = scale2*(db - S1/M - xhat2*S2/M)
-// and, for a projection shortcut, dys = scale_s*(de - T1/M - xhat_s*T2/M).
-template <int MODE>
+// pass 3 (streaming skeleton): dy2 = c1*dc + c0 + cy*y2 + cm*[pl == pstar];  dys = es*de + e0 + ey*ys
 __global__ void __launch_bounds__(NT)
-rb_bwd34_kernel(const bf16* __restrict__ de, long de_ld, const bf16* __restrict__ y2, long y2_ld, int HW, int C,
-                int chunk_px, RbCtx k, float* __restrict__ partials, const float* __restrict__ sums, float invM,
-                bf16* __restrict__ dy2, long dy2_ld, const bf16* __restrict__ ys, long ys_ld, bf16* __restrict__ dys,
-                long dys_ld, const float* __restrict__ scale_s, const float* __restrict__ mean_s,
-                const float* __restrict__ rstd_s, const float* __restrict__ sums_s) {
-  const int G = C >> 3, rows = NT / G;
-  const int cg = threadIdx.x % G, row = threadIdx.x / G;
-  const int n = blockIdx.y, chunk = blockIdx.x;
-  const int p0 = chunk * chunk_px, p1 = min(p0 + chunk_px, HW);
-  float gc[8], dua[8], dum[8], mu[8], rs[8], acc1[8], acc2[8];
+rb_bwd3_kernel(const bf16* __restrict__ de, long de_ld, const bf16* __restrict__ y2, long y2_ld, bf16* __restrict__ dy2,
+               long dy2_ld, const bf16* __restrict__ ys, long ys_ld, bf16* __restrict__ dys, long dys_ld, int HW, int C,
+               int lg, const float* __restrict__ gs, const float2* __restrict__ ds, const int* __restrict__ amax_c,
+               const int* __restrict__ nc_arg, const float* __restrict__ c1, const float* __restrict__ c0,
+               const float* __restrict__ cm, const float* __restrict__ cy, const float* __restrict__ es,
+               const float* __restrict__ e0, const float* __restrict__ ey) {
+  const int n = blockIdx.y, G = 1 << lg, items = HW << lg;
+  const int cg = threadIdx.x & (G - 1);
+  float k1[8], k0[8], km[8], ky[8];
   int pstar[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    const int c = cg * 8 + e;
-    gc[e] = k.g_c[(long)n * C + c];
-    dua[e] = k.du_avg[(long)n * C + c];
-    dum[e] = k.du_max[(long)n * C + c];
-    pstar[e] = k.scale2[c] >= 0.f ? k.nc_amax[(long)n * C + c] : k.nc_amin[(long)n * C + c];
-    mu[e] = k.mean2[c];
-    rs[e] = k.rstd2[c];
-    acc1[e] = 0.f;
-    acc2[e] = 0.f;
+    const long o = (long)n * C + cg * 8 + e;
+    k1[e] = c1[o]; k0[e] = c0[o]; km[e] = cm[o]; ky[e] = cy[cg * 8 + e];
+    pstar[e] = nc_arg[o];
   }
-  const float invC = 1.f / (float)C, invHW = 1.f / (float)HW;
-  if (row < rows) {
-#pragma unroll 2
-    for (int pl = p0 + row; pl < p1; pl += rows) {
-      const long p = (long)n * HW + pl;
-      float g[8], y[8], db[8];
-      unpack8(ld_bf16x8_stream(de + p * de_ld + cg * 8), g);
-      unpack8(ld_bf16x8_stream(y2 + p * y2_ld + cg * 8), y);
-      rb_db(k, n, pl, p, cg, C, invC, invHW, g, gc, dua, dum, pstar, db);
-      if (MODE == 0) {
+  const float invC = 1.f / (float)C;
+  const long ib = (long)n * HW;
+  constexpr int U = 2;
+  for (int base = blockIdx.x * (NT * U) + threadIdx.x; base < items; base += gridDim.x * (NT * U)) {
+    bf16x8 rg[U], ry[U], rs[U];
+    float gsp[U];
+    float2 d[U];
+    int am[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = base + u * NT;
+      if (i < items) {
+        const long p = ib + (i >> lg);
+        rg[u] = ld_bf16x8_stream(de + p * de_ld + cg * 8);
+        ry[u] = ld_bf16x8_stream(y2 + p * y2_ld + cg * 8);
+        if (ys) rs[u] = ld_bf16x8_stream(ys + p * ys_ld + cg * 8);
+        gsp[u] = __ldg(gs + p);
+        d[u] = __ldg(ds + p);
+        am[u] = __ldg(amax_c + p) - cg * 8;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = base + u * NT;
+      if (i < items) {
+        const int pl = i >> lg;
+        const long p = ib + pl;
+        float g[8], y[8], o[8];
+        unpack8(rg[u], g);
+        unpack8(ry[u], y);
+        const float bse = d[u].x * invC;
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          acc1[e] += db[e];
-          acc2[e] += db[e] * (y[e] - mu[e]) * rs[e];
-        }
-      } else {
-        float o[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int c = cg * 8 + e;
-          const float xh = (y[e] - mu[e]) * rs[e];
-          o[e] = k.scale2[c] * (db[e] - sums[c] * invM - xh * sums[C + c] * invM);
+          const float dc = g[e] * gsp[u] + bse + (e == am[u] ? d[u].y : 0.f);
+          o[e] = k1[e] * dc + k0[e] + ky[e] * y[e] + (pl == pstar[e] ? km[e] : 0.f);
         }
         st_bf16x8(dy2 + p * dy2_ld + cg * 8, pack8(o));
         if (ys) {
-          float s[8];
-          unpack8(ld_bf16x8_stream(ys + p * ys_ld + cg * 8), s);
+          float sv8[8];
+          unpack8(rs[u], sv8);
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const int c = cg * 8 + e;
-            const float xh = (s[e] - mean_s[c]) * rstd_s[c];
-            o[e] = scale_s[c] * (g[e] - sums_s[c] * invM - xh * sums_s[C + c] * invM);
+            o[e] = es[c] * g[e] + e0[c] + ey[c] * sv8[e];
           }
           st_bf16x8(dys + p * dys_ld + cg * 8, pack8(o));
         }
       }
     }
   }
-  if (MODE == 0) {
-    __shared__ float sv[NT][8];
-    float* dst = partials + ((long)n * gridDim.x + chunk) * 2 * C;
-    rows_reduce_store(acc1, G, rows, sv, dst);
-    rows_reduce_store(acc2, G, rows, sv, dst + C);
-  }
 }
 
 // ChannelAttention backward (Main_Final.py:97-101), one block per image
 __global__ void __launch_bounds__(NT)
-ca_bwd_n_kernel(const float* __restrict__ dT, const float* __restrict__ g, const float* __restrict__ h_avg,
+ca_bwd_n_kernel(const double* __restrict__ D, const float* __restrict__ scale2, const float* __restrict__ shift2,
+                const float* __restrict__ g, const float* __restrict__ h_avg,
                 const float* __restrict__ h_max, const float* __restrict__ V1, const float* __restrict__ V2, int C, int Ch,
                 float* __restrict__ dt_out, float* __restrict__ dh_avg_out, float* __restrict__ dh_max_out,
                 float* __restrict__ du_avg, float* __restrict__ du_max) {
@@ -399,7 +428,9 @@ ca_bwd_n_kernel(const float* __restrict__ dT, const float* __restrict__ g, const
   const int n = blockIdx.x;
   for (int c = threadIdx.x; c < C; c += NT) {
     const float gg = g[(long)n * C + c];
-    const float v = dT[(long)n * C + c] * gg * (1.f - gg);
+    // dT[n,c] = sum_hw dc * b,  b = scale2*y2 + shift2  ->  scale2*D1 + shift2*D0
+    const float dT = (float)((double)scale2[c] * D[((long)n * 2 + 1) * C + c] + (double)shift2[c] * D[((long)n * 2 + 0) * C + c]);
+    const float v = dT * gg * (1.f - gg);
     dt[c] = v;
     dt_out[(long)n * C + c] = v;
   }
@@ -451,6 +482,71 @@ __global__ void ca_bwd_w_kernel(const float* __restrict__ dt, const float* __res
     for (int n = 0; n < N; ++n)
       s += dt[(long)n * C + c] * (fmaxf(h_avg[(long)n * Ch + j], 0.f) + fmaxf(h_max[(long)n * Ch + j], 0.f));
     dV2[i] = s;
+  }
+}
+
+// BatchNorm2 sums and the pass-3 coefficients, block = 32 channels x 8 lanes (lane j handles images j, j+8, ...;
+// lane sums are combined in lane order -> deterministic):
+//   S1[c] = sum_n (g*D0 + du_avg + du_max)
+//   S2[c] = sum_n (g*rs*(D1 - mu*D0) + du_avg*(nc_mean - mu)*rs + du_max*(tv - mu)*rs)
+//   c1 = scale2*g;  c0 = scale2*(du_avg/HW - S1/M + rs*mu*S2/M);  cy = -scale2*rs*S2/M;  cm = scale2*du_max
+// and, for a projection shortcut with raw sums T1 = sum de, R = sum de*ys:
+//   T2 = rs_s*(R - mu_s*T1);  es = scale_s;  e0 = scale_s*(-T1/M + rs_s*mu_s*T2/M);  ey = -scale_s*rs_s*T2/M
+__global__ void __launch_bounds__(256)
+rb_coef_kernel(const double* __restrict__ D, const float* __restrict__ g, const float* __restrict__ du_avg,
+               const float* __restrict__ du_max, const float* __restrict__ nc_mean, const float* __restrict__ tv,
+               const float* __restrict__ scale2, const float* __restrict__ mean2, const float* __restrict__ rstd2, int N,
+               int HW, int C, float* __restrict__ sums2, float* __restrict__ c1, float* __restrict__ c0,
+               float* __restrict__ cm, float* __restrict__ cy, const float* __restrict__ sraw /* [2C] or NULL */,
+               const float* __restrict__ scale_s, const float* __restrict__ mean_s, const float* __restrict__ rstd_s,
+               float* __restrict__ sums_s, float* __restrict__ es, float* __restrict__ e0, float* __restrict__ ey) {
+  __shared__ double sh[2][8][32];
+  __shared__ float bc[2][32];
+  const int cx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  const bool ok = c < C;
+  const double mu = ok ? (double)mean2[c] : 0.0, rs = ok ? (double)rstd2[c] : 0.0;
+  double s1 = 0.0, s2 = 0.0;
+  if (ok)
+    for (int n = ly; n < N; n += 8) {
+      const long o = (long)n * C + c;
+      const double d0 = D[((long)n * 2 + 0) * C + c], d1 = D[((long)n * 2 + 1) * C + c];
+      const double gg = g[o], da = du_avg[o], dm = du_max[o];
+      s1 += gg * d0 + da + dm;
+      s2 += gg * rs * (d1 - mu * d0) + da * ((double)nc_mean[o] - mu) * rs + dm * ((double)tv[o] - mu) * rs;
+    }
+  sh[0][ly][cx] = s1;
+  sh[1][ly][cx] = s2;
+  __syncthreads();
+  const double M = (double)N * (double)HW;
+  if (ly == 0 && ok) {
+    double S1 = 0.0, S2 = 0.0;
+    for (int j = 0; j < 8; ++j) { S1 += sh[0][j][cx]; S2 += sh[1][j][cx]; }
+    sums2[c] = (float)S1;
+    sums2[C + c] = (float)S2;
+    bc[0][cx] = (float)(S1 / M);
+    bc[1][cx] = (float)(S2 / M);
+    cy[c] = (float)(-(double)scale2[c] * rs * S2 / M);
+    if (sraw) {
+      const double T1 = sraw[c], R = sraw[C + c], mus = mean_s[c], rss = rstd_s[c], scs = scale_s[c];
+      const double T2 = rss * (R - mus * T1);
+      sums_s[c] = (float)T1;
+      sums_s[C + c] = (float)T2;
+      es[c] = (float)scs;
+      e0[c] = (float)(scs * (-T1 / M + rss * mus * T2 / M));
+      ey[c] = (float)(-scs * rss * T2 / M);
+    }
+  }
+  __syncthreads();
+  if (ok) {
+    const float s1m = bc[0][cx], s2m = bc[1][cx], sc = scale2[c];
+    const float invHW = 1.f / (float)HW;
+    for (int n = ly; n < N; n += 8) {
+      const long o = (long)n * C + c;
+      c1[o] = sc * g[o];
+      c0[o] = sc * (du_avg[o] * invHW - s1m + (float)(rs * mu) * s2m);
+      cm[o] = sc * du_max[o];
+    }
   }
 }
 
@@ -754,20 +850,20 @@ extern "C" int rbu_head_backward(const float* dprobs, const float* probs, const 
 
 extern "C" int rbu_rb_bwd1(const void* dout, int64_t dout_ld, const void* out, int64_t out_ld, const void* y2,
                            int64_t y2_ld, void* de, int64_t de_ld, const void* ys, int64_t ys_ld, int N, int HW, int C,
-                           const float* A2g, const float* B2g, const float* mean_s, const float* rstd_s, float* dG,
-                           float* sums_s, void* workspace, size_t workspace_bytes, void* stream_) {
+                           const float* A2g, const float* B2g, float* dG, float* sums_s_raw, void* workspace,
+                           size_t workspace_bytes, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   RBU_CHECK_ARG(VIEW_OK(dout, dout_ld) && VIEW_OK(out, out_ld) && VIEW_OK(y2, y2_ld) && VIEW_OK(de, de_ld) && A2g && B2g &&
                     dG && CH_OK(C) && N > 0 && N <= 65535 && HW > 0, "rbu_rb_bwd1: bad arguments");
-  RBU_CHECK_ARG(!ys || (VIEW_OK(ys, ys_ld) && mean_s && rstd_s && sums_s), "rbu_rb_bwd1: projection-shortcut arguments missing");
+  RBU_CHECK_ARG(!ys || (VIEW_OK(ys, ys_ld) && sums_s_raw), "rbu_rb_bwd1: projection-shortcut arguments missing");
   const int chunks = bwd_chunks(N, HW, C);
   RBU_CHECK_ARG(workspace && workspace_bytes >= (size_t)N * chunks * 2 * C * sizeof(float), "rbu_rb_bwd1: workspace too small");
   rb_bwd1_kernel<<<dim3(chunks, N), NT, 0, st>>>((const bf16*)dout, dout_ld, (const bf16*)out, out_ld, (const bf16*)y2,
                                                  y2_ld, (bf16*)de, de_ld, (const bf16*)ys, ys_ld, HW, C,
-                                                 rbu_cdiv(HW, chunks), A2g, B2g, mean_s, rstd_s, dG, (float*)workspace);
+                                                 rbu_cdiv(HW, chunks), A2g, B2g, dG, (float*)workspace);
   RBU_CHECK_LAUNCH();
   if (ys) {
-    colsum_kernel<<<rbu_cdiv(2 * C, 32), 256, 0, st>>>((const float*)workspace, N * chunks, 2 * C, 2 * C, sums_s, 1.f);
+    colsum_kernel<<<rbu_cdiv(2 * C, 32), 256, 0, st>>>((const float*)workspace, N * chunks, 2 * C, 2 * C, sums_s_raw, 1.f);
     RBU_CHECK_LAUNCH();
   }
   return RBU_OK;
@@ -789,67 +885,81 @@ extern "C" int rbu_sa_bwd(const float* dG, const float* gs, const float* s, int 
   return RBU_OK;
 }
 
-// pass selector: 2 -> dT[N,C];  3 -> sums2[2C] (= dbeta2, dgamma2);  4 -> dy2 (+ dys)
-extern "C" int rbu_rb_bwd_pass(int pass, const void* de, int64_t de_ld, const void* y2, int64_t y2_ld, int N, int HW, int C,
-                               const float* gs, const float* ds, const int* amax_c, const float* g_c,
-                               const float* du_avg, const float* du_max, const int* nc_amax, const int* nc_amin,
-                               const float* scale2, const float* shift2, const float* mean2, const float* rstd2,
-                               float* dT, float* sums2, void* dy2, int64_t dy2_ld, const void* ys, int64_t ys_ld,
-                               void* dys, int64_t dys_ld, const float* scale_s, const float* mean_s,
-                               const float* rstd_s, const float* sums_s, void* workspace, size_t workspace_bytes,
-                               void* stream_) {
+// pass 2: D[N][2][C] (double) = per-(n,c) sum dc, sum dc*y2
+extern "C" int rbu_rb_bwd2(const void* de, int64_t de_ld, const void* y2, int64_t y2_ld, int N, int HW, int C,
+                           const float* gs, const float* ds, const int* amax_c, double* D, void* workspace,
+                           size_t workspace_bytes, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
-  RBU_CHECK_ARG(pass >= 2 && pass <= 4, "rbu_rb_bwd_pass: pass must be 2, 3 or 4");
-  RBU_CHECK_ARG(VIEW_OK(de, de_ld) && VIEW_OK(y2, y2_ld) && CH_OK(C) && N > 0 && N <= 65535 && HW > 0 && gs && ds && amax_c &&
-                    scale2 && shift2, "rbu_rb_bwd_pass: bad arguments");
-  RbCtx k;
-  k.gs = gs; k.ds = (const float2*)ds; k.amax_c = amax_c; k.g_c = g_c; k.du_avg = du_avg; k.du_max = du_max;
-  k.nc_amax = nc_amax; k.nc_amin = nc_amin; k.scale2 = scale2; k.shift2 = shift2; k.mean2 = mean2; k.rstd2 = rstd2;
+  RBU_CHECK_ARG(VIEW_OK(de, de_ld) && VIEW_OK(y2, y2_ld) && CH_OK(C) && N > 0 && N <= 65535 && HW > 0 && gs && ds && amax_c && D,
+                "rbu_rb_bwd2: bad arguments");
   const int chunks = bwd_chunks(N, HW, C);
-  const int chunk_px = rbu_cdiv(HW, chunks);
-  const float invM = 1.f / ((float)N * (float)HW);
-  float* part = (float*)workspace;
-  if (pass == 2) {
-    RBU_CHECK_ARG(dT && workspace_bytes >= (size_t)N * chunks * C * sizeof(float), "rbu_rb_bwd_pass(2): bad arguments");
-    rb_bwd2_kernel<<<dim3(chunks, N), NT, 0, st>>>((const bf16*)de, de_ld, (const bf16*)y2, y2_ld, HW, C, chunk_px, k, part);
-    RBU_CHECK_LAUNCH();
-    colsum_nc_kernel<<<dim3(rbu_cdiv(C, 128), N), 128, 0, st>>>(part, N, chunks, C, dT);
-    RBU_CHECK_LAUNCH();
-    return RBU_OK;
-  }
-  RBU_CHECK_ARG(g_c && du_avg && du_max && nc_amax && nc_amin && mean2 && rstd2 && sums2, "rbu_rb_bwd_pass: null pointer");
-  if (pass == 3) {
-    RBU_CHECK_ARG(workspace_bytes >= (size_t)N * chunks * 2 * C * sizeof(float), "rbu_rb_bwd_pass(3): workspace too small");
-    rb_bwd34_kernel<0><<<dim3(chunks, N), NT, 0, st>>>((const bf16*)de, de_ld, (const bf16*)y2, y2_ld, HW, C, chunk_px, k,
-                                                      part, nullptr, invM, nullptr, 0, nullptr, 0, nullptr, 0, nullptr,
-                                                      nullptr, nullptr, nullptr);
-    RBU_CHECK_LAUNCH();
-    colsum_kernel<<<rbu_cdiv(2 * C, 32), 256, 0, st>>>(part, N * chunks, 2 * C, 2 * C, sums2, 1.f);
-    RBU_CHECK_LAUNCH();
-    return RBU_OK;
-  }
-  RBU_CHECK_ARG(VIEW_OK(dy2, dy2_ld), "rbu_rb_bwd_pass(4): bad dy2 view");
-  RBU_CHECK_ARG(!ys || (VIEW_OK(ys, ys_ld) && VIEW_OK(dys, dys_ld) && scale_s && mean_s && rstd_s && sums_s),
-                "rbu_rb_bwd_pass(4): projection-shortcut arguments missing");
-  rb_bwd34_kernel<1><<<dim3(chunks, N), NT, 0, st>>>((const bf16*)de, de_ld, (const bf16*)y2, y2_ld, HW, C, chunk_px, k,
-                                                    nullptr, sums2, invM, (bf16*)dy2, dy2_ld, (const bf16*)ys, ys_ld,
-                                                    (bf16*)dys, dys_ld, scale_s, mean_s, rstd_s, sums_s);
+  RBU_CHECK_ARG(workspace && workspace_bytes >= (size_t)N * chunks * 2 * C * sizeof(float), "rbu_rb_bwd2: workspace too small");
+  rb_bwd2_kernel<<<dim3(chunks, N), NT, 0, st>>>((const bf16*)de, de_ld, (const bf16*)y2, y2_ld, HW, C, rbu_cdiv(HW, chunks),
+                                                 gs, (const float2*)ds, amax_c, (float*)workspace);
+  RBU_CHECK_LAUNCH();
+  rb_d_reduce_kernel<<<dim3(rbu_cdiv(2 * C, 128), N), 128, 0, st>>>((const float*)workspace, chunks, C, D);
   RBU_CHECK_LAUNCH();
   return RBU_OK;
 }
 
-extern "C" int rbu_ca_bwd(const float* dT, const float* g, const float* h_avg, const float* h_max, const float* u_avg,
-                          const float* u_max, const float* V1, const float* V2, int N, int C, int Ch, float* dt,
-                          float* dh_avg, float* dh_max, float* du_avg, float* du_max, float* dV1, float* dV2,
-                          void* stream_) {
+// Between passes 2 and 3: ChannelAttention MLP backward (Main_Final.py:97-101), BatchNorm2 / shortcut-BN sums and the
+// pass-3 coefficient arrays.  coef = float[(3*N + 1)*C] (c1, c0, cm per (n,c); cy per c); coef_s = float[3*C] (es, e0, ey).
+extern "C" int rbu_rb_mid(const double* D, const float* g, const float* h_avg, const float* h_max, const float* u_avg,
+                          const float* u_max, const float* nc_mean, const float* tv, const float* V1, const float* V2,
+                          const float* scale2, const float* shift2, const float* mean2, const float* rstd2, int N, int HW,
+                          int C, int Ch, float* scratch /* float[3*N*C + 2*N*Ch] */, float* dV1, float* dV2, float* sums2,
+                          float* coef, const float* sums_s_raw, const float* scale_s, const float* mean_s,
+                          const float* rstd_s, float* sums_s, float* coef_s, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
-  RBU_CHECK_ARG(dT && g && h_avg && h_max && u_avg && u_max && V1 && V2 && dt && dh_avg && dh_max && du_avg && du_max &&
-                    dV1 && dV2 && N > 0 && C > 0 && Ch > 0 && (C + 2 * Ch) * 4 <= 48 * 1024, "rbu_ca_bwd: bad arguments");
-  ca_bwd_n_kernel<<<N, NT, (C + 2 * Ch) * sizeof(float), st>>>(dT, g, h_avg, h_max, V1, V2, C, Ch, dt, dh_avg, dh_max,
-                                                               du_avg, du_max);
+  RBU_CHECK_ARG(D && g && h_avg && h_max && u_avg && u_max && nc_mean && tv && V1 && V2 && scale2 && shift2 && mean2 && rstd2 &&
+                    scratch && dV1 && dV2 && sums2 && coef && N > 0 && C > 0 && Ch > 0 && HW > 0 &&
+                    (C + 2 * Ch) * 4 <= 48 * 1024, "rbu_rb_mid: bad arguments");
+  RBU_CHECK_ARG(!sums_s_raw || (scale_s && mean_s && rstd_s && sums_s && coef_s), "rbu_rb_mid: projection-shortcut arguments missing");
+  float* dt = scratch;
+  float* du_avg = dt + (size_t)N * C;
+  float* du_max = du_avg + (size_t)N * C;
+  float* dh_avg = du_max + (size_t)N * C;
+  float* dh_max = dh_avg + (size_t)N * Ch;
+  ca_bwd_n_kernel<<<N, NT, (C + 2 * Ch) * sizeof(float), st>>>(D, scale2, shift2, g, h_avg, h_max, V1, V2, C, Ch, dt, dh_avg,
+                                                               dh_max, du_avg, du_max);
   RBU_CHECK_LAUNCH();
   ca_bwd_w_kernel<<<rbu_cdiv((long)C * Ch, 128), 128, 0, st>>>(dt, dh_avg, dh_max, h_avg, h_max, u_avg, u_max, N, C, Ch,
                                                                dV1, dV2);
+  RBU_CHECK_LAUNCH();
+  float* c1 = coef;
+  float* c0 = c1 + (size_t)N * C;
+  float* cm = c0 + (size_t)N * C;
+  float* cy = cm + (size_t)N * C;
+  rb_coef_kernel<<<rbu_cdiv(C, 32), 256, 0, st>>>(D, g, du_avg, du_max, nc_mean, tv, scale2, mean2, rstd2, N, HW, C, sums2, c1,
+                                                   c0, cm, cy, sums_s_raw, scale_s, mean_s, rstd_s, sums_s,
+                                                   coef_s, coef_s ? coef_s + C : nullptr, coef_s ? coef_s + 2 * C : nullptr);
+  RBU_CHECK_LAUNCH();
+  return RBU_OK;
+}
+
+// pass 3: dy2 (and dys for a projection shortcut)
+extern "C" int rbu_rb_bwd3(const void* de, int64_t de_ld, const void* y2, int64_t y2_ld, void* dy2, int64_t dy2_ld,
+                           const void* ys, int64_t ys_ld, void* dys, int64_t dys_ld, int N, int HW, int C, const float* gs,
+                           const float* ds, const int* amax_c, const int* nc_arg, const float* coef, const float* coef_s,
+                           void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  RBU_CHECK_ARG(VIEW_OK(de, de_ld) && VIEW_OK(y2, y2_ld) && VIEW_OK(dy2, dy2_ld) && CH_OK(C) && N > 0 && N <= 65535 && HW > 0 &&
+                    gs && ds && amax_c && nc_arg && coef, "rbu_rb_bwd3: bad arguments");
+  RBU_CHECK_ARG(!ys || (VIEW_OK(ys, ys_ld) && VIEW_OK(dys, dys_ld) && coef_s), "rbu_rb_bwd3: projection-shortcut arguments missing");
+  int lg = 0;
+  while ((1 << (lg + 1)) <= (C >> 3)) ++lg;
+  const long items = (long)HW << lg;
+  long blocks = (items + NT * 2 - 1) / (NT * 2);
+  long cap = ((long)rbu_num_sms() * 32 + N - 1) / N;
+  if (blocks > cap) blocks = cap;
+  const float* c1 = coef;
+  const float* c0 = c1 + (size_t)N * C;
+  const float* cm = c0 + (size_t)N * C;
+  const float* cy = cm + (size_t)N * C;
+  rb_bwd3_kernel<<<dim3((unsigned)blocks, N), NT, 0, st>>>(
+      (const bf16*)de, de_ld, (const bf16*)y2, y2_ld, (bf16*)dy2, dy2_ld, (const bf16*)ys, ys_ld, (bf16*)dys, dys_ld, HW, C, lg,
+      gs, (const float2*)ds, amax_c, nc_arg, c1, c0, cm, cy, coef_s, coef_s ? coef_s + C : nullptr,
+      coef_s ? coef_s + 2 * C : nullptr);
   RBU_CHECK_LAUNCH();
   return RBU_OK;
 }

@@ -15,9 +15,9 @@ constexpr int NT = 256;
 // (Main_Final.py:87-88,98-99) need — computed on the raw conv output; BN is a per-channel affine map.
 // grid (chunks, N); thread = (channel group of 8, pixel row)
 // ------------------------------------------------------------------------------------------------
+template <int POOL>
 __global__ void __launch_bounds__(NT)
-bn_stats_kernel(const bf16* __restrict__ x, long ld, int HW, int C, int chunk_px, int pool,
-                float* __restrict__ part_f, int* __restrict__ part_i) {
+bn_stats_kernel(const bf16* __restrict__ x, long ld, int HW, int C, int chunk_px, float* __restrict__ part_f) {
   const int G = C >> 3;
   const int rows = NT / G;
   const int cg = threadIdx.x % G;
@@ -26,35 +26,37 @@ bn_stats_kernel(const bf16* __restrict__ x, long ld, int HW, int C, int chunk_px
   const int p0 = chunk * chunk_px;
   const int p1 = min(p0 + chunk_px, HW);
   float sum[8], sq[8], mx[8], mn[8];
-  int amx[8], amn[8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    sum[e] = 0.f; sq[e] = 0.f; mx[e] = -INFINITY; mn[e] = INFINITY; amx[e] = 0x7fffffff; amn[e] = 0x7fffffff;
-  }
+  for (int e = 0; e < 8; ++e) { sum[e] = 0.f; sq[e] = 0.f; mx[e] = -INFINITY; mn[e] = INFINITY; }
   if (row < rows) {
     const bf16* base = x + (long)n * HW * ld + cg * 8;
-#pragma unroll 4
-    for (int p = p0 + row; p < p1; p += rows) {
-      float v[8];
-      unpack8(ld_bf16x8(base + (long)p * ld), v);
+    constexpr int U = 4;   // independent 16-byte loads in flight per thread
+    for (int p = p0 + row; p < p1; p += rows * U) {
+      bf16x8 raw[U];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        sum[e] += v[e];
-        sq[e] += v[e] * v[e];
-        if (pool) {
-          if (v[e] > mx[e]) { mx[e] = v[e]; amx[e] = p; }
-          if (v[e] < mn[e]) { mn[e] = v[e]; amn[e] = p; }
+      for (int u = 0; u < U; ++u)
+        if (p + u * rows < p1) raw[u] = ld_bf16x8_stream(base + (long)(p + u * rows) * ld);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (p + u * rows < p1) {
+          float v[8];
+          unpack8(raw[u], v);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            sum[e] += v[e];
+            sq[e] += v[e] * v[e];
+            if (POOL) { mx[e] = fmaxf(mx[e], v[e]); mn[e] = fminf(mn[e], v[e]); }
+          }
         }
       }
     }
   }
   __shared__ float sv[NT][8];
-  __shared__ int si[NT][8];
   const long obase = ((long)n * chunks + chunk);
-  // sum, sumsq
-  for (int q = 0; q < 2; ++q) {
+  // q = 0: sum, 1: sum of squares, 2: max, 3: min; rows combined in row order
+  for (int q = 0; q < (POOL ? 4 : 2); ++q) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) sv[threadIdx.x][e] = q == 0 ? sum[e] : sq[e];
+    for (int e = 0; e < 8; ++e) sv[threadIdx.x][e] = q == 0 ? sum[e] : q == 1 ? sq[e] : q == 2 ? mx[e] : mn[e];
     __syncthreads();
     if (row == 0) {
       float a[8];
@@ -62,59 +64,34 @@ bn_stats_kernel(const bf16* __restrict__ x, long ld, int HW, int C, int chunk_px
       for (int e = 0; e < 8; ++e) a[e] = sv[cg][e];
       for (int r = 1; r < rows; ++r)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) a[e] += sv[r * G + cg][e];
+        for (int e = 0; e < 8; ++e) {
+          const float t = sv[r * G + cg][e];
+          a[e] = q < 2 ? a[e] + t : q == 2 ? fmaxf(a[e], t) : fminf(a[e], t);
+        }
 #pragma unroll
       for (int e = 0; e < 8; ++e) part_f[(obase * 4 + q) * C + cg * 8 + e] = a[e];
     }
     __syncthreads();
   }
-  if (pool) {
-    for (int q = 0; q < 2; ++q) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        sv[threadIdx.x][e] = q == 0 ? mx[e] : -mn[e];   // min handled as max of the negation
-        si[threadIdx.x][e] = q == 0 ? amx[e] : amn[e];
-      }
-      __syncthreads();
-      if (row == 0) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          float bv = sv[cg][e];
-          int bi = si[cg][e];
-          for (int r = 1; r < rows; ++r) {
-            const float v = sv[r * G + cg][e];
-            const int i = si[r * G + cg][e];
-            if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
-          }
-          part_f[(obase * 4 + 2 + q) * C + cg * 8 + e] = q == 0 ? bv : -bv;
-          part_i[(obase * 2 + q) * C + cg * 8 + e] = bi;
-        }
-      }
-      __syncthreads();
-    }
-  }
 }
 
-// Stage 2 of the statistics: thread per (n, c) combines the chunk partials of image n in chunk order (strict
-// comparisons keep the first index on ties) -> per-(n,c) sum / sumsq (double, workspace) and the pooled outputs.
-__global__ void bn_reduce_nc_kernel(const float* __restrict__ part_f, const int* __restrict__ part_i, int chunks, int HW,
-                                    int C, int pool, double* __restrict__ nsum /* [N][2][C] */,
-                                    float* __restrict__ nc_mean, float* __restrict__ nc_max, float* __restrict__ nc_min,
-                                    int* __restrict__ nc_amax, int* __restrict__ nc_amin) {
+// Stage 2 of the statistics: thread per (n, c) combines the chunk partials of image n in chunk order
+// -> per-(n,c) sum / sumsq (double, workspace) and the pooled mean / max / min.
+__global__ void bn_reduce_nc_kernel(const float* __restrict__ part_f, int chunks, int HW, int C, int pool,
+                                    double* __restrict__ nsum /* [N][2][C] */, float* __restrict__ nc_mean,
+                                    float* __restrict__ nc_max, float* __restrict__ nc_min) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = blockIdx.y;
   if (c >= C) return;
   double s = 0.0, q = 0.0;
   float bmx = -INFINITY, bmn = INFINITY;
-  int imx = 0, imn = 0;
   for (int k = 0; k < chunks; ++k) {
     const long o = (long)n * chunks + k;
     s += (double)part_f[(o * 4 + 0) * C + c];
     q += (double)part_f[(o * 4 + 1) * C + c];
     if (pool) {
-      const float vmx = part_f[(o * 4 + 2) * C + c], vmn = part_f[(o * 4 + 3) * C + c];
-      if (vmx > bmx) { bmx = vmx; imx = part_i[(o * 2 + 0) * C + c]; }
-      if (vmn < bmn) { bmn = vmn; imn = part_i[(o * 2 + 1) * C + c]; }
+      bmx = fmaxf(bmx, part_f[(o * 4 + 2) * C + c]);
+      bmn = fminf(bmn, part_f[(o * 4 + 3) * C + c]);
     }
   }
   nsum[((long)n * 2 + 0) * C + c] = s;
@@ -123,8 +100,6 @@ __global__ void bn_reduce_nc_kernel(const float* __restrict__ part_f, const int*
     nc_mean[(long)n * C + c] = (float)(s / (double)HW);
     nc_max[(long)n * C + c] = bmx;
     nc_min[(long)n * C + c] = bmn;
-    nc_amax[(long)n * C + c] = imx;
-    nc_amin[(long)n * C + c] = imn;
   }
 }
 
@@ -175,28 +150,49 @@ bn_finalize_kernel(const double* __restrict__ nsum, int N, int HW, int C, int tr
   if (rstd_out) rstd_out[c] = rstd;
 }
 
+// Streaming skeleton shared by the elementwise kernels: grid = (blocks, N); a block walks the HW*G 16-byte items of
+// image n = blockIdx.y in steps of NT*U, every thread issuing its U independent 16-byte loads before the first use
+// (memory-level parallelism), all index math in 32 bits with G = C/8 a power of two.  NT % G == 0, so the channel
+// group of a thread never changes and its per-channel parameters live in registers.
+constexpr int EW_U = 4;
+
 // y = [relu](scale[c]*x + shift[c]) * drop[n,c]     (BN apply + ReLU + Dropout2d, Main_Final.py:182-184,220-221)
 __global__ void __launch_bounds__(NT)
-affine_act_kernel(const bf16* __restrict__ x, long x_ld, bf16* __restrict__ y, long y_ld, long P, int HW, int C,
+affine_act_kernel(const bf16* __restrict__ x, long x_ld, bf16* __restrict__ y, long y_ld, int HW, int C, int lg,
                   const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ drop,
                   int relu) {
-  const int G = C >> 3;
-  const long total = P * G;
-  for (long i = blockIdx.x * (long)NT + threadIdx.x; i < total; i += (long)gridDim.x * NT) {
-    const long p = i / G;
-    const int cg = (int)(i - p * G);
-    float v[8];
-    unpack8(ld_bf16x8_stream(x + p * x_ld + cg * 8), v);
-    const int n = (int)(p / HW);
+  const int n = blockIdx.y, G = 1 << lg, items = HW << lg;
+  const int cg = threadIdx.x & (G - 1);
+  float sc[8], sh[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int c = cg * 8 + e;
-      float t = scale[c] * v[e] + shift[c];
-      if (relu) t = fmaxf(t, 0.f);
-      if (drop) t *= drop[(long)n * C + c];
-      v[e] = t;
+  for (int e = 0; e < 8; ++e) {
+    const float d = drop ? drop[(long)n * C + cg * 8 + e] : 1.f;   // d >= 0: relu(t) * d == relu(t * d)
+    sc[e] = scale[cg * 8 + e] * d;
+    sh[e] = shift[cg * 8 + e] * d;
+  }
+  const bf16* xb = x + (long)n * HW * x_ld + cg * 8;
+  bf16* yb = y + (long)n * HW * y_ld + cg * 8;
+  for (int base = blockIdx.x * (NT * EW_U) + threadIdx.x; base < items; base += gridDim.x * (NT * EW_U)) {
+    bf16x8 raw[EW_U];
+#pragma unroll
+    for (int u = 0; u < EW_U; ++u) {
+      const int i = base + u * NT;
+      if (i < items) raw[u] = ld_bf16x8_stream(xb + (long)(i >> lg) * x_ld);
     }
-    st_bf16x8(y + p * y_ld + cg * 8, pack8(v));
+#pragma unroll
+    for (int u = 0; u < EW_U; ++u) {
+      const int i = base + u * NT;
+      if (i < items) {
+        float v[8];
+        unpack8(raw[u], v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float t = sc[e] * v[e] + sh[e];
+          v[e] = relu ? fmaxf(t, 0.f) : t;
+        }
+        st_bf16x8(yb + (long)(i >> lg) * y_ld, pack8(v));
+      }
+    }
   }
 }
 
@@ -210,7 +206,8 @@ ca_gate_kernel(const float* __restrict__ nc_mean, const float* __restrict__ nc_m
                const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ V1,
                const float* __restrict__ V2, int C, int Ch, float* __restrict__ g_out, float* __restrict__ A2g,
                float* __restrict__ B2g, float* __restrict__ u_avg_out, float* __restrict__ u_max_out,
-               float* __restrict__ h_avg_out, float* __restrict__ h_max_out) {
+               float* __restrict__ h_avg_out, float* __restrict__ h_max_out, float* __restrict__ tv_out,
+               int* __restrict__ arg_init) {
   extern __shared__ float sm[];
   float* u_avg = sm;            // [C]
   float* u_max = sm + C;        // [C]
@@ -220,7 +217,12 @@ ca_gate_kernel(const float* __restrict__ nc_mean, const float* __restrict__ nc_m
   for (int c = threadIdx.x; c < C; c += NT) {
     const float sc = scale[c], sh = shift[c];
     const float ua = sc * nc_mean[(long)n * C + c] + sh;
-    const float um = sc * (sc >= 0.f ? nc_max[(long)n * C + c] : nc_min[(long)n * C + c]) + sh;
+    // AdaptiveMaxPool of b = sc*y2 + sh picks max(y2) when sc >= 0, min(y2) otherwise; tv is that raw value and
+    // arg_init resets the slot in which rbu_sa_reduce records the FIRST pixel attaining it (gradient routing)
+    const float tv = sc >= 0.f ? nc_max[(long)n * C + c] : nc_min[(long)n * C + c];
+    const float um = sc * tv + sh;
+    tv_out[(long)n * C + c] = tv;
+    arg_init[(long)n * C + c] = 0x7fffffff;
     u_avg[c] = ua;
     u_max[c] = um;
     u_avg_out[(long)n * C + c] = ua;
@@ -259,41 +261,77 @@ ca_gate_kernel(const float* __restrict__ nc_mean, const float* __restrict__ nc_m
 // SpatialAttention reduce (Main_Final.py:113-115): per pixel mean_c / max_c (+ first argmax) of
 // c = A2g[n,c]*y2 + B2g[n,c].  TPP lanes cooperate on one pixel.
 // ------------------------------------------------------------------------------------------------
-template <int TPP>
+// Also records, per (n,c), the FIRST pixel at which the raw conv output equals the pooled extreme `tv` chosen by
+// ChannelAttention's max-pool (atomicMin on the pixel index; one hit per (n,c) in general) -- the arg-max that
+// adaptive_max_pool2d_backward routes the gradient to.  grid = (blocks, N); lane li of a TPP-lane group owns the
+// channel groups li, li+TPP, ... (K of them), whose per-(n,c) coefficients stay in registers.
+template <int TPP, int K>
 __global__ void __launch_bounds__(NT)
-sa_reduce_kernel(const bf16* __restrict__ y2, long ld, long P, int HW, int C, const float* __restrict__ A2g,
-                 const float* __restrict__ B2g, float2* __restrict__ s_out, int* __restrict__ amax_out) {
+sa_reduce_kernel(const bf16* __restrict__ y2, long ld, int HW, int C, const float* __restrict__ A2g,
+                 const float* __restrict__ B2g, const float* __restrict__ tv, int* __restrict__ nc_arg,
+                 float2* __restrict__ s_out, int* __restrict__ amax_out) {
+  constexpr int SLOTS = NT / TPP;
+  constexpr int U = K == 1 ? 4 : (K == 2 ? 2 : 1);
   const int G = C >> 3;
+  const int n = blockIdx.y;
   const int li = threadIdx.x % TPP;
   const int slot = threadIdx.x / TPP;
-  constexpr int SLOTS = NT / TPP;
-  for (long p = blockIdx.x * (long)SLOTS + slot; p < P; p += (long)gridDim.x * SLOTS) {
-    const int n = (int)(p / HW);
-    const float* a = A2g + (long)n * C;
-    const float* b = B2g + (long)n * C;
-    float sum = 0.f, best = -INFINITY;
-    int bi = 0x7fffffff;
-    for (int cg = li; cg < G; cg += TPP) {
-      float v[8];
-      unpack8(ld_bf16x8(y2 + p * ld + cg * 8), v);
+  float a[K][8], b[K][8], t[K][8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int c = cg * 8 + e;
-        const float t = a[c] * v[e] + b[c];
-        sum += t;
-        if (t > best) { best = t; bi = c; }
+  for (int k = 0; k < K; ++k) {
+    const int cg = li + k * TPP;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const long o = (long)n * C + cg * 8 + e;
+      a[k][e] = cg < G ? A2g[o] : 0.f;
+      b[k][e] = cg < G ? B2g[o] : 0.f;
+      t[k][e] = cg < G ? tv[o] : 0.f;
+    }
+  }
+  const bf16* base = y2 + (long)n * HW * ld;
+  const float invC = 1.f / (float)C;
+  for (int pb = blockIdx.x * (SLOTS * U); pb < HW; pb += gridDim.x * (SLOTS * U)) {
+    bf16x8 raw[U][K];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int pp = pb + u * SLOTS + slot;
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+        if (pp < HW && li + k * TPP < G) raw[u][k] = ld_bf16x8(base + (long)pp * ld + (li + k * TPP) * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int pp = pb + u * SLOTS + slot;
+      float sum = 0.f, best = -INFINITY;
+      int bi = 0x7fffffff;
+      if (pp < HW) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const int cg = li + k * TPP;
+          if (cg < G) {
+            float v[8];
+            unpack8(raw[u][k], v);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float c = a[k][e] * v[e] + b[k][e];
+              sum += c;
+              if (c > best) { best = c; bi = cg * 8 + e; }
+              if (v[e] == t[k][e]) atomicMin(nc_arg + (long)n * C + cg * 8 + e, pp);
+            }
+          }
+        }
       }
-    }
 #pragma unroll
-    for (int o = TPP / 2; o > 0; o >>= 1) {
-      sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-    }
-    if (li == 0) {
-      s_out[p] = make_float2(sum / (float)C, best);
-      amax_out[p] = bi;
+      for (int o = TPP / 2; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+      }
+      if (li == 0 && pp < HW) {
+        s_out[(long)n * HW + pp] = make_float2(sum * invC, best);
+        amax_out[(long)n * HW + pp] = bi;
+      }
     }
   }
 }
@@ -330,25 +368,48 @@ sa_gate_kernel(const float2* __restrict__ s, int N, int H, int W, const float* _
 // (Main_Final.py:179,190-194)
 __global__ void __launch_bounds__(NT)
 rb_out_kernel(const bf16* __restrict__ y2, long y2_ld, const bf16* __restrict__ rsrc, long r_ld, bf16* __restrict__ out,
-              long out_ld, long P, int HW, int C, const float* __restrict__ A2g, const float* __restrict__ B2g,
+              long out_ld, int HW, int C, int lg, const float* __restrict__ A2g, const float* __restrict__ B2g,
               const float* __restrict__ gs, const float* __restrict__ As, const float* __restrict__ Bs) {
-  const int G = C >> 3;
-  const long total = P * G;
-  for (long i = blockIdx.x * (long)NT + threadIdx.x; i < total; i += (long)gridDim.x * NT) {
-    const long p = i / G;
-    const int cg = (int)(i - p * G);
-    const int n = (int)(p / HW);
-    float v[8], r[8];
-    unpack8(ld_bf16x8_stream(y2 + p * y2_ld + cg * 8), v);
-    unpack8(ld_bf16x8_stream(rsrc + p * r_ld + cg * 8), r);
-    const float g = gs[p];
+  const int n = blockIdx.y, G = 1 << lg, items = HW << lg;
+  const int cg = threadIdx.x & (G - 1);
+  float a2[8], b2[8], as[8], bs[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int c = cg * 8 + e;
-      const float res = As ? As[c] * r[e] + Bs[c] : r[e];
-      v[e] = fmaxf((A2g[(long)n * C + c] * v[e] + B2g[(long)n * C + c]) * g + res, 0.f);
+  for (int e = 0; e < 8; ++e) {
+    const int c = cg * 8 + e;
+    a2[e] = A2g[(long)n * C + c];
+    b2[e] = B2g[(long)n * C + c];
+    as[e] = As ? As[c] : 1.f;
+    bs[e] = As ? Bs[c] : 0.f;
+  }
+  const bf16* yb = y2 + (long)n * HW * y2_ld + cg * 8;
+  const bf16* rb = rsrc + (long)n * HW * r_ld + cg * 8;
+  bf16* ob = out + (long)n * HW * out_ld + cg * 8;
+  const float* gb = gs + (long)n * HW;
+  for (int base = blockIdx.x * (NT * EW_U) + threadIdx.x; base < items; base += gridDim.x * (NT * EW_U)) {
+    bf16x8 ry[EW_U], rr[EW_U];
+    float g[EW_U];
+#pragma unroll
+    for (int u = 0; u < EW_U; ++u) {
+      const int i = base + u * NT;
+      if (i < items) {
+        const int pl = i >> lg;
+        ry[u] = ld_bf16x8_stream(yb + (long)pl * y2_ld);
+        rr[u] = ld_bf16x8_stream(rb + (long)pl * r_ld);
+        g[u] = __ldg(gb + pl);
+      }
     }
-    st_bf16x8(out + p * out_ld + cg * 8, pack8(v));
+#pragma unroll
+    for (int u = 0; u < EW_U; ++u) {
+      const int i = base + u * NT;
+      if (i < items) {
+        float v[8], r[8];
+        unpack8(ry[u], v);
+        unpack8(rr[u], r);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = fmaxf((a2[e] * v[e] + b2[e]) * g[u] + (as[e] * r[e] + bs[e]), 0.f);
+        st_bf16x8(ob + (long)(i >> lg) * out_ld, pack8(v));
+      }
+    }
   }
 }
 
@@ -459,21 +520,38 @@ __global__ void scalar_bn_finalize_kernel(const float* __restrict__ partials, in
 }
 
 __global__ void __launch_bounds__(NT)
-ag_apply_kernel(const bf16* __restrict__ skip, long s_ld, bf16* __restrict__ out, long o_ld, long P, int C,
+ag_apply_kernel(const bf16* __restrict__ skip, long s_ld, bf16* __restrict__ out, long o_ld, long P, int lg,
                 const float* __restrict__ q0, const float* __restrict__ stats, float* __restrict__ psi_out) {
-  const int G = C >> 3;
-  const long total = P * G;
+  const int G = 1 << lg;
+  const long items = P << lg;
+  const int cg = threadIdx.x & (G - 1);
   const float a = stats[0], b = stats[1];
-  for (long i = blockIdx.x * (long)NT + threadIdx.x; i < total; i += (long)gridDim.x * NT) {
-    const long p = i / G;
-    const int cg = (int)(i - p * G);
-    const float psi = sigmoidf_acc(a * q0[p] + b);
-    if (cg == 0) psi_out[p] = psi;
-    float v[8];
-    unpack8(ld_bf16x8(skip + p * s_ld + cg * 8), v);
+  const bf16* sb = skip + cg * 8;
+  bf16* ob = out + cg * 8;
+  for (long base = (long)blockIdx.x * (NT * EW_U) + threadIdx.x; base < items; base += (long)gridDim.x * (NT * EW_U)) {
+    bf16x8 raw[EW_U];
+    float q[EW_U];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] *= psi;
-    st_bf16x8(out + p * o_ld + cg * 8, pack8(v));
+    for (int u = 0; u < EW_U; ++u) {
+      const long i = base + u * NT;
+      if (i < items) {
+        raw[u] = ld_bf16x8(sb + (i >> lg) * s_ld);
+        q[u] = __ldg(q0 + (i >> lg));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < EW_U; ++u) {
+      const long i = base + u * NT;
+      if (i < items) {
+        const float psi = sigmoidf_acc(a * q[u] + b);
+        if (cg == 0) psi_out[i >> lg] = psi;
+        float v[8];
+        unpack8(raw[u], v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] *= psi;
+        st_bf16x8(ob + (i >> lg) * o_ld, pack8(v));
+      }
+    }
   }
 }
 
@@ -541,6 +619,21 @@ int grid_for(long items, int per_block) {
   return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
+int ilog2(int v) {
+  int l = 0;
+  while ((1 << (l + 1)) <= v) ++l;
+  return l;
+}
+
+// grid.x for the streaming skeleton: enough blocks for ~32 resident warps per SM over >= 4 waves, at most one
+// block per NT*EW_U items
+int ew_blocks(long items_per_image, int images) {
+  long b = (items_per_image + NT * EW_U - 1) / (NT * EW_U);
+  long cap = ((long)rbu_num_sms() * 32 + images - 1) / images;
+  if (cap < 1) cap = 1;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
 int pick_tpp(int C) {
   const int G = C >> 3;
   int t = 4;
@@ -561,23 +654,24 @@ int stats_chunks(int N, int HW, int C) {
 }  // namespace
 
 #define VIEW_OK(ptr, ld) ((ptr) != nullptr && ((uintptr_t)(ptr) & 15) == 0 && (ld) % 8 == 0)
+#define EW_CH_OK(C) ((C) >= 8 && (C) <= 2048 && ((C) & ((C) - 1)) == 0)
 
 extern "C" size_t rbu_bn_stats_workspace_bytes(int N, int HW, int C) {
   if (C < 8 || C % 8 || C > 2048) return 0;
-  return (size_t)N * stats_chunks(N, HW, C) * 6 * C * sizeof(float) + (size_t)N * 2 * C * sizeof(double) + 16;
+  return (size_t)N * stats_chunks(N, HW, C) * 4 * C * sizeof(float) + (size_t)N * 2 * C * sizeof(double) + 16;
 }
 
 extern "C" int rbu_bn_stats(const void* x, int64_t ld, int N, int HW, int C, int pool, int training,
                             const float* gamma, const float* beta, float* running_mean, float* running_var,
                             float momentum, float eps, float* scale, float* shift, float* mean_out, float* rstd_out,
-                            float* nc_mean, float* nc_max, float* nc_min, int* nc_amax, int* nc_amin, void* workspace,
-                            size_t workspace_bytes, void* stream_) {
+                            float* nc_mean, float* nc_max, float* nc_min, void* workspace, size_t workspace_bytes,
+                            void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   RBU_CHECK_ARG(VIEW_OK(x, ld), "rbu_bn_stats: misaligned view");
   RBU_CHECK_ARG(N > 0 && HW > 0 && C >= 8 && C % 8 == 0 && C <= 2048, "rbu_bn_stats: unsupported shape N=%d HW=%d C=%d", N, HW, C);
   RBU_CHECK_ARG(gamma && beta && scale && shift, "rbu_bn_stats: null parameter pointer");
   RBU_CHECK_ARG(training || (running_mean && running_var), "rbu_bn_stats: eval mode needs running statistics");
-  RBU_CHECK_ARG(!pool || (nc_mean && nc_max && nc_min && nc_amax && nc_amin), "rbu_bn_stats: pool outputs missing");
+  RBU_CHECK_ARG(!pool || (nc_mean && nc_max && nc_min), "rbu_bn_stats: pool outputs missing");
   if (!training && !pool) {  // pure eval affine: no pass over the data
     bn_finalize_kernel<<<rbu_cdiv(C, 32), 256, 0, stream>>>(nullptr, 0, HW, C, 0, gamma, beta, running_mean, running_var,
                                                              momentum, eps, scale, shift, mean_out, rstd_out);
@@ -589,12 +683,14 @@ extern "C" int rbu_bn_stats(const void* x, int64_t ld, int N, int HW, int C, int
   const int chunks = stats_chunks(N, HW, C);
   const int chunk_px = rbu_cdiv(HW, chunks);
   float* part_f = (float*)workspace;
-  int* part_i = (int*)(part_f + (size_t)N * chunks * 4 * C);
-  bn_stats_kernel<<<dim3(chunks, N), NT, 0, stream>>>((const bf16*)x, ld, HW, C, chunk_px, pool, part_f, part_i);
+  if (pool)
+    bn_stats_kernel<1><<<dim3(chunks, N), NT, 0, stream>>>((const bf16*)x, ld, HW, C, chunk_px, part_f);
+  else
+    bn_stats_kernel<0><<<dim3(chunks, N), NT, 0, stream>>>((const bf16*)x, ld, HW, C, chunk_px, part_f);
   RBU_CHECK_LAUNCH();
-  double* nsum = (double*)(((uintptr_t)(part_i + (size_t)N * chunks * 2 * C) + 15) & ~(uintptr_t)15);
-  bn_reduce_nc_kernel<<<dim3(rbu_cdiv(C, 128), N), 128, 0, stream>>>(part_f, part_i, chunks, HW, C, pool, nsum, nc_mean,
-                                                                      nc_max, nc_min, nc_amax, nc_amin);
+  double* nsum = (double*)(((uintptr_t)(part_f + (size_t)N * chunks * 4 * C) + 15) & ~(uintptr_t)15);
+  bn_reduce_nc_kernel<<<dim3(rbu_cdiv(C, 128), N), 128, 0, stream>>>(part_f, chunks, HW, C, pool, nsum, nc_mean, nc_max,
+                                                                      nc_min);
   RBU_CHECK_LAUNCH();
   bn_finalize_kernel<<<rbu_cdiv(C, 32), 256, 0, stream>>>(nsum, N, HW, C, training, gamma, beta, running_mean, running_var,
                                                            momentum, eps, scale, shift, mean_out, rstd_out);
@@ -604,35 +700,47 @@ extern "C" int rbu_bn_stats(const void* x, int64_t ld, int N, int HW, int C, int
 
 extern "C" int rbu_affine_act(const void* x, int64_t x_ld, void* y, int64_t y_ld, int64_t P, int HW, int C,
                               const float* scale, const float* shift, const float* drop, int relu, void* stream_) {
-  RBU_CHECK_ARG(VIEW_OK(x, x_ld) && VIEW_OK(y, y_ld) && scale && shift && C % 8 == 0 && P > 0 && HW > 0,
-                "rbu_affine_act: bad arguments");
-  affine_act_kernel<<<grid_for(P * (C >> 3), NT * 4), NT, 0, (cudaStream_t)stream_>>>(
-      (const bf16*)x, x_ld, (bf16*)y, y_ld, P, HW, C, scale, shift, drop, relu);
+  RBU_CHECK_ARG(VIEW_OK(x, x_ld) && VIEW_OK(y, y_ld) && scale && shift && EW_CH_OK(C) && P > 0 && HW > 0 && P % HW == 0 &&
+                    P / HW <= 65535, "rbu_affine_act: bad arguments (C must be a power of two in [8, 2048])");
+  const int lg = ilog2(C >> 3);
+  affine_act_kernel<<<dim3(ew_blocks((long)HW << lg, (int)(P / HW)), (unsigned)(P / HW)), NT, 0, (cudaStream_t)stream_>>>(
+      (const bf16*)x, x_ld, (bf16*)y, y_ld, HW, C, lg, scale, shift, drop, relu);
   RBU_CHECK_LAUNCH();
   return RBU_OK;
 }
 
 extern "C" int rbu_ca_gate(const float* nc_mean, const float* nc_max, const float* nc_min, const float* scale,
                            const float* shift, const float* V1, const float* V2, int N, int C, int Ch, float* g,
-                           float* A2g, float* B2g, float* u_avg, float* u_max, float* h_avg, float* h_max,
-                           void* stream_) {
+                           float* A2g, float* B2g, float* u_avg, float* u_max, float* h_avg, float* h_max, float* tv,
+                           int* nc_arg, void* stream_) {
   RBU_CHECK_ARG(nc_mean && nc_max && nc_min && scale && shift && V1 && V2 && g && A2g && B2g && u_avg && u_max &&
-                    h_avg && h_max, "rbu_ca_gate: null pointer");
+                    h_avg && h_max && tv && nc_arg, "rbu_ca_gate: null pointer");
   RBU_CHECK_ARG(N > 0 && C > 0 && Ch > 0 && (2 * C + 2 * Ch) * 4 <= 48 * 1024, "rbu_ca_gate: unsupported shape");
   ca_gate_kernel<<<N, NT, (2 * C + 2 * Ch) * sizeof(float), (cudaStream_t)stream_>>>(
-      nc_mean, nc_max, nc_min, scale, shift, V1, V2, C, Ch, g, A2g, B2g, u_avg, u_max, h_avg, h_max);
+      nc_mean, nc_max, nc_min, scale, shift, V1, V2, C, Ch, g, A2g, B2g, u_avg, u_max, h_avg, h_max, tv, nc_arg);
   RBU_CHECK_LAUNCH();
   return RBU_OK;
 }
 
 extern "C" int rbu_sa_reduce(const void* y2, int64_t ld, int64_t P, int HW, int C, const float* A2g, const float* B2g,
-                             float* s_out, int* amax_out, void* stream_) {
-  RBU_CHECK_ARG(VIEW_OK(y2, ld) && A2g && B2g && s_out && amax_out && C >= 8 && C % 8 == 0, "rbu_sa_reduce: bad arguments");
+                             const float* tv, int* nc_arg, float* s_out, int* amax_out, void* stream_) {
+  RBU_CHECK_ARG(VIEW_OK(y2, ld) && A2g && B2g && tv && nc_arg && s_out && amax_out && EW_CH_OK(C) && HW > 0 && P > 0 &&
+                    P % HW == 0 && P / HW <= 65535, "rbu_sa_reduce: bad arguments");
   cudaStream_t st = (cudaStream_t)stream_;
-  const int tpp = pick_tpp(C);
-  const int grid = grid_for(P, NT / tpp * 4);
-#define LAUNCH(T) sa_reduce_kernel<T><<<grid, NT, 0, st>>>((const bf16*)y2, ld, P, HW, C, A2g, B2g, (float2*)s_out, amax_out)
-  if (tpp == 4) LAUNCH(4); else if (tpp == 8) LAUNCH(8); else if (tpp == 16) LAUNCH(16); else LAUNCH(32);
+  const int G = C >> 3, N = (int)(P / HW);
+  const int tpp = G >= 32 ? 32 : (G < 4 ? 4 : G);
+  const int K = G > 32 ? G / 32 : 1;
+  const int U = K == 1 ? 4 : (K == 2 ? 2 : 1);
+  const int per_block = NT / tpp * U;
+  long blocks = (HW + per_block - 1) / per_block;
+  long cap = ((long)rbu_num_sms() * 32 + N - 1) / N;
+  if (blocks > cap) blocks = cap;
+  const dim3 grid((unsigned)blocks, (unsigned)N);
+#define LAUNCH(T, KK) sa_reduce_kernel<T, KK><<<grid, NT, 0, st>>>((const bf16*)y2, ld, HW, C, A2g, B2g, tv, nc_arg, (float2*)s_out, amax_out)
+  if (K == 1) { if (tpp == 4) LAUNCH(4, 1); else if (tpp == 8) LAUNCH(8, 1); else if (tpp == 16) LAUNCH(16, 1); else LAUNCH(32, 1); }
+  else if (K == 2) LAUNCH(32, 2);
+  else if (K == 4) LAUNCH(32, 4);
+  else { RBU_CHECK_ARG(K == 8, "rbu_sa_reduce: unsupported channel count %d", C); LAUNCH(32, 8); }
 #undef LAUNCH
   RBU_CHECK_LAUNCH();
   return RBU_OK;
@@ -648,11 +756,12 @@ extern "C" int rbu_sa_gate(const float* s, int N, int H, int W, const float* k7,
 extern "C" int rbu_rb_out(const void* y2, int64_t y2_ld, const void* rsrc, int64_t r_ld, void* out, int64_t out_ld,
                           int64_t P, int HW, int C, const float* A2g, const float* B2g, const float* gs,
                           const float* As, const float* Bs, void* stream_) {
-  RBU_CHECK_ARG(VIEW_OK(y2, y2_ld) && VIEW_OK(rsrc, r_ld) && VIEW_OK(out, out_ld) && A2g && B2g && gs && C % 8 == 0,
-                "rbu_rb_out: bad arguments");
+  RBU_CHECK_ARG(VIEW_OK(y2, y2_ld) && VIEW_OK(rsrc, r_ld) && VIEW_OK(out, out_ld) && A2g && B2g && gs && EW_CH_OK(C) &&
+                    HW > 0 && P > 0 && P % HW == 0 && P / HW <= 65535, "rbu_rb_out: bad arguments");
   RBU_CHECK_ARG((As == nullptr) == (Bs == nullptr), "rbu_rb_out: As/Bs must both be set or both NULL");
-  rb_out_kernel<<<grid_for(P * (C >> 3), NT * 4), NT, 0, (cudaStream_t)stream_>>>(
-      (const bf16*)y2, y2_ld, (const bf16*)rsrc, r_ld, (bf16*)out, out_ld, P, HW, C, A2g, B2g, gs, As, Bs);
+  const int lg = ilog2(C >> 3);
+  rb_out_kernel<<<dim3(ew_blocks((long)HW << lg, (int)(P / HW)), (unsigned)(P / HW)), NT, 0, (cudaStream_t)stream_>>>(
+      (const bf16*)y2, y2_ld, (const bf16*)rsrc, r_ld, (bf16*)out, out_ld, HW, C, lg, A2g, B2g, gs, As, Bs);
   RBU_CHECK_LAUNCH();
   return RBU_OK;
 }
@@ -690,9 +799,10 @@ extern "C" int rbu_ag_psi(const void* yg, int64_t yg_ld, const void* yx, int64_t
 
 extern "C" int rbu_ag_apply(const void* skip, int64_t s_ld, void* out, int64_t o_ld, int64_t P, int C, const float* q0,
                             const float* stats, float* psi, void* stream_) {
-  RBU_CHECK_ARG(VIEW_OK(skip, s_ld) && VIEW_OK(out, o_ld) && q0 && stats && psi && C % 8 == 0, "rbu_ag_apply: bad arguments");
-  ag_apply_kernel<<<grid_for(P * (C >> 3), NT * 4), NT, 0, (cudaStream_t)stream_>>>((const bf16*)skip, s_ld, (bf16*)out,
-                                                                                   o_ld, P, C, q0, stats, psi);
+  RBU_CHECK_ARG(VIEW_OK(skip, s_ld) && VIEW_OK(out, o_ld) && q0 && stats && psi && EW_CH_OK(C), "rbu_ag_apply: bad arguments");
+  const int lg = ilog2(C >> 3);
+  ag_apply_kernel<<<ew_blocks(P << lg, 1), NT, 0, (cudaStream_t)stream_>>>((const bf16*)skip, s_ld, (bf16*)out, o_ld, P, lg,
+                                                                          q0, stats, psi);
   RBU_CHECK_LAUNCH();
   return RBU_OK;
 }

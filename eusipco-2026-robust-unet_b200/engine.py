@@ -91,16 +91,13 @@ class Engine:
                "mean": self.f32(C, device=dev), "rstd": self.f32(C, device=dev)}
         if pool:
             out.update(nc_mean=self.f32(N, C, device=dev), nc_max=self.f32(N, C, device=dev),
-                       nc_min=self.f32(N, C, device=dev),
-                       nc_amax=torch.empty((N, C), dtype=torch.int32, device=dev),
-                       nc_amin=torch.empty((N, C), dtype=torch.int32, device=dev))
+                       nc_min=self.f32(N, C, device=dev))
         nbytes = _lib.lib().rbu_bn_stats_workspace_bytes(N, HW, C)
         ws = self.ws(nbytes, dev)
         call("rbu_bn_stats", _vp(x), x.ld, N, HW, C, int(pool), int(training), _p(bn.weight), _p(bn.bias),
              _p(bn.running_mean), _p(bn.running_var), float(bn.momentum), float(bn.eps), _p(out["scale"]),
              _p(out["shift"]), _p(out["mean"]), _p(out["rstd"]), _p(out.get("nc_mean")), _p(out.get("nc_max")),
-             _p(out.get("nc_min")), _p(out.get("nc_amax")), _p(out.get("nc_amin")), _p(ws), ws.numel() * 4,
-             stream_ptr())
+             _p(out.get("nc_min")), _p(ws), ws.numel() * 4, stream_ptr())
         if training:
             bn.num_batches_tracked += 1
         return out
@@ -157,14 +154,16 @@ class Engine:
         conv_gemm(N, H, W, [(a1, self.pack(blk.conv2.weight, 0), 9, 1, False)], C, y2)
         bn2 = self.bn_stats(y2, N, HW, blk.bn2, training, pool=True)
         Ch = blk.ca.fc[0].out_channels
-        ca = {k: self.f32(N, C, device=dev) for k in ("g", "A2g", "B2g", "u_avg", "u_max")}
+        ca = {k: self.f32(N, C, device=dev) for k in ("g", "A2g", "B2g", "u_avg", "u_max", "tv")}
+        ca["nc_arg"] = torch.empty((N, C), dtype=torch.int32, device=dev)
         ca["h_avg"], ca["h_max"] = self.f32(N, Ch, device=dev), self.f32(N, Ch, device=dev)
         call("rbu_ca_gate", _p(bn2["nc_mean"]), _p(bn2["nc_max"]), _p(bn2["nc_min"]), _p(bn2["scale"]), _p(bn2["shift"]),
              _p(blk.ca.fc[0].weight), _p(blk.ca.fc[2].weight), N, C, Ch, _p(ca["g"]), _p(ca["A2g"]), _p(ca["B2g"]),
-             _p(ca["u_avg"]), _p(ca["u_max"]), _p(ca["h_avg"]), _p(ca["h_max"]), stream_ptr())
+             _p(ca["u_avg"]), _p(ca["u_max"]), _p(ca["h_avg"]), _p(ca["h_max"]), _p(ca["tv"]), _p(ca["nc_arg"]), stream_ptr())
         sa_s = self.f32(P, 2, device=dev)
         amax_c = torch.empty(P, dtype=torch.int32, device=dev)
-        call("rbu_sa_reduce", _vp(y2), y2.ld, P, HW, C, _p(ca["A2g"]), _p(ca["B2g"]), _p(sa_s), _p(amax_c), stream_ptr())
+        call("rbu_sa_reduce", _vp(y2), y2.ld, P, HW, C, _p(ca["A2g"]), _p(ca["B2g"]), _p(ca["tv"]), _p(ca["nc_arg"]),
+             _p(sa_s), _p(amax_c), stream_ptr())
         gs = self.f32(P, device=dev)
         call("rbu_sa_gate", _p(sa_s), N, H, W, _p(blk.sa.conv1.weight), _p(gs), stream_ptr())
         bns = self.bn_stats(ys, N, HW, blk.shortcut[1], training) if proj else None
@@ -188,47 +187,41 @@ class Engine:
         st = stream_ptr()
         de = dout
         dG = self.f32(P, device=dev)
-        sums_s = self.f32(2 * C, device=dev) if proj else None
+        sraw = self.f32(2 * C, device=dev) if proj else None
         call("rbu_rb_bwd1", _vp(dout), dout.ld, _vp(s["out"]), s["out"].ld, _vp(y2), y2.ld, _vp(de), de.ld,
-             _vp(ys) if proj else NULL, ys.ld if proj else 0, N, HW, C, _p(ca["A2g"]), _p(ca["B2g"]),
-             _p(bns["mean"]) if proj else NULL, _p(bns["rstd"]) if proj else NULL, _p(dG), _p(sums_s), _p(ws), wsb, st)
+             _vp(ys) if proj else NULL, ys.ld if proj else 0, N, HW, C, _p(ca["A2g"]), _p(ca["B2g"]), _p(dG), _p(sraw),
+             _p(ws), wsb, st)
         ds = self.f32(P, 2, device=dev)
         dk7 = self.f32(98, device=dev)
         call("rbu_sa_bwd", _p(dG), _p(s["gs"]), _p(s["sa_s"]), N, H, W, _p(blk.sa.conv1.weight), _p(ds), _p(dk7), _p(ws),
              wsb, st)
         grads[prefix + ".sa.conv1.weight"] = dk7.view(1, 2, 7, 7)
-
-        def rb_pass(k, dT=None, sums2=None, dy2=None, dys=None):
-            call("rbu_rb_bwd_pass", k, _vp(de), de.ld, _vp(y2), y2.ld, N, HW, C, _p(s["gs"]), _p(ds), _p(s["amax_c"]),
-                 _p(ca["g"]), _p(du_avg), _p(du_max), _p(bn2["nc_amax"]), _p(bn2["nc_amin"]), _p(bn2["scale"]),
-                 _p(bn2["shift"]), _p(bn2["mean"]), _p(bn2["rstd"]), _p(dT), _p(sums2),
-                 _vp(dy2) if dy2 is not None else NULL, dy2.ld if dy2 is not None else 0,
-                 _vp(ys) if (proj and dys is not None) else NULL, ys.ld if (proj and dys is not None) else 0,
-                 _vp(dys) if dys is not None else NULL, dys.ld if dys is not None else 0,
-                 _p(bns["scale"]) if proj else NULL, _p(bns["mean"]) if proj else NULL,
-                 _p(bns["rstd"]) if proj else NULL, _p(sums_s), _p(ws), wsb, st)
-
-        du_avg = du_max = None
-        dT = self.f32(N, C, device=dev)
-        rb_pass(2, dT=dT)
+        D = torch.empty((N, 2, C), dtype=torch.float64, device=dev)
+        call("rbu_rb_bwd2", _vp(de), de.ld, _vp(y2), y2.ld, N, HW, C, _p(s["gs"]), _p(ds), _p(s["amax_c"]), _p(D), _p(ws),
+             wsb, st)
         Ch = s["Ch"]
-        dt, du_avg, du_max = (self.f32(N, C, device=dev) for _ in range(3))
-        dh_avg, dh_max = self.f32(N, Ch, device=dev), self.f32(N, Ch, device=dev)
+        scratch = self.f32(3 * N * C + 2 * N * Ch, device=dev)
         dV1, dV2 = self.f32(Ch, C, 1, 1, device=dev), self.f32(C, Ch, 1, 1, device=dev)
-        call("rbu_ca_bwd", _p(dT), _p(ca["g"]), _p(ca["h_avg"]), _p(ca["h_max"]), _p(ca["u_avg"]), _p(ca["u_max"]),
-             _p(blk.ca.fc[0].weight), _p(blk.ca.fc[2].weight), N, C, Ch, _p(dt), _p(dh_avg), _p(dh_max), _p(du_avg),
-             _p(du_max), _p(dV1), _p(dV2), st)
+        sums2 = self.f32(2 * C, device=dev)
+        coef = self.f32((3 * N + 1) * C, device=dev)
+        sums_s = self.f32(2 * C, device=dev) if proj else None
+        coef_s = self.f32(3 * C, device=dev) if proj else None
+        call("rbu_rb_mid", _p(D), _p(ca["g"]), _p(ca["h_avg"]), _p(ca["h_max"]), _p(ca["u_avg"]), _p(ca["u_max"]),
+             _p(bn2["nc_mean"]), _p(ca["tv"]), _p(blk.ca.fc[0].weight), _p(blk.ca.fc[2].weight), _p(bn2["scale"]),
+             _p(bn2["shift"]), _p(bn2["mean"]), _p(bn2["rstd"]), N, HW, C, Ch, _p(scratch), _p(dV1), _p(dV2), _p(sums2),
+             _p(coef), _p(sraw), _p(bns["scale"]) if proj else NULL, _p(bns["mean"]) if proj else NULL,
+             _p(bns["rstd"]) if proj else NULL, _p(sums_s), _p(coef_s), st)
         grads[prefix + ".ca.fc.0.weight"] = dV1
         grads[prefix + ".ca.fc.2.weight"] = dV2
-        sums2 = self.f32(2 * C, device=dev)
-        rb_pass(3, sums2=sums2)
         grads[prefix + ".bn2.bias"], grads[prefix + ".bn2.weight"] = sums2[:C], sums2[C:]
         # dy1 | dys share one buffer so the stem's fused GEMM sees them as one operand
         dy12 = self.new(N, H, W, 2 * C if proj else C, dev)
         dy1 = dy12.slice(0, C)
         dys = dy12.slice(C, C) if proj else None
         dy2 = self.new(N, H, W, C, dev)
-        rb_pass(4, sums2=sums2, dy2=dy2, dys=dys)
+        call("rbu_rb_bwd3", _vp(de), de.ld, _vp(y2), y2.ld, _vp(dy2), dy2.ld, _vp(ys) if proj else NULL,
+             ys.ld if proj else 0, _vp(dys) if proj else NULL, dys.ld if proj else 0, N, HW, C, _p(s["gs"]), _p(ds),
+             _p(s["amax_c"]), _p(ca["nc_arg"]), _p(coef), _p(coef_s), st)
         if proj:
             grads[prefix + ".shortcut.1.bias"], grads[prefix + ".shortcut.1.weight"] = sums_s[:C], sums_s[C:]
         # conv2

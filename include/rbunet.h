@@ -130,23 +130,27 @@ int rbu_wgrad_gemm(const rbu_wgrad_args* args, void* workspace, size_t workspace
  * BatchNorm2d statistics + affine (Main_Final.py:158,160,173,127,132,210): scale = gamma*rstd,
  * shift = beta - mean*scale; training=1 uses batch statistics (biased variance) and updates the running
  * buffers (momentum, unbiased variance); training=0 uses the running buffers.  pool=1 additionally emits
- * per-(n,c) mean/max/min and first-index argmax/argmin over H*W of the raw input — the
- * AdaptiveAvg/MaxPool2d of ChannelAttention (Main_Final.py:87-88,98-99). */
+ * per-(n,c) mean/max/min over H*W of the raw input — the AdaptiveAvg/MaxPool2d of ChannelAttention
+ * (Main_Final.py:87-88,98-99); the arg-max needed by the backward pass is found by rbu_sa_reduce.
+ * All elementwise kernels below need C = a power of two in [8, 2048]. */
 size_t rbu_bn_stats_workspace_bytes(int N, int HW, int C);
 int rbu_bn_stats(const void* x, int64_t ld, int N, int HW, int C, int pool, int training, const float* gamma,
                  const float* beta, float* running_mean, float* running_var, float momentum, float eps,
                  float* scale, float* shift, float* mean_out, float* rstd_out, float* nc_mean, float* nc_max,
-                 float* nc_min, int* nc_amax, int* nc_amin, void* workspace, size_t workspace_bytes, void* stream);
+                 float* nc_min, void* workspace, size_t workspace_bytes, void* stream);
 /* y = [relu](scale[c]*x + shift[c]) * drop[n,c]   (BN apply + ReLU + Dropout2d; Main_Final.py:182-184,220-221) */
 int rbu_affine_act(const void* x, int64_t x_ld, void* y, int64_t y_ld, int64_t P, int HW, int C, const float* scale,
                    const float* shift, const float* drop, int relu, void* stream);
-/* ChannelAttention gate (Main_Final.py:97-101) from the pooled statistics; also A2g = scale*g, B2g = shift*g. */
+/* ChannelAttention gate (Main_Final.py:97-101) from the pooled statistics; also A2g = scale*g, B2g = shift*g,
+ * tv[n,c] = the raw extreme the max-pool selected (max if scale >= 0 else min) and nc_arg[n,c] reset to INT_MAX. */
 int rbu_ca_gate(const float* nc_mean, const float* nc_max, const float* nc_min, const float* scale,
                 const float* shift, const float* V1, const float* V2, int N, int C, int Ch, float* g, float* A2g,
-                float* B2g, float* u_avg, float* u_max, float* h_avg, float* h_max, void* stream);
-/* SpatialAttention (Main_Final.py:112-117): channel mean/max (+argmax) of A2g*y2+B2g, then the 7x7 gate. */
+                float* B2g, float* u_avg, float* u_max, float* h_avg, float* h_max, float* tv, int* nc_arg,
+                void* stream);
+/* SpatialAttention (Main_Final.py:112-117): channel mean/max (+argmax) of A2g*y2+B2g, then the 7x7 gate.  The same
+ * pass records nc_arg[n,c] = first pixel with y2 == tv[n,c] (the AdaptiveMaxPool2d arg-max for the backward). */
 int rbu_sa_reduce(const void* y2, int64_t ld, int64_t P, int HW, int C, const float* A2g, const float* B2g,
-                  float* s_out /* [P][2] */, int* amax_out, void* stream);
+                  const float* tv, int* nc_arg, float* s_out /* [P][2] */, int* amax_out, void* stream);
 int rbu_sa_gate(const float* s, int N, int H, int W, const float* k7, float* gs, void* stream);
 /* out = relu((A2g*y2+B2g)*gs + r), r = As*ys+Bs (projection) or the identity input (Main_Final.py:179,190-194) */
 int rbu_rb_out(const void* y2, int64_t y2_ld, const void* rsrc, int64_t r_ld, void* out, int64_t out_ld, int64_t P,
@@ -177,22 +181,28 @@ size_t rbu_bwd_workspace_bytes(int N, int HW, int C);
 int rbu_head_backward(const float* dprobs, const float* probs, const void* x, int64_t x_ld, void* dx, int64_t dx_ld,
                       int64_t P, int C, const float* w, float* dw, float* db, void* workspace, size_t workspace_bytes,
                       void* stream);
+/* ResidualBlock backward in three passes over the activations:
+ *  rbu_rb_bwd1: de = dout*[out>0] (may alias dout); dG[p] = sum_c de*(A2g*y2+B2g); shortcut: sums_s_raw = sum de, sum de*ys
+ *  rbu_sa_bwd : SpatialAttention backward on the per-pixel maps -> ds[P][2], dk7[98]
+ *  rbu_rb_bwd2: D[N][2][C] (double) = per-(n,c) sum dc, sum dc*y2;  dc = de*gs + ds_avg/C + ds_max*[c == argmax_c]
+ *  rbu_rb_mid : ChannelAttention MLP backward, BatchNorm sums (sums2 = dbeta2|dgamma2, sums_s likewise) and the
+ *               coefficients of the last pass, all from D and forward statistics (no pass over the data)
+ *  rbu_rb_bwd3: dy2 = c1*dc + c0 + cy*y2 + cm*[pixel == nc_arg]; dys = es*de + e0 + ey*ys */
 int rbu_rb_bwd1(const void* dout, int64_t dout_ld, const void* out, int64_t out_ld, const void* y2, int64_t y2_ld,
                 void* de, int64_t de_ld, const void* ys, int64_t ys_ld, int N, int HW, int C, const float* A2g,
-                const float* B2g, const float* mean_s, const float* rstd_s, float* dG, float* sums_s, void* workspace,
-                size_t workspace_bytes, void* stream);
+                const float* B2g, float* dG, float* sums_s_raw, void* workspace, size_t workspace_bytes, void* stream);
 int rbu_sa_bwd(const float* dG, const float* gs, const float* s, int N, int H, int W, const float* k7, float* ds,
                float* dk7, void* workspace, size_t workspace_bytes, void* stream);
-int rbu_rb_bwd_pass(int pass, const void* de, int64_t de_ld, const void* y2, int64_t y2_ld, int N, int HW, int C,
-                    const float* gs, const float* ds, const int* amax_c, const float* g_c, const float* du_avg,
-                    const float* du_max, const int* nc_amax, const int* nc_amin, const float* scale2,
-                    const float* shift2, const float* mean2, const float* rstd2, float* dT, float* sums2, void* dy2,
-                    int64_t dy2_ld, const void* ys, int64_t ys_ld, void* dys, int64_t dys_ld, const float* scale_s,
-                    const float* mean_s, const float* rstd_s, const float* sums_s, void* workspace,
-                    size_t workspace_bytes, void* stream);
-int rbu_ca_bwd(const float* dT, const float* g, const float* h_avg, const float* h_max, const float* u_avg,
-               const float* u_max, const float* V1, const float* V2, int N, int C, int Ch, float* dt, float* dh_avg,
-               float* dh_max, float* du_avg, float* du_max, float* dV1, float* dV2, void* stream);
+int rbu_rb_bwd2(const void* de, int64_t de_ld, const void* y2, int64_t y2_ld, int N, int HW, int C, const float* gs,
+                const float* ds, const int* amax_c, double* D, void* workspace, size_t workspace_bytes, void* stream);
+int rbu_rb_mid(const double* D, const float* g, const float* h_avg, const float* h_max, const float* u_avg,
+               const float* u_max, const float* nc_mean, const float* tv, const float* V1, const float* V2,
+               const float* scale2, const float* shift2, const float* mean2, const float* rstd2, int N, int HW, int C,
+               int Ch, float* scratch, float* dV1, float* dV2, float* sums2, float* coef, const float* sums_s_raw,
+               const float* scale_s, const float* mean_s, const float* rstd_s, float* sums_s, float* coef_s, void* stream);
+int rbu_rb_bwd3(const void* de, int64_t de_ld, const void* y2, int64_t y2_ld, void* dy2, int64_t dy2_ld, const void* ys,
+                int64_t ys_ld, void* dys, int64_t dys_ld, int N, int HW, int C, const float* gs, const float* ds,
+                const int* amax_c, const int* nc_arg, const float* coef, const float* coef_s, void* stream);
 int rbu_bn_bwd(const void* dy, int64_t dy_ld, const void* y, int64_t y_ld, void* dx, int64_t dx_ld, int N, int HW,
                int C, const float* scale, const float* shift, const float* mean, const float* rstd, const float* drop,
                int relu, float* sums /* [2C]: dbeta, dgamma */, void* workspace, size_t workspace_bytes, void* stream);
