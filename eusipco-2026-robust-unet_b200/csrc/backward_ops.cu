@@ -552,51 +552,139 @@ rb_coef_kernel(const double* __restrict__ D, const float* __restrict__ g, const 
 
 // ------------------------------------------------------------------------------------------------
 // Generic BatchNorm(+ReLU)(+Dropout2d) backward: dz = dy * drop[n,c] * [scale*y+shift > 0]
-//   MODE 0: per-channel sum(dz), sum(dz * xhat);   MODE 1: dx = scale*(dz - S1/M - xhat*S2/M)
+//   reduce : per-channel A1 = sum dz, A2 = sum dz*y (raw y; the x-hat form follows in the finalize kernel)
+//   final  : dbeta = A1, dgamma = rstd*(A2 - mean*A1); ky = -scale*rstd*dgamma/M, kc = -scale*A1/M - ky*mean
+//   apply  : dx = scale*dz + kc + ky*y                                   (streaming skeleton)
 // ------------------------------------------------------------------------------------------------
-template <int MODE>
 __global__ void __launch_bounds__(NT)
-bn_bwd_kernel(const bf16* __restrict__ dy, long dy_ld, const bf16* __restrict__ y, long y_ld, int HW, int C, int chunk_px,
-              const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
-              const float* __restrict__ rstd, const float* __restrict__ drop, int relu, float* __restrict__ partials,
-              const float* __restrict__ sums, float invM, bf16* __restrict__ dx, long dx_ld) {
+bn_bwd_reduce_kernel(const bf16* __restrict__ dy, long dy_ld, const bf16* __restrict__ y, long y_ld, int HW, int C,
+                     int chunk_px, const float* __restrict__ scale, const float* __restrict__ shift,
+                     const float* __restrict__ drop, int relu, float* __restrict__ partials) {
   const int G = C >> 3, rows = NT / G;
   const int cg = threadIdx.x % G, row = threadIdx.x / G;
   const int n = blockIdx.y, chunk = blockIdx.x;
   const int p0 = chunk * chunk_px, p1 = min(p0 + chunk_px, HW);
-  float sc[8], sh[8], mu[8], rs[8], dr[8], s1[8], s2[8], acc1[8], acc2[8];
+  float sc[8], sh[8], acc1[8], acc2[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const int c = cg * 8 + e;
-    sc[e] = scale[c]; sh[e] = shift[c]; mu[e] = mean[c]; rs[e] = rstd[c];
-    dr[e] = drop ? drop[(long)n * C + c] : 1.f;
-    s1[e] = MODE ? sums[c] * invM : 0.f;
-    s2[e] = MODE ? sums[C + c] * invM : 0.f;
+    sc[e] = scale[c]; sh[e] = shift[c];
     acc1[e] = 0.f; acc2[e] = 0.f;
   }
+  constexpr int U = 4;
   if (row < rows) {
-#pragma unroll 2
-    for (int pl = p0 + row; pl < p1; pl += rows) {
-      const long p = (long)n * HW + pl;
-      float g[8], v[8];
-      unpack8(ld_bf16x8_stream(dy + p * dy_ld + cg * 8), g);
-      unpack8(ld_bf16x8_stream(y + p * y_ld + cg * 8), v);
+    for (int pl0 = p0 + row; pl0 < p1; pl0 += rows * U) {
+      bf16x8 rg[U], rv[U];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        float dz = g[e] * dr[e];
-        if (relu && !(sc[e] * v[e] + sh[e] > 0.f)) dz = 0.f;
-        const float xh = (v[e] - mu[e]) * rs[e];
-        if (MODE == 0) { acc1[e] += dz; acc2[e] += dz * xh; }
-        else g[e] = sc[e] * (dz - s1[e] - xh * s2[e]);
+      for (int u = 0; u < U; ++u) {
+        const int pl = pl0 + u * rows;
+        if (pl < p1) {
+          const long p = (long)n * HW + pl;
+          rg[u] = ld_bf16x8_stream(dy + p * dy_ld + cg * 8);
+          rv[u] = ld_bf16x8_stream(y + p * y_ld + cg * 8);
+        }
       }
-      if (MODE == 1) st_bf16x8(dx + p * dx_ld + cg * 8, pack8(g));
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (pl0 + u * rows < p1) {
+          float g[8], v[8];
+          unpack8(rg[u], g);
+          unpack8(rv[u], v);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float dz = (relu && !(sc[e] * v[e] + sh[e] > 0.f)) ? 0.f : g[e];
+            acc1[e] += dz;
+            acc2[e] += dz * v[e];
+          }
+        }
+      }
     }
   }
-  if (MODE == 0) {
-    __shared__ float sv[NT][8];
-    float* dst = partials + ((long)n * gridDim.x + chunk) * 2 * C;
-    rows_reduce_store(acc1, G, rows, sv, dst);
-    rows_reduce_store(acc2, G, rows, sv, dst + C);
+  // Dropout2d scale is constant per (n,c): apply it once per block instead of per element
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float d = drop ? drop[(long)n * C + cg * 8 + e] : 1.f;
+    acc1[e] *= d;
+    acc2[e] *= d;
+  }
+  __shared__ float sv[NT][8];
+  float* dst = partials + ((long)n * gridDim.x + chunk) * 2 * C;
+  rows_reduce_store(acc1, G, rows, sv, dst);
+  rows_reduce_store(acc2, G, rows, sv, dst + C);
+}
+
+// block = 32 channels x 8 lanes over the nblk partial rows (fixed order); writes sums[2C] and coef[2C] = (kc, ky)
+__global__ void __launch_bounds__(256)
+bn_bwd_final_kernel(const float* __restrict__ part, int nblk, int C, const float* __restrict__ scale,
+                    const float* __restrict__ mean, const float* __restrict__ rstd, float invM, float* __restrict__ sums,
+                    float* __restrict__ coef) {
+  __shared__ double sh[2][8][32];
+  const int cx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  double a1 = 0.0, a2 = 0.0;
+  if (c < C)
+    for (int b = ly; b < nblk; b += 8) {
+      a1 += (double)part[(long)b * 2 * C + c];
+      a2 += (double)part[(long)b * 2 * C + C + c];
+    }
+  sh[0][ly][cx] = a1;
+  sh[1][ly][cx] = a2;
+  __syncthreads();
+  if (ly == 0 && c < C) {
+    double A1 = 0.0, A2 = 0.0;
+    for (int j = 0; j < 8; ++j) { A1 += sh[0][j][cx]; A2 += sh[1][j][cx]; }
+    const double mu = mean[c], rs = rstd[c], sc = scale[c];
+    const double dgamma = rs * (A2 - mu * A1);
+    sums[c] = (float)A1;
+    sums[C + c] = (float)dgamma;
+    const double ky = -sc * rs * dgamma * (double)invM;
+    coef[c] = (float)(-sc * A1 * (double)invM - ky * mu);
+    coef[C + c] = (float)ky;
+  }
+}
+
+__global__ void __launch_bounds__(NT)
+bn_bwd_apply_kernel(const bf16* __restrict__ dy, long dy_ld, const bf16* __restrict__ y, long y_ld, bf16* __restrict__ dx,
+                    long dx_ld, int HW, int C, int lg, const float* __restrict__ scale, const float* __restrict__ shift,
+                    const float* __restrict__ drop, int relu, const float* __restrict__ coef) {
+  const int n = blockIdx.y, G = 1 << lg, items = HW << lg;
+  const int cg = threadIdx.x & (G - 1);
+  float sc[8], sh[8], sd[8], kc[8], ky[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = cg * 8 + e;
+    sc[e] = scale[c]; sh[e] = shift[c];
+    sd[e] = sc[e] * (drop ? drop[(long)n * C + c] : 1.f);
+    kc[e] = coef[c]; ky[e] = coef[C + c];
+  }
+  const long ib = (long)n * HW;
+  constexpr int U = 4;
+  for (int base = blockIdx.x * (NT * U) + threadIdx.x; base < items; base += gridDim.x * (NT * U)) {
+    bf16x8 rg[U], rv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = base + u * NT;
+      if (i < items) {
+        const long p = ib + (i >> lg);
+        rg[u] = ld_bf16x8_stream(dy + p * dy_ld + cg * 8);
+        rv[u] = ld_bf16x8_stream(y + p * y_ld + cg * 8);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = base + u * NT;
+      if (i < items) {
+        float g[8], v[8];
+        unpack8(rg[u], g);
+        unpack8(rv[u], v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float dz = (relu && !(sc[e] * v[e] + sh[e] > 0.f)) ? 0.f : g[e];
+          g[e] = sd[e] * dz + kc[e] + ky[e] * v[e];
+        }
+        st_bf16x8(dx + (ib + (i >> lg)) * dx_ld + cg * 8, pack8(g));
+      }
+    }
   }
 }
 
@@ -613,30 +701,46 @@ ag_bwd1_kernel(const bf16* __restrict__ da, long da_ld, const bf16* __restrict__
   const int cg = threadIdx.x % G, row = threadIdx.x / G;
   const int n = blockIdx.y, chunk = blockIdx.x;
   const int p0 = chunk * chunk_px, p1 = min(p0 + chunk_px, HW);
-  const int iters = (p1 - p0 + rows - 1) / rows;
+  constexpr int U = 2;
+  const int iters = (p1 - p0 + rows * U - 1) / (rows * U);
   __shared__ float red[NT / 32];
   const float mean = stats[2], rstd = stats[3];
   float l0 = 0.f, l1 = 0.f;
   for (int it = 0; it < iters; ++it) {
-    const int pl = p0 + it * rows + row;
-    const bool act = row < rows && pl < p1;
-    const long p = (long)n * HW + pl;
-    float part = 0.f, ps = 0.f;
-    if (act) {
-      float g[8], x[8];
-      unpack8(ld_bf16x8_stream(da + p * da_ld + cg * 8), g);
-      unpack8(ld_bf16x8(skip + p * s_ld + cg * 8), x);
-      ps = psi[p];
+    bf16x8 rg[U], rx[U];
+    float ps[U];
+    bool act[U];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { part += g[e] * x[e]; g[e] *= ps; }
-      st_bf16x8(dskip + p * ds_ld + cg * 8, pack8(g));
+    for (int u = 0; u < U; ++u) {
+      const int pl = p0 + (it * U + u) * rows + row;
+      act[u] = row < rows && pl < p1;
+      if (act[u]) {
+        const long p = (long)n * HW + pl;
+        rg[u] = ld_bf16x8_stream(da + p * da_ld + cg * 8);
+        rx[u] = ld_bf16x8(skip + p * s_ld + cg * 8);
+        ps[u] = __ldg(psi + p);
+      }
     }
-    part = row_sum(part, G, red);
-    if (act && cg == 0) {
-      const float dq = part * ps * (1.f - ps);
-      dq_out[p] = dq;
-      l0 += dq;
-      l1 += dq * (q0[p] - mean) * rstd;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int pl = p0 + (it * U + u) * rows + row;
+      const long p = (long)n * HW + pl;
+      float part = 0.f;
+      if (act[u]) {
+        float g[8], x[8];
+        unpack8(rg[u], g);
+        unpack8(rx[u], x);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { part += g[e] * x[e]; g[e] *= ps[u]; }
+        st_bf16x8(dskip + p * ds_ld + cg * 8, pack8(g));
+      }
+      part = row_sum(part, G, red);
+      if (act[u] && cg == 0) {
+        const float dq = part * ps[u] * (1.f - ps[u]);
+        dq_out[p] = dq;
+        l0 += dq;
+        l1 += dq * (q0[p] - mean) * rstd;
+      }
     }
   }
   __shared__ float r0[NT / 32], r1[NT / 32];
@@ -654,68 +758,163 @@ ag_bwd1_kernel(const bf16* __restrict__ da, long da_ld, const bf16* __restrict__
   }
 }
 
-// pass 2/3 (over F): dq0 = a_psi*(dq - c1 - qhat*c2); t = relu(Ag yg+Bg+Ax yx+Bx); dt = wpsi*dq0*[t>0]
-//   MODE 0: per-channel sum(t*dq0) [dwpsi], sum(dt), sum(dt*xhat_g), sum(dt*xhat_x)
-//   MODE 1: dyg = Ag*(dt - S1/M - xhat_g*S2g/M), dyx likewise
-template <int MODE>
+// pass 2 (over F), reduce: dq0 = a_psi*(dq - c1 - qhat*c2); t = Ag yg + Ax yx + (Bg+Bx); dt = wpsi*dq0*[t>0]
+//   per-channel sums: relu(t)*dq0 [dwpsi], dt, dt*yg, dt*yx (raw; x-hat forms follow in the finalize kernel)
 __global__ void __launch_bounds__(NT)
-ag_bwd23_kernel(const bf16* __restrict__ yg, long yg_ld, const bf16* __restrict__ yx, long yx_ld, int HW, int F,
-                int chunk_px, const float* __restrict__ Ag, const float* __restrict__ Bg, const float* __restrict__ Ax,
-                const float* __restrict__ Bx, const float* __restrict__ mg, const float* __restrict__ rg,
-                const float* __restrict__ mx, const float* __restrict__ rx, const float* __restrict__ wpsi,
-                const float* __restrict__ dq, const float* __restrict__ q0, const float* __restrict__ stats,
-                const float* __restrict__ csum /* [2]: sum(dq), sum(dq*qhat) */, float invM,
-                float* __restrict__ partials, const float* __restrict__ sums /* [4][F] */, bf16* __restrict__ dyg,
-                long dyg_ld, bf16* __restrict__ dyx, long dyx_ld) {
+ag_bwd2_kernel(const bf16* __restrict__ yg, long yg_ld, const bf16* __restrict__ yx, long yx_ld, int HW, int F,
+               int chunk_px, const float* __restrict__ Ag, const float* __restrict__ Bg, const float* __restrict__ Ax,
+               const float* __restrict__ Bx, const float* __restrict__ wpsi, const float* __restrict__ dq,
+               const float* __restrict__ q0, const float* __restrict__ stats,
+               const float* __restrict__ csum /* [2]: sum(dq), sum(dq*qhat) */, float invM, float* __restrict__ partials) {
   const int G = F >> 3, rows = NT / G;
   const int cg = threadIdx.x % G, row = threadIdx.x / G;
   const int n = blockIdx.y, chunk = blockIdx.x;
   const int p0 = chunk * chunk_px, p1 = min(p0 + chunk_px, HW);
   const float a_psi = stats[0], mean = stats[2], rstd = stats[3];
   const float c1 = csum[0] * invM, c2 = csum[1] * invM;
-  float acc[4][8];
+  float ag[8], ax[8], bs[8], wp[8], acc[4][8];
 #pragma unroll
-  for (int q = 0; q < 4; ++q)
+  for (int e = 0; e < 8; ++e) {
+    const int c = cg * 8 + e;
+    ag[e] = Ag[c]; ax[e] = Ax[c]; bs[e] = Bg[c] + Bx[c]; wp[e] = wpsi[c];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) acc[q][e] = 0.f;
+    for (int q = 0; q < 4; ++q) acc[q][e] = 0.f;
+  }
+  constexpr int U = 2;
   if (row < rows) {
-#pragma unroll 2
-    for (int pl = p0 + row; pl < p1; pl += rows) {
-      const long p = (long)n * HW + pl;
-      float a[8], b[8];
-      unpack8(ld_bf16x8_stream(yg + p * yg_ld + cg * 8), a);
-      unpack8(ld_bf16x8_stream(yx + p * yx_ld + cg * 8), b);
-      const float dq0 = a_psi * (dq[p] - c1 - (q0[p] - mean) * rstd * c2);
-      float og[8], ox[8];
+    for (int pl0 = p0 + row; pl0 < p1; pl0 += rows * U) {
+      bf16x8 ra[U], rb[U];
+      float dqv[U], qv[U];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int c = cg * 8 + e;
-        const float t = Ag[c] * a[e] + Bg[c] + Ax[c] * b[e] + Bx[c];
-        const float dt = t > 0.f ? wpsi[c] * dq0 : 0.f;
-        const float xg = (a[e] - mg[c]) * rg[c];
-        const float xx = (b[e] - mx[c]) * rx[c];
-        if (MODE == 0) {
-          acc[0][e] += fmaxf(t, 0.f) * dq0;
-          acc[1][e] += dt;
-          acc[2][e] += dt * xg;
-          acc[3][e] += dt * xx;
-        } else {
-          const float s1 = sums[F + c] * invM;
-          og[e] = Ag[c] * (dt - s1 - xg * sums[2 * F + c] * invM);
-          ox[e] = Ax[c] * (dt - s1 - xx * sums[3 * F + c] * invM);
+      for (int u = 0; u < U; ++u) {
+        const int pl = pl0 + u * rows;
+        if (pl < p1) {
+          const long p = (long)n * HW + pl;
+          ra[u] = ld_bf16x8_stream(yg + p * yg_ld + cg * 8);
+          rb[u] = ld_bf16x8_stream(yx + p * yx_ld + cg * 8);
+          dqv[u] = __ldg(dq + p);
+          qv[u] = __ldg(q0 + p);
         }
       }
-      if (MODE == 1) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (pl0 + u * rows < p1) {
+          float a[8], b[8];
+          unpack8(ra[u], a);
+          unpack8(rb[u], b);
+          const float dq0 = a_psi * (dqv[u] - c1 - (qv[u] - mean) * rstd * c2);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float t = ag[e] * a[e] + ax[e] * b[e] + bs[e];
+            const float dt = t > 0.f ? wp[e] * dq0 : 0.f;
+            acc[0][e] += fmaxf(t, 0.f) * dq0;
+            acc[1][e] += dt;
+            acc[2][e] += dt * a[e];
+            acc[3][e] += dt * b[e];
+          }
+        }
+      }
+    }
+  }
+  __shared__ float sv[NT][8];
+  float* dst = partials + ((long)n * gridDim.x + chunk) * 4 * F;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) rows_reduce_store(acc[q], G, rows, sv, dst + q * F);
+}
+
+// sums_f[4][F] = dwpsi, dbeta (shared by W_g.1 / W_x.1), dgamma_g, dgamma_x; coef[4][F] = kgc, kgy, kxc, kxy with
+// dyg = Ag*dt + kgc + kgy*yg and dyx = Ax*dt + kxc + kxy*yx
+__global__ void __launch_bounds__(256)
+ag_bwd_final_kernel(const float* __restrict__ part, int nblk, int F, const float* __restrict__ Ag,
+                    const float* __restrict__ Ax, const float* __restrict__ mg, const float* __restrict__ rg,
+                    const float* __restrict__ mx, const float* __restrict__ rx, float invM, float* __restrict__ sums_f,
+                    float* __restrict__ coef) {
+  __shared__ double sh[4][8][32];
+  const int cx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  double a[4] = {0.0, 0.0, 0.0, 0.0};
+  if (c < F)
+    for (int b = ly; b < nblk; b += 8)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) a[q] += (double)part[(long)b * 4 * F + q * F + c];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) sh[q][ly][cx] = a[q];
+  __syncthreads();
+  if (ly == 0 && c < F) {
+    double A[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) A[q] += sh[q][j][cx];
+    const double dgg = (double)rg[c] * (A[2] - (double)mg[c] * A[1]);
+    const double dgx = (double)rx[c] * (A[3] - (double)mx[c] * A[1]);
+    sums_f[c] = (float)A[0];
+    sums_f[F + c] = (float)A[1];
+    sums_f[2 * F + c] = (float)dgg;
+    sums_f[3 * F + c] = (float)dgx;
+    const double kgy = -(double)Ag[c] * rg[c] * dgg * invM, kxy = -(double)Ax[c] * rx[c] * dgx * invM;
+    coef[c] = (float)(-(double)Ag[c] * A[1] * invM - kgy * mg[c]);
+    coef[F + c] = (float)kgy;
+    coef[2 * F + c] = (float)(-(double)Ax[c] * A[1] * invM - kxy * mx[c]);
+    coef[3 * F + c] = (float)kxy;
+  }
+}
+
+// pass 3 (over F), streaming skeleton: dyg, dyx
+__global__ void __launch_bounds__(NT)
+ag_bwd3_kernel(const bf16* __restrict__ yg, long yg_ld, const bf16* __restrict__ yx, long yx_ld, bf16* __restrict__ dyg,
+               long dyg_ld, bf16* __restrict__ dyx, long dyx_ld, int HW, int F, int lg, const float* __restrict__ Ag,
+               const float* __restrict__ Bg, const float* __restrict__ Ax, const float* __restrict__ Bx,
+               const float* __restrict__ wpsi, const float* __restrict__ dq, const float* __restrict__ q0,
+               const float* __restrict__ stats, const float* __restrict__ csum, float invM,
+               const float* __restrict__ coef) {
+  const int n = blockIdx.y, G = 1 << lg, items = HW << lg;
+  const int cg = threadIdx.x & (G - 1);
+  const float a_psi = stats[0], mean = stats[2], rstd = stats[3];
+  const float c1 = csum[0] * invM, c2 = csum[1] * invM;
+  float ag[8], ax[8], bs[8], agw[8], axw[8], kgc[8], kgy[8], kxc[8], kxy[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = cg * 8 + e;
+    ag[e] = Ag[c]; ax[e] = Ax[c]; bs[e] = Bg[c] + Bx[c];
+    agw[e] = ag[e] * wpsi[c]; axw[e] = ax[e] * wpsi[c];
+    kgc[e] = coef[c]; kgy[e] = coef[F + c]; kxc[e] = coef[2 * F + c]; kxy[e] = coef[3 * F + c];
+  }
+  const long ib = (long)n * HW;
+  constexpr int U = 2;
+  for (int base = blockIdx.x * (NT * U) + threadIdx.x; base < items; base += gridDim.x * (NT * U)) {
+    bf16x8 ra[U], rb[U];
+    float dqv[U], qv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = base + u * NT;
+      if (i < items) {
+        const long p = ib + (i >> lg);
+        ra[u] = ld_bf16x8_stream(yg + p * yg_ld + cg * 8);
+        rb[u] = ld_bf16x8_stream(yx + p * yx_ld + cg * 8);
+        dqv[u] = __ldg(dq + p);
+        qv[u] = __ldg(q0 + p);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = base + u * NT;
+      if (i < items) {
+        const long p = ib + (i >> lg);
+        float a[8], b[8], og[8], ox[8];
+        unpack8(ra[u], a);
+        unpack8(rb[u], b);
+        const float dq0 = a_psi * (dqv[u] - c1 - (qv[u] - mean) * rstd * c2);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float t = ag[e] * a[e] + ax[e] * b[e] + bs[e];
+          const float m = t > 0.f ? dq0 : 0.f;
+          og[e] = agw[e] * m + kgc[e] + kgy[e] * a[e];
+          ox[e] = axw[e] * m + kxc[e] + kxy[e] * b[e];
+        }
         st_bf16x8(dyg + p * dyg_ld + cg * 8, pack8(og));
         st_bf16x8(dyx + p * dyx_ld + cg * 8, pack8(ox));
       }
     }
-  }
-  if (MODE == 0) {
-    __shared__ float sv[NT][8];
-    float* dst = partials + ((long)n * gridDim.x + chunk) * 4 * F;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) rows_reduce_store(acc[q], G, rows, sv, dst + q * F);
   }
 }
 
@@ -821,7 +1020,7 @@ int grid1d(long items, int per_block) {
 extern "C" size_t rbu_bwd_workspace_bytes(int N, int HW, int C) {
   if (!CH_OK(C)) return 0;
   int ppb;
-  const size_t a = (size_t)N * bwd_chunks(N, HW, C) * 4 * C;
+  const size_t a = (size_t)N * bwd_chunks(N, HW, C) * 4 * C + 4 * C;
   const size_t b = (size_t)flat_blocks((long)N * HW, C, &ppb) * (C + 8);
   const size_t c = (size_t)rbu_num_sms() * 8 * 98;
   size_t m = a > b ? a : b;
@@ -974,16 +1173,24 @@ extern "C" int rbu_bn_bwd(const void* dy, int64_t dy_ld, const void* y, int64_t 
                     scale && shift && mean && rstd && sums, "rbu_bn_bwd: bad arguments");
   const int chunks = bwd_chunks(N, HW, C);
   const int chunk_px = rbu_cdiv(HW, chunks);
-  RBU_CHECK_ARG(workspace && workspace_bytes >= (size_t)N * chunks * 2 * C * sizeof(float), "rbu_bn_bwd: workspace too small");
+  const size_t part_floats = (size_t)N * chunks * 2 * C;
+  RBU_CHECK_ARG(workspace && workspace_bytes >= (part_floats + 2 * C) * sizeof(float), "rbu_bn_bwd: workspace too small");
+  float* part = (float*)workspace;
+  float* coef = part + part_floats;
   const float invM = 1.f / ((float)N * (float)HW);
-  bn_bwd_kernel<0><<<dim3(chunks, N), NT, 0, st>>>((const bf16*)dy, dy_ld, (const bf16*)y, y_ld, HW, C, chunk_px, scale,
-                                                  shift, mean, rstd, drop, relu, (float*)workspace, nullptr, invM,
-                                                  nullptr, 0);
+  bn_bwd_reduce_kernel<<<dim3(chunks, N), NT, 0, st>>>((const bf16*)dy, dy_ld, (const bf16*)y, y_ld, HW, C, chunk_px, scale,
+                                                       shift, drop, relu, part);
   RBU_CHECK_LAUNCH();
-  colsum_kernel<<<rbu_cdiv(2 * C, 32), 256, 0, st>>>((const float*)workspace, N * chunks, 2 * C, 2 * C, sums, 1.f);
+  bn_bwd_final_kernel<<<rbu_cdiv(C, 32), 256, 0, st>>>(part, N * chunks, C, scale, mean, rstd, invM, sums, coef);
   RBU_CHECK_LAUNCH();
-  bn_bwd_kernel<1><<<dim3(chunks, N), NT, 0, st>>>((const bf16*)dy, dy_ld, (const bf16*)y, y_ld, HW, C, chunk_px, scale,
-                                                  shift, mean, rstd, drop, relu, nullptr, sums, invM, (bf16*)dx, dx_ld);
+  int lg = 0;
+  while ((1 << (lg + 1)) <= (C >> 3)) ++lg;
+  const long items = (long)HW << lg;
+  long blocks = (items + NT * 4 - 1) / (NT * 4);
+  long cap = ((long)rbu_num_sms() * 32 + N - 1) / N;
+  if (blocks > cap) blocks = cap;
+  bn_bwd_apply_kernel<<<dim3((unsigned)blocks, N), NT, 0, st>>>((const bf16*)dy, dy_ld, (const bf16*)y, y_ld, (bf16*)dx, dx_ld,
+                                                                HW, C, lg, scale, shift, drop, relu, coef);
   RBU_CHECK_LAUNCH();
   return RBU_OK;
 }
@@ -1017,16 +1224,23 @@ extern "C" int rbu_ag_bwd(const void* da, int64_t da_ld, const void* skip, int64
   {
     const int chunks = bwd_chunks(N, HW, F);
     const int chunk_px = rbu_cdiv(HW, chunks);
-    RBU_CHECK_ARG(workspace_bytes >= (size_t)N * chunks * 4 * F * sizeof(float), "rbu_ag_bwd: workspace too small");
-    ag_bwd23_kernel<0><<<dim3(chunks, N), NT, 0, st>>>((const bf16*)yg, yg_ld, (const bf16*)yx, yx_ld, HW, F, chunk_px, Ag, Bg,
-                                                      Ax, Bx, mg, rg, mx, rx, wpsi, dq, q0, stats, sums_psi, invM, part,
-                                                      nullptr, nullptr, 0, nullptr, 0);
+    const size_t part_floats = (size_t)N * chunks * 4 * F;
+    RBU_CHECK_ARG(workspace_bytes >= (part_floats + 4 * F) * sizeof(float), "rbu_ag_bwd: workspace too small");
+    float* coef = part + part_floats;
+    ag_bwd2_kernel<<<dim3(chunks, N), NT, 0, st>>>((const bf16*)yg, yg_ld, (const bf16*)yx, yx_ld, HW, F, chunk_px, Ag, Bg, Ax,
+                                                   Bx, wpsi, dq, q0, stats, sums_psi, invM, part);
     RBU_CHECK_LAUNCH();
-    colsum_kernel<<<rbu_cdiv(4 * F, 32), 256, 0, st>>>(part, N * chunks, 4 * F, 4 * F, sums_f, 1.f);
+    ag_bwd_final_kernel<<<rbu_cdiv(F, 32), 256, 0, st>>>(part, N * chunks, F, Ag, Ax, mg, rg, mx, rx, invM, sums_f, coef);
     RBU_CHECK_LAUNCH();
-    ag_bwd23_kernel<1><<<dim3(chunks, N), NT, 0, st>>>((const bf16*)yg, yg_ld, (const bf16*)yx, yx_ld, HW, F, chunk_px, Ag, Bg,
-                                                      Ax, Bx, mg, rg, mx, rx, wpsi, dq, q0, stats, sums_psi, invM, nullptr,
-                                                      sums_f, (bf16*)dyg, dyg_ld, (bf16*)dyx, dyx_ld);
+    int lg = 0;
+    while ((1 << (lg + 1)) <= (F >> 3)) ++lg;
+    const long items = (long)HW << lg;
+    long blocks = (items + NT * 2 - 1) / (NT * 2);
+    long cap = ((long)rbu_num_sms() * 32 + N - 1) / N;
+    if (blocks > cap) blocks = cap;
+    ag_bwd3_kernel<<<dim3((unsigned)blocks, N), NT, 0, st>>>((const bf16*)yg, yg_ld, (const bf16*)yx, yx_ld, (bf16*)dyg, dyg_ld,
+                                                             (bf16*)dyx, dyx_ld, HW, F, lg, Ag, Bg, Ax, Bx, wpsi, dq, q0, stats,
+                                                             sums_psi, invM, coef);
     RBU_CHECK_LAUNCH();
   }
   return RBU_OK;
