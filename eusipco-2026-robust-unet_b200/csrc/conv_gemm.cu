@@ -10,14 +10,15 @@
 // into one accumulator).  Replaces aten::convolution / convolution_backward(input) of
 // Main_Final.py:157,159,172,126,131,205-208,261-270.
 //
-// Structure (persistent, warp specialised, 192 threads, 1 CTA / SM):
+// Structure (persistent, warp specialised, 320 threads, 1 CTA / SM):
 //   warp 0 / lane 0 : TMA producer   (A tile: 128 pixels x 64 ch, B tile: block_n x 64)   -> full[s]
 //   warp 1 / lane 0 : MMA issuer     (4 x tcgen05.mma K=16 per stage, commit -> empty[s], tmem_full[a])
-//   warps 2..5      : epilogue       (tcgen05.ld 32x32b, bias/addend, bf16 pack, 16 B stores) -> tmem_empty[a]
+//   warps 2..9      : epilogue       (gemm_epilogue.cuh: tcgen05.ld 32x32b, bias/addend, bf16 pack, 16 B stores) -> tmem_empty[a]
 // Two TMEM accumulator buffers let the epilogue of tile i overlap the MMAs of tile i+1.
 #include "rbu_common.cuh"
 #include "rbu_ptx.cuh"
 #include "tma_host.cuh"
+#include "gemm_epilogue.cuh"
 #include <stdlib.h>
 
 namespace {
@@ -25,7 +26,7 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;   // TMA warp, MMA warp, 8 epilogue warps
 constexpr int MAX_STAGES = 8;
 constexpr int SMEM_LIMIT = 232448;  // 227 KB
 
@@ -78,7 +79,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tfull[a], 1);
-      ptx::mbar_init(&tempty[a], 4);
+      ptx::mbar_init(&tempty[a], 8);
     }
     ptx::fence_barrier_init();
   }
@@ -178,9 +179,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       __syncwarp();
     }
   } else {
-    // ============================== epilogue (warps 2..5) ==============================
-    const int lg = warp & 3;  // TMEM lane group this warp may access
+    // ============================== epilogue (warps 2..9) ==============================
+    const int lg = warp & 3;              // TMEM lane group this warp may access
+    const int half = (warp - 2) >> 2;     // which of the interleaved 32-column chunks this warp drains
     const int row = lg * 32 + lane;
+    EpiOut eo;
+    eo.y = p.y; eo.y_ld = p.y_ld; eo.bias = p.bias; eo.addend = p.addend; eo.addend_ld = p.addend_ld;
+    eo.Ncols = p.Ncols; eo.scatter = p.scatter; eo.Cout = p.Cout; eo.H = p.H; eo.W = p.W;
     int t = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
       const int nb = tile % p.n_blocks;
@@ -208,52 +213,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         }
       }
       const long long pix = ((long long)n * p.H + h) * p.W + w;
-
       const int a = t & 1;
       const uint32_t aph = (t >> 1) & 1;
       ptx::mbar_wait(&tfull[a], aph);
       ptx::tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(a * p.block_n);
-      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32(t_addr + (uint32_t)c0, r);
-        ptx::tmem_ld_wait();
-        const int col = nb * p.block_n + c0;
-        if (valid && col < p.Ncols) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int c8 = col + g * 8;
-            if (c8 < p.Ncols) {
-              bf16* dst;
-              int cb = c8;  // bias channel
-              if (p.scatter) {
-                const int q = c8 / p.Cout;
-                cb = c8 - q * p.Cout;
-                const long long opix = ((long long)n * (2 * p.H) + 2 * h + (q >> 1)) * (2 * p.W) + 2 * w + (q & 1);
-                dst = p.y + opix * p.y_ld + cb;
-              } else {
-                dst = p.y + pix * p.y_ld + c8;
-              }
-              float f[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(r[g * 8 + e]);
-              if (p.bias) {
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + cb));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + cb + 4));
-                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-              }
-              if (p.addend) {
-                float ad[8];
-                unpack8(ld_bf16x8(p.addend + pix * p.addend_ld + c8), ad);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] += ad[e];
-              }
-              st_bf16x8(dst, pack8(f));
-            }
-          }
-        }
-      }
+      for (int c0 = half * 32; c0 < p.block_n; c0 += 64)
+        epilogue_chunk32(eo, t_addr + (uint32_t)c0, nb * p.block_n + c0, valid, pix, n, h, w);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty[a]);

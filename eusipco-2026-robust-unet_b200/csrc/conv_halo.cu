@@ -14,16 +14,17 @@
 // the phase: every 3x3 parity test failed with it, all pass without).
 // L2->SM traffic per 64-channel slab drops from 9 x 16 KB to 36 KB for A; B (weights) still streams per tap.
 //
-// Structure (persistent, warp specialised, 192 threads, 1 CTA / SM), as conv_gemm.cu:
+// Structure (persistent, warp specialised, 320 threads, 1 CTA / SM), as conv_gemm.cu:
 //   warp 0 lane 0 : TMA producer -- A ring (halo tiles, 2-3 stages) and B ring (one weight tile per tap)
 //   warp 1 lane 0 : MMA issuer   -- per slab 9 taps x 4 tcgen05.mma (K = 16) into one of two TMEM accumulators
-//   warps 2..5    : epilogue     -- tcgen05.ld, bias / addend, bf16 pack, 16-byte stores
+//   warps 2..9    : epilogue     -- tcgen05.ld, bias / addend, bf16 pack, 16-byte stores (gemm_epilogue.cuh)
 // Two accumulated segments are supported (conv1 3x3 dgrad + shortcut 1x1 dgrad; 1x1 segments use a plain
 // 16 x 8-pixel box with a 1024-byte pitch).
 // Replaces aten::convolution / convolution_backward(input) of Main_Final.py:157,159,172,126,131.
 #include "rbu_common.cuh"
 #include "rbu_ptx.cuh"
 #include "tma_host.cuh"
+#include "gemm_epilogue.cuh"
 #include <stdlib.h>
 
 namespace {
@@ -34,7 +35,7 @@ constexpr int TILE_W = 8, TILE_H = 16;
 constexpr int HALO_W = 16, HALO_H = 18;               // 16 column slots (10 used): row pitch 2048 B = 2 swizzle atoms
 constexpr int A_HALO_BYTES = HALO_H * HALO_W * 128;   // 36864
 constexpr int A_PLAIN_BYTES = BLOCK_M * 128;          // 16384
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;   // TMA warp, MMA warp, 8 epilogue warps
 constexpr int MAX_B_STAGES = 8;
 constexpr int SMEM_LIMIT = 232448;
 constexpr int LOOKAHEAD_TAP = 4;                      // the next slab's A tile is requested after this tap's B tile
@@ -120,7 +121,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tfull[a], 1);
-      ptx::mbar_init(&tempty[a], 4);
+      ptx::mbar_init(&tempty[a], 8);
     }
     ptx::fence_barrier_init();
   }
@@ -241,9 +242,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       ++t;
     }
   } else {
-    // ============================== epilogue (warps 2..5) ==============================
+    // ============================== epilogue (warps 2..9) ==============================
     const int lg = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = lg * 32 + lane;
+    EpiOut eo;
+    eo.y = p.y; eo.y_ld = p.y_ld; eo.bias = p.bias; eo.addend = p.addend; eo.addend_ld = p.addend_ld;
+    eo.Ncols = p.Ncols; eo.scatter = 0; eo.Cout = p.Ncols; eo.H = p.H; eo.W = p.W;
     int t = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
       int nb, w0, h0, n;
@@ -256,36 +261,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       ptx::mbar_wait(&tfull[a], aph);
       ptx::tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(a * p.block_n);
-      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32(t_addr + (uint32_t)c0, r);
-        ptx::tmem_ld_wait();
-        const int col = nb * p.block_n + c0;
-        if (valid && col < p.Ncols) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int c8 = col + g * 8;
-            if (c8 < p.Ncols) {
-              float f[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(r[g * 8 + e]);
-              if (p.bias) {
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c8));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + c8 + 4));
-                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-              }
-              if (p.addend) {
-                float ad[8];
-                unpack8(ld_bf16x8(p.addend + pix * p.addend_ld + c8), ad);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] += ad[e];
-              }
-              st_bf16x8(p.y + pix * p.y_ld + c8, pack8(f));
-            }
-          }
-        }
-      }
+      for (int c0 = half * 32; c0 < p.block_n; c0 += 64)
+        epilogue_chunk32(eo, t_addr + (uint32_t)c0, nb * p.block_n + c0, valid, pix, n, h, w);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty[a]);

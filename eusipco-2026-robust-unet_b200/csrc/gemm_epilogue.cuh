@@ -1,0 +1,68 @@
+// Shared epilogue of the implicit-GEMM convolution kernels: one warp drains 32 fp32 accumulator columns of its
+// 32 TMEM lanes (= 32 output pixels), adds bias / addend, rounds to bf16 and stores 16 bytes per 8 channels.
+// Eight epilogue warps per CTA (two per TMEM lane group, interleaved over the 32-column chunks) keep enough global
+// loads / stores in flight for the small-K GEMMs whose epilogue, not the MMA, bounds the tile time; the addend and
+// bias loads of a chunk are issued BEFORE waiting on tcgen05.ld so their latency overlaps the TMEM read.
+#pragma once
+#include "rbu_common.cuh"
+#include "rbu_ptx.cuh"
+
+struct EpiOut {
+  bf16* y;
+  long long y_ld;
+  const float* bias;
+  const bf16* addend;
+  long long addend_ld;
+  int Ncols;
+  int scatter, Cout, H, W;   // scatter: ConvTranspose2d pixel shuffle, column (2i+j)*Cout+co of (n,h,w) -> y[n,2h+i,2w+j,co]
+};
+
+// taddr: TMEM address of (lane group base, first column of the chunk); col: first GEMM column of the chunk
+__device__ __forceinline__ void epilogue_chunk32(const EpiOut& o, uint32_t taddr, int col, bool valid, long long pix, int n,
+                                                 int h, int w) {
+  uint4 ad[4];
+  const bool live = valid && col < o.Ncols;
+  if (o.addend && live) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      if (col + g * 8 < o.Ncols) ad[g] = __ldg(reinterpret_cast<const uint4*>(o.addend + pix * o.addend_ld + col + g * 8));
+  }
+  uint32_t r[32];
+  ptx::tmem_ld_32x32(taddr, r);
+  ptx::tmem_ld_wait();
+  if (!live) return;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int c8 = col + g * 8;
+    if (c8 < o.Ncols) {
+      bf16* dst;
+      int cb = c8;  // bias channel
+      if (o.scatter) {
+        const int q = c8 / o.Cout;
+        cb = c8 - q * o.Cout;
+        const long long opix = ((long long)n * (2 * o.H) + 2 * h + (q >> 1)) * (2 * o.W) + 2 * w + (q & 1);
+        dst = o.y + opix * o.y_ld + cb;
+      } else {
+        dst = o.y + pix * o.y_ld + c8;
+      }
+      float f[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(r[g * 8 + e]);
+      if (o.bias) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(o.bias + cb));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(o.bias + cb + 4));
+        f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+        f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+      }
+      if (o.addend) {
+        float a8[8];
+        bf16x8 t;
+        *reinterpret_cast<uint4*>(&t) = ad[g];
+        unpack8(t, a8);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] += a8[e];
+      }
+      st_bf16x8(dst, pack8(f));
+    }
+  }
+}
