@@ -11,8 +11,8 @@ from . import _lib  # noqa: F401
 from .loss import (METRIC_KEYS, RobustBCEDiceLoss, batch_metrics, calculate_metrics,  # noqa: F401
                    confusion_counts, metrics_from_counts)
 from .model import RobustUNet  # noqa: F401
-from .ops import View  # noqa: F401
+from .ops import View, preprocess  # noqa: F401
 from .parallel import DataParallel, GradBucketer  # noqa: F401
 
 __all__ = ["RobustUNet", "RobustBCEDiceLoss", "calculate_metrics", "batch_metrics", "confusion_counts",
-           "metrics_from_counts", "METRIC_KEYS", "View", "DataParallel", "GradBucketer"]
+           "metrics_from_counts", "METRIC_KEYS", "View", "preprocess", "DataParallel", "GradBucketer"]

@@ -130,3 +130,15 @@ def confusion_counts(pred, target, threshold=0.5):
     counts = torch.empty((B, 4), dtype=torch.int64, device=pred.device)
     call("rbu_confusion_counts", _p(pred), _p(target), B, HW, threshold, _p(counts), stream_ptr())
     return counts
+
+
+def preprocess(img_u8: torch.Tensor, n_channels: int = 3) -> torch.Tensor:
+    """uint8 RGB [B,H,W,3] CUDA tensor -> fp32 NCHW [B,n_channels,H,W] (Normalize of Main_Final.py:697-701; channels
+    beyond 3 are the build-defined HSV planes)."""
+    if not img_u8.is_cuda or img_u8.dtype != torch.uint8 or img_u8.dim() != 4 or img_u8.shape[-1] != 3:
+        raise RuntimeError("rbunet.preprocess expects a uint8 CUDA tensor [B,H,W,3] (no CPU fallback)")
+    img_u8 = img_u8.contiguous()
+    B, H, W, _ = img_u8.shape
+    out = torch.empty((B, n_channels, H, W), dtype=torch.float32, device=img_u8.device)
+    call("rbu_preprocess", _p(img_u8), B, H, W, n_channels, _p(out), stream_ptr())
+    return out

@@ -41,6 +41,12 @@ int rbu_sm_count(void);
 /* Number of CUDA kernels this library has launched in the calling process (bench.py's gpu_launches). */
 unsigned long long rbu_launch_count(void);
 
+/* ------------------------------------------------------------------ input preprocessing
+ * uint8 RGB [B,H,W,3] -> fp32 NCHW [B,n_channels,H,W]: ToTensor + Normalize(ImageNet) of Main_Final.py:697-701 in
+ * channels 0-2; n_channels 4 appends the HSV saturation plane, 6 appends H/360, S, V (OpenCV float semantics; the
+ * reference has no HSV code).  Bit-identical to the numpy oracle. */
+int rbu_preprocess(const uint8_t* img, int B, int H, int W, int n_channels, float* out, void* stream);
+
 /* ------------------------------------------------------------------ tensor-core implicit GEMM
  * Replaces aten::convolution for 3x3 (dilation 1/2/4), 1x1 and ConvTranspose2d(2, stride 2)
  * (Main_Final.py:157,159,172,126,131,205-208,261-270) and, with re-packed weights, their data

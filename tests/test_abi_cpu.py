@@ -1,0 +1,64 @@
+"""CPU: the C-ABI library loads without a GPU and exports every symbol include/rbunet.h declares; the product package
+imports nothing from oracle/ and has no CPU fallback."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "eusipco-2026-robust-unet_b200")
+
+
+def test_library_exports_every_declared_symbol():
+    from rbunet import _lib
+    sigs = _lib.parse_header()
+    assert len(sigs) >= 35
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sigs:
+        assert hasattr(handle, name), f"{name} declared in rbunet.h but not exported"
+    assert _lib.lib().rbu_version() >= 100
+    assert _lib.lib().rbu_last_error() is not None
+
+
+def test_header_prototypes_parse_to_ctypes():
+    from rbunet import _lib
+    sigs = _lib.parse_header()
+    res, args = sigs["rbu_conv_gemm"]
+    assert res is ctypes.c_int and args == [ctypes.c_void_p, ctypes.c_void_p]
+    res, args = sigs["rbu_loss_workspace_bytes"]
+    assert res is ctypes.c_size_t and args == [ctypes.c_int, ctypes.c_int64]
+    assert sigs["rbu_launch_count"][0] is ctypes.c_ulonglong
+
+
+def test_product_never_imports_the_oracle():
+    for fn in os.listdir(PKG):
+        if fn.endswith(".py"):
+            src = open(os.path.join(PKG, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), fn
+
+
+def test_no_cpu_fallback():
+    import torch
+    import rbunet
+    model = rbunet.RobustUNet(3, 1, 16)
+    with pytest.raises(RuntimeError):
+        model(torch.zeros((1, 3, 32, 32)))
+    with pytest.raises(RuntimeError):
+        rbunet.RobustBCEDiceLoss()(torch.rand((1, 1, 4, 4)), torch.rand((1, 1, 4, 4)))
+    with pytest.raises(RuntimeError):
+        rbunet.confusion_counts(torch.rand((1, 4)), torch.rand((1, 4)))
+
+
+def test_state_dict_schema_and_init_match_the_reference_schema():
+    import torch
+    import rbunet
+    from oracle import robust_unet_ref as R
+    for nc in (3, 4):
+        m = rbunet.RobustUNet(nc, 1, 64)
+        sd = m.state_dict()
+        shapes = R.robust_unet_shapes(nc, 1, 64)
+        assert list(sd.keys()) == list(shapes.keys()) and len(sd) == 290
+        for k, v in sd.items():
+            assert tuple(v.shape) == tuple(shapes[k]), k
+    assert sum(p.numel() for p in rbunet.RobustUNet(3).parameters()) == 40872223
