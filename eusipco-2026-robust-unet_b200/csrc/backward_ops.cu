@@ -50,6 +50,37 @@ __device__ __forceinline__ void rows_reduce_store(const float* acc, int G, int r
 }
 
 // out[k] (+ optional out2) = sum over blocks of part[blk][k], fixed order, double accumulation
+// Stage 1 of a long column reduction: slice s = blockIdx.y of the rows (rows s, s+S, ...) -> part2[s][K].  Rows of a
+// slice are visited in order by 8 lanes with 4 independent loads in flight each; everything downstream sums the S
+// slice rows in order, so the result is deterministic.
+constexpr int COLSUM_SLICES = 32;
+__global__ void __launch_bounds__(256)
+colsum_stage1_kernel(const float* __restrict__ part, int nblk, int K, long blk_stride, float* __restrict__ part2) {
+  __shared__ float sh[8][32];
+  const int kx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  const int k = blockIdx.x * 32 + kx;
+  const int S = gridDim.y, sl = blockIdx.y;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (k < K) {
+    int b = sl + ly * S;
+    const int step = 8 * S;
+    for (; b + 3 * step < nblk; b += 4 * step) {
+      a0 += part[(long)b * blk_stride + k];
+      a1 += part[(long)(b + step) * blk_stride + k];
+      a2 += part[(long)(b + 2 * step) * blk_stride + k];
+      a3 += part[(long)(b + 3 * step) * blk_stride + k];
+    }
+    for (; b < nblk; b += step) a0 += part[(long)b * blk_stride + k];
+  }
+  sh[ly][kx] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (ly == 0 && k < K) {
+    float t = 0.f;
+    for (int j = 0; j < 8; ++j) t += sh[j][kx];
+    part2[(long)sl * K + k] = t;
+  }
+}
+
 // block = 32 columns x 8 lanes (launch with 256 threads, grid = ceil(K / 32))
 __global__ void __launch_bounds__(256)
 colsum_kernel(const float* __restrict__ part, int nblk, int K, long blk_stride, float* __restrict__ out, float post_scale) {
@@ -472,6 +503,7 @@ __global__ void ca_bwd_w_kernel(const float* __restrict__ dt, const float* __res
   {  // dV1[j][c]
     const int j = i / C, c = i % C;
     float s = 0.f;
+#pragma unroll 8
     for (int n = 0; n < N; ++n)
       s += dh_avg[(long)n * Ch + j] * u_avg[(long)n * C + c] + dh_max[(long)n * Ch + j] * u_max[(long)n * C + c];
     dV1[i] = s;
@@ -479,6 +511,7 @@ __global__ void ca_bwd_w_kernel(const float* __restrict__ dt, const float* __res
   {  // dV2[c][j]
     const int c = i / Ch, j = i % Ch;
     float s = 0.f;
+#pragma unroll 8
     for (int n = 0; n < N; ++n)
       s += dt[(long)n * C + c] * (fmaxf(h_avg[(long)n * Ch + j], 0.f) + fmaxf(h_max[(long)n * Ch + j], 0.f));
     dV2[i] = s;
@@ -1010,19 +1043,32 @@ int grid1d(long items, int per_block) {
   return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
+// Long partial lists ([nblk][stride] rows) are first folded into COLSUM_SLICES rows of K columns in `scratch`
+// (which must hold COLSUM_SLICES*K floats); short ones are passed through.  Updates part / nblk / stride in place.
+int colsum_fold(const float*& part, int& nblk, long& stride, int K, float* scratch, cudaStream_t st) {
+  if (nblk <= 4 * COLSUM_SLICES) return RBU_OK;
+  colsum_stage1_kernel<<<dim3(rbu_cdiv(K, 32), COLSUM_SLICES), 256, 0, st>>>(part, nblk, K, stride, scratch);
+  RBU_CHECK_LAUNCH();
+  part = scratch;
+  nblk = COLSUM_SLICES;
+  stride = K;
+  return RBU_OK;
+}
+
 }  // namespace
 
 #define VIEW_OK(ptr, ld) ((ptr) != nullptr && ((uintptr_t)(ptr) & 15) == 0 && (ld) % 8 == 0)
 #define CH_OK(C) ((C) >= 8 && (C) <= 2048 && pow2(C))
+#define FOLD_FLOATS(K) ((size_t)COLSUM_SLICES * (K))
 
 // Workspace (floats) large enough for every backward pass of a [N,HW,C] tensor: max partial layout is
 // [N*chunks][4][C] (AttentionGate pass 2); the head / chan_sum layouts are smaller.
 extern "C" size_t rbu_bwd_workspace_bytes(int N, int HW, int C) {
   if (!CH_OK(C)) return 0;
   int ppb;
-  const size_t a = (size_t)N * bwd_chunks(N, HW, C) * 4 * C + 4 * C;
-  const size_t b = (size_t)flat_blocks((long)N * HW, C, &ppb) * (C + 8);
-  const size_t c = (size_t)rbu_num_sms() * 8 * 98;
+  const size_t a = (size_t)N * bwd_chunks(N, HW, C) * 4 * C + 4 * C + FOLD_FLOATS(4 * C + 128);
+  const size_t b = (size_t)flat_blocks((long)N * HW, C, &ppb) * (C + 8) + FOLD_FLOATS(C + 8);
+  const size_t c = (size_t)rbu_num_sms() * 8 * 98 + FOLD_FLOATS(128);
   size_t m = a > b ? a : b;
   if (c > m) m = c;
   return m * sizeof(float);
@@ -1040,9 +1086,15 @@ extern "C" int rbu_head_backward(const float* dprobs, const float* probs, const 
   float* part = (float*)workspace;
   head_bwd_kernel<<<blocks, NT, 0, st>>>(dprobs, probs, (const bf16*)x, x_ld, (bf16*)dx, dx_ld, P, C, w, ppb, part);
   RBU_CHECK_LAUNCH();
-  colsum_kernel<<<rbu_cdiv(C, 32), 256, 0, st>>>(part, blocks, C, C + 8, dw, 1.f);
+  const float* pp = part;
+  int nb2 = blocks;
+  long stride = C + 8;
+  RBU_CHECK_ARG(workspace_bytes >= ((size_t)blocks * (C + 8) + FOLD_FLOATS(C + 8)) * sizeof(float), "rbu_head_backward: workspace too small");
+  int rc = colsum_fold(pp, nb2, stride, C + 1, part + (size_t)blocks * (C + 8), st);
+  if (rc) return rc;
+  colsum_kernel<<<rbu_cdiv(C, 32), 256, 0, st>>>(pp, nb2, C, stride, dw, 1.f);
   RBU_CHECK_LAUNCH();
-  colsum_kernel<<<1, 256, 0, st>>>(part + C, blocks, 1, C + 8, db, 1.f);
+  colsum_kernel<<<1, 256, 0, st>>>(pp + C, nb2, 1, stride, db, 1.f);
   RBU_CHECK_LAUNCH();
   return RBU_OK;
 }
@@ -1062,7 +1114,13 @@ extern "C" int rbu_rb_bwd1(const void* dout, int64_t dout_ld, const void* out, i
                                                  rbu_cdiv(HW, chunks), A2g, B2g, dG, (float*)workspace);
   RBU_CHECK_LAUNCH();
   if (ys) {
-    colsum_kernel<<<rbu_cdiv(2 * C, 32), 256, 0, st>>>((const float*)workspace, N * chunks, 2 * C, 2 * C, sums_s_raw, 1.f);
+    const float* pp = (const float*)workspace;
+    int nb2 = N * chunks;
+    long stride = 2 * C;
+    RBU_CHECK_ARG(workspace_bytes >= ((size_t)N * chunks * 2 * C + FOLD_FLOATS(2 * C)) * sizeof(float), "rbu_rb_bwd1: workspace too small");
+    int rc = colsum_fold(pp, nb2, stride, 2 * C, (float*)workspace + (size_t)N * chunks * 2 * C, st);
+    if (rc) return rc;
+    colsum_kernel<<<rbu_cdiv(2 * C, 32), 256, 0, st>>>(pp, nb2, 2 * C, stride, sums_s_raw, 1.f);
     RBU_CHECK_LAUNCH();
   }
   return RBU_OK;
@@ -1079,7 +1137,13 @@ extern "C" int rbu_sa_bwd(const float* dG, const float* gs, const float* s, int 
   RBU_CHECK_ARG(workspace && workspace_bytes >= (size_t)blocks * 98 * sizeof(float), "rbu_sa_bwd: workspace too small");
   sa_bwd_weight_kernel<<<blocks, NT, 0, st>>>(dG, gs, (const float2*)s, N, H, W, (float*)workspace);
   RBU_CHECK_LAUNCH();
-  colsum_kernel<<<rbu_cdiv(98, 32), 256, 0, st>>>((const float*)workspace, blocks, 98, 98, dk7, 1.f);
+  const float* pp = (const float*)workspace;
+  int nb2 = blocks;
+  long stride = 98;
+  RBU_CHECK_ARG(workspace_bytes >= ((size_t)blocks * 98 + FOLD_FLOATS(98)) * sizeof(float), "rbu_sa_bwd: workspace too small");
+  int rc = colsum_fold(pp, nb2, stride, 98, (float*)workspace + (size_t)blocks * 98, st);
+  if (rc) return rc;
+  colsum_kernel<<<rbu_cdiv(98, 32), 256, 0, st>>>(pp, nb2, 98, stride, dk7, 1.f);
   RBU_CHECK_LAUNCH();
   return RBU_OK;
 }
@@ -1174,15 +1238,22 @@ extern "C" int rbu_bn_bwd(const void* dy, int64_t dy_ld, const void* y, int64_t 
   const int chunks = bwd_chunks(N, HW, C);
   const int chunk_px = rbu_cdiv(HW, chunks);
   const size_t part_floats = (size_t)N * chunks * 2 * C;
-  RBU_CHECK_ARG(workspace && workspace_bytes >= (part_floats + 2 * C) * sizeof(float), "rbu_bn_bwd: workspace too small");
+  RBU_CHECK_ARG(workspace && workspace_bytes >= (part_floats + 2 * C + FOLD_FLOATS(2 * C)) * sizeof(float), "rbu_bn_bwd: workspace too small");
   float* part = (float*)workspace;
   float* coef = part + part_floats;
   const float invM = 1.f / ((float)N * (float)HW);
   bn_bwd_reduce_kernel<<<dim3(chunks, N), NT, 0, st>>>((const bf16*)dy, dy_ld, (const bf16*)y, y_ld, HW, C, chunk_px, scale,
                                                        shift, drop, relu, part);
   RBU_CHECK_LAUNCH();
-  bn_bwd_final_kernel<<<rbu_cdiv(C, 32), 256, 0, st>>>(part, N * chunks, C, scale, mean, rstd, invM, sums, coef);
-  RBU_CHECK_LAUNCH();
+  {
+    const float* pp = part;
+    int nb2 = N * chunks;
+    long stride = 2 * C;
+    int rc = colsum_fold(pp, nb2, stride, 2 * C, coef + 2 * C, st);
+    if (rc) return rc;
+    bn_bwd_final_kernel<<<rbu_cdiv(C, 32), 256, 0, st>>>(pp, nb2, C, scale, mean, rstd, invM, sums, coef);
+    RBU_CHECK_LAUNCH();
+  }
   int lg = 0;
   while ((1 << (lg + 1)) <= (C >> 3)) ++lg;
   const long items = (long)HW << lg;
@@ -1218,20 +1289,33 @@ extern "C" int rbu_ag_bwd(const void* da, int64_t da_ld, const void* skip, int64
     ag_bwd1_kernel<<<dim3(chunks, N), NT, 0, st>>>((const bf16*)da, da_ld, (const bf16*)skip, s_ld, (bf16*)dskip, ds_ld, HW,
                                                    C, rbu_cdiv(HW, chunks), psi, q0, stats, dq, part);
     RBU_CHECK_LAUNCH();
-    colsum_kernel<<<1, 256, 0, st>>>(part, N * chunks, 2, 2, sums_psi, 1.f);
+    const float* pp = part;
+    int nb2 = N * chunks;
+    long stride = 2;
+    RBU_CHECK_ARG(workspace_bytes >= ((size_t)N * chunks * 2 + FOLD_FLOATS(2)) * sizeof(float), "rbu_ag_bwd: workspace too small");
+    int rc = colsum_fold(pp, nb2, stride, 2, part + (size_t)N * chunks * 2, st);
+    if (rc) return rc;
+    colsum_kernel<<<1, 256, 0, st>>>(pp, nb2, 2, stride, sums_psi, 1.f);
     RBU_CHECK_LAUNCH();
   }
   {
     const int chunks = bwd_chunks(N, HW, F);
     const int chunk_px = rbu_cdiv(HW, chunks);
     const size_t part_floats = (size_t)N * chunks * 4 * F;
-    RBU_CHECK_ARG(workspace_bytes >= (part_floats + 4 * F) * sizeof(float), "rbu_ag_bwd: workspace too small");
+    RBU_CHECK_ARG(workspace_bytes >= (part_floats + 4 * F + FOLD_FLOATS(4 * F)) * sizeof(float), "rbu_ag_bwd: workspace too small");
     float* coef = part + part_floats;
     ag_bwd2_kernel<<<dim3(chunks, N), NT, 0, st>>>((const bf16*)yg, yg_ld, (const bf16*)yx, yx_ld, HW, F, chunk_px, Ag, Bg, Ax,
                                                    Bx, wpsi, dq, q0, stats, sums_psi, invM, part);
     RBU_CHECK_LAUNCH();
-    ag_bwd_final_kernel<<<rbu_cdiv(F, 32), 256, 0, st>>>(part, N * chunks, F, Ag, Ax, mg, rg, mx, rx, invM, sums_f, coef);
-    RBU_CHECK_LAUNCH();
+    {
+      const float* pp = part;
+      int nb2 = N * chunks;
+      long stride = 4 * F;
+      int rc = colsum_fold(pp, nb2, stride, 4 * F, coef + 4 * F, st);
+      if (rc) return rc;
+      ag_bwd_final_kernel<<<rbu_cdiv(F, 32), 256, 0, st>>>(pp, nb2, F, Ag, Ax, mg, rg, mx, rx, invM, sums_f, coef);
+      RBU_CHECK_LAUNCH();
+    }
     int lg = 0;
     while ((1 << (lg + 1)) <= (F >> 3)) ++lg;
     const long items = (long)HW << lg;
@@ -1265,7 +1349,13 @@ extern "C" int rbu_chan_sum(const void* x, int64_t ld, int64_t P, int C, float* 
   RBU_CHECK_ARG(workspace && workspace_bytes >= (size_t)blocks * C * sizeof(float), "rbu_chan_sum: workspace too small");
   chan_sum_kernel<<<blocks, NT, 0, st>>>((const bf16*)x, ld, P, C, ppb, (float*)workspace);
   RBU_CHECK_LAUNCH();
-  colsum_kernel<<<rbu_cdiv(C, 32), 256, 0, st>>>((const float*)workspace, blocks, C, C, out, 1.f);
+  const float* pp = (const float*)workspace;
+  int nb2 = blocks;
+  long stride = C;
+  RBU_CHECK_ARG(workspace_bytes >= ((size_t)blocks * C + FOLD_FLOATS(C)) * sizeof(float), "rbu_chan_sum: workspace too small");
+  int rc = colsum_fold(pp, nb2, stride, C, (float*)workspace + (size_t)blocks * C, st);
+  if (rc) return rc;
+  colsum_kernel<<<rbu_cdiv(C, 32), 256, 0, st>>>(pp, nb2, C, stride, out, 1.f);
   RBU_CHECK_LAUNCH();
   return RBU_OK;
 }

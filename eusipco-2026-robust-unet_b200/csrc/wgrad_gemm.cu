@@ -238,8 +238,16 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int kspli
     const int n = (int)(i % Ntot);
     const int t = (int)((i / Ntot) % taps);
     const int m = (int)(i / ((long)Ntot * taps));
-    float s = 0.f;
-    for (int k = 0; k < ksplit; ++k) s += partial[(long)k * total + i];
+    // eight independent accumulators (fixed assignment k mod 8, combined in a fixed order): the loads of a long
+    // split-K chain overlap instead of serialising on one add, and the result stays deterministic
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int k = 0;
+    for (; k + 8 <= ksplit; k += 8) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += __ldg(partial + (long)(k + j) * total + i);
+    }
+    for (int j = 0; k < ksplit; ++k, ++j) acc[j] += __ldg(partial + (long)k * total + i);
+    const float s = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
     float* o = out + ((long)m * Ntot + n) * taps + t;
     *o = accumulate ? *o + s : s;
   }
