@@ -47,6 +47,7 @@ struct HParams {
   int nseg;
   int taps[2], C[2];
   int a_stages, b_stages, tmem_cols, total_tiles;
+  int tps;   // taps per B stage for a 3x3 segment (3 = one kernel row per stage when block_n <= 128, else 1)
   bf16* y;
   long long y_ld;
   const float* bias;
@@ -87,10 +88,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                  const __grid_constant__ HParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int b_bytes = p.block_n * 128;
+  const int b_bytes = p.block_n * 128;          // one tap's weight tile
+  const int bs_bytes = b_bytes * p.tps;         // one B stage
   uint8_t* smA = smem;
   uint8_t* smB = smem + p.a_stages * A_HALO_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smB + p.b_stages * b_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smB + p.b_stages * bs_bytes);
   uint64_t* fullA = bars;                      // [4]
   uint64_t* emptyA = bars + 4;                 // [4]
   uint64_t* fullB = bars + 8;                  // [MAX_B_STAGES]
@@ -163,16 +165,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         int nb, w0, h0, n;
         tile_coords(p, ib.tile, nb, w0, h0, n);
         const int taps = p.taps[ib.seg];
+        const int tps = taps == 9 ? p.tps : 1;
         const int look = taps - 1 < LOOKAHEAD_TAP ? taps - 1 : LOOKAHEAD_TAP;
         const CUtensorMap* mB = ib.seg ? &tmB1 : &tmB0;
-        for (int tap = 0; tap < taps; ++tap) {
+        for (int tap0 = 0; tap0 < taps; tap0 += tps) {
           const int s = sb;
           const uint32_t ph = phb;
           if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
           ptx::mbar_wait(&emptyB[s], ph ^ 1);
-          ptx::mbar_arrive_expect_tx(&fullB[s], (uint32_t)b_bytes);
-          ptx::tma_load_2d(smB + s * b_bytes, mB, &fullB[s], tap * p.C[ib.seg] + ib.kc * BLOCK_K, nb * p.block_n);
-          if (tap == look && ia.valid) issue_a();
+          ptx::mbar_arrive_expect_tx(&fullB[s], (uint32_t)(b_bytes * tps));
+          for (int j = 0; j < tps; ++j)
+            ptx::tma_load_2d(smB + s * bs_bytes + j * b_bytes, mB, &fullB[s], (tap0 + j) * p.C[ib.seg] + ib.kc * BLOCK_K,
+                             nb * p.block_n);
+          if (tap0 <= look && look < tap0 + tps && ia.valid) issue_a();
         }
         ib.next(p);
       }
@@ -210,27 +215,57 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const int rem = p.C[it.seg] - it.kc * BLOCK_K;
         const int ksteps = rem >= BLOCK_K ? 4 : (rem + 15) / 16;   // channels past C are TMA zero fill
         // halo origin is pixel (h0-1, w0-1): tap (dy,dx) starts dy halo rows (2048 B) down and dx pixels (128 B) right
-        uint32_t a_row = a_lo0, a_lo = a_lo0;
-        int dx = 0;
-        for (int tap = 0; tap < taps; ++tap) {
-          ptx::mbar_wait_s(fullB_s + sb * 8, phb);
-          ptx::tc_fence_after();
-          if (ptx::elect_one()) {
-            const uint32_t b_lo = ptx::desc_lo(smB_s, 16) + sb * b_step;
+        if (halo && p.tps == 3 && ksteps == 4) {
+          // one kernel row (3 taps x 4 K-steps = 12 MMAs) per B stage, fully unrolled with immediate offsets
+          uint32_t a_row = a_lo0;
+          for (int dy = 0; dy < 3; ++dy) {
+            ptx::mbar_wait_s(fullB_s + sb * 8, phb);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+              const uint32_t b_lo = ptx::desc_lo(smB_s, 16) + sb * (3 * b_step);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              if (k < ksteps) {
-                ptx::umma_bf16(d_tmem, ptx::pack_desc(a_lo + 2 * k, a_hi), ptx::pack_desc(b_lo + 2 * k, b_hi), idesc,
-                               accumulate);
-                accumulate = 1;
+              for (int dx = 0; dx < 3; ++dx) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  ptx::umma_bf16(d_tmem, ptx::pack_desc(a_row + dx * 8 + 2 * k, a_hi),
+                                 ptx::pack_desc(b_lo + dx * b_step + 2 * k, b_hi), idesc, (dx | k) ? 1u : accumulate);
               }
+              ptx::umma_commit_s(emptyB_s + sb * 8);
             }
-            ptx::umma_commit_s(emptyB_s + sb * 8);
+            accumulate = 1;
+            __syncwarp();
+            if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
+            a_row += (HALO_W * 128) >> 4;
           }
-          accumulate = 1;
-          __syncwarp();
-          if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
-          if (++dx == 3) { dx = 0; a_row += (HALO_W * 128) >> 4; a_lo = a_row; } else { a_lo += 128 >> 4; }
+        } else {
+          const int tps = halo ? p.tps : 1;
+          uint32_t a_row = a_lo0, a_lo = a_lo0;
+          int dx = 0, j = 0;
+          for (int tap = 0; tap < taps; ++tap) {
+            if (j == 0) {
+              ptx::mbar_wait_s(fullB_s + sb * 8, phb);
+              ptx::tc_fence_after();
+            }
+            if (ptx::elect_one()) {
+              const uint32_t b_lo = ptx::desc_lo(smB_s, 16) + sb * (p.tps * b_step) + j * b_step;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (k < ksteps) {
+                  ptx::umma_bf16(d_tmem, ptx::pack_desc(a_lo + 2 * k, a_hi), ptx::pack_desc(b_lo + 2 * k, b_hi), idesc,
+                                 accumulate);
+                  accumulate = 1;
+                }
+              }
+              if (j == tps - 1) ptx::umma_commit_s(emptyB_s + sb * 8);
+            }
+            accumulate = 1;
+            __syncwarp();
+            if (++j == tps) {
+              j = 0;
+              if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
+            }
+            if (++dx == 3) { dx = 0; a_row += (HALO_W * 128) >> 4; a_lo = a_row; } else { a_lo += 128 >> 4; }
+          }
         }
         if (ptx::elect_one()) ptx::umma_commit_s(emptyA_s + sa * 8);
         __syncwarp();
@@ -306,8 +341,9 @@ int rbu_conv_halo_launch(const rbu_conv_gemm_args* a, cudaStream_t stream) {
     p.C[s] = a->seg[s].C;
   }
   const int b_bytes = p.block_n * 128;
-  p.a_stages = p.block_n >= 256 ? 2 : 3;
-  p.b_stages = (SMEM_LIMIT - 2048 - p.a_stages * A_HALO_BYTES) / b_bytes;
+  p.tps = p.block_n <= 128 ? 3 : 1;
+  p.a_stages = p.block_n >= 128 ? 2 : 3;
+  p.b_stages = (SMEM_LIMIT - 2048 - p.a_stages * A_HALO_BYTES) / (b_bytes * p.tps);
   if (p.b_stages > MAX_B_STAGES) p.b_stages = MAX_B_STAGES;
   p.tmem_cols = 32;
   while (p.tmem_cols < 2 * p.block_n) p.tmem_cols <<= 1;
@@ -340,7 +376,7 @@ int rbu_conv_halo_launch(const rbu_conv_gemm_args* a, cudaStream_t stream) {
     tmA[1] = tmA[0];
     tmB[1] = tmB[0];
   }
-  const int smem_bytes = p.a_stages * A_HALO_BYTES + p.b_stages * b_bytes + 1024 + 512;
+  const int smem_bytes = p.a_stages * A_HALO_BYTES + p.b_stages * b_bytes * p.tps + 1024 + 512;
   static bool attr_set = false;
   if (!attr_set) {
     RBU_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));

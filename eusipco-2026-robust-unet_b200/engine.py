@@ -379,10 +379,15 @@ class Engine:
         Kp = ((9 * nc + 7) // 8) * 8
         patches = View(torch.empty((N, H, W, Kp), dtype=torch.bfloat16, device=dev))
         call("rbu_stem_im2col", _p(x), N, nc, H, W, Kp, _vp(patches), stream_ptr())
-        b = m.inc.conv2.out_channels
         enc = []
-        cur, s_inc = self.rb_forward("inc", m.inc, None, N, H, W, training, stem_patches=patches)
-        S["inc"] = s_inc
+
+        def keep(key, st):          # inference: intermediates are released as soon as their block has run
+            if save:
+                S[key] = st
+
+        cur, st = self.rb_forward("inc", m.inc, None, N, H, W, training, stem_patches=patches)
+        keep("inc", st)
+        del st, patches
         enc.append(cur)
         h, w = H, W
         pools = []
@@ -390,17 +395,25 @@ class Engine:
             h, w = h // 2, w // 2
             pooled = self.new(N, h, w, cur.C, dev)
             call("rbu_maxpool2x2", _vp(cur), cur.ld, _vp(pooled), pooled.ld, N, h, w, cur.C, stream_ptr())
-            pools.append(pooled)
-            cur, S[name] = self.rb_forward(name + ".1", getattr(m, name)[1], pooled, N, h, w, training)
+            if save:
+                pools.append(pooled)
+            cur, st = self.rb_forward(name + ".1", getattr(m, name)[1], pooled, N, h, w, training)
+            keep(name, st)
+            del st, pooled
             enc.append(cur)
         h, w = h // 2, w // 2
         pooled = self.new(N, h, w, cur.C, dev)
         call("rbu_maxpool2x2", _vp(cur), cur.ld, _vp(pooled), pooled.ld, N, h, w, cur.C, stream_ptr())
-        pools.append(pooled)
-        x5a, S["dil"] = self.dil_forward(m.bottleneck[1], pooled, N, h, w, training)
-        cur, S["bott"] = self.rb_forward("bottleneck.2", m.bottleneck[2], x5a, N, h, w, training)
+        if save:
+            pools.append(pooled)
+        x5a, st = self.dil_forward(m.bottleneck[1], pooled, N, h, w, training)
+        keep("dil", st)
+        cur, st = self.rb_forward("bottleneck.2", m.bottleneck[2], x5a, N, h, w, training)
+        keep("bott", st)
+        del st, pooled, x5a
         S["pools"] = pools
-        S["enc"] = enc
+        if save:
+            S["enc"] = enc
         for k in (4, 3, 2, 1):
             up = getattr(m, f"up{k}")
             C = up.out_channels
@@ -408,10 +421,15 @@ class Engine:
             cat = self.new(N, 2 * h, 2 * w, 2 * C, dev)
             conv_gemm(N, h, w, [(cur, self.pack(up.weight, 2), 1, 0, False)], 4 * C, cat.slice(C, C), scatter=True,
                       Cout=C, bias=up.bias)
-            S[f"up{k}"] = {"x": cur, "N": N, "H": h, "W": w, "C": C}
+            keep(f"up{k}", {"x": cur, "N": N, "H": h, "W": w, "C": C})
             h, w = 2 * h, 2 * w
-            S[f"att{k}"] = self.ag_forward(getattr(m, f"att{k}"), cat.slice(C, C), skip, cat.slice(0, C), N, h, w, training)
-            cur, S[f"dec{k}"] = self.rb_forward(f"dec{k}", getattr(m, f"dec{k}"), cat, N, h, w, training)
+            st = self.ag_forward(getattr(m, f"att{k}"), cat.slice(C, C), skip, cat.slice(0, C), N, h, w, training)
+            keep(f"att{k}", st)
+            if not save:
+                enc[k - 1] = None            # the skip tensor has been consumed
+            cur, st = self.rb_forward(f"dec{k}", getattr(m, f"dec{k}"), cat, N, h, w, training)
+            keep(f"dec{k}", st)
+            del st, cat, skip
         P = N * H * W
         probs = torch.empty((N, 1, H, W), dtype=torch.float32, device=dev)
         hc = m.outc[0]
