@@ -15,3 +15,8 @@ int rbu_encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uin
 // conv_halo.cu: halo-reuse variant of the implicit-GEMM convolution (3x3 dilation 1 / 1x1 segments).
 int rbu_conv_halo_supported(const rbu_conv_gemm_args* a);
 int rbu_conv_halo_launch(const rbu_conv_gemm_args* a, cudaStream_t stream);
+
+// wgrad_halo.cu: all-taps-from-one-halo variant of the weight-gradient GEMM (3x3, dilation 1).
+int rbu_wgrad_halo_supported(const rbu_wgrad_args* a);
+size_t rbu_wgrad_halo_workspace_bytes(const rbu_wgrad_args* a);
+int rbu_wgrad_halo_launch(const rbu_wgrad_args* a, void* workspace, cudaStream_t stream);

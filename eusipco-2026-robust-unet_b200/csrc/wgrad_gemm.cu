@@ -16,6 +16,7 @@
 #include "rbu_common.cuh"
 #include "rbu_ptx.cuh"
 #include "tma_host.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -253,6 +254,12 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int kspli
   }
 }
 
+bool use_halo(const rbu_wgrad_args* a) {
+  static int no_halo = -1;   // RBU_NO_HALO=1 forces the generic per-tap kernel (A/B comparisons)
+  if (no_halo < 0) no_halo = getenv("RBU_NO_HALO") ? 1 : 0;
+  return !no_halo && rbu_wgrad_halo_supported(a);
+}
+
 int pow2ceil_w(int v) {
   int r = 1;
   while (r < v) r <<= 1;
@@ -322,8 +329,16 @@ int check_args(const rbu_wgrad_args* a) {
 
 }  // namespace
 
+void rbu_wgrad_reduce_launch(const float* partial, int ksplit, int Mtot, int taps, int Ntot, float* out, int accumulate,
+                             cudaStream_t stream) {
+  const long total = (long)Mtot * taps * Ntot;
+  const int rblocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+  wgrad_reduce_kernel<<<rblocks, 256, 0, stream>>>(partial, ksplit, Mtot, taps, Ntot, out, accumulate);
+}
+
 extern "C" size_t rbu_wgrad_workspace_bytes(const rbu_wgrad_args* a) {
   if (check_args(a) != RBU_OK) return 0;
+  if (use_halo(a)) return rbu_wgrad_halo_workspace_bytes(a);
   Plan pl;
   make_plan(a, &pl);
   return pl.ws_bytes;
@@ -335,6 +350,11 @@ extern "C" int rbu_wgrad_gemm(const rbu_wgrad_args* a, void* workspace, size_t w
   if (rc) return rc;
   RBU_CHECK_ARG(a->a && a->b && a->out && ((uintptr_t)a->a & 15) == 0 && ((uintptr_t)a->b & 15) == 0,
                 "rbu_wgrad_gemm: null or misaligned pointer");
+  if (use_halo(a)) {
+    RBU_CHECK_ARG(workspace && workspace_bytes >= rbu_wgrad_halo_workspace_bytes(a) && ((uintptr_t)workspace & 15) == 0,
+                  "rbu_wgrad_gemm: workspace too small");
+    return rbu_wgrad_halo_launch(a, workspace, stream);
+  }
   Plan pl;
   make_plan(a, &pl);
   WParams& p = pl.p;

@@ -1,0 +1,273 @@
+// K11, halo variant: weight gradient of a 3x3 (dilation 1) convolution on tcgen05 tensor cores with ALL NINE TAPS
+// accumulated from ONE activation tile.
+//
+//   dW[cout][cin][tap] = sum over pixels p of  dy[p, cout] * x[p (+) tap, cin]
+//
+// The generic kernel (wgrad_gemm.cu) streams one shifted x tile per tap and, for 64-channel layers, runs M = 64 MMAs
+// (half rate): 280-460 TFLOP/s on the 64-channel level, 750-850 elsewhere (L2->SM traffic bound, 98 FLOP/B).
+// Here a work item is (64 input channels) x (64 output channels) x (a range of 8x16-pixel tiles):
+//   * the x operand is the tile's 10 x 24-slot halo (18 slots used; 3072-byte row pitch), loaded by ONE TMA box and
+//     reused by all 9 taps through the start address of the MN-major UMMA descriptor (same trick as conv_halo.cu);
+//   * the x side is the MMA's M dimension and two taps are stacked into one M = 128 instruction: the descriptor's
+//     leading-byte-offset (distance between the two 64-channel column blocks) is simply the distance between the
+//     two taps' start addresses in the halo buffer -- 128 B for (dx, dx+1), 3072 B for (dy, dy+1).  Pairs
+//     (0,1) (3,4) (6,7) (2,5) and the single tap 8 (M = 64) give 5 accumulators x 64 columns = 320 TMEM columns;
+//   * the dy operand (N = 64) is one plain 8x16-pixel box.
+// Per tile: 46 KB from L2 for 9.4 MFLOP (205 FLOP/B), 40 MMAs per barrier round trip.
+// Split-K over tile ranges with fp32 partials and the ordered reduction of wgrad_gemm.cu (deterministic).
+// Replaces aten::convolution_backward(weight) of Main_Final.py:157,159,205-206.
+#include "rbu_common.cuh"
+#include "rbu_ptx.cuh"
+#include "tma_host.cuh"
+
+namespace {
+
+constexpr int TILE_W = 16, TILE_H = 8;
+constexpr int HALO_W = 24, HALO_H = 10;
+constexpr int X_BYTES = HALO_W * HALO_H * 128;   // 30720
+constexpr int DY_BYTES = TILE_W * TILE_H * 128;  // 16384
+constexpr int STAGE_BYTES = X_BYTES + DY_BYTES;  // 47104 (multiple of 1024)
+constexpr int STAGES = 4;
+constexpr int NUM_THREADS = 192;
+constexpr int SMEM_LIMIT = 232448;
+constexpr int NACC = 5;
+
+struct HWParams {
+  int N, H, W;
+  int tiles_w, tiles_h, tiles_total;
+  int Cout, Cin;
+  int cin_blocks, cout_blocks, ksplit, items;
+  float* partial;   // [ksplit][Cout][9][Cin]
+};
+
+__device__ __forceinline__ void decode(const HWParams& p, int item, int& cb, int& ob, int& ks) {
+  cb = item % p.cin_blocks; item /= p.cin_blocks;
+  ob = item % p.cout_blocks;
+  ks = item / p.cout_blocks;
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDy,
+                  const __grid_constant__ HWParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full = bars;             // [STAGES]
+  uint64_t* empty = bars + STAGES;   // [STAGES]
+  uint64_t* tfull = bars + 2 * STAGES;
+  uint64_t* tempty = tfull + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmX);
+    ptx::prefetch_tmap(&tmDy);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+    ptx::mbar_init(tfull, 1);
+    ptx::mbar_init(tempty, 4);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        int cb, ob, ks;
+        decode(p, item, cb, ob, ks);
+        const int tile0 = (int)((long)ks * p.tiles_total / p.ksplit);
+        const int tile1 = (int)((long)(ks + 1) * p.tiles_total / p.ksplit);
+        int tw = tile0 % p.tiles_w, t2 = tile0 / p.tiles_w;
+        int th = t2 % p.tiles_h, n = t2 / p.tiles_h;
+        for (int tile = tile0; tile < tile1; ++tile) {
+          ptx::mbar_wait(&empty[s], ph ^ 1);
+          ptx::mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
+          uint8_t* dst = smem + s * STAGE_BYTES;
+          ptx::tma_load_4d(dst, &tmX, &full[s], cb * 64, tw * TILE_W - 1, th * TILE_H - 1, n);
+          ptx::tma_load_4d(dst + X_BYTES, &tmDy, &full[s], ob * 64, tw * TILE_W, th * TILE_H, n);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+          if (++tw == p.tiles_w) { tw = 0; if (++th == p.tiles_h) { th = 0; ++n; } }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer ==============================
+    const uint32_t idesc128 = ptx::make_idesc_bf16(128, 64, 1, 1);
+    const uint32_t idesc64 = ptx::make_idesc_bf16(64, 64, 1, 1);
+    const uint32_t full_s = ptx::smem_u32(full), empty_s = ptx::smem_u32(empty);
+    const uint32_t hi = ptx::desc_hi(1024);
+    const uint32_t base_lo = (ptx::smem_u32(smem) & 0x3FFFFu) >> 4;
+    constexpr uint32_t LBO_DX = (128u >> 4) << 16;               // pair (dx, dx+1): 128 B apart
+    constexpr uint32_t LBO_DY = ((HALO_W * 128u) >> 4) << 16;    // pair (dy, dy+1): one halo row apart
+    constexpr uint32_t ROW = (HALO_W * 128) >> 4;                // halo row pitch in 16-byte units
+    int s = 0, it = 0;
+    uint32_t ph = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+      int cb, ob, ks;
+      decode(p, item, cb, ob, ks);
+      const int tile0 = (int)((long)ks * p.tiles_total / p.ksplit);
+      const int tile1 = (int)((long)(ks + 1) * p.tiles_total / p.ksplit);
+      ptx::mbar_wait(tempty, (it & 1) ^ 1);
+      ptx::tc_fence_after();
+      uint32_t accumulate = 0;
+      for (int tile = tile0; tile < tile1; ++tile) {
+        ptx::mbar_wait_s(full_s + s * 8, ph);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint32_t x_lo = base_lo + s * (STAGE_BYTES >> 4);
+          const uint32_t y_lo = x_lo + (X_BYTES >> 4);
+#pragma unroll
+          for (int kk = 0; kk < TILE_H; ++kk) {      // K step = one tile row of 16 pixels
+            const uint32_t acc = kk ? 1u : accumulate;
+            const uint32_t b = y_lo + kk * ((TILE_W * 128) >> 4);
+            const uint64_t db = ptx::pack_desc(b | ((1024u >> 4) << 16), hi);
+            const uint32_t xr = x_lo + kk * ROW;     // halo pixel (kk, 0): tap (dy,dx) starts at (kk+dy, dx)
+            // accumulators: 0 = taps (0,1), 1 = taps (3,4), 2 = taps (6,7), 3 = taps (2,5), 4 = tap 8
+            ptx::umma_bf16(tmem_base + 0 * 64, ptx::pack_desc((xr + 0 * ROW + 0 * 8) | LBO_DX, hi), db, idesc128, acc);
+            ptx::umma_bf16(tmem_base + 1 * 64, ptx::pack_desc((xr + 1 * ROW + 0 * 8) | LBO_DX, hi), db, idesc128, acc);
+            ptx::umma_bf16(tmem_base + 2 * 64, ptx::pack_desc((xr + 2 * ROW + 0 * 8) | LBO_DX, hi), db, idesc128, acc);
+            ptx::umma_bf16(tmem_base + 3 * 64, ptx::pack_desc((xr + 0 * ROW + 2 * 8) | LBO_DY, hi), db, idesc128, acc);
+            ptx::umma_bf16(tmem_base + 4 * 64, ptx::pack_desc((xr + 2 * ROW + 2 * 8) | LBO_DX, hi), db, idesc64, acc);
+          }
+          ptx::umma_commit_s(empty_s + s * 8);
+        }
+        accumulate = 1;
+        __syncwarp();
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+      if (ptx::elect_one()) ptx::umma_commit(tfull);
+      __syncwarp();
+    }
+  } else {
+    // ============================== epilogue (warps 2..5) ==============================
+    const int lg = warp & 3;
+    int it = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+      int cb, ob, ks;
+      decode(p, item, cb, ob, ks);
+      ptx::mbar_wait(tfull, it & 1);
+      ptx::tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
+      for (int a = 0; a < NACC; ++a) {
+        // which (tap, cin) does this thread's TMEM lane hold?
+        int tap, cl;
+        bool ok = true;
+        if (a < 4) {                       // M = 128: lane group 0,1 -> first tap, 2,3 -> second tap
+          const int first = a < 3 ? 3 * a : 2, second = a < 3 ? 3 * a + 1 : 5;
+          tap = lg < 2 ? first : second;
+          cl = (lg & 1) * 32 + lane;
+        } else {                           // M = 64: rows 16*lg + lane live in lanes 0..15 of lane group lg
+          tap = 8;
+          cl = lg * 16 + lane;
+          ok = lane < 16;
+        }
+        const int cin = cb * 64 + cl;
+        ok = ok && cin < p.Cin;
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(t_addr + (uint32_t)(a * 64 + c0), r);
+          ptx::tmem_ld_wait();
+          if (ok) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const int cout = ob * 64 + c0 + e;
+              if (cout < p.Cout) p.partial[(((long)ks * p.Cout + cout) * 9 + tap) * p.Cin + cin] = __uint_as_float(r[e]);
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(tempty);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+void plan(const rbu_wgrad_args* a, HWParams* p) {
+  memset(p, 0, sizeof(*p));
+  p->N = a->N; p->H = a->H; p->W = a->W;
+  p->tiles_w = rbu_cdiv(a->W, TILE_W);
+  p->tiles_h = rbu_cdiv(a->H, TILE_H);
+  p->tiles_total = p->tiles_w * p->tiles_h * a->N;
+  p->Cout = a->Ca;
+  p->Cin = a->Cb;
+  p->cin_blocks = rbu_cdiv(a->Cb, 64);
+  p->cout_blocks = rbu_cdiv(a->Ca, 64);
+  const int base_items = p->cin_blocks * p->cout_blocks;
+  // split-K factor: the smallest one that fills the machine with at most ~15 % of the last wave idle (every item
+  // pays an un-overlapped epilogue and a partial-sum round trip, so fewer, longer items win), else the best found
+  const int sms = rbu_num_sms();
+  int ks = 1;
+  double best = -1.0;
+  for (int k = 1; k <= p->tiles_total && (long)k * base_items <= 8L * sms; ++k) {
+    const long items = (long)k * base_items;
+    const double util = (double)items / (double)(((items + sms - 1) / sms) * sms);
+    if (util > best + 1e-9) { best = util; ks = k; }
+    if (items >= sms && util >= 0.85) break;
+  }
+  p->ksplit = ks;
+  p->items = base_items * ks;
+}
+
+}  // namespace
+
+int rbu_wgrad_halo_supported(const rbu_wgrad_args* a) {
+  return a->taps == 9 && a->dil == 1 && !a->gather && a->H >= TILE_H && a->W >= TILE_W;
+}
+
+size_t rbu_wgrad_halo_workspace_bytes(const rbu_wgrad_args* a) {
+  HWParams p;
+  plan(a, &p);
+  return (size_t)p.ksplit * a->Ca * 9 * a->Cb * sizeof(float);
+}
+
+void rbu_wgrad_reduce_launch(const float* partial, int ksplit, int Mtot, int taps, int Ntot, float* out, int accumulate,
+                             cudaStream_t stream);
+
+// Argument validation is done by the caller (rbu_wgrad_gemm).
+int rbu_wgrad_halo_launch(const rbu_wgrad_args* a, void* workspace, cudaStream_t stream) {
+  HWParams p;
+  plan(a, &p);
+  p.partial = reinterpret_cast<float*>(workspace);
+  CUtensorMap tmX, tmDy;
+  {
+    const uint64_t dims[4] = {(uint64_t)a->Cb, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->N};
+    const uint64_t str[3] = {(uint64_t)a->b_ld * 2, (uint64_t)a->b_ld * 2 * a->W, (uint64_t)a->b_ld * 2 * a->W * a->H};
+    const uint32_t box[4] = {64, HALO_W, HALO_H, 1};
+    int rc = rbu_encode_tmap_bf16(&tmX, a->b, 4, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)a->Ca, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->N};
+    const uint64_t str[3] = {(uint64_t)a->a_ld * 2, (uint64_t)a->a_ld * 2 * a->W, (uint64_t)a->a_ld * 2 * a->W * a->H};
+    const uint32_t box[4] = {64, TILE_W, TILE_H, 1};
+    int rc = rbu_encode_tmap_bf16(&tmDy, a->a, 4, dims, str, box);
+    if (rc) return rc;
+  }
+  const int smem_bytes = STAGES * STAGE_BYTES + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RBU_CHECK_CUDA(cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    attr_set = true;
+  }
+  const int grid = p.items < rbu_num_sms() ? p.items : rbu_num_sms();
+  wgrad_halo_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(tmX, tmDy, p);
+  RBU_CHECK_LAUNCH();
+  rbu_wgrad_reduce_launch(p.partial, p.ksplit, a->Ca, 9, a->Cb, a->out, a->accumulate, stream);
+  RBU_CHECK_LAUNCH();
+  return RBU_OK;
+}
