@@ -39,8 +39,11 @@ def _ctype(decl: str):
         return None
     if "*" in decl:
         return c_char_p if decl.replace(" ", "") == "constchar*" else c_void_p
-    if decl.replace("const", "").split() == ["unsigned", "long", "long"]:
+    words = decl.replace("const", "").split()
+    if words[:3] == ["unsigned", "long", "long"]:
         return c_ulonglong
+    if words[:2] == ["long", "long"]:
+        return c_int64
     base = decl.replace("const", "").split()[0]
     return _SCALARS[base]
 
@@ -49,6 +52,7 @@ def parse_header(path: str = HEADER_PATH):
     """{name: (restype, [argtypes])} for every `rbu_*` prototype in the header."""
     text = open(path).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"typedef\s+struct\s*\{.*?\}\s*\w+\s*;", "", text, flags=re.S)     # struct bodies are not prototypes
     sigs = {}
     for m in re.finditer(r"([A-Za-z_][\w\s\*]*?)\b(rbu_\w+)\s*\(([^;{}]*?)\)\s*;", text):
         ret, name, args = m.group(1).strip(), m.group(2), m.group(3)

@@ -25,6 +25,53 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, bf16* __restri
   }
 }
 
+__device__ __forceinline__ long pack_src_index(int mode, int Nn, int T, int K, int Cout, int n, int t, int k) {
+  if (mode == 0) return ((long)n * K + k) * T + t;
+  if (mode == 1) return ((long)k * Nn + n) * T + (T - 1 - t);
+  if (mode == 2) { const int q = n / Cout, co = n % Cout; return ((long)k * Cout + co) * 4 + q; }
+  return ((long)n * K + k) * 4 + t;
+}
+
+// All weight operands of the network in ONE launch: a block looks its job up in the table by binary search over the
+// jobs' first-block prefix and converts 1024 consecutive destination elements.
+//   mode 0-3: as pack_weight_kernel;  mode 4: stem operand [2C][Kp] -- rows 0..C-1 the 3x3 conv1 weights as
+//   (tap-major, channel) columns, rows C..2C-1 the 1x1 shortcut weights in the centre-tap columns, zero elsewhere
+//   (Nn = 2C, K = Kp, T = number of input channels, src = conv1 weight, src2 = shortcut weight).
+__global__ void __launch_bounds__(256)
+pack_multi_kernel(const rbu_pack_job* __restrict__ jobs, int njobs) {
+  int lo = 0, hi = njobs - 1;
+  const long long b = blockIdx.x;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].first_block <= b) lo = mid; else hi = mid - 1;
+  }
+  const rbu_pack_job j = jobs[lo];
+  bf16* dst = reinterpret_cast<bf16*>(j.dst);
+  const long long base = (b - j.first_block) * 1024;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const long long i = base + u * 256 + threadIdx.x;
+    if (i >= j.total) return;
+    float v;
+    if (j.mode == 4) {
+      const int C = j.Nn / 2, nc = j.T;
+      const int k = (int)(i % j.K), n = (int)(i / j.K);
+      v = 0.f;
+      if (n < C) {
+        if (k < 9 * nc) { const int tap = k / nc, c = k - tap * nc; v = j.src[((long)n * nc + c) * 9 + tap]; }
+      } else if (k >= 4 * nc && k < 5 * nc) {
+        v = j.src2[(long)(n - C) * nc + (k - 4 * nc)];
+      }
+    } else {
+      const int k = (int)(i % j.K);
+      const int t = (int)((i / j.K) % j.T);
+      const int n = (int)(i / ((long long)j.K * j.T));
+      v = j.src[pack_src_index(j.mode, j.Nn, j.T, j.K, j.Cout, n, t, k)];
+    }
+    dst[i] = __float2bfloat16_rn(v);
+  }
+}
+
 __global__ void conv_direct_ref_kernel(const bf16* __restrict__ x, long x_ld, int N, int H, int W, int Cin,
                                        const float* __restrict__ w, const float* __restrict__ bias, int Cout,
                                        int ksz, int dil, float* __restrict__ out) {
@@ -61,6 +108,13 @@ extern "C" int rbu_pack_weight(const float* src, void* dst, int Nn, int T, int K
   const long total = (long)Nn * T * K;
   const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
   pack_weight_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, Nn, T, K, mode, Cout);
+  RBU_CHECK_LAUNCH();
+  return RBU_OK;
+}
+
+extern "C" int rbu_pack_weights_multi(const rbu_pack_job* jobs_device, int njobs, long long total_blocks, void* stream) {
+  RBU_CHECK_ARG(jobs_device && njobs > 0 && total_blocks > 0 && total_blocks < (1LL << 31), "rbu_pack_weights_multi: bad arguments");
+  pack_multi_kernel<<<(unsigned)total_blocks, 256, 0, (cudaStream_t)stream>>>(jobs_device, njobs);
   RBU_CHECK_LAUNCH();
   return RBU_OK;
 }

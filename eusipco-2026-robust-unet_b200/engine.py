@@ -46,6 +46,7 @@ class Engine:
     def __init__(self, model):
         self.model = model
         self._packs = {}
+        self._pack_table = None
         self._ws = None
         self.drop_mask_fn = None     # optional callable(name, N, C) -> float32 [N,C] device tensor (tests)
         self.kernel_launches = 0
@@ -57,25 +58,94 @@ class Engine:
         return self._ws.get(int(nbytes))
 
     def pack(self, param: torch.Tensor, mode: int):
+        """bf16 GEMM operand of a parameter.  Inside the whole-model path every operand has just been rebuilt by
+        refresh_packs(); standalone block calls (tests) pack on first use."""
         key = (id(param), mode)
         ent = self._packs.get(key)
-        if ent is None or ent[0] != param._version or ent[1].device != param.device:
-            ent = (param._version, pack_weight(param.detach().contiguous(), mode))
+        if ent is None or ent.device != param.device:
+            ent = pack_weight(param.detach().contiguous(), mode)
             self._packs[key] = ent
-        return ent[1]
+        return ent
 
     def pack_stem(self, w1, wsc, Kp):
         key = (id(w1), "stem")
         ent = self._packs.get(key)
-        ver = (w1._version, wsc._version)
-        if ent is None or ent[0] != ver or ent[1].device != w1.device:
+        if ent is None or ent.device != w1.device:
             C, nc = w1.shape[0], w1.shape[1]
             m = torch.zeros((2 * C, Kp), dtype=torch.float32, device=w1.device)
             m[:C, :9 * nc] = w1.detach().permute(0, 2, 3, 1).reshape(C, 9 * nc)
             m[C:, 4 * nc:5 * nc] = wsc.detach().reshape(C, nc)
-            ent = (ver, m.to(torch.bfloat16).reshape(2 * C, 1, Kp).contiguous())
+            ent = m.to(torch.bfloat16).reshape(2 * C, 1, Kp).contiguous()
             self._packs[key] = ent
-        return ent[1]
+        return ent
+
+    def _pack_plan(self):
+        """[(key, src, src2, dst shape, Nn, T, K, mode, Cout)] for every tensor-core weight operand of the model."""
+        m = self.model
+        jobs = []
+
+        def conv(w, mode):
+            if mode == 0:
+                Nn, K, T = w.shape[0], w.shape[1], w.shape[2] * w.shape[3]
+            else:
+                Nn, K, T = w.shape[1], w.shape[0], w.shape[2] * w.shape[3]
+            jobs.append(((id(w), mode), w, None, (Nn, T, K), Nn, T, K, mode, 0))
+
+        nc = m.inc.conv1.in_channels
+        C0 = m.inc.conv1.out_channels
+        Kp = ((9 * nc + 7) // 8) * 8
+        jobs.append(((id(m.inc.conv1.weight), "stem"), m.inc.conv1.weight, m.inc.shortcut[0].weight, (2 * C0, 1, Kp),
+                     2 * C0, nc, Kp, 4, 0))
+        blocks = [m.inc, m.down1[1], m.down2[1], m.down3[1], m.bottleneck[2], m.dec4, m.dec3, m.dec2, m.dec1]
+        for blk in blocks:
+            stem = blk is m.inc
+            if not stem:
+                conv(blk.conv1.weight, 0)
+                conv(blk.conv1.weight, 1)
+            conv(blk.conv2.weight, 0)
+            conv(blk.conv2.weight, 1)
+            if not stem and not isinstance(blk.shortcut, nn.Identity):
+                conv(blk.shortcut[0].weight, 0)
+                conv(blk.shortcut[0].weight, 1)
+        for cv in (m.bottleneck[1].conv1, m.bottleneck[1].conv2, m.bottleneck[1].conv3, m.bottleneck[1].conv4):
+            conv(cv.weight, 0)
+            conv(cv.weight, 1)
+        for k in (4, 3, 2, 1):
+            gate = getattr(m, f"att{k}")
+            for cv in (gate.W_g[0], gate.W_x[0]):
+                conv(cv.weight, 0)
+                conv(cv.weight, 1)
+            w = getattr(m, f"up{k}").weight          # ConvTranspose2d [Cin, Cout, 2, 2]
+            jobs.append(((id(w), 2), w, None, (4 * w.shape[1], 1, w.shape[0]), 4 * w.shape[1], 1, w.shape[0], 2, w.shape[1]))
+            jobs.append(((id(w), 3), w, None, (w.shape[0], 4, w.shape[1]), w.shape[0], 4, w.shape[1], 3, 0))
+        return jobs
+
+    def refresh_packs(self):
+        """Rebuild every bf16 weight operand from the fp32 masters with ONE kernel launch.  Done at the start of every
+        forward: optimizers that update parameters through fused multi-tensor kernels (torch.optim.Adam(fused=True))
+        do not bump tensor version counters, so staleness cannot be detected -- it is simply never allowed."""
+        import numpy as np
+        plan = self._pack_plan()
+        sig = tuple(j[1].data_ptr() for j in plan)
+        if self._pack_table is None or self._pack_table[0] != sig:
+            dev = plan[0][1].device
+            dt = np.dtype([("src", "<u8"), ("src2", "<u8"), ("dst", "<u8"), ("first_block", "<i8"), ("total", "<i8"),
+                           ("Nn", "<i4"), ("T", "<i4"), ("K", "<i4"), ("mode", "<i4"), ("Cout", "<i4"), ("reserved", "<i4")])
+            tab = np.zeros(len(plan), dtype=dt)
+            first = 0
+            for i, (key, src, src2, shape, Nn, T, K, mode, cout) in enumerate(plan):
+                if not (src.is_cuda and src.dtype == torch.float32 and src.is_contiguous()):
+                    raise RuntimeError("rbunet: parameters must be contiguous fp32 CUDA tensors")
+                dst = torch.empty(shape, dtype=torch.bfloat16, device=dev)
+                self._packs[key] = dst
+                total = Nn * K if mode == 4 else Nn * T * K      # the stem operand's T carries the channel count
+                tab[i] = (src.data_ptr(), src2.data_ptr() if src2 is not None else 0, dst.data_ptr(), first, total, Nn, T, K,
+                          mode, cout, 0)
+                first += (total + 1023) // 1024
+            dev_tab = torch.from_numpy(tab.view(np.uint8).copy()).to(dev)
+            self._pack_table = (sig, dev_tab, len(plan), first)
+        _, dev_tab, njobs, blocks = self._pack_table
+        call("rbu_pack_weights_multi", _p(dev_tab), njobs, blocks, stream_ptr())
 
     @staticmethod
     def new(N, H, W, C, device):
@@ -375,6 +445,7 @@ class Engine:
             raise RuntimeError(f"expected {m.inc.conv1.in_channels} input channels, got {nc}")
         dev = x.device
         x = x.contiguous().float()
+        self.refresh_packs()
         S = {"N": N, "H": H, "W": W}
         Kp = ((9 * nc + 7) // 8) * 8
         patches = View(torch.empty((N, H, W, Kp), dtype=torch.bfloat16, device=dev))

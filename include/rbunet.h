@@ -86,6 +86,20 @@ int rbu_conv_gemm(const rbu_conv_gemm_args* args, void* stream);
  * Replaces nothing in the reference (layout change only; Main_Final.py:157-172,261-270 parameters). */
 int rbu_pack_weight(const float* src, void* dst, int Nn, int T, int K, int mode, int Cout, void* stream);
 
+/* Every weight operand of a model in one launch.  `jobs_device` is a DEVICE array of njobs descriptors sorted by
+ * first_block (job i owns blocks [first_block_i, first_block_{i+1}), 1024 destination elements per block; total =
+ * Nn*T*K destination elements).  mode 0-3 as rbu_pack_weight; mode 4 builds the stem operand [2C][Kp] from the 3x3
+ * conv1 weight (src) and the 1x1 shortcut weight (src2): Nn = 2C, K = Kp, T = input channels. */
+typedef struct {
+  const float* src;
+  const float* src2;
+  void* dst;
+  long long first_block;
+  long long total;
+  int Nn, T, K, mode, Cout, reserved;
+} rbu_pack_job;
+int rbu_pack_weights_multi(const rbu_pack_job* jobs_device, int njobs, long long total_blocks, void* stream);
+
 /* TEST-ONLY device reference: direct (CUDA-core) convolution, bf16 NHWC in, fp32 torch-layout weights
  * (rounded to bf16 on the fly), fp32 dense NHWC out.  Used by the parity tests at sizes where the CPU
  * oracle is too slow; never called by the product path. */

@@ -192,3 +192,25 @@ def test_training_reduces_loss_at_reference_init():
         first = loss.item() if first is None else first
         last = loss.item()
     assert np.isfinite(last) and last < 0.6 * first, (first, last)
+
+
+def test_weights_are_repacked_after_a_fused_optimizer_step():
+    """torch.optim.Adam(fused=True) does not bump tensor version counters; the bf16 GEMM operands must follow the fp32
+    masters anyway (they are rebuilt at every forward)."""
+    import rbunet
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    model = rbunet.RobustUNet(3, 1, 16).to(dev).eval()
+    x, _ = R.synthetic_inputs(2, 3, 32, 32, seed=5, blobby=True)
+    x = x.to(dev)
+    with torch.no_grad():
+        p0 = model(x).clone()
+    opt = torch.optim.Adam(model.parameters(), lr=0.05, fused=True)
+    for prm in model.parameters():
+        prm.grad = torch.ones_like(prm)
+    opt.step()
+    with torch.no_grad():
+        p1 = model(x)
+        pref = R.robust_unet_forward({k: v.cpu() for k, v in model.state_dict().items()}, x.cpu(), training=False, st=R.BF16)
+    assert (p1 - p0).abs().max().item() > 1e-3                  # the update is visible
+    assert rel_l2(p1, pref) < 5e-2                              # and it is the update the masters hold
