@@ -8,6 +8,7 @@ Layout: activations are NHWC bf16 (`View`s, possibly channel slices of a wider b
 from __future__ import annotations
 
 import ctypes
+import os
 from ctypes import c_void_p
 
 import torch
@@ -47,6 +48,11 @@ class Engine:
         self.model = model
         self._packs = {}
         self._pack_table = None
+        self._side_stream = None
+        self._side_ws = None
+        self._side_dirty = False
+        self._side_keep = []
+        self.overlap_wgrad = os.environ.get("RBU_NO_OVERLAP") is None
         self._ws = None
         self.drop_mask_fn = None     # optional callable(name, N, C) -> float32 [N,C] device tensor (tests)
         self.kernel_launches = 0
@@ -172,7 +178,35 @@ class Engine:
             bn.num_batches_tracked += 1
         return out
 
+    # -- weight gradients run on a side stream: they are tensor-pipe work with no consumer inside the backward pass,
+    #    so they overlap the bandwidth-bound elementwise kernels of the data-gradient chain on the main stream
+    def _side(self, device):
+        if self._side_stream is None or self._side_stream.device != device:
+            self._side_stream = torch.cuda.Stream(device=device)
+            self._side_ws = Workspace(device)
+        return self._side_stream
+
+    def join_side(self, device):
+        """Make the current stream wait for every weight-gradient kernel issued so far."""
+        if self._side_stream is not None and self._side_dirty:
+            torch.cuda.current_stream(device).wait_stream(self._side_stream)
+            self._side_dirty = False
+            self._side_keep.clear()      # operands may be recycled now: later main-stream work is ordered after the join
+
     def wgrad(self, N, H, W, a: View, b: View, taps, dil, gather, out: torch.Tensor):
+        if self.overlap_wgrad:
+            dev = out.device
+            main = torch.cuda.current_stream(dev)
+            side = self._side(dev)
+            side.wait_stream(main)                       # operands were produced on the main stream
+            self._side_keep.extend((a.base, b.base, out))    # keep their memory alive until the next join
+            with torch.cuda.stream(side):
+                self._wgrad(N, H, W, a, b, taps, dil, gather, out, self._side_ws)
+            self._side_dirty = True
+        else:
+            self._wgrad(N, H, W, a, b, taps, dil, gather, out, None)
+
+    def _wgrad(self, N, H, W, a: View, b: View, taps, dil, gather, out: torch.Tensor, wspace):
         args = WgradArgs()
         args.N, args.H, args.W = N, H, W
         args.a, args.a_ld, args.Ca = a.ptr, a.ld, a.C
@@ -180,7 +214,7 @@ class Engine:
         args.taps, args.dil, args.gather = taps, dil, int(gather)
         args.out, args.accumulate = out.data_ptr(), 0
         nbytes = _lib.lib().rbu_wgrad_workspace_bytes(ctypes.byref(args))
-        ws = self.ws(nbytes, out.device)
+        ws = wspace.get(int(nbytes)) if wspace is not None else self.ws(nbytes, out.device)
         call("rbu_wgrad_gemm", ctypes.byref(args), _p(ws), ws.numel() * 4, stream_ptr(), tag="wgrad_gemm",
              flops=2.0 * N * H * W * a.C * b.C * taps,
              label=f"wgrad {N}x{H}x{W} {a.C}x{b.C} t{taps}{'g' if gather else ''}d{dil}")
@@ -313,6 +347,7 @@ class Engine:
             nc = blk.conv1.in_channels
             gst = self.f32(2 * C, pt.C, device=dev)
             self.wgrad(N, H, W, dy12, pt, 1, 0, False, gst)
+            self.join_side(dev)                    # the slicing below runs on the main stream
             grads[prefix + ".conv1.weight"] = gst[:C, :9 * nc].reshape(C, 3, 3, nc).permute(0, 3, 1, 2).contiguous()
             grads[prefix + ".shortcut.0.weight"] = gst[C:, 4 * nc:5 * nc].reshape(C, nc, 1, 1).contiguous()
             return None
@@ -528,6 +563,7 @@ class Engine:
 
         def done(*prefixes):
             if allreduce_hook is not None:
+                self.join_side(dev)
                 allreduce_hook([k for k in grads if any(k == p or k.startswith(p + ".") for p in prefixes)], grads)
 
         done("outc")
@@ -570,4 +606,5 @@ class Engine:
             else:
                 self.rb_backward(m.inc, S["inc"], denc[0], grads, "inc", need_dx=False)
                 done("inc")
+        self.join_side(dev)
         return grads
