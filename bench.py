@@ -189,8 +189,13 @@ def run_ours(args):
     if roof["achieved"]:
         roof["frac"] = roof["achieved"] / peak_tf
     classes = {k: {"calls": v["calls"], "ms": round(v["ms"], 3), "share": round(v["ms"] / lib_ms, 4) if lib_ms else None,
-                   **({"tflops": round(v["flops"] / v["ms"] / 1e9, 1)} if v["flops"] and v["ms"] else {})}
+                   **({"tflops": round(v["flops"] / v["ms"] / 1e9, 1),
+                       "tensor_frac": round(v["flops"] / v["ms"] / 1e9 / peak_tf, 3)} if v["flops"] and v["ms"] else {}),
+                   **({"gbps": round(v["bytes"] / v["ms"] / 1e6, 0),
+                       "hbm_frac": round(v["bytes"] / v["ms"] / 1e6 / peaks["hbm_gbs"], 3)} if v["bytes"] and v["ms"] else {})}
                for k, v in sorted(summ.items(), key=lambda kv: -kv[1]["ms"])}
+    ew_ms = sum(v["ms"] for v in summ.values() if v["bytes"] and not v["flops"])
+    ew_bytes = sum(v["bytes"] for v in summ.values() if v["bytes"] and not v["flops"])
 
     out = None
     if rank == 0:
@@ -214,7 +219,12 @@ def run_ours(args):
                "gpu_launches": int(launches),
                "model_tflops": round(value * gflop_img / 1e3, 1),
                "model_frac_of_sustained_peak": round(value * gflop_img / 1e3 / peak_tf, 4),
-               "roofline": roof, "kernel_classes": classes}
+               "roofline": roof,
+               "hbm_kernels": {"ms": round(ew_ms, 3), "gbps": round(ew_bytes / ew_ms / 1e6, 0) if ew_ms else None,
+                               "hbm_frac": round(ew_bytes / ew_ms / 1e6 / peaks["hbm_gbs"], 3) if ew_ms else None,
+                               "peak": peaks["hbm_gbs"], "peak_source": peaks["source"],
+                               "note": "all bandwidth-bound kernels of one step: algorithmic bytes / summed CUDA-event time"},
+               "kernel_classes": classes}
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_port(R, infer, nc, S, budget_s=20.0)
         print(json.dumps(out), flush=True)

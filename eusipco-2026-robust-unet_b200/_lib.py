@@ -124,6 +124,39 @@ class Profiler:
 PROFILER = None
 
 
+def _nz(a):
+    """True if a ctypes pointer argument is non-NULL."""
+    return bool(getattr(a, "value", a))
+
+
+# Algorithmic bytes of the bandwidth-bound entry points (distinct tensor bytes read + written, each once, SURVEY.md
+# §8d) as a function of the positional arguments declared in include/rbunet.h -- used only by the profiler.
+ALGO_BYTES = {
+    "rbu_bn_stats": lambda a: a[2] * a[3] * a[4] * 2 if (a[5] or a[6]) else 0,
+    "rbu_affine_act": lambda a: 2 * a[4] * a[6] * 2,
+    "rbu_sa_reduce": lambda a: a[2] * a[4] * 2 + a[2] * 12,
+    "rbu_sa_gate": lambda a: a[1] * a[2] * a[3] * 12,
+    "rbu_rb_out": lambda a: 3 * a[6] * a[8] * 2 + a[6] * 4,
+    "rbu_maxpool2x2": lambda a: a[4] * a[5] * a[6] * a[7] * 2 * 5,
+    "rbu_ag_psi": lambda a: 2 * a[4] * a[5] * 2 + a[4] * 4,
+    "rbu_ag_apply": lambda a: 2 * a[4] * a[5] * 2 + a[4] * 8,
+    "rbu_stem_im2col": lambda a: a[1] * a[3] * a[4] * (a[2] * 4 + a[5] * 2),
+    "rbu_head_forward": lambda a: a[2] * a[3] * 2 + a[2] * 4,
+    "rbu_head_backward": lambda a: a[6] * 8 + 2 * a[6] * a[7] * 2,
+    "rbu_rb_bwd1": lambda a: (4 + (1 if _nz(a[8]) else 0)) * a[10] * a[11] * a[12] * 2 + a[10] * a[11] * 4,
+    "rbu_sa_bwd": lambda a: a[3] * a[4] * a[5] * 24,
+    "rbu_rb_bwd2": lambda a: 2 * a[4] * a[5] * a[6] * 2 + a[4] * a[5] * 16,
+    "rbu_rb_bwd3": lambda a: (3 + (2 if _nz(a[6]) else 0)) * a[10] * a[11] * a[12] * 2 + a[10] * a[11] * 16,
+    "rbu_bn_bwd": lambda a: 5 * a[6] * a[7] * a[8] * 2,
+    "rbu_ag_bwd": lambda a: (3 * a[16] + 6 * a[17]) * a[14] * a[15] * 2 + a[14] * a[15] * 16,
+    "rbu_maxpool2x2_bwd": lambda a: a[6] * a[7] * a[8] * a[9] * 2 * (9 + 4 * a[10]),
+    "rbu_chan_sum": lambda a: a[2] * a[3] * 2,
+    "rbu_loss_forward": lambda a: a[2] * a[3] * 8,
+    "rbu_loss_backward": lambda a: a[2] * 12,
+    "rbu_confusion_counts": lambda a: a[2] * a[3] * 8,
+}
+
+
 def call(name: str, *args, tag=None, flops=0.0, nbytes=0.0, label=None):
     """Call an int-returning entry point and raise RuntimeError with rbu_last_error() on failure."""
     prof = PROFILER
@@ -135,6 +168,8 @@ def call(name: str, *args, tag=None, flops=0.0, nbytes=0.0, label=None):
     e0.record()
     check(getattr(lib(), name)(*args), name)
     e1.record()
+    if not nbytes and name in ALGO_BYTES:
+        nbytes = float(ALGO_BYTES[name](args))
     prof.records.append((name, tag, flops, nbytes, e0, e1, label))
 
 

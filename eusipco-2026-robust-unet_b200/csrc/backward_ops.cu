@@ -234,79 +234,75 @@ rb_bwd1_kernel(const bf16* __restrict__ dout, long dout_ld, const bf16* __restri
   }
 }
 
-// SpatialAttention backward (Main_Final.py:112-117): dq = dG * gs (1-gs);
-//   ds[k][h,w] = sum_{r,q} K7[k][r][q] * dq[h-r+3, w-q+3]      (data gradient wrt [s_avg, s_max])
-__global__ void __launch_bounds__(NT)
-sa_bwd_data_kernel(const float* __restrict__ dG, const float* __restrict__ gs, int N, int H, int W,
-                   const float* __restrict__ k7, float2* __restrict__ ds) {
+// SpatialAttention backward (Main_Final.py:112-117), one shared-memory tiled kernel: dq = dG * gs (1-gs);
+//   ds[k][h,w]   = sum_{r,q} K7[k][r][q] * dq[h-r+3, w-q+3]      (data gradient wrt [s_avg, s_max])
+//   dK7[k][r][q] = sum_p dq[p] * s_k[p + (r-3, q-3)]             (98 per-thread accumulators, block partials)
+// A block walks 32 x 8 tiles (grid-stride) holding the 38 x 14 halos of dq and s in shared memory.
+constexpr int SB_TX = 32, SB_TY = 4, SB_HX = SB_TX + 6, SB_HY = SB_TY + 6;
+__global__ void __launch_bounds__(SB_TX * SB_TY)
+sa_bwd_kernel(const float* __restrict__ dG, const float* __restrict__ gs, const float2* __restrict__ s, int N, int H, int W,
+              const float* __restrict__ k7, float2* __restrict__ ds, float* __restrict__ partials) {
   __shared__ float wk[98];
-  if (threadIdx.x < 98) wk[threadIdx.x] = k7[threadIdx.x];
-  __syncthreads();
-  const long P = (long)N * H * W;
-  for (long p = blockIdx.x * (long)NT + threadIdx.x; p < P; p += (long)gridDim.x * NT) {
-    const int w = (int)(p % W);
-    const int h = (int)((p / W) % H);
-    const long nb = p - (long)h * W - w;
-    float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-    for (int r = 0; r < 7; ++r) {
-      const int hh = h - r + 3;
-      if (hh < 0 || hh >= H) continue;
-#pragma unroll
-      for (int q = 0; q < 7; ++q) {
-        const int ww = w - q + 3;
-        if (ww < 0 || ww >= W) continue;
-        const long o = nb + (long)hh * W + ww;
-        const float g = __ldg(&gs[o]);
-        const float dq = __ldg(&dG[o]) * g * (1.f - g);
-        a0 += wk[r * 7 + q] * dq;
-        a1 += wk[49 + r * 7 + q] * dq;
-      }
-    }
-    ds[p] = make_float2(a0, a1);
-  }
-}
-
-//   dK7[k][r][q] = sum_p dq[p] * s_k[p + (r-3, q-3)]      (98 per-thread accumulators, block partials)
-__global__ void __launch_bounds__(NT)
-sa_bwd_weight_kernel(const float* __restrict__ dG, const float* __restrict__ gs, const float2* __restrict__ s, int N,
-                     int H, int W, float* __restrict__ partials) {
+  __shared__ float tq[SB_HY][SB_HX];
+  __shared__ float2 tsv[SB_HY][SB_HX];
+  const int tid = threadIdx.x;
+  if (tid < 98) wk[tid] = k7[tid];
   float acc[98];
 #pragma unroll
   for (int i = 0; i < 98; ++i) acc[i] = 0.f;
-  const long P = (long)N * H * W;
-  for (long p = blockIdx.x * (long)NT + threadIdx.x; p < P; p += (long)gridDim.x * NT) {
-    const int w = (int)(p % W);
-    const int h = (int)((p / W) % H);
-    const long nb = p - (long)h * W - w;
-    const float g = gs[p];
-    const float dq = dG[p] * g * (1.f - g);
+  const int tiles_x = (W + SB_TX - 1) / SB_TX, tiles_y = (H + SB_TY - 1) / SB_TY;
+  const int tiles = tiles_x * tiles_y * N;
+  const int tx = tid % SB_TX, ty = tid / SB_TX;
+  for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+    const int bx = t % tiles_x, by = (t / tiles_x) % tiles_y, n = t / (tiles_x * tiles_y);
+    const int x0 = bx * SB_TX, y0 = by * SB_TY;
+    const long nb = (long)n * H * W;
+    __syncthreads();
+    for (int i = tid; i < SB_HX * SB_HY; i += SB_TX * SB_TY) {
+      const int hy = i / SB_HX, hx = i - hy * SB_HX;
+      const int yy = y0 + hy - 3, xx = x0 + hx - 3;
+      float q = 0.f;
+      float2 sv = make_float2(0.f, 0.f);
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+        const long o = nb + (long)yy * W + xx;
+        const float g = __ldg(&gs[o]);
+        q = __ldg(&dG[o]) * g * (1.f - g);
+        sv = __ldg(&s[o]);
+      }
+      tq[hy][hx] = q;
+      tsv[hy][hx] = sv;
+    }
+    __syncthreads();
+    const int x = x0 + tx, y = y0 + ty;
+    if (x < W && y < H) {
+      const float dq = tq[ty + 3][tx + 3];
+      float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-    for (int r = 0; r < 7; ++r) {
-      const int hh = h + r - 3;
+      for (int r = 0; r < 7; ++r)
 #pragma unroll
-      for (int q = 0; q < 7; ++q) {
-        const int ww = w + q - 3;
-        if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
-          const float2 v = __ldg(&s[nb + (long)hh * W + ww]);
+        for (int q = 0; q < 7; ++q) {
+          const float2 v = tsv[ty + r][tx + q];                 // s at (y + r - 3, x + q - 3)
           acc[r * 7 + q] += dq * v.x;
           acc[49 + r * 7 + q] += dq * v.y;
+          const float dqq = tq[ty + 6 - r][tx + 6 - q];          // dq at (y - r + 3, x - q + 3)
+          a0 += wk[r * 7 + q] * dqq;
+          a1 += wk[49 + r * 7 + q] * dqq;
         }
-      }
+      ds[nb + (long)y * W + x] = make_float2(a0, a1);
     }
   }
-  __shared__ float sm[98][NT / 32];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __shared__ float sm[98][SB_TX * SB_TY / 32];
+  const int warp = tid >> 5, lane = tid & 31;
 #pragma unroll
   for (int i = 0; i < 98; ++i) {
     const float v = warp_sum(acc[i]);
     if (lane == 0) sm[i][warp] = v;
   }
   __syncthreads();
-  if (threadIdx.x < 98) {
-    float t = 0.f;
-    for (int wq = 0; wq < NT / 32; ++wq) t += sm[threadIdx.x][wq];
-    partials[(long)blockIdx.x * 98 + threadIdx.x] = t;
+  if (tid < 98) {
+    float tsum = 0.f;
+    for (int wq = 0; wq < SB_TX * SB_TY / 32; ++wq) tsum += sm[tid][wq];
+    partials[(long)blockIdx.x * 98 + tid] = tsum;
   }
 }
 
@@ -376,6 +372,7 @@ __global__ void rb_d_reduce_kernel(const float* __restrict__ part, int chunks, i
 }
 
 // pass 3 (streaming skeleton): dy2 = c1*dc + c0 + cy*y2 + cm*[pl == pstar];  dys = es*de + e0 + ey*ys
+template <bool PROJ>
 __global__ void __launch_bounds__(NT)
 rb_bwd3_kernel(const bf16* __restrict__ de, long de_ld, const bf16* __restrict__ y2, long y2_ld, bf16* __restrict__ dy2,
                long dy2_ld, const bf16* __restrict__ ys, long ys_ld, bf16* __restrict__ dys, long dys_ld, int HW, int C,
@@ -393,6 +390,11 @@ rb_bwd3_kernel(const bf16* __restrict__ de, long de_ld, const bf16* __restrict__
     k1[e] = c1[o]; k0[e] = c0[o]; km[e] = cm[o]; ky[e] = cy[cg * 8 + e];
     pstar[e] = nc_arg[o];
   }
+  float se[8], s0[8], sy[8];
+  if (PROJ) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { se[e] = es[cg * 8 + e]; s0[e] = e0[cg * 8 + e]; sy[e] = ey[cg * 8 + e]; }
+  }
   const float invC = 1.f / (float)C;
   const long ib = (long)n * HW;
   constexpr int U = 2;
@@ -408,7 +410,7 @@ rb_bwd3_kernel(const bf16* __restrict__ de, long de_ld, const bf16* __restrict__
         const long p = ib + (i >> lg);
         rg[u] = ld_bf16x8_stream(de + p * de_ld + cg * 8);
         ry[u] = ld_bf16x8_stream(y2 + p * y2_ld + cg * 8);
-        if (ys) rs[u] = ld_bf16x8_stream(ys + p * ys_ld + cg * 8);
+        if (PROJ) rs[u] = ld_bf16x8_stream(ys + p * ys_ld + cg * 8);
         gsp[u] = __ldg(gs + p);
         d[u] = __ldg(ds + p);
         am[u] = __ldg(amax_c + p) - cg * 8;
@@ -430,14 +432,11 @@ rb_bwd3_kernel(const bf16* __restrict__ de, long de_ld, const bf16* __restrict__
           o[e] = k1[e] * dc + k0[e] + ky[e] * y[e] + (pl == pstar[e] ? km[e] : 0.f);
         }
         st_bf16x8(dy2 + p * dy2_ld + cg * 8, pack8(o));
-        if (ys) {
+        if (PROJ) {
           float sv8[8];
           unpack8(rs[u], sv8);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int c = cg * 8 + e;
-            o[e] = es[c] * g[e] + e0[c] + ey[c] * sv8[e];
-          }
+          for (int e = 0; e < 8; ++e) o[e] = se[e] * g[e] + s0[e] + sy[e] * sv8[e];
           st_bf16x8(dys + p * dys_ld + cg * 8, pack8(o));
         }
       }
@@ -1130,12 +1129,11 @@ extern "C" int rbu_sa_bwd(const float* dG, const float* gs, const float* s, int 
                           float* ds, float* dk7, void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   RBU_CHECK_ARG(dG && gs && s && k7 && ds && dk7 && N > 0 && H > 0 && W > 0, "rbu_sa_bwd: bad arguments");
-  const long P = (long)N * H * W;
-  sa_bwd_data_kernel<<<grid1d(P, NT), NT, 0, st>>>(dG, gs, N, H, W, k7, (float2*)ds);
-  RBU_CHECK_LAUNCH();
-  const int blocks = grid1d(P, NT * 8);
+  const long tiles = (long)rbu_cdiv(W, SB_TX) * rbu_cdiv(H, SB_TY) * N;
+  const long cap = (long)rbu_num_sms() * 6;
+  const int blocks = (int)(tiles < cap ? tiles : cap);
   RBU_CHECK_ARG(workspace && workspace_bytes >= (size_t)blocks * 98 * sizeof(float), "rbu_sa_bwd: workspace too small");
-  sa_bwd_weight_kernel<<<blocks, NT, 0, st>>>(dG, gs, (const float2*)s, N, H, W, (float*)workspace);
+  sa_bwd_kernel<<<blocks, SB_TX * SB_TY, 0, st>>>(dG, gs, (const float2*)s, N, H, W, k7, (float2*)ds, (float*)workspace);
   RBU_CHECK_LAUNCH();
   const float* pp = (const float*)workspace;
   int nb2 = blocks;
@@ -1219,10 +1217,14 @@ extern "C" int rbu_rb_bwd3(const void* de, int64_t de_ld, const void* y2, int64_
   const float* c0 = c1 + (size_t)N * C;
   const float* cm = c0 + (size_t)N * C;
   const float* cy = cm + (size_t)N * C;
-  rb_bwd3_kernel<<<dim3((unsigned)blocks, N), NT, 0, st>>>(
-      (const bf16*)de, de_ld, (const bf16*)y2, y2_ld, (bf16*)dy2, dy2_ld, (const bf16*)ys, ys_ld, (bf16*)dys, dys_ld, HW, C, lg,
-      gs, (const float2*)ds, amax_c, nc_arg, c1, c0, cm, cy, coef_s, coef_s ? coef_s + C : nullptr,
-      coef_s ? coef_s + 2 * C : nullptr);
+  if (ys)
+    rb_bwd3_kernel<true><<<dim3((unsigned)blocks, N), NT, 0, st>>>(
+        (const bf16*)de, de_ld, (const bf16*)y2, y2_ld, (bf16*)dy2, dy2_ld, (const bf16*)ys, ys_ld, (bf16*)dys, dys_ld, HW, C, lg,
+        gs, (const float2*)ds, amax_c, nc_arg, c1, c0, cm, cy, coef_s, coef_s + C, coef_s + 2 * C);
+  else
+    rb_bwd3_kernel<false><<<dim3((unsigned)blocks, N), NT, 0, st>>>(
+        (const bf16*)de, de_ld, (const bf16*)y2, y2_ld, (bf16*)dy2, dy2_ld, nullptr, 0, nullptr, 0, HW, C, lg, gs,
+        (const float2*)ds, amax_c, nc_arg, c1, c0, cm, cy, nullptr, nullptr, nullptr);
   RBU_CHECK_LAUNCH();
   return RBU_OK;
 }
