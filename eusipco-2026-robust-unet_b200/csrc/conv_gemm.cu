@@ -186,43 +186,58 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     EpiOut eo;
     eo.y = p.y; eo.y_ld = p.y_ld; eo.bias = p.bias; eo.addend = p.addend; eo.addend_ld = p.addend_ld;
     eo.Ncols = p.Ncols; eo.scatter = p.scatter; eo.Cout = p.Cout; eo.H = p.H; eo.W = p.W;
-    int t = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
-      const int nb = tile % p.n_blocks;
+    // pixel of tile `tile` owned by this thread
+    auto locate = [&](int tile, int& nb, bool& valid, long long& pix, int& n, int& h, int& w) {
+      nb = tile % p.n_blocks;
       int sp = tile / p.n_blocks;
       const int w0 = (sp % p.tiles_w) * p.TW;
       sp /= p.tiles_w;
       const int h0 = (sp % p.tiles_h) * p.TH;
       const int n0 = (sp / p.tiles_h) * p.TN;
-      // pixel owned by this thread
-      bool valid;
-      int n, h, w;
-      {
-        const int wl = row % p.TW;
-        const int r2 = row / p.TW;
-        w = w0 + wl;
-        if (p.gather) {
-          const int nh = h0 + r2;
-          valid = (w < p.W) && (nh < p.N * p.H);
-          n = nh / p.H;
-          h = nh - n * p.H;
-        } else {
-          h = h0 + (r2 % p.TH);
-          n = n0 + r2 / p.TH;
-          valid = (w < p.W) && (h < p.H) && (n < p.N);
-        }
+      const int wl = row % p.TW;
+      const int r2 = row / p.TW;
+      w = w0 + wl;
+      if (p.gather) {
+        const int nh = h0 + r2;
+        valid = (w < p.W) && (nh < p.N * p.H);
+        n = nh / p.H;
+        h = nh - n * p.H;
+      } else {
+        h = h0 + (r2 % p.TH);
+        n = n0 + r2 / p.TH;
+        valid = (w < p.W) && (h < p.H) && (n < p.N);
       }
-      const long long pix = ((long long)n * p.H + h) * p.W + w;
+      pix = ((long long)n * p.H + h) * p.W + w;
+    };
+    int t = 0;
+    int nb, n, h, w;
+    bool valid;
+    long long pix;
+    uint4 ad[4];
+    if (blockIdx.x < p.total_tiles) {
+      locate(blockIdx.x, nb, valid, pix, n, h, w);
+      epi_prefetch(eo, nb * p.block_n + half * 32, valid, pix, ad);
+    }
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
       const int a = t & 1;
       const uint32_t aph = (t >> 1) & 1;
+      int nb2 = 0, n2 = 0, h2 = 0, w2 = 0;
+      bool valid2 = false;
+      long long pix2 = 0;
+      const bool more = tile + gridDim.x < p.total_tiles;
+      if (more) locate(tile + gridDim.x, nb2, valid2, pix2, n2, h2, w2);
       ptx::mbar_wait(&tfull[a], aph);
       ptx::tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(a * p.block_n);
-      for (int c0 = half * 32; c0 < p.block_n; c0 += 64)
-        epilogue_chunk32(eo, t_addr + (uint32_t)c0, nb * p.block_n + c0, valid, pix, n, h, w);
+      for (int c0 = half * 32; c0 < p.block_n; c0 += 64) {
+        if (c0 != half * 32) epi_prefetch(eo, nb * p.block_n + c0, valid, pix, ad);
+        epi_finish(eo, t_addr + (uint32_t)c0, nb * p.block_n + c0, valid, pix, n, h, w, ad);
+        if (c0 + 64 >= p.block_n && more) epi_prefetch(eo, nb2 * p.block_n + half * 32, valid2, pix2, ad);   // next tile
+      }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty[a]);
+      nb = nb2; n = n2; h = h2; w = w2; valid = valid2; pix = pix2;
     }
   }
 

@@ -284,23 +284,43 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     EpiOut eo;
     eo.y = p.y; eo.y_ld = p.y_ld; eo.bias = p.bias; eo.addend = p.addend; eo.addend_ld = p.addend_ld;
     eo.Ncols = p.Ncols; eo.scatter = 0; eo.Cout = p.Ncols; eo.H = p.H; eo.W = p.W;
-    int t = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
-      int nb, w0, h0, n;
+    auto locate = [&](int tile, int& nb, bool& valid, long long& pix, int& n, int& h, int& w) {
+      int w0, h0;
       tile_coords(p, tile, nb, w0, h0, n);
-      const int h = h0 + row / TILE_W, w = w0 + row % TILE_W;
-      const bool valid = h < p.H && w < p.W;
-      const long long pix = ((long long)n * p.H + h) * p.W + w;
+      h = h0 + row / TILE_W;
+      w = w0 + row % TILE_W;
+      valid = h < p.H && w < p.W;
+      pix = ((long long)n * p.H + h) * p.W + w;
+    };
+    int t = 0;
+    int nb, n, h, w;
+    bool valid;
+    long long pix;
+    uint4 ad[4];
+    if (blockIdx.x < p.total_tiles) {
+      locate(blockIdx.x, nb, valid, pix, n, h, w);
+      epi_prefetch(eo, nb * p.block_n + half * 32, valid, pix, ad);
+    }
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
       const int a = t & 1;
       const uint32_t aph = (t >> 1) & 1;
+      int nb2 = 0, n2 = 0, h2 = 0, w2 = 0;
+      bool valid2 = false;
+      long long pix2 = 0;
+      const bool more = tile + gridDim.x < p.total_tiles;
+      if (more) locate(tile + gridDim.x, nb2, valid2, pix2, n2, h2, w2);
       ptx::mbar_wait(&tfull[a], aph);
       ptx::tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(a * p.block_n);
-      for (int c0 = half * 32; c0 < p.block_n; c0 += 64)
-        epilogue_chunk32(eo, t_addr + (uint32_t)c0, nb * p.block_n + c0, valid, pix, n, h, w);
+      for (int c0 = half * 32; c0 < p.block_n; c0 += 64) {
+        if (c0 != half * 32) epi_prefetch(eo, nb * p.block_n + c0, valid, pix, ad);
+        epi_finish(eo, t_addr + (uint32_t)c0, nb * p.block_n + c0, valid, pix, n, h, w, ad);
+        if (c0 + 64 >= p.block_n && more) epi_prefetch(eo, nb2 * p.block_n + half * 32, valid2, pix2, ad);   // next tile
+      }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty[a]);
+      nb = nb2; n = n2; h = h2; w = w2; valid = valid2; pix = pix2;
     }
   }
 

@@ -17,16 +17,22 @@ struct EpiOut {
   int scatter, Cout, H, W;   // scatter: ConvTranspose2d pixel shuffle, column (2i+j)*Cout+co of (n,h,w) -> y[n,2h+i,2w+j,co]
 };
 
-// taddr: TMEM address of (lane group base, first column of the chunk); col: first GEMM column of the chunk
-__device__ __forceinline__ void epilogue_chunk32(const EpiOut& o, uint32_t taddr, int col, bool valid, long long pix, int n,
-                                                 int h, int w) {
-  uint4 ad[4];
-  const bool live = valid && col < o.Ncols;
-  if (o.addend && live) {
+// Issue the addend loads of one 32-column chunk (no-op without an addend).  They are consumed by epi_finish(); the
+// tile loops issue them for the NEXT tile's first chunk before waiting on the current accumulator, so the global-load
+// latency of the small-K GEMMs (attention-gate data gradients: K = 32..256, read-modify-write of a 2x wider tensor)
+// overlaps the previous tile instead of sitting on every tile's critical path.
+__device__ __forceinline__ void epi_prefetch(const EpiOut& o, int col, bool valid, long long pix, uint4 (&ad)[4]) {
+  if (o.addend && valid && col < o.Ncols) {
 #pragma unroll
     for (int g = 0; g < 4; ++g)
       if (col + g * 8 < o.Ncols) ad[g] = __ldg(reinterpret_cast<const uint4*>(o.addend + pix * o.addend_ld + col + g * 8));
   }
+}
+
+// taddr: TMEM address of (lane group base, first column of the chunk); col: first GEMM column of the chunk
+__device__ __forceinline__ void epi_finish(const EpiOut& o, uint32_t taddr, int col, bool valid, long long pix, int n, int h,
+                                           int w, const uint4 (&ad)[4]) {
+  const bool live = valid && col < o.Ncols;
   uint32_t r[32];
   ptx::tmem_ld_32x32(taddr, r);
   ptx::tmem_ld_wait();
