@@ -108,7 +108,7 @@ def run_ours(args):
         model.train()
         if world > 1:
             net = rbunet.DataParallel(model)
-        opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=1e-4, fused=True)      # Main_Final.py:552
+        opt = rbunet.FusedAdam(model.parameters(), lr=1e-4, weight_decay=1e-4)      # = torch.optim.Adam of Main_Final.py:552
     x_cpu, y_cpu = R.synthetic_inputs(B, nc, S, S, seed=123 + rank, blobby=True)
     x_pin, y_pin = x_cpu.pin_memory(), y_cpu.pin_memory()
     x_dev, y_dev = x_cpu.to(dev), y_cpu.to(dev)
@@ -212,7 +212,7 @@ def run_ours(args):
                                        f"{nc} channels, base 64"),
                           "global_batch": B * world, "image": [nc, S, S], "parallelism": f"dp{world}",
                           "l2": "256 MiB flush buffer written between timed steps; per-step activations exceed L2",
-                          "weights": "reference init (seed 0), random", "optimizer": "torch.optim.Adam(fused) lr 1e-4 wd 1e-4"},
+                          "weights": "reference init (seed 0), random", "optimizer": "rbunet.FusedAdam (= torch.optim.Adam, coupled L2) lr 1e-4 wd 1e-4"},
                "clocks": clocks,
                "e2e": {"value": round(imgs / (ms_e2e / 1e3), 2), "unit": "img/s", "h2d_bytes_per_step": h2d,
                        "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_e2e / args.steps, 3)},

@@ -12,7 +12,8 @@ from .loss import (METRIC_KEYS, RobustBCEDiceLoss, batch_metrics, calculate_metr
                    confusion_counts, metrics_from_counts)
 from .model import RobustUNet  # noqa: F401
 from .ops import View, preprocess  # noqa: F401
+from .optim import FusedAdam  # noqa: F401
 from .parallel import DataParallel, GradBucketer  # noqa: F401
 
 __all__ = ["RobustUNet", "RobustBCEDiceLoss", "calculate_metrics", "batch_metrics", "confusion_counts",
-           "metrics_from_counts", "METRIC_KEYS", "View", "preprocess", "DataParallel", "GradBucketer"]
+           "metrics_from_counts", "METRIC_KEYS", "View", "preprocess", "DataParallel", "GradBucketer", "FusedAdam"]

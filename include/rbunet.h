@@ -100,6 +100,20 @@ typedef struct {
 } rbu_pack_job;
 int rbu_pack_weights_multi(const rbu_pack_job* jobs_device, int njobs, long long total_blocks, void* stream);
 
+/* Fused multi-tensor Adam with coupled L2 weight decay = torch.optim.Adam(params, lr, betas, eps, weight_decay) as used
+ * by the reference (Main_Final.py:552,582), one launch for all parameter tensors.  `jobs_device`: DEVICE array sorted by
+ * first_block (1024 elements per block); step is the 1-based step count of the bias corrections. */
+typedef struct {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  long long first_block;
+  long long numel;
+} rbu_adam_job;
+int rbu_adam_step(const rbu_adam_job* jobs_device, int njobs, long long total_blocks, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, int step, void* stream);
+
 /* TEST-ONLY device reference: direct (CUDA-core) convolution, bf16 NHWC in, fp32 torch-layout weights
  * (rounded to bf16 on the fly), fp32 dense NHWC out.  Used by the parity tests at sizes where the CPU
  * oracle is too slow; never called by the product path. */
