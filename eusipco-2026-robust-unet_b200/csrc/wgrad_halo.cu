@@ -216,8 +216,9 @@ void plan(const rbu_wgrad_args* a, HWParams* p) {
   for (int k = 1; k <= p->tiles_total && (long)k * base_items <= 8L * sms; ++k) {
     const long items = (long)k * base_items;
     const double util = (double)items / (double)(((items + sms - 1) / sms) * sms);
-    if (util > best + 1e-9) { best = util; ks = k; }
-    if (items >= sms && util >= 0.85) break;
+    if (items >= sms && util >= 0.85) { ks = k; break; }
+    const double score = items >= sms ? util : util - 1.0;      // a full machine always beats a partially filled one
+    if (score > best + 1e-9) { best = score; ks = k; }
   }
   p->ksplit = ks;
   p->items = base_items * ks;
