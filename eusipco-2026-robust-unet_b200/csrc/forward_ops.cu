@@ -288,6 +288,18 @@ sa_reduce_kernel(const bf16* __restrict__ y2, long ld, int HW, int C, const floa
       t[k][e] = cg < G ? tv[o] : 0.f;
     }
   }
+  // bf16 bit patterns of the targets: one packed halfword compare per channel pair finds candidate hits; the exact
+  // float comparison runs only then (or always for a target of +-0, whose two encodings compare equal as floats)
+  uint4 tp[K];
+  bool tz[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const bf16x8 pk = pack8(t[k]);
+    tp[k] = *reinterpret_cast<const uint4*>(&pk);
+    tz[k] = false;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) tz[k] = tz[k] || t[k][e] == 0.f;
+  }
   const bf16* base = y2 + (long)n * HW * ld;
   const float invC = 1.f / (float)C;
   for (int pb = blockIdx.x * (SLOTS * U); pb < HW; pb += gridDim.x * (SLOTS * U)) {
@@ -316,7 +328,14 @@ sa_reduce_kernel(const bf16* __restrict__ y2, long ld, int HW, int C, const floa
               const float c = a[k][e] * v[e] + b[k][e];
               sum += c;
               if (c > best) { best = c; bi = cg * 8 + e; }
-              if (v[e] == t[k][e]) atomicMin(nc_arg + (long)n * C + cg * 8 + e, pp);
+            }
+            const uint4 rw = *reinterpret_cast<const uint4*>(&raw[u][k]);
+            const unsigned hit = __vcmpeq2(rw.x, tp[k].x) | __vcmpeq2(rw.y, tp[k].y) | __vcmpeq2(rw.z, tp[k].z) |
+                                 __vcmpeq2(rw.w, tp[k].w);
+            if (hit != 0u || tz[k]) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                if (v[e] == t[k][e]) atomicMin(nc_arg + (long)n * C + cg * 8 + e, pp);
             }
           }
         }
@@ -446,37 +465,70 @@ maxpool_kernel(const bf16* __restrict__ x, long x_ld, bf16* __restrict__ y, long
 //   finalize  : BatchNorm2d(1) over all pixels (scalar statistics)
 //   apply     : psi = sigmoid(a*q0+b); out = skip * psi
 // ------------------------------------------------------------------------------------------------
-template <int TPP>
+// TPP lanes cooperate on a pixel; lane li owns channel groups li, li+TPP, ... (K of them) whose per-channel
+// coefficients (Ag, Ax, Bg+Bx, w_psi) stay in registers; U pixels per slot are loaded before the first use.
+template <int TPP, int K>
 __global__ void __launch_bounds__(NT)
 ag_psi_kernel(const bf16* __restrict__ yg, long yg_ld, const bf16* __restrict__ yx, long yx_ld, long P, int F,
               const float* __restrict__ Ag, const float* __restrict__ Bg, const float* __restrict__ Ax,
               const float* __restrict__ Bx, const float* __restrict__ wpsi, const float* __restrict__ bpsi,
               float* __restrict__ q0, float* __restrict__ partials) {
+  constexpr int SLOTS = NT / TPP;
+  constexpr int U = K == 1 ? 4 : (K == 2 ? 2 : 1);
   const int G = F >> 3;
   const int li = threadIdx.x % TPP;
   const int slot = threadIdx.x / TPP;
-  constexpr int SLOTS = NT / TPP;
-  float ls = 0.f, lq = 0.f;
-  for (long p = blockIdx.x * (long)SLOTS + slot; p < P; p += (long)gridDim.x * SLOTS) {
-    float acc = 0.f;
-    for (int cg = li; cg < G; cg += TPP) {
-      float a[8], b[8];
-      unpack8(ld_bf16x8_stream(yg + p * yg_ld + cg * 8), a);
-      unpack8(ld_bf16x8_stream(yx + p * yx_ld + cg * 8), b);
+  float ag[K][8], ax[K][8], bs[K][8], wp[K][8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int c = cg * 8 + e;
-        const float t = fmaxf(Ag[c] * a[e] + Bg[c] + Ax[c] * b[e] + Bx[c], 0.f);
-        acc += wpsi[c] * t;
-      }
+  for (int k = 0; k < K; ++k) {
+    const int cg = li + k * TPP;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = cg * 8 + e;
+      const bool ok = cg < G;
+      ag[k][e] = ok ? Ag[c] : 0.f;
+      ax[k][e] = ok ? Ax[c] : 0.f;
+      bs[k][e] = ok ? Bg[c] + Bx[c] : 0.f;
+      wp[k][e] = ok ? wpsi[c] : 0.f;
+    }
+  }
+  const float bias = bpsi[0];
+  float ls = 0.f, lq = 0.f;
+  for (long pb = (long)blockIdx.x * (SLOTS * U); pb < P; pb += (long)gridDim.x * (SLOTS * U)) {
+    bf16x8 ra[U][K], rb[U][K];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long pp = pb + u * SLOTS + slot;
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+        if (pp < P && li + k * TPP < G) {
+          ra[u][k] = ld_bf16x8_stream(yg + pp * yg_ld + (li + k * TPP) * 8);
+          rb[u][k] = ld_bf16x8_stream(yx + pp * yx_ld + (li + k * TPP) * 8);
+        }
     }
 #pragma unroll
-    for (int o = TPP / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (li == 0) {
-      const float q = acc + bpsi[0];
-      q0[p] = q;
-      ls += q;
-      lq += q * q;
+    for (int u = 0; u < U; ++u) {
+      const long pp = pb + u * SLOTS + slot;
+      float acc = 0.f;
+      if (pp < P) {
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+          if (li + k * TPP < G) {
+            float a[8], b[8];
+            unpack8(ra[u][k], a);
+            unpack8(rb[u][k], b);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc += wp[k][e] * fmaxf(ag[k][e] * a[e] + ax[k][e] * b[e] + bs[k][e], 0.f);
+          }
+      }
+#pragma unroll
+      for (int o = TPP / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (li == 0 && pp < P) {
+        const float q = acc + bias;
+        q0[pp] = q;
+        ls += q;
+        lq += q * q;
+      }
     }
   }
   __shared__ float r0[NT / 32], r1[NT / 32];
@@ -492,16 +544,25 @@ ag_psi_kernel(const bf16* __restrict__ yg, long yg_ld, const bf16* __restrict__ 
   }
 }
 
-// scalar BN finalize: stats[0..3] = scale, shift, mean, rstd
-__global__ void scalar_bn_finalize_kernel(const float* __restrict__ partials, int nblk, long M, int training,
-                                          const float* __restrict__ gamma, const float* __restrict__ beta,
-                                          float* __restrict__ running_mean, float* __restrict__ running_var,
-                                          float momentum, float eps, float* __restrict__ stats) {
+// scalar BN finalize: stats[0..3] = scale, shift, mean, rstd.  One block of 256 threads: thread j adds partials
+// j, j+256, ... in double, then the 256 lane sums are combined in lane order (fixed order -> deterministic).
+__global__ void __launch_bounds__(256)
+scalar_bn_finalize_kernel(const float* __restrict__ partials, int nblk, long M, int training,
+                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                          float* __restrict__ running_mean, float* __restrict__ running_var, float momentum, float eps,
+                          float* __restrict__ stats) {
+  __shared__ double sh[2][256];
+  double s = 0.0, q = 0.0;
+  if (training)
+    for (int i = threadIdx.x; i < nblk; i += 256) { s += (double)partials[2 * i]; q += (double)partials[2 * i + 1]; }
+  sh[0][threadIdx.x] = s;
+  sh[1][threadIdx.x] = q;
+  __syncthreads();
   if (threadIdx.x != 0) return;
   float mean, var;
   if (training) {
-    double s = 0.0, q = 0.0;
-    for (int i = 0; i < nblk; ++i) { s += (double)partials[2 * i]; q += (double)partials[2 * i + 1]; }
+    s = 0.0; q = 0.0;
+    for (int j = 0; j < 256; ++j) { s += sh[0][j]; q += sh[1][j]; }
     const double m = s / (double)M;
     double v = q / (double)M - m * m;
     if (v < 0.0) v = 0.0;
@@ -564,28 +625,30 @@ ag_apply_kernel(const bf16* __restrict__ skip, long s_ld, bf16* __restrict__ out
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NT)
 stem_im2col_kernel(const float* __restrict__ x, int N, int nc, int H, int W, int Kp, bf16* __restrict__ out) {
+  // one thread per pixel: the reads of a warp are 32 consecutive pixels of one (tap, channel) plane (coalesced),
+  // the writes are the thread's own contiguous Kp*2-byte patch row in 16-byte pieces
   const long P = (long)N * H * W;
   const int KG = Kp >> 3;
-  const long total = P * KG;
-  for (long i = blockIdx.x * (long)NT + threadIdx.x; i < total; i += (long)gridDim.x * NT) {
-    const long p = i % P;     // pixel fastest: coalesced fp32 reads
-    const int kg = (int)(i / P);
+  for (long p = blockIdx.x * (long)NT + threadIdx.x; p < P; p += (long)gridDim.x * NT) {
     const int w = (int)(p % W);
     const int h = (int)((p / W) % H);
     const int n = (int)(p / ((long)W * H));
-    float v[8];
+    const float* xn = x + (long)n * nc * H * W;
+    for (int kg = 0; kg < KG; ++kg) {
+      float v[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int k = kg * 8 + e;
-      float t = 0.f;
-      if (k < 9 * nc) {
-        const int tap = k / nc, c = k - tap * nc;
-        const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
-        if (hh >= 0 && hh < H && ww >= 0 && ww < W) t = x[(((long)n * nc + c) * H + hh) * W + ww];
+      for (int e = 0; e < 8; ++e) {
+        const int k = kg * 8 + e;
+        float t = 0.f;
+        if (k < 9 * nc) {
+          const int tap = k / nc, c = k - tap * nc;
+          const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+          if (hh >= 0 && hh < H && ww >= 0 && ww < W) t = __ldg(xn + ((long)c * H + hh) * W + ww);
+        }
+        v[e] = t;
       }
-      v[e] = t;
+      st_bf16x8(out + p * Kp + kg * 8, pack8(v));
     }
-    st_bf16x8(out + p * Kp + kg * 8, pack8(v));
   }
 }
 
@@ -780,7 +843,23 @@ extern "C" int rbu_maxpool2x2(const void* x, int64_t x_ld, void* y, int64_t y_ld
   return RBU_OK;
 }
 
-extern "C" int rbu_ag_psi_blocks(int64_t P, int F) { return grid_for(P, NT / pick_tpp(F) * 4); }
+namespace {
+void ag_psi_cfg(int F, int& tpp, int& K, int& per_block) {
+  const int G = F >> 3;
+  tpp = G >= 32 ? 32 : (G < 4 ? 4 : G);
+  K = G > 32 ? G / 32 : 1;
+  const int U = K == 1 ? 4 : (K == 2 ? 2 : 1);
+  per_block = NT / tpp * U;
+}
+}  // namespace
+
+extern "C" int rbu_ag_psi_blocks(int64_t P, int F) {
+  int tpp, K, per_block;
+  ag_psi_cfg(F, tpp, K, per_block);
+  long b = (P + per_block - 1) / per_block;
+  const long cap = (long)rbu_num_sms() * 16;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
 
 extern "C" int rbu_ag_psi(const void* yg, int64_t yg_ld, const void* yx, int64_t yx_ld, int64_t P, int F,
                           const float* Ag, const float* Bg, const float* Ax, const float* Bx, const float* wpsi,
@@ -789,14 +868,17 @@ extern "C" int rbu_ag_psi(const void* yg, int64_t yg_ld, const void* yx, int64_t
                           void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   RBU_CHECK_ARG(VIEW_OK(yg, yg_ld) && VIEW_OK(yx, yx_ld) && Ag && Bg && Ax && Bx && wpsi && bpsi && q0 && stats &&
-                    partials && gamma && beta && F >= 8 && F % 8 == 0, "rbu_ag_psi: bad arguments");
-  const int tpp = pick_tpp(F);
+                    partials && gamma && beta && EW_CH_OK(F), "rbu_ag_psi: bad arguments");
+  int tpp, K, per_block;
+  ag_psi_cfg(F, tpp, K, per_block);
   const int grid = rbu_ag_psi_blocks(P, F);
-#define LAUNCH(T) ag_psi_kernel<T><<<grid, NT, 0, st>>>((const bf16*)yg, yg_ld, (const bf16*)yx, yx_ld, P, F, Ag, Bg, Ax, Bx, wpsi, bpsi, q0, partials)
-  if (tpp == 4) LAUNCH(4); else if (tpp == 8) LAUNCH(8); else if (tpp == 16) LAUNCH(16); else LAUNCH(32);
+#define LAUNCH(T, KK) ag_psi_kernel<T, KK><<<grid, NT, 0, st>>>((const bf16*)yg, yg_ld, (const bf16*)yx, yx_ld, P, F, Ag, Bg, Ax, Bx, wpsi, bpsi, q0, partials)
+  if (K == 1) { if (tpp == 4) LAUNCH(4, 1); else if (tpp == 8) LAUNCH(8, 1); else if (tpp == 16) LAUNCH(16, 1); else LAUNCH(32, 1); }
+  else if (K == 2) LAUNCH(32, 2);
+  else { RBU_CHECK_ARG(K == 4, "rbu_ag_psi: unsupported channel count %d", F); LAUNCH(32, 4); }
 #undef LAUNCH
   RBU_CHECK_LAUNCH();
-  scalar_bn_finalize_kernel<<<1, 32, 0, st>>>(partials, grid, P, training, gamma, beta, running_mean, running_var,
+  scalar_bn_finalize_kernel<<<1, 256, 0, st>>>(partials, grid, P, training, gamma, beta, running_mean, running_var,
                                               momentum, eps, stats);
   RBU_CHECK_LAUNCH();
   return RBU_OK;
@@ -815,8 +897,7 @@ extern "C" int rbu_ag_apply(const void* skip, int64_t s_ld, void* out, int64_t o
 extern "C" int rbu_stem_im2col(const float* x, int N, int nc, int H, int W, int Kp, void* out, void* stream_) {
   RBU_CHECK_ARG(x && out && N > 0 && nc > 0 && H > 0 && W > 0 && Kp % 8 == 0 && Kp >= 9 * nc && ((uintptr_t)out & 15) == 0,
                 "rbu_stem_im2col: bad arguments");
-  stem_im2col_kernel<<<grid_for((long)N * H * W * (Kp >> 3), NT * 2), NT, 0, (cudaStream_t)stream_>>>(x, N, nc, H, W, Kp,
-                                                                                                     (bf16*)out);
+  stem_im2col_kernel<<<grid_for((long)N * H * W, NT), NT, 0, (cudaStream_t)stream_>>>(x, N, nc, H, W, Kp, (bf16*)out);
   RBU_CHECK_LAUNCH();
   return RBU_OK;
 }
