@@ -28,7 +28,7 @@ constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr int NUM_THREADS = 320;   // TMA warp, MMA warp, 8 epilogue warps
 constexpr int MAX_STAGES = 8;
-constexpr int SMEM_LIMIT = 232448;  // 227 KB
+constexpr int SMEM_LIMIT = 232448 - EPI_STAT_FLOATS * 4;  // 227 KB minus the static statistics accumulators
 
 struct KParams {
   int N, H, W;
@@ -45,6 +45,7 @@ struct KParams {
   const float* bias;
   const bf16* addend;
   long long addend_ld;
+  float* stats;   // [4*SMs][2][Ncols] per-(CTA, lane group) column sum / sum of squares of the stored output, or NULL
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -63,6 +64,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  __shared__ __align__(16) float stat_smem[EPI_STAT_FLOATS];
+  if (p.stats)
+    for (int i = threadIdx.x; i < EPI_STAT_FLOATS; i += NUM_THREADS) stat_smem[i] = 0.f;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA0);
@@ -184,6 +188,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const int half = (warp - 2) >> 2;     // which of the interleaved 32-column chunks this warp drains
     const int row = lg * 32 + lane;
     EpiOut eo;
+    eo.stat_acc = p.stats ? stat_smem + (warp - 2) * (EPI_STAT_CHUNKS * 64) : nullptr;
     eo.y = p.y; eo.y_ld = p.y_ld; eo.bias = p.bias; eo.addend = p.addend; eo.addend_ld = p.addend_ld;
     eo.Ncols = p.Ncols; eo.scatter = p.scatter; eo.Cout = p.Cout; eo.H = p.H; eo.W = p.W;
     // pixel of tile `tile` owned by this thread
@@ -231,13 +236,26 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(a * p.block_n);
       for (int c0 = half * 32; c0 < p.block_n; c0 += 64) {
         if (c0 != half * 32) epi_prefetch(eo, nb * p.block_n + c0, valid, pix, ad);
-        epi_finish(eo, t_addr + (uint32_t)c0, nb * p.block_n + c0, valid, pix, n, h, w, ad);
+        epi_finish(eo, t_addr + (uint32_t)c0, nb * p.block_n + c0, valid, pix, n, h, w, ad, (c0 - half * 32) >> 6);
         if (c0 + 64 >= p.block_n && more) epi_prefetch(eo, nb2 * p.block_n + half * 32, valid2, pix2, ad);   // next tile
       }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty[a]);
       nb = nb2; n = n2; h = h2; w = w2; valid = valid2; pix = pix2;
+    }
+    if (p.stats) {
+      // every tile of this CTA has the same column block (grid % n_blocks == 0): flush the warp's accumulators
+      const int nbf = blockIdx.x % p.n_blocks;
+      float* row_out = p.stats + (long long)(blockIdx.x * 4 + lg) * 2 * p.Ncols;
+      for (int c0 = half * 32, j = 0; c0 < p.block_n; c0 += 64, ++j) {
+        const int col = nbf * p.block_n + c0 + lane;
+        if (col < p.Ncols) {
+          const float2 v = reinterpret_cast<const float2*>(eo.stat_acc)[j * 32 + lane];
+          row_out[col] = v.x;
+          row_out[p.Ncols + col] = v.y;
+        }
+      }
     }
   }
 
@@ -253,6 +271,63 @@ int pow2ceil(int v) {
 }
 
 }  // namespace
+
+extern "C" size_t rbu_conv_stats_floats(int Ncols) { return (size_t)4 * rbu_num_sms() * 2 * Ncols; }
+
+// BatchNorm affine from the per-(CTA, lane group) partial sums written by rbu_conv_gemm(stats != NULL):
+// block = 32 channels x 8 lanes over the 4*SMs rows (lane sums combined in lane order -> deterministic).
+namespace {
+__global__ void __launch_bounds__(256)
+bn_finalize_partials_kernel(const float* __restrict__ part, int rows, int Ncols, int col_off, int C, double M, int training,
+                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                            float* __restrict__ running_mean, float* __restrict__ running_var, float momentum, float eps,
+                            float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
+                            float* __restrict__ rstd_out) {
+  __shared__ double sh[2][8][32];
+  const int cx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  double s = 0.0, q = 0.0;
+  if (c < C)
+    for (int r = ly; r < rows; r += 8) {
+      s += (double)part[(long)r * 2 * Ncols + col_off + c];
+      q += (double)part[(long)r * 2 * Ncols + Ncols + col_off + c];
+    }
+  sh[0][ly][cx] = s;
+  sh[1][ly][cx] = q;
+  __syncthreads();
+  if (ly != 0 || c >= C) return;
+  double ts = 0.0, tq = 0.0;
+  for (int j = 0; j < 8; ++j) { ts += sh[0][j][cx]; tq += sh[1][j][cx]; }
+  const double m = ts / M;
+  double v = tq / M - m * m;
+  if (v < 0.0) v = 0.0;
+  const float mean = (float)m, var = (float)v;
+  if (training && running_mean) {
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+    const float unbiased = M > 1.0 ? (float)(v * M / (M - 1.0)) : var;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+  }
+  const float rstd = 1.0f / sqrtf(var + eps);
+  const float sc = gamma[c] * rstd;
+  scale[c] = sc;
+  shift[c] = beta[c] - mean * sc;
+  if (mean_out) mean_out[c] = mean;
+  if (rstd_out) rstd_out[c] = rstd;
+}
+}  // namespace
+
+extern "C" int rbu_bn_finalize_partials(const float* part, int Ncols, int col_off, int C, int64_t count, const float* gamma,
+                                        const float* beta, float* running_mean, float* running_var, float momentum,
+                                        float eps, float* scale, float* shift, float* mean_out, float* rstd_out,
+                                        void* stream_) {
+  RBU_CHECK_ARG(part && gamma && beta && scale && shift && Ncols > 0 && C > 0 && col_off >= 0 && col_off + C <= Ncols &&
+                    count > 0, "rbu_bn_finalize_partials: bad arguments");
+  bn_finalize_partials_kernel<<<rbu_cdiv(C, 32), 256, 0, (cudaStream_t)stream_>>>(
+      part, 4 * rbu_num_sms(), Ncols, col_off, C, (double)count, 1, gamma, beta, running_mean, running_var, momentum, eps,
+      scale, shift, mean_out, rstd_out);
+  RBU_CHECK_LAUNCH();
+  return RBU_OK;
+}
 
 extern "C" int rbu_conv_gemm(const rbu_conv_gemm_args* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -332,6 +407,7 @@ extern "C" int rbu_conv_gemm(const rbu_conv_gemm_args* a, void* stream_) {
   p.bias = a->bias;
   p.addend = reinterpret_cast<const bf16*>(a->addend);
   p.addend_ld = a->addend_ld;
+  p.stats = a->stats;
 
   CUtensorMap tmA[2], tmB[2];
   memset(tmA, 0, sizeof(tmA));
@@ -372,6 +448,11 @@ extern "C" int rbu_conv_gemm(const rbu_conv_gemm_args* a, void* stream_) {
     attr_set = true;
   }
   int grid = p.total_tiles < rbu_num_sms() ? p.total_tiles : rbu_num_sms();
+  if (a->stats) {
+    RBU_CHECK_ARG(!a->scatter && p.block_n <= 64 * EPI_STAT_CHUNKS && grid % p.n_blocks == 0 && ((uintptr_t)a->stats & 15) == 0,
+                  "rbu_conv_gemm: output statistics are not supported for this shape");
+    RBU_CHECK_CUDA(cudaMemsetAsync(a->stats, 0, rbu_conv_stats_floats(a->Ncols) * sizeof(float), stream));
+  }
   conv_gemm_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(tmA[0], tmB[0], tmA[1], tmB[1], p);
   RBU_CHECK_LAUNCH();
   return RBU_OK;

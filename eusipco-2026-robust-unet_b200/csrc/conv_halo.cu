@@ -37,7 +37,7 @@ constexpr int A_HALO_BYTES = HALO_H * HALO_W * 128;   // 36864
 constexpr int A_PLAIN_BYTES = BLOCK_M * 128;          // 16384
 constexpr int NUM_THREADS = 320;   // TMA warp, MMA warp, 8 epilogue warps
 constexpr int MAX_B_STAGES = 8;
-constexpr int SMEM_LIMIT = 232448;
+constexpr int SMEM_LIMIT = 232448 - EPI_STAT_FLOATS * 4;   // minus the static statistics accumulators
 constexpr int LOOKAHEAD_TAP = 4;                      // the next slab's A tile is requested after this tap's B tile
 
 struct HParams {
@@ -53,6 +53,7 @@ struct HParams {
   const float* bias;
   const bf16* addend;
   long long addend_ld;
+  float* stats;   // [4*SMs][2][Ncols] per-(CTA, lane group) column sum / sum of squares of the stored output, or NULL
 };
 
 // Enumerates the (tile, segment, 64-channel slab) sequence of this CTA; producer and MMA issuer walk it in lockstep.
@@ -103,6 +104,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  __shared__ __align__(16) float stat_smem[EPI_STAT_FLOATS];
+  if (p.stats)
+    for (int i = threadIdx.x; i < EPI_STAT_FLOATS; i += NUM_THREADS) stat_smem[i] = 0.f;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA0);
@@ -282,6 +286,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const int half = (warp - 2) >> 2;
     const int row = lg * 32 + lane;
     EpiOut eo;
+    eo.stat_acc = p.stats ? stat_smem + (warp - 2) * (EPI_STAT_CHUNKS * 64) : nullptr;
     eo.y = p.y; eo.y_ld = p.y_ld; eo.bias = p.bias; eo.addend = p.addend; eo.addend_ld = p.addend_ld;
     eo.Ncols = p.Ncols; eo.scatter = 0; eo.Cout = p.Ncols; eo.H = p.H; eo.W = p.W;
     auto locate = [&](int tile, int& nb, bool& valid, long long& pix, int& n, int& h, int& w) {
@@ -314,13 +319,26 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(a * p.block_n);
       for (int c0 = half * 32; c0 < p.block_n; c0 += 64) {
         if (c0 != half * 32) epi_prefetch(eo, nb * p.block_n + c0, valid, pix, ad);
-        epi_finish(eo, t_addr + (uint32_t)c0, nb * p.block_n + c0, valid, pix, n, h, w, ad);
+        epi_finish(eo, t_addr + (uint32_t)c0, nb * p.block_n + c0, valid, pix, n, h, w, ad, (c0 - half * 32) >> 6);
         if (c0 + 64 >= p.block_n && more) epi_prefetch(eo, nb2 * p.block_n + half * 32, valid2, pix2, ad);   // next tile
       }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty[a]);
       nb = nb2; n = n2; h = h2; w = w2; valid = valid2; pix = pix2;
+    }
+    if (p.stats) {
+      // every tile of this CTA has the same column block (grid % n_blocks == 0): flush the warp's accumulators
+      const int nbf = blockIdx.x % p.n_blocks;
+      float* row_out = p.stats + (long long)(blockIdx.x * 4 + lg) * 2 * p.Ncols;
+      for (int c0 = half * 32, j = 0; c0 < p.block_n; c0 += 64, ++j) {
+        const int col = nbf * p.block_n + c0 + lane;
+        if (col < p.Ncols) {
+          const float2 v = reinterpret_cast<const float2*>(eo.stat_acc)[j * 32 + lane];
+          row_out[col] = v.x;
+          row_out[p.Ncols + col] = v.y;
+        }
+      }
     }
   }
 
@@ -373,6 +391,7 @@ int rbu_conv_halo_launch(const rbu_conv_gemm_args* a, cudaStream_t stream) {
   p.bias = a->bias;
   p.addend = reinterpret_cast<const bf16*>(a->addend);
   p.addend_ld = a->addend_ld;
+  p.stats = a->stats;
 
   CUtensorMap tmA[2], tmB[2];
   memset(tmA, 0, sizeof(tmA));
@@ -403,6 +422,11 @@ int rbu_conv_halo_launch(const rbu_conv_gemm_args* a, cudaStream_t stream) {
     attr_set = true;
   }
   const int grid = p.total_tiles < rbu_num_sms() ? p.total_tiles : rbu_num_sms();
+  if (a->stats) {
+    RBU_CHECK_ARG(p.block_n <= 64 * EPI_STAT_CHUNKS && grid % p.n_blocks == 0 && ((uintptr_t)a->stats & 15) == 0,
+                  "rbu_conv_gemm: output statistics are not supported for this shape");
+    RBU_CHECK_CUDA(cudaMemsetAsync(a->stats, 0, rbu_conv_stats_floats(a->Ncols) * sizeof(float), stream));
+  }
   conv_halo_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(tmA[0], tmB[0], tmA[1], tmB[1], p);
   RBU_CHECK_LAUNCH();
   return RBU_OK;

@@ -7,7 +7,29 @@
 #include "rbu_common.cuh"
 #include "rbu_ptx.cuh"
 
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_STAT_CHUNKS = 4;                                   // 32-column chunks per epilogue warp (block_n <= 256)
+constexpr int EPI_STAT_FLOATS = EPI_WARPS * EPI_STAT_CHUNKS * 64;    // per-CTA BatchNorm accumulators: 8 KB of shared memory
+
+// Column sums over the 32 lanes of a warp of 32 per-lane values (recursive halving: 31 shuffles): lane l returns
+// the sum over all lanes of v[l].  Destroys v.
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#define RBU_HALVE(OFF, HALF)                                                        \
+  {                                                                                 \
+    const bool up = (lane & (OFF)) != 0;                                            \
+    _Pragma("unroll") for (int i = 0; i < (HALF); ++i) {                            \
+      const float send = up ? v[i] : v[i + (HALF)];                                 \
+      const float keep = up ? v[i + (HALF)] : v[i];                                 \
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, (OFF));                      \
+    }                                                                               \
+  }
+  RBU_HALVE(16, 16) RBU_HALVE(8, 8) RBU_HALVE(4, 4) RBU_HALVE(2, 2) RBU_HALVE(1, 1)
+#undef RBU_HALVE
+  return v[0];
+}
+
 struct EpiOut {
+  float* stat_acc;   // this warp's [EPI_STAT_CHUNKS][32][2] shared-memory accumulators, or nullptr (statistics off)
   bf16* y;
   long long y_ld;
   const float* bias;
@@ -30,17 +52,18 @@ __device__ __forceinline__ void epi_prefetch(const EpiOut& o, int col, bool vali
 }
 
 // taddr: TMEM address of (lane group base, first column of the chunk); col: first GEMM column of the chunk
+// `chunk` = index of this chunk among the warp's chunks of the tile (selects the statistics accumulator).
 __device__ __forceinline__ void epi_finish(const EpiOut& o, uint32_t taddr, int col, bool valid, long long pix, int n, int h,
-                                           int w, const uint4 (&ad)[4]) {
+                                           int w, const uint4 (&ad)[4], int chunk = 0) {
   const bool live = valid && col < o.Ncols;
   uint32_t r[32];
   ptx::tmem_ld_32x32(taddr, r);
   ptx::tmem_ld_wait();
-  if (!live) return;
+  float rv[32];      // the values as stored (bf16-rounded), zero for rows / columns outside the tensor
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     const int c8 = col + g * 8;
-    if (c8 < o.Ncols) {
+    if (live && c8 < o.Ncols) {
       bf16* dst;
       int cb = c8;  // bias channel
       if (o.scatter) {
@@ -68,7 +91,27 @@ __device__ __forceinline__ void epi_finish(const EpiOut& o, uint32_t taddr, int 
 #pragma unroll
         for (int e = 0; e < 8; ++e) f[e] += a8[e];
       }
-      st_bf16x8(dst, pack8(f));
+      const bf16x8 packed = pack8(f);
+      st_bf16x8(dst, packed);
+      if (o.stat_acc) unpack8(packed, &rv[g * 8]);
+    } else if (o.stat_acc) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) rv[g * 8 + e] = 0.f;
     }
+  }
+  if (o.stat_acc) {
+    // BatchNorm batch statistics of the stored tensor: per-column sum and sum of squares over this warp's 32 pixels,
+    // accumulated in the warp's private shared-memory slots (no atomics; fixed order -> deterministic)
+    const int lane = threadIdx.x & 31;
+    float sq[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) sq[i] = rv[i] * rv[i];
+    const float cs = warp_colsum32(rv, lane);
+    const float cq = warp_colsum32(sq, lane);
+    float2* slot = reinterpret_cast<float2*>(o.stat_acc) + chunk * 32 + lane;
+    float2 cur = *slot;
+    cur.x += cs;
+    cur.y += cq;
+    *slot = cur;
   }
 }

@@ -20,3 +20,5 @@ int rbu_conv_halo_launch(const rbu_conv_gemm_args* a, cudaStream_t stream);
 int rbu_wgrad_halo_supported(const rbu_wgrad_args* a);
 size_t rbu_wgrad_halo_workspace_bytes(const rbu_wgrad_args* a);
 int rbu_wgrad_halo_launch(const rbu_wgrad_args* a, void* workspace, cudaStream_t stream);
+
+extern "C" size_t rbu_conv_stats_floats(int Ncols);

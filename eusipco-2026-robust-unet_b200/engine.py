@@ -53,6 +53,10 @@ class Engine:
         self._side_dirty = False
         self._side_keep = []
         self.overlap_wgrad = os.environ.get("RBU_NO_OVERLAP") is None
+        # BatchNorm batch statistics fused into the producing convolution's epilogue (rbu_conv_gemm stats=...): one pass
+        # over the activations less, but the warp-transpose reduction slows the epilogue-sensitive small-N GEMMs by
+        # about as much (measured on B200: 44.9 vs 45.0 ms/step) -- off by default, exercised by the tests.
+        self.fuse_bn_stats = os.environ.get("RBU_FUSE_BN_STATS") == "1"
         self._ws = None
         self.drop_mask_fn = None     # optional callable(name, N, C) -> float32 [N,C] device tensor (tests)
         self.kernel_launches = 0
@@ -178,6 +182,26 @@ class Engine:
             bn.num_batches_tracked += 1
         return out
 
+    def conv_stats_buf(self, Ncols, device):
+        """Scratch for the BatchNorm partial sums a convolution's epilogue emits (training only)."""
+        return torch.empty(_lib.lib().rbu_conv_stats_floats(Ncols), dtype=torch.float32, device=device)
+
+    def bn_from_conv(self, part, Ncols, col_off, C, count, bn: nn.BatchNorm2d, off=0, out=None):
+        """Train-mode BatchNorm affine from the statistics fused into the producing convolution's epilogue.  `off`
+        selects a channel range of a wider BatchNorm (DilatedBlock: four convolutions feed one BN)."""
+        dev = part.device
+        if out is None:
+            nC = bn.num_features
+            out = {k: self.f32(nC, device=dev) for k in ("scale", "shift", "mean", "rstd")}
+
+        def sl(t):
+            return c_void_p(t.data_ptr() + 4 * off)
+
+        call("rbu_bn_finalize_partials", _p(part), Ncols, col_off, C, count, sl(bn.weight), sl(bn.bias),
+             sl(bn.running_mean), sl(bn.running_var), float(bn.momentum), float(bn.eps), sl(out["scale"]), sl(out["shift"]),
+             sl(out["mean"]), sl(out["rstd"]), stream_ptr())
+        return out
+
     # -- weight gradients run on a side stream: they are tensor-pipe work with no consumer inside the backward pass,
     #    so they overlap the bandwidth-bound elementwise kernels of the data-gradient chain on the main stream
     def _side(self, device):
@@ -236,20 +260,36 @@ class Engine:
         HW, P = H * W, N * H * W
         proj = not isinstance(blk.shortcut, nn.Identity)
         s = {"name": name, "x": x, "N": N, "H": H, "W": W, "C": C, "proj": proj, "patches": stem_patches}
+        bns = None
+        fuse = training and self.fuse_bn_stats
         if stem_patches is not None:
             y12 = self.new(N, H, W, 2 * C, dev)
             wst = self.pack_stem(blk.conv1.weight, blk.shortcut[0].weight, stem_patches.C)
+            st12 = self.conv_stats_buf(2 * C, dev) if fuse else None
             conv_gemm(N, H, W, [(stem_patches, wst, 1, 0, False)], 2 * C, y12,
-                      flops=2.0 * N * H * W * C * 10 * blk.conv1.in_channels)
+                      flops=2.0 * N * H * W * C * 10 * blk.conv1.in_channels, stats=st12)
             y1, ys = y12.slice(0, C), y12.slice(C, C)
+            if fuse:
+                bn1 = self.bn_from_conv(st12, 2 * C, 0, C, P, blk.bn1)
+                bns = self.bn_from_conv(st12, 2 * C, C, C, P, blk.shortcut[1])
         else:
             y1 = self.new(N, H, W, C, dev)
-            conv_gemm(N, H, W, [(x, self.pack(blk.conv1.weight, 0), 9, 1, False)], C, y1)
+            st1 = self.conv_stats_buf(C, dev) if fuse else None
+            conv_gemm(N, H, W, [(x, self.pack(blk.conv1.weight, 0), 9, 1, False)], C, y1, stats=st1)
+            if fuse:
+                bn1 = self.bn_from_conv(st1, C, 0, C, P, blk.bn1)
             ys = None
             if proj:
                 ys = self.new(N, H, W, C, dev)
-                conv_gemm(N, H, W, [(x, self.pack(blk.shortcut[0].weight, 0), 1, 0, False)], C, ys)
-        bn1 = self.bn_stats(y1, N, HW, blk.bn1, training)
+                sts = self.conv_stats_buf(C, dev) if fuse else None
+                conv_gemm(N, H, W, [(x, self.pack(blk.shortcut[0].weight, 0), 1, 0, False)], C, ys, stats=sts)
+                if fuse:
+                    bns = self.bn_from_conv(sts, C, 0, C, P, blk.shortcut[1])
+        if fuse:
+            for b_ in ((blk.bn1, blk.shortcut[1]) if proj else (blk.bn1,)):
+                b_.num_batches_tracked += 1
+        else:
+            bn1 = self.bn_stats(y1, N, HW, blk.bn1, training)
         drop = self.drop_mask(name, N, C, blk.dropout.p, dev) if training and blk.dropout.p > 0 else None
         a1 = self.new(N, H, W, C, dev)
         call("rbu_affine_act", _vp(y1), y1.ld, _vp(a1), a1.ld, P, HW, C, _p(bn1["scale"]), _p(bn1["shift"]), _p(drop), 1,
@@ -270,7 +310,8 @@ class Engine:
              _p(sa_s), _p(amax_c), stream_ptr())
         gs = self.f32(P, device=dev)
         call("rbu_sa_gate", _p(sa_s), N, H, W, _p(blk.sa.conv1.weight), _p(gs), stream_ptr())
-        bns = self.bn_stats(ys, N, HW, blk.shortcut[1], training) if proj else None
+        if proj and bns is None:
+            bns = self.bn_stats(ys, N, HW, blk.shortcut[1], training)
         if out is None:
             out = self.new(N, H, W, C, dev)
         rsrc = ys if proj else x
@@ -375,10 +416,19 @@ class Engine:
         C, F = skip.C, gate.W_g[0].out_channels
         HW, P = H * W, N * H * W
         yg, yx = self.new(N, H, W, F, dev), self.new(N, H, W, F, dev)
-        conv_gemm(N, H, W, [(g, self.pack(gate.W_g[0].weight, 0), 1, 0, False)], F, yg, bias=gate.W_g[0].bias)
-        conv_gemm(N, H, W, [(skip, self.pack(gate.W_x[0].weight, 0), 1, 0, False)], F, yx, bias=gate.W_x[0].bias)
-        bg = self.bn_stats(yg, N, HW, gate.W_g[1], training)
-        bx = self.bn_stats(yx, N, HW, gate.W_x[1], training)
+        fuse = training and self.fuse_bn_stats
+        stg = self.conv_stats_buf(F, dev) if fuse else None
+        stx = self.conv_stats_buf(F, dev) if fuse else None
+        conv_gemm(N, H, W, [(g, self.pack(gate.W_g[0].weight, 0), 1, 0, False)], F, yg, bias=gate.W_g[0].bias, stats=stg)
+        conv_gemm(N, H, W, [(skip, self.pack(gate.W_x[0].weight, 0), 1, 0, False)], F, yx, bias=gate.W_x[0].bias, stats=stx)
+        if fuse:
+            bg = self.bn_from_conv(stg, F, 0, F, P, gate.W_g[1])
+            bx = self.bn_from_conv(stx, F, 0, F, P, gate.W_x[1])
+            gate.W_g[1].num_batches_tracked += 1
+            gate.W_x[1].num_batches_tracked += 1
+        else:
+            bg = self.bn_stats(yg, N, HW, gate.W_g[1], training)
+            bx = self.bn_stats(yx, N, HW, gate.W_x[1], training)
         q0 = self.f32(P, device=dev)
         stats = self.f32(4, device=dev)
         nblk = _lib.lib().rbu_ag_psi_blocks(P, F)
@@ -431,11 +481,19 @@ class Engine:
         HW, P = H * W, N * H * W
         ycat = self.new(N, H, W, C, dev)
         convs = (blk.conv1, blk.conv2, blk.conv3, blk.conv4)
+        bn = None
+        fuse = training and self.fuse_bn_stats
         for i, cv in enumerate(convs):
             taps = 1 if i == 0 else 9
+            sti = self.conv_stats_buf(Cq, dev) if fuse else None
             conv_gemm(N, H, W, [(x, self.pack(cv.weight, 0), taps, cv.dilation[0], False)], Cq, ycat.slice(i * Cq, Cq),
-                      bias=cv.bias)
-        bn = self.bn_stats(ycat, N, HW, blk.bn, training)
+                      bias=cv.bias, stats=sti)
+            if fuse:
+                bn = self.bn_from_conv(sti, Cq, 0, Cq, P, blk.bn, off=i * Cq, out=bn)
+        if fuse:
+            blk.bn.num_batches_tracked += 1
+        else:
+            bn = self.bn_stats(ycat, N, HW, blk.bn, training)
         out = self.new(N, H, W, C, dev)
         call("rbu_affine_act", _vp(ycat), ycat.ld, _vp(out), out.ld, P, HW, C, _p(bn["scale"]), _p(bn["shift"]), NULL, 1,
              stream_ptr())

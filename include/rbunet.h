@@ -74,9 +74,19 @@ typedef struct {
   const float* bias;        /* fp32 [Cout] or NULL                                                 */
   const void* addend;       /* optional bf16 NHWC view added to the result (scatter=0 only)        */
   int64_t addend_ld;
+  float* stats;             /* optional: rbu_conv_stats_floats(Ncols) floats receiving per-(CTA, lane group)  */
+                            /* partial sum / sum of squares per output column of the STORED (bf16) result --  */
+                            /* the BatchNorm batch statistics, fused into the epilogue (scatter=0 only)        */
 } rbu_conv_gemm_args;
 
 int rbu_conv_gemm(const rbu_conv_gemm_args* args, void* stream);
+size_t rbu_conv_stats_floats(int Ncols);
+/* nn.BatchNorm2d train-mode affine (Main_Final.py:158,173,127,132,210) from the partials above: columns
+ * [col_off, col_off + C) of a conv whose GEMM had Ncols columns, `count` = N*H*W values per channel.  Updates the
+ * running statistics (momentum, unbiased variance) when running_mean != NULL. */
+int rbu_bn_finalize_partials(const float* part, int Ncols, int col_off, int C, int64_t count, const float* gamma,
+                             const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                             float* scale, float* shift, float* mean_out, float* rstd_out, void* stream);
 
 /* Re-pack fp32 torch-layout weights into the bf16 GEMM operand [Nn][T][K] (K contiguous).
  *  mode 0: Conv2d weight [Nn=Cout][K=Cin][T] for the forward GEMM
