@@ -227,6 +227,10 @@ def run_ours(args):
                "kernel_classes": classes}
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_port(R, infer, nc, S, budget_s=20.0)
+        if world == 1 and args.eager_baseline and not infer:
+            del model, net
+            torch.cuda.empty_cache()
+            out["torch_eager_same_gpu"] = eager_cuda_leg(R, nc, B, S, dev)
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
@@ -279,6 +283,53 @@ def cpu_port(R, infer, nc, S, budget_s, steps=None, warmup=1, batch=None):
             "ms_per_step": round(1e3 * total / n_steps, 1), "batch": b}
 
 
+def eager_cuda_leg(R, nc, B, S, dev, steps=3):
+    """Informational: the reference arithmetic (the oracle's torch ops = what the unmodified reference dispatches)
+    executed by eager PyTorch on the SAME GPU -- cuDNN/ATen kernels, autocast(bfloat16) + channels_last and plain fp32
+    (SURVEY.md §2.1 calls this the existing-Blackwell-kernel bar).  Not part of the timed arm."""
+    import torch
+    out = {}
+    for mode in ("bf16_autocast_channels_last", "fp32"):
+        try:
+            sd = {k: v.to(dev) for k, v in R.synthetic_state_dict(R.robust_unet_shapes(nc, 1, 64), seed=0).items()}
+            names = [k for k, v in sd.items() if v.is_floating_point() and "running" not in k]
+            params = [sd[n].requires_grad_(True) for n in names]
+            opt = torch.optim.Adam(params, lr=1e-4, weight_decay=1e-4, fused=True)
+            x, y = R.synthetic_inputs(B, nc, S, S, seed=5, blobby=True)
+            x, y = x.to(dev), y.to(dev)
+            if mode != "fp32":
+                x = x.contiguous(memory_format=torch.channels_last)
+
+            def one():
+                opt.zero_grad(set_to_none=True)
+                if mode == "fp32":
+                    p = R.robust_unet_forward(sd, x, training=True, new_buffers={})
+                else:
+                    with torch.autocast("cuda", dtype=torch.bfloat16):
+                        z = R.robust_unet_forward(sd, x, training=True, new_buffers={}, return_logits=True)
+                    p = torch.sigmoid(z.float())
+                loss = R.bce_loss(p, y)
+                loss.backward()
+                opt.step()
+
+            one()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                one()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[mode] = {"img_per_s": round(B / ms * 1e3, 1), "ms_per_step": round(ms, 2), "batch": B}
+            del sd, params, opt
+            torch.cuda.empty_cache()
+        except Exception as e:      # e.g. out of memory at this batch: report, do not fail the bench
+            out[mode] = {"error": f"{type(e).__name__}: {str(e)[:80]}"}
+            torch.cuda.empty_cache()
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -314,6 +365,8 @@ def main():
     ap.add_argument("--size", type=int, default=0)
     ap.add_argument("--channels", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager-baseline", action="store_true",
+                    help="also time the reference arithmetic through eager PyTorch (cuDNN) on the same GPU (informational)")
     ap.add_argument("--detail", default="", help="write the per-call device times of one profiled step to this file")
     args = ap.parse_args()
     if args.impl == "reference":
