@@ -14,6 +14,7 @@ from .model import RobustUNet  # noqa: F401
 from .ops import View, preprocess  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
 from .parallel import DataParallel, GradBucketer  # noqa: F401
+from .unet import CrossEntropyArgmaxLoss, UNet  # noqa: F401
 
 __all__ = ["RobustUNet", "RobustBCEDiceLoss", "calculate_metrics", "batch_metrics", "confusion_counts",
-           "metrics_from_counts", "METRIC_KEYS", "View", "preprocess", "DataParallel", "GradBucketer", "FusedAdam"]
+           "metrics_from_counts", "METRIC_KEYS", "View", "preprocess", "DataParallel", "GradBucketer", "FusedAdam", "UNet", "CrossEntropyArgmaxLoss"]

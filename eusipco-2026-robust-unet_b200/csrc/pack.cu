@@ -53,7 +53,12 @@ pack_multi_kernel(const rbu_pack_job* __restrict__ jobs, int njobs) {
     const long long i = base + u * 256 + threadIdx.x;
     if (i >= j.total) return;
     float v;
-    if (j.mode == 4) {
+    if (j.mode == 5) {          // stem operand of a plain conv (no shortcut rows): [C][Kp], Nn = C, T = input channels
+      const int nc = j.T;
+      const int k = (int)(i % j.K), n = (int)(i / j.K);
+      v = 0.f;
+      if (k < 9 * nc) { const int tap = k / nc, c = k - tap * nc; v = j.src[((long)n * nc + c) * 9 + tap]; }
+    } else if (j.mode == 4) {
       const int C = j.Nn / 2, nc = j.T;
       const int k = (int)(i % j.K), n = (int)(i / j.K);
       v = 0.f;

@@ -148,7 +148,7 @@ class Engine:
                     raise RuntimeError("rbunet: parameters must be contiguous fp32 CUDA tensors")
                 dst = torch.empty(shape, dtype=torch.bfloat16, device=dev)
                 self._packs[key] = dst
-                total = Nn * K if mode == 4 else Nn * T * K      # the stem operand's T carries the channel count
+                total = Nn * K if mode in (4, 5) else Nn * T * K   # the stem operands' T carries the channel count
                 tab[i] = (src.data_ptr(), src2.data_ptr() if src2 is not None else 0, dst.data_ptr(), first, total, Nn, T, K,
                           mode, cout, 0)
                 first += (total + 1023) // 1024

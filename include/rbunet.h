@@ -261,6 +261,21 @@ int rbu_maxpool2x2_bwd(const void* x, int64_t x_ld, const void* dy, int64_t dy_l
 int rbu_chan_sum(const void* x, int64_t ld, int64_t P, int C, float* out, void* workspace, size_t workspace_bytes,
                  void* stream);
 
+/* ------------------------------------------------------------------ plain 2-class U-Net path
+ * `final` 1x1 convolution to two logits (train_water_segmentation.py:246,288): logits fp32 NCHW [B,2,H,W]; its
+ * backward (dx bf16 view, dw [2][C], db [2]); nn.CrossEntropyLoss() on those logits (train_water_segmentation.py:304)
+ * fused with the argmax confusion counts behind accuracy / IoU (:384-388, class 1 = water, ties -> class 0). */
+int rbu_head2_forward(const void* x, int64_t ld, int64_t P, int HW, int C, const float* w, const float* b, float* logits,
+                      void* stream);
+size_t rbu_head2_backward_workspace_bytes(int64_t P, int C);
+int rbu_head2_backward(const float* dlogits, const void* x, int64_t x_ld, void* dx, int64_t dx_ld, int64_t P, int HW, int C,
+                       const float* w, float* dw, float* db, void* workspace, size_t workspace_bytes, void* stream);
+size_t rbu_ce2_workspace_bytes(int B, int64_t HW);
+int rbu_ce2_forward(const float* logits, const int64_t* target, int B, int64_t HW, void* workspace, size_t workspace_bytes,
+                    float* loss_out, int64_t* counts, void* stream);
+int rbu_ce2_backward(const float* logits, const int64_t* target, int B, int64_t HW, const float* grad_out, float* dlogits,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

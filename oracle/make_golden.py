@@ -194,6 +194,46 @@ def metric_goldens(MF):
     np.savez_compressed(os.path.join(OUT, "metrics.npz"), **cases)
 
 
+def unet_golden():
+    """Plain 2-class U-Net (train_water_segmentation.UNet): eval logits, one CrossEntropy train step."""
+    import train_water_segmentation as T     # importable once load_reference() has installed the stubs
+    from oracle import unet_ref as U
+    shapes = U.unet_shapes(3, 2)
+    torch.manual_seed(0)
+    model = T.UNet(3, 2)
+    ref_sd = model.state_dict()
+    assert list(ref_sd.keys()) == list(shapes.keys()), "UNet state_dict schema drifted"
+    for k, v in ref_sd.items():
+        assert tuple(v.shape) == tuple(shapes[k]), k
+    sd = R.synthetic_state_dict(shapes, seed=11)
+    # positive BatchNorm scales keep this reference close to a trained network (defaults are gamma = 1)
+    for k in sd:
+        if k.endswith(".weight") and sd[k].dim() == 1:
+            sd[k] = sd[k].abs()
+    model.load_state_dict(sd)
+    x, y = R.synthetic_inputs(2, 3, 32, 32, seed=321, blobby=True)
+    t = y[:, 0].long()
+    model.train()
+    z = model(x)
+    loss = nn.CrossEntropyLoss()(z, t)
+    loss.backward()
+    out = {"logits_train": z.detach().numpy(), "loss_train": np.float64(loss.item())}
+    out["param_names"] = np.array([k for k, _ in model.named_parameters()])
+    out["grad_summary"] = np.stack([grad_summary(p.grad) for _, p in model.named_parameters()])
+    model.load_state_dict(sd)
+    model.eval()
+    with torch.no_grad():
+        ze = model(x)
+    out["logits_eval"] = ze.numpy()
+    out["loss_eval"] = np.float64(nn.CrossEntropyLoss()(ze, t).item())
+    pred = torch.argmax(ze, dim=1)
+    out["accuracy_eval"] = np.float64((pred == t).float().mean().item())
+    tr = T.WaterSegmentationTrainer.calculate_iou(None, pred == 1, t == 1)
+    out["iou_eval"] = np.float64(float(tr))
+    np.savez_compressed(os.path.join(OUT, "unet_c3_32x32.npz"), **out)
+    print("unet loss", loss.item(), "eval loss", out["loss_eval"], "acc", out["accuracy_eval"], "iou", out["iou_eval"])
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
@@ -202,6 +242,7 @@ def main():
     model_golden(MF, "c4_b16_32x48", 4, 16, 2, 32, 48, w_dice=0.5)
     module_goldens(MF)
     metric_goldens(MF)
+    unet_golden()
     print("wrote", sorted(os.listdir(OUT)))
 
 
