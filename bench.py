@@ -95,21 +95,24 @@ def run_ours(args):
     _lib.check(_lib.lib().rbu_device_check(), "rbu_device_check")
 
     infer = args.workload == "infer"
+    unet = args.workload == "unet"          # the plain 2-class U-Net of train_water_segmentation.py
     B = args.batch or (32 if infer else 64)
     S = args.size or (1024 if infer else 256)
     nc = args.channels
     torch.manual_seed(0)
-    model = rbunet.RobustUNet(nc, 1, 64).to(dev)
-    crit = rbunet.RobustBCEDiceLoss()
+    model = (rbunet.UNet(nc, 2) if unet else rbunet.RobustUNet(nc, 1, 64)).to(dev)
+    crit = rbunet.CrossEntropyArgmaxLoss() if unet else rbunet.RobustBCEDiceLoss()
     net = model
     if infer:
         model.eval()
     else:
         model.train()
-        if world > 1:
+        if world > 1 and not unet:
             net = rbunet.DataParallel(model)
         opt = rbunet.FusedAdam(model.parameters(), lr=1e-4, weight_decay=1e-4)      # = torch.optim.Adam of Main_Final.py:552
     x_cpu, y_cpu = R.synthetic_inputs(B, nc, S, S, seed=123 + rank, blobby=True)
+    if unet:
+        y_cpu = y_cpu[:, 0].long()           # class-index masks, nn.CrossEntropyLoss style
     x_pin, y_pin = x_cpu.pin_memory(), y_cpu.pin_memory()
     x_dev, y_dev = x_cpu.to(dev), y_cpu.to(dev)
     x_stage, y_stage = torch.empty_like(x_dev), torch.empty_like(y_dev)
@@ -200,14 +203,16 @@ def run_ours(args):
     out = None
     if rank == 0:
         imgs = B * world * args.steps
-        gflop_img = (FWD_GFLOP_PER_IMG_256 if infer else TRAIN_GFLOP_PER_IMG_256) * (S * S) / (256 * 256)
+        gflop_img = (FWD_GFLOP_PER_IMG_256 if infer else (289.2 if unet else TRAIN_GFLOP_PER_IMG_256)) * (S * S) / (256 * 256)
         value = imgs / (ms / 1e3)
-        h2d = x_pin.numel() * 4 + y_pin.numel() * 4
+        h2d = x_pin.numel() * 4 + y_pin.numel() * y_pin.element_size()
         d2h = (B * 4 * 8) if infer else 4
         out = {"metric": "infer_images_per_sec" if infer else "train_images_per_sec", "value": round(value, 2), "unit": "img/s",
                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                "config": {"workload": (f"Robust U-Net inference {S}x{S} batch {B}/GPU, thresholded counts" if infer else
+                                       f"plain 2-class U-Net (train_water_segmentation.py) training step (fwd+CE+bwd+Adam), "
+                                       f"batch {B}/GPU at {S}x{S}" if unet else
                                        f"Robust U-Net bf16 training step (fwd+BCE+bwd+Adam), batch {B}/GPU at {S}x{S}, "
                                        f"{nc} channels, base 64"),
                           "global_batch": B * world, "image": [nc, S, S], "parallelism": f"dp{world}",
@@ -225,7 +230,7 @@ def run_ours(args):
                                "peak": peaks["hbm_gbs"], "peak_source": peaks["source"],
                                "note": "all bandwidth-bound kernels of one step: algorithmic bytes / summed CUDA-event time"},
                "kernel_classes": classes}
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not unet:
             out["cpu_baseline"] = cpu_port(R, infer, nc, S, budget_s=20.0)
         if world == 1 and args.eager_baseline and not infer:
             del model, net
@@ -360,7 +365,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="train", choices=["train", "infer"])
+    ap.add_argument("--workload", default="train", choices=["train", "infer", "unet"])
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--size", type=int, default=0)
     ap.add_argument("--channels", type=int, default=3)
