@@ -400,6 +400,8 @@ def main():
     else:
         if args.warmup < 3:
             args.warmup = 3
+        if args.workload == "infer" and args.warmup < 6:
+            args.warmup = 6        # 1024x1024 activations: the caching allocator needs a few passes to settle
         run_ours(args)
 
 

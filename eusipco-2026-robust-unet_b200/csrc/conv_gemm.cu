@@ -43,6 +43,8 @@ struct KParams {
   long long y_ld;
   int scatter, Cout;
   const float* bias;
+  const float* scale;
+  int relu;
   const bf16* addend;
   long long addend_ld;
   float* stats;   // [4*SMs][2][Ncols] per-(CTA, lane group) column sum / sum of squares of the stored output, or NULL
@@ -189,7 +191,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const int row = lg * 32 + lane;
     EpiOut eo;
     eo.stat_acc = p.stats ? stat_smem + (warp - 2) * (EPI_STAT_CHUNKS * 64) : nullptr;
-    eo.y = p.y; eo.y_ld = p.y_ld; eo.bias = p.bias; eo.addend = p.addend; eo.addend_ld = p.addend_ld;
+    eo.y = p.y; eo.y_ld = p.y_ld; eo.bias = p.bias; eo.scale = p.scale; eo.relu = p.relu; eo.addend = p.addend; eo.addend_ld = p.addend_ld;
     eo.Ncols = p.Ncols; eo.scatter = p.scatter; eo.Cout = p.Cout; eo.H = p.H; eo.W = p.W;
     // pixel of tile `tile` owned by this thread
     auto locate = [&](int tile, int& nb, bool& valid, long long& pix, int& n, int& h, int& w) {
@@ -338,6 +340,7 @@ extern "C" int rbu_conv_gemm(const rbu_conv_gemm_args* a, void* stream_) {
   RBU_CHECK_ARG(a->y != nullptr && a->y_ld % 8 == 0 && ((uintptr_t)a->y & 15) == 0,
                 "rbu_conv_gemm: output view must be 16-byte aligned with ld %% 8 == 0");
   RBU_CHECK_ARG(a->bias == nullptr || ((uintptr_t)a->bias & 15) == 0, "rbu_conv_gemm: bias must be 16-byte aligned");
+  RBU_CHECK_ARG(a->scale == nullptr || ((uintptr_t)a->scale & 15) == 0, "rbu_conv_gemm: scale must be 16-byte aligned");
   if (a->scatter) {
     RBU_CHECK_ARG(a->Cout > 0 && a->Ncols == 4 * a->Cout && a->Cout % 8 == 0,
                   "rbu_conv_gemm: scatter needs Ncols == 4*Cout and Cout %% 8 == 0");
@@ -405,6 +408,8 @@ extern "C" int rbu_conv_gemm(const rbu_conv_gemm_args* a, void* stream_) {
   p.scatter = a->scatter;
   p.Cout = a->scatter ? a->Cout : a->Ncols;
   p.bias = a->bias;
+  p.scale = a->scale;
+  p.relu = a->relu;
   p.addend = reinterpret_cast<const bf16*>(a->addend);
   p.addend_ld = a->addend_ld;
   p.stats = a->stats;

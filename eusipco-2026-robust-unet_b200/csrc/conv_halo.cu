@@ -51,6 +51,8 @@ struct HParams {
   bf16* y;
   long long y_ld;
   const float* bias;
+  const float* scale;
+  int relu;
   const bf16* addend;
   long long addend_ld;
   float* stats;   // [4*SMs][2][Ncols] per-(CTA, lane group) column sum / sum of squares of the stored output, or NULL
@@ -287,7 +289,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const int row = lg * 32 + lane;
     EpiOut eo;
     eo.stat_acc = p.stats ? stat_smem + (warp - 2) * (EPI_STAT_CHUNKS * 64) : nullptr;
-    eo.y = p.y; eo.y_ld = p.y_ld; eo.bias = p.bias; eo.addend = p.addend; eo.addend_ld = p.addend_ld;
+    eo.y = p.y; eo.y_ld = p.y_ld; eo.bias = p.bias; eo.scale = p.scale; eo.relu = p.relu; eo.addend = p.addend; eo.addend_ld = p.addend_ld;
     eo.Ncols = p.Ncols; eo.scatter = 0; eo.Cout = p.Ncols; eo.H = p.H; eo.W = p.W;
     auto locate = [&](int tile, int& nb, bool& valid, long long& pix, int& n, int& h, int& w) {
       int w0, h0;
@@ -389,6 +391,8 @@ int rbu_conv_halo_launch(const rbu_conv_gemm_args* a, cudaStream_t stream) {
   p.y = reinterpret_cast<bf16*>(a->y);
   p.y_ld = a->y_ld;
   p.bias = a->bias;
+  p.scale = a->scale;
+  p.relu = a->relu;
   p.addend = reinterpret_cast<const bf16*>(a->addend);
   p.addend_ld = a->addend_ld;
   p.stats = a->stats;

@@ -33,6 +33,8 @@ struct EpiOut {
   bf16* y;
   long long y_ld;
   const float* bias;
+  const float* scale;   // optional per-column scale applied to the accumulator before the bias (eval-mode BatchNorm fold)
+  int relu;             // ReLU after scale / bias / addend on the first `relu` output channels (0: none)
   const bf16* addend;
   long long addend_ld;
   int Ncols;
@@ -77,6 +79,12 @@ __device__ __forceinline__ void epi_finish(const EpiOut& o, uint32_t taddr, int 
       float f[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(r[g * 8 + e]);
+      if (o.scale) {
+        const float4 s0 = __ldg(reinterpret_cast<const float4*>(o.scale + cb));
+        const float4 s1 = __ldg(reinterpret_cast<const float4*>(o.scale + cb + 4));
+        f[0] *= s0.x; f[1] *= s0.y; f[2] *= s0.z; f[3] *= s0.w;
+        f[4] *= s1.x; f[5] *= s1.y; f[6] *= s1.z; f[7] *= s1.w;
+      }
       if (o.bias) {
         const float4 b0 = __ldg(reinterpret_cast<const float4*>(o.bias + cb));
         const float4 b1 = __ldg(reinterpret_cast<const float4*>(o.bias + cb + 4));
@@ -90,6 +98,10 @@ __device__ __forceinline__ void epi_finish(const EpiOut& o, uint32_t taddr, int 
         unpack8(t, a8);
 #pragma unroll
         for (int e = 0; e < 8; ++e) f[e] += a8[e];
+      }
+      if (cb < o.relu) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
       }
       const bf16x8 packed = pack8(f);
       st_bf16x8(dst, packed);

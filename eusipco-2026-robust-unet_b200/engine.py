@@ -52,6 +52,7 @@ class Engine:
         self._side_ws = None
         self._side_dirty = False
         self._side_keep = []
+        self._saving = False
         self.overlap_wgrad = os.environ.get("RBU_NO_OVERLAP") is None
         # BatchNorm batch statistics fused into the producing convolution's epilogue (rbu_conv_gemm stats=...): one pass
         # over the activations less, but the warp-transpose reduction slows the epilogue-sensitive small-N GEMMs by
@@ -182,6 +183,23 @@ class Engine:
             bn.num_batches_tracked += 1
         return out
 
+    def bn_eval_affine(self, bn: nn.BatchNorm2d, any_view: View, conv_bias=None):
+        """Eval-mode BatchNorm as a per-channel (scale, shift) pair from the running statistics, with the producing
+        convolution's bias folded in: BN(acc + b) = scale*acc + (shift + scale*b).  Feeds the conv epilogue."""
+        st = self._bn_eval(bn, any_view)
+        if conv_bias is not None:
+            st = dict(st)
+            st["shift"] = torch.addcmul(st["shift"], st["scale"], conv_bias.detach())
+        return st
+
+    def _bn_eval(self, bn, any_view):
+        C, dev = bn.num_features, any_view.base.device
+        out = {k: self.f32(C, device=dev) for k in ("scale", "shift", "mean", "rstd")}
+        call("rbu_bn_stats", _vp(any_view), any_view.ld, 1, 1, C, 0, 0, _p(bn.weight), _p(bn.bias), _p(bn.running_mean),
+             _p(bn.running_var), float(bn.momentum), float(bn.eps), _p(out["scale"]), _p(out["shift"]), _p(out["mean"]),
+             _p(out["rstd"]), NULL, NULL, NULL, NULL, 0, stream_ptr())
+        return out
+
     def conv_stats_buf(self, Ncols, device):
         """Scratch for the BatchNorm partial sums a convolution's epilogue emits (training only)."""
         return torch.empty(_lib.lib().rbu_conv_stats_floats(Ncols), dtype=torch.float32, device=device)
@@ -273,9 +291,16 @@ class Engine:
                 bn1 = self.bn_from_conv(st12, 2 * C, 0, C, P, blk.bn1)
                 bns = self.bn_from_conv(st12, 2 * C, C, C, P, blk.shortcut[1])
         else:
-            y1 = self.new(N, H, W, C, dev)
+            folded = not training and not self._saving   # inference: BN1 + ReLU ride in conv1's epilogue, no y1
+            y1 = None if folded else self.new(N, H, W, C, dev)
             st1 = self.conv_stats_buf(C, dev) if fuse else None
-            conv_gemm(N, H, W, [(x, self.pack(blk.conv1.weight, 0), 9, 1, False)], C, y1, stats=st1)
+            if folded:
+                bn1 = self.bn_eval_affine(blk.bn1, x)
+                a1 = self.new(N, H, W, C, dev)
+                conv_gemm(N, H, W, [(x, self.pack(blk.conv1.weight, 0), 9, 1, False)], C, a1, scale=bn1["scale"],
+                          bias=bn1["shift"], relu=C)
+            else:
+                conv_gemm(N, H, W, [(x, self.pack(blk.conv1.weight, 0), 9, 1, False)], C, y1, stats=st1)
             if fuse:
                 bn1 = self.bn_from_conv(st1, C, 0, C, P, blk.bn1)
             ys = None
@@ -288,12 +313,13 @@ class Engine:
         if fuse:
             for b_ in ((blk.bn1, blk.shortcut[1]) if proj else (blk.bn1,)):
                 b_.num_batches_tracked += 1
-        else:
+        elif y1 is not None:
             bn1 = self.bn_stats(y1, N, HW, blk.bn1, training)
         drop = self.drop_mask(name, N, C, blk.dropout.p, dev) if training and blk.dropout.p > 0 else None
-        a1 = self.new(N, H, W, C, dev)
-        call("rbu_affine_act", _vp(y1), y1.ld, _vp(a1), a1.ld, P, HW, C, _p(bn1["scale"]), _p(bn1["shift"]), _p(drop), 1,
-             stream_ptr())
+        if y1 is not None:
+            a1 = self.new(N, H, W, C, dev)
+            call("rbu_affine_act", _vp(y1), y1.ld, _vp(a1), a1.ld, P, HW, C, _p(bn1["scale"]), _p(bn1["shift"]), _p(drop), 1,
+                 stream_ptr())
         y2 = self.new(N, H, W, C, dev)
         conv_gemm(N, H, W, [(a1, self.pack(blk.conv2.weight, 0), 9, 1, False)], C, y2)
         bn2 = self.bn_stats(y2, N, HW, blk.bn2, training, pool=True)
@@ -539,6 +565,7 @@ class Engine:
         dev = x.device
         x = x.contiguous().float()
         self.refresh_packs()
+        self._saving = bool(save)
         S = {"N": N, "H": H, "W": W}
         Kp = ((9 * nc + 7) // 8) * 8
         patches = View(torch.empty((N, H, W, Kp), dtype=torch.bfloat16, device=dev))

@@ -58,6 +58,24 @@ class UNetEngine(Engine):
         dev = (x if x is not None else patches).base.device
         C = seq[0].out_channels
         HW, P = H * W, N * H * W
+        if not training and not self._saving:
+            # inference: both BatchNorm + ReLU pairs are folded into the convolutions' epilogues
+            # (scale*acc + (shift + scale*bias), ReLU): the block is two GEMM launches
+            src = x if x is not None else patches
+            f1 = self.bn_eval_affine(seq[1], src, seq[0].bias)
+            a1 = self.new(N, H, W, C, dev)
+            if patches is not None:
+                conv_gemm(N, H, W, [(patches, self._packs[(id(seq[0].weight), "stem")], 1, 0, False)], C, a1,
+                          scale=f1["scale"], bias=f1["shift"], relu=C, flops=2.0 * P * C * 9 * seq[0].in_channels)
+            else:
+                conv_gemm(N, H, W, [(x, self.pack(seq[0].weight, 0), 9, 1, False)], C, a1, scale=f1["scale"],
+                          bias=f1["shift"], relu=C)
+            f2 = self.bn_eval_affine(seq[4], a1, seq[3].bias)
+            if out is None:
+                out = self.new(N, H, W, C, dev)
+            conv_gemm(N, H, W, [(a1, self.pack(seq[3].weight, 0), 9, 1, False)], C, out, scale=f2["scale"],
+                      bias=f2["shift"], relu=C)
+            return out, None
         y1 = self.new(N, H, W, C, dev)
         if patches is not None:
             conv_gemm(N, H, W, [(patches, self._packs[(id(seq[0].weight), "stem")], 1, 0, False)], C, y1, bias=seq[0].bias,
@@ -132,6 +150,7 @@ class UNetEngine(Engine):
         dev = x.device
         x = x.contiguous().float()
         self.refresh_packs()
+        self._saving = bool(save)
         S = {"N": N, "H": H, "W": W}
         Kp = ((9 * nc + 7) // 8) * 8
         patches = View(torch.empty((N, H, W, Kp), dtype=torch.bfloat16, device=dev))

@@ -74,6 +74,8 @@ typedef struct {
   const float* bias;        /* fp32 [Cout] or NULL                                                 */
   const void* addend;       /* optional bf16 NHWC view added to the result (scatter=0 only)        */
   int64_t addend_ld;
+  const float* scale;       /* optional fp32 [Cout]: y = scale*acc + bias (eval-mode BatchNorm folded into the conv) */
+  int relu;                 /* ReLU after scale / bias / addend on output channels [0, relu) (0: none)         */
   float* stats;             /* optional: rbu_conv_stats_floats(Ncols) floats receiving per-(CTA, lane group)  */
                             /* partial sum / sum of squares per output column of the STORED (bf16) result --  */
                             /* the BatchNorm batch statistics, fused into the epilogue (scatter=0 only)        */
