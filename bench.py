@@ -40,17 +40,35 @@ def load_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+    """Samples SM clock and throttle reasons through NVML while the timed region runs.  NVML is initialised once, up
+    front (nvmlInit inside the timed region stalls kernel launches for ~100 ms)."""
+    _nv = None
+    _handles = {}
+
+    @classmethod
+    def prepare(cls, index):
+        try:
+            import pynvml as nv
+            if cls._nv is None:
+                nv.nvmlInit()
+                cls._nv = nv
+            if index not in cls._handles:
+                cls._handles[index] = nv.nvmlDeviceGetHandleByIndex(index)
+        except Exception as e:
+            cls._nv = None
+            cls._err = f"nvml_unavailable:{type(e).__name__}"
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
 
     def run(self):
+        nv = ClockSampler._nv
+        if nv is None:
+            self.reasons.add(getattr(ClockSampler, "_err", "nvml_unavailable"))
+            return
         try:
-            import pynvml as nv
-            nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            h = ClockSampler._handles[self.index]
             self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
             names = {nv.nvmlClocksEventReasonHwSlowdown: "hw_slowdown",
                      nv.nvmlClocksEventReasonHwThermalSlowdown: "hw_thermal_slowdown",
@@ -65,9 +83,9 @@ class ClockSampler(threading.Thread):
                 for bit, nm in names.items():
                     if r & bit:
                         self.reasons.add(nm)
-                time.sleep(0.05)
-        except Exception as e:   # NVML missing: report that instead of failing the bench
-            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+                time.sleep(0.1)
+        except Exception as e:   # NVML trouble: report that instead of failing the bench
+            self.reasons.add(f"nvml_error:{type(e).__name__}")
 
     def result(self):
         self.stop_flag = True
@@ -93,6 +111,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.check(_lib.lib().rbu_device_check(), "rbu_device_check")
+    ClockSampler.prepare(local)
 
     infer = args.workload == "infer"
     unet = args.workload == "unet"          # the plain 2-class U-Net of train_water_segmentation.py
@@ -172,7 +191,8 @@ def run_ours(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
-            flush.zero_()                   # L2 flush between timed iterations (the batch itself is also > L2)
+            if not args.no_flush:
+                flush.zero_()               # L2 flush between timed iterations
             fn()
         e1.record()
         barrier()
@@ -391,6 +411,7 @@ def main():
     ap.add_argument("--size", type=int, default=0)
     ap.add_argument("--channels", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-flush", action="store_true", help="skip the 256 MiB L2-flush write between timed steps")
     ap.add_argument("--eager-baseline", action="store_true",
                     help="also time the reference arithmetic through eager PyTorch (cuDNN) on the same GPU (informational)")
     ap.add_argument("--detail", default="", help="write the per-call device times of one profiled step to this file")
