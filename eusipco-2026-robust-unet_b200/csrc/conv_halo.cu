@@ -48,6 +48,7 @@ struct HParams {
   int taps[2], C[2];
   int a_stages, b_stages, tmem_cols, total_tiles;
   int tps;   // taps per B stage for a 3x3 segment (3 = one kernel row per stage when block_n <= 128, else 1)
+  int resident;   // 1: the whole weight operand (slabs x 9 taps) stays in shared memory for the life of the CTA
   bf16* y;
   long long y_ld;
   const float* bias;
@@ -123,7 +124,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       ptx::mbar_init(&fullA[s], 1);
       ptx::mbar_init(&emptyA[s], 1);
     }
-    for (int s = 0; s < p.b_stages; ++s) {
+    for (int s = 0; s < (p.b_stages < MAX_B_STAGES ? p.b_stages : MAX_B_STAGES); ++s) {
       ptx::mbar_init(&fullB[s], 1);
       ptx::mbar_init(&emptyB[s], 1);
     }
@@ -166,8 +167,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           ptx::tma_load_4d(smA + s * A_HALO_BYTES, mA, &fullA[s], ia.kc * BLOCK_K, w0, h0, n);
         ia.next(p);
       };
-      if (ia.valid) issue_a();
-      while (ib.valid) {
+      if (p.resident) {
+        // the weights of a 64-output-channel layer fit in shared memory: fetch them once, then stream only A tiles
+        const int slabs = p.C[0] / BLOCK_K;
+        ptx::mbar_arrive_expect_tx(&fullB[0], (uint32_t)(slabs * 9 * b_bytes));
+        for (int kc = 0; kc < slabs; ++kc)
+          for (int tap = 0; tap < 9; ++tap)
+            ptx::tma_load_2d(smB + (kc * 9 + tap) * b_bytes, &tmB0, &fullB[0], tap * p.C[0] + kc * BLOCK_K, 0);
+        while (ia.valid) issue_a();
+      }
+      if (!p.resident && ia.valid) issue_a();
+      while (!p.resident && ib.valid) {
         int nb, w0, h0, n;
         tile_coords(p, ib.tile, nb, w0, h0, n);
         const int taps = p.taps[ib.seg];
@@ -204,6 +214,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     it.init(p);
     int sa = 0, sb = 0, t = 0;
     uint32_t pha = 0, phb = 0;
+    bool bres_ready = false;
     while (it.valid) {
       const int a = t & 1;
       ptx::mbar_wait(&tempty[a], ((t >> 1) & 1) ^ 1);
@@ -221,7 +232,28 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const int rem = p.C[it.seg] - it.kc * BLOCK_K;
         const int ksteps = rem >= BLOCK_K ? 4 : (rem + 15) / 16;   // channels past C are TMA zero fill
         // halo origin is pixel (h0-1, w0-1): tap (dy,dx) starts dy halo rows (2048 B) down and dx pixels (128 B) right
-        if (halo && p.tps == 3 && ksteps == 4) {
+        if (p.resident) {
+          // 36 MMAs per slab straight from the resident weights: one barrier wait (the A tile) per 36 instructions
+          if (!bres_ready) {
+            ptx::mbar_wait_s(fullB_s, 0);
+            ptx::tc_fence_after();
+            bres_ready = true;
+          }
+          if (ptx::elect_one()) {
+            const uint32_t b_lo = ptx::desc_lo(smB_s, 16) + it.kc * (9 * b_step);
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+              for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  ptx::umma_bf16(d_tmem, ptx::pack_desc(a_lo0 + dy * ((HALO_W * 128) >> 4) + dx * 8 + 2 * k, a_hi),
+                                 ptx::pack_desc(b_lo + (dy * 3 + dx) * b_step + 2 * k, b_hi), idesc,
+                                 (dy | dx | k) ? 1u : accumulate);
+          }
+          accumulate = 1;
+          __syncwarp();
+        } else if (halo && p.tps == 3 && ksteps == 4) {
           // one kernel row (3 taps x 4 K-steps = 12 MMAs) per B stage, fully unrolled with immediate offsets
           uint32_t a_row = a_lo0;
           for (int dy = 0; dy < 3; ++dy) {
@@ -385,6 +417,22 @@ int rbu_conv_halo_launch(const rbu_conv_gemm_args* a, cudaStream_t stream) {
   p.a_stages = p.block_n >= 128 ? 2 : 3;
   p.b_stages = (SMEM_LIMIT - 2048 - p.a_stages * A_HALO_BYTES) / (b_bytes * p.tps);
   if (p.b_stages > MAX_B_STAGES) p.b_stages = MAX_B_STAGES;
+  {
+    // resident weights: one 3x3 segment, one column block, whole operand <= the shared memory left beside 2-3 A stages
+    static int no_res = -1;
+    if (no_res < 0) no_res = getenv("RBU_NO_RESIDENT") ? 1 : 0;
+    const long wbytes = (long)(a->seg[0].C / BLOCK_K) * 9 * b_bytes;
+    if (!no_res && a->nseg == 1 && a->seg[0].taps == 9 && p.n_blocks == 1 && a->seg[0].C % BLOCK_K == 0) {
+      int as = 3;
+      if (wbytes + as * A_HALO_BYTES > SMEM_LIMIT - 2048) as = 2;
+      if (wbytes + as * A_HALO_BYTES <= SMEM_LIMIT - 2048) {
+        p.resident = 1;
+        p.a_stages = as;
+        p.tps = 1;
+        p.b_stages = (int)(wbytes / b_bytes);       // the B region is sized in single-tap tiles
+      }
+    }
+  }
   p.tmem_cols = 32;
   while (p.tmem_cols < 2 * p.block_n) p.tmem_cols <<= 1;
   p.total_tiles = p.tiles_w * p.tiles_h * a->N * p.n_blocks;
