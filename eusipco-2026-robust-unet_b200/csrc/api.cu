@@ -56,6 +56,11 @@ typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 
 int rbu_encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                          const uint64_t* strides_bytes, const uint32_t* box) {
+  return rbu_encode_tmap_bf16_sw(out, base, rank, dims, strides_bytes, box, 128);
+}
+
+int rbu_encode_tmap_bf16_sw(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                            const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
   static encode_tiled_fn fn = nullptr;
   if (!fn) {
     void* sym = nullptr;
@@ -78,7 +83,8 @@ int rbu_encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uin
     if (i + 1 < rank) gstr[i] = strides_bytes[i];
   }
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim,
-                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     rbu_set_error("cuTensorMapEncodeTiled failed (CUresult %d): rank %d dims [%llu %llu %llu %llu %llu] box [%u %u %u %u %u] "

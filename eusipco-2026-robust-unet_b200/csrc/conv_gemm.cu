@@ -48,11 +48,31 @@ struct KParams {
   const bf16* addend;
   long long addend_ld;
   float* stats;   // [4*SMs][2][Ncols] per-(CTA, lane group) column sum / sum of squares of the stored output, or NULL
+  // staged epilogue (TMA stores): see the epilogue branch of the kernel
+  int tma_store;          // 1: outputs leave through the y tensor map, 0: per-thread 16-byte stores
+  int st_bufs;            // staging buffers per epilogue warp (2, or 3 when an addend box is prefetched one job ahead)
+  int log_tw, log_th;     // TW and TH are powers of two
+  int Hg, Ng;             // extent of the (h, n) tile coordinates: (H, N), or (N*H, 1) for merged rows (gather)
+  FastDiv fd_nb, fd_tw, fd_th, fd_cout;
 };
+
+constexpr int STG_BYTES = 32 * 32 * 2;   // one staging buffer: 32 pixels x 32 channels bf16
+constexpr int BAR_BYTES = 512;           // mbarriers + TMEM slot
+
+__device__ __forceinline__ void decode_tile(const KParams& p, int tile, int& nb, int& w0, int& h0, int& n0) {
+  const int sp = fast_div(tile, p.fd_nb);
+  nb = tile - sp * p.n_blocks;
+  const int q = fast_div(sp, p.fd_tw);
+  w0 = (sp - q * p.tiles_w) * p.TW;
+  const int q2 = fast_div(q, p.fd_th);
+  h0 = (q - q2 * p.tiles_h) * p.TH;
+  n0 = q2 * p.TN;
+}
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                  const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
+                 const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmAd,
                  const __grid_constant__ KParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -62,7 +82,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   uint64_t* empty = bars + MAX_STAGES;
   uint64_t* tfull = bars + 2 * MAX_STAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* adbar = tempty + 2;            // [8 epilogue warps][3] addend-box arrival barriers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(adbar + 24);
+  uint8_t* stg_base = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(bars) + BAR_BYTES + 1023) & ~uintptr_t(1023));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -77,6 +100,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       ptx::prefetch_tmap(&tmA1);
       ptx::prefetch_tmap(&tmB1);
     }
+    if (p.tma_store) {
+      ptx::prefetch_tmap(&tmY);
+      if (p.addend) ptx::prefetch_tmap(&tmAd);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.num_stages; ++s) {
@@ -85,8 +112,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tfull[a], 1);
-      ptx::mbar_init(&tempty[a], 8);
+      ptx::mbar_init(&tempty[a], (p.tma_store && p.block_n <= 32) ? 4 : 8);   // epilogue warps that own columns
     }
+    for (int i = 0; i < 24; ++i) ptx::mbar_init(&adbar[i], 1);
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
@@ -107,12 +135,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       int s = 0;
       uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int nb = tile % p.n_blocks;
-        int sp = tile / p.n_blocks;
-        const int w0 = (sp % p.tiles_w) * p.TW;
-        sp /= p.tiles_w;
-        const int h0 = (sp % p.tiles_h) * p.TH;
-        const int n0 = (sp / p.tiles_h) * p.TN;
+        int nb, w0, h0, n0;
+        decode_tile(p, tile, nb, w0, h0, n0);
         for (int seg = 0; seg < p.nseg; ++seg) {
           const CUtensorMap* mA = seg ? &tmA1 : &tmA0;
           const CUtensorMap* mB = seg ? &tmB1 : &tmB0;
@@ -124,7 +148,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
               dw = (tap % 3 - 1) * p.dil[seg];
             }
             for (int kc = 0; kc < kch; ++kc) {
-              ptx::mbar_wait(&empty[s], ph ^ 1);
+              ptx::mbar_wait_backoff(&empty[s], ph ^ 1);
               ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)stage_bytes);
               uint8_t* a_dst = smem + s * stage_bytes;
               uint8_t* b_dst = a_dst + A_BYTES;
@@ -184,8 +208,147 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       if (ptx::elect_one()) ptx::umma_commit(&tfull[a]);  // accumulator complete
       __syncwarp();
     }
+  } else if (p.tma_store) {
+    // ============================== epilogue, staged (warps 2..9) ==============================
+    // Warp (lg, half) owns accumulator rows [32 lg, 32 lg + 32) -- 32 consecutive pixels of the tile in (n, h, w)
+    // order -- and the 32-column chunks c0 = 32 half, 32 half + 64, ...  A "job" is one chunk of one tile:
+    //   tcgen05.ld -> scale / bias / addend / ReLU -> bf16 -> swizzled shared-memory box -> TMA store.
+    // Buffers rotate; `cp.async.bulk.wait_group.read 1` at the top of job k proves the store of job k-2 has drained its
+    // buffer, which is the one job k writes (2 buffers) or the one the addend box of job k+1 is loaded into (3).
+    const int ew = warp - 2;
+    const int lg = warp & 3;
+    const int half = ew >> 2;
+    if (half * 32 < p.block_n) {
+      const int nbuf = p.st_bufs;
+      uint64_t* abar = adbar + ew * 3;
+      const int r2g = (lg * 32) >> p.log_tw;                       // first pixel row of the warp's group, in tile rows
+      const int hg = p.gather ? r2g : (r2g & (p.TH - 1));
+      const int ng = p.gather ? 0 : (r2g >> p.log_th);
+      const int row = lg * 32 + lane;                              // own pixel: only the statistics mask needs it
+      const int wl = row & (p.TW - 1);
+      const int r2 = row >> p.log_tw;
+      const int hl = p.gather ? r2 : (r2 & (p.TH - 1));
+      const int nl = p.gather ? 0 : (r2 >> p.log_th);
+      const bool has_add = p.addend != nullptr;
+      uint8_t* stg = stg_base + ew * p.st_bufs * STG_BYTES;
+      const uint32_t my_x = ((uint32_t)lane >> 1) & 3u;
+      // 32-bit shared addresses of this thread's four 16-byte pieces in buffer 0 (SWIZZLE_64B)
+      const uint32_t stg_s = ptx::smem_u32(stg) + (uint32_t)lane * 64u;
+      const uint32_t pc0 = stg_s + ((0u ^ my_x) << 4), pc1 = stg_s + ((1u ^ my_x) << 4);
+      const uint32_t pc2 = stg_s + ((2u ^ my_x) << 4), pc3 = stg_s + ((3u ^ my_x) << 4);
+      const int mode = (has_add ? 1 : 0) | (p.bias ? 2 : 0) | ((p.scale || p.relu) ? 4 : 0);
+      float* stat_acc = p.stats ? stat_smem + ew * (EPI_STAT_CHUNKS * 64) : nullptr;
+
+      int tile = blockIdx.x, c0 = half * 32;
+      int nb = 0, w0 = 0, h0 = 0, n0 = 0;
+      bool live = tile < p.total_tiles;
+      if (live) decode_tile(p, tile, nb, w0, h0, n0);
+      // box origin of a job in the output (or addend) tensor map
+      auto box = [&](const CUtensorMap* m, bool store, uint8_t* buf, uint64_t* bar, int jnb, int jc0, int jw0, int jh0,
+                     int jn0) {
+        const int col = jnb * p.block_n + jc0;
+        if (p.scatter) {   // (co, j, w, i, n*H + h) view of the 2x up-sampled tensor; stores only
+          const int q = fast_div(col, p.fd_cout);
+          if (jh0 + hg < p.H)
+            ptx::tma_store_5d(m, buf, col - q * p.Cout, q & 1, jw0, q >> 1, (jn0 + ng) * p.H + jh0 + hg);
+        } else if (store) {
+          ptx::tma_store_4d(m, buf, col, jw0, jh0 + hg, jn0 + ng);
+        } else {
+          ptx::mbar_arrive_expect_tx(bar, STG_BYTES);
+          ptx::tma_load_4d(buf, m, bar, col, jw0, jh0 + hg, jn0 + ng);
+        }
+      };
+      int b = 0, t = 0;
+      uint32_t aphase = 0;
+      if (has_add && live && lane == 0) box(&tmAd, false, stg, &abar[0], nb, c0, w0, h0, n0);
+      while (live) {
+        // next job
+        int tile2 = tile, c2 = c0 + 64, nb2 = nb, w2 = w0, h2 = h0, n2 = n0;
+        if (c2 >= p.block_n) {
+          c2 = half * 32;
+          tile2 = tile + gridDim.x;
+          if (tile2 < p.total_tiles) decode_tile(p, tile2, nb2, w2, h2, n2);
+        }
+        const bool live2 = tile2 < p.total_tiles;
+        const int b2 = (b + 1 == nbuf) ? 0 : b + 1;
+        if (lane == 0) {
+          ptx::bulk_wait_read<1>();
+          if (has_add && live2) box(&tmAd, false, stg + b2 * STG_BYTES, &abar[b2], nb2, c2, w2, h2, n2);
+        }
+        __syncwarp();
+        const int a = t & 1;
+        if (c0 == half * 32) {   // first chunk of the tile: the accumulator must be complete
+          ptx::mbar_wait(&tfull[a], (t >> 1) & 1);
+          ptx::tc_fence_after();
+        }
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(a * p.block_n + c0), r);
+        uint8_t* buf = stg + b * STG_BYTES;
+        const uint32_t boff = (uint32_t)(b * STG_BYTES);
+        uint4 ad[4];
+        if (has_add) {
+          ptx::mbar_wait(&abar[b], (aphase >> b) & 1);
+          aphase ^= 1u << b;
+          ad[0] = ptx::ld_shared_v4(pc0 + boff);
+          ad[1] = ptx::ld_shared_v4(pc1 + boff);
+          ad[2] = ptx::ld_shared_v4(pc2 + boff);
+          ad[3] = ptx::ld_shared_v4(pc3 + boff);
+        }
+        ptx::tmem_ld_wait();
+        const bool last = c0 + 64 >= p.block_n;
+        if (last) {   // accumulator drained by this warp: hand it back before the arithmetic
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&tempty[a]);
+          ++t;
+        }
+        const int col = nb * p.block_n + c0;
+        const int cb = p.scatter ? col - fast_div(col, p.fd_cout) * p.Cout : col;
+        uint4 out[4];
+        switch (mode) {   // warp-uniform: one lean arithmetic body per combination
+          case 0: epi_math<false, false, false>(r, p.bias, p.scale, p.relu, cb, ad, out); break;
+          case 1: epi_math<true, false, false>(r, p.bias, p.scale, p.relu, cb, ad, out); break;
+          case 2: epi_math<false, true, false>(r, p.bias, p.scale, p.relu, cb, ad, out); break;
+          case 3: epi_math<true, true, false>(r, p.bias, p.scale, p.relu, cb, ad, out); break;
+          case 4: epi_math<false, false, true>(r, p.bias, p.scale, p.relu, cb, ad, out); break;
+          case 5: epi_math<true, false, true>(r, p.bias, p.scale, p.relu, cb, ad, out); break;
+          case 6: epi_math<false, true, true>(r, p.bias, p.scale, p.relu, cb, ad, out); break;
+          default: epi_math<true, true, true>(r, p.bias, p.scale, p.relu, cb, ad, out); break;
+        }
+        ptx::st_shared_v4(pc0 + boff, out[0]);
+        ptx::st_shared_v4(pc1 + boff, out[1]);
+        ptx::st_shared_v4(pc2 + boff, out[2]);
+        ptx::st_shared_v4(pc3 + boff, out[3]);
+        if (stat_acc) {
+          const bool valid = (w0 + wl < p.W) && (h0 + hl < p.Hg) && (n0 + nl < p.Ng);
+          epi_stats(stat_acc, (c0 - half * 32) >> 6, out, valid);
+        }
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          box(&tmY, true, buf, nullptr, nb, c0, w0, h0, n0);
+          ptx::bulk_commit();
+        }
+        tile = tile2; c0 = c2; nb = nb2; w0 = w2; h0 = h2; n0 = n2;
+        live = live2;
+        b = b2;
+      }
+      if (lane == 0) ptx::bulk_wait_read<0>();
+      if (p.stats) {
+        const int nbf = blockIdx.x % p.n_blocks;
+        float* row_out = p.stats + (long long)(blockIdx.x * 4 + lg) * 2 * p.Ncols;
+        for (int cc = half * 32, j = 0; cc < p.block_n; cc += 64, ++j) {
+          const int col = nbf * p.block_n + cc + lane;
+          if (col < p.Ncols) {
+            const float2 v = reinterpret_cast<const float2*>(stat_acc)[j * 32 + lane];
+            row_out[col] = v.x;
+            row_out[p.Ncols + col] = v.y;
+          }
+        }
+      }
+    }
   } else {
-    // ============================== epilogue (warps 2..9) ==============================
+    // ============================== epilogue, per-thread stores (warps 2..9) ==============================
     const int lg = warp & 3;              // TMEM lane group this warp may access
     const int half = (warp - 2) >> 2;     // which of the interleaved 32-column chunks this warp drains
     const int row = lg * 32 + lane;
@@ -397,8 +560,32 @@ extern "C" int rbu_conv_gemm(const rbu_conv_gemm_args* a, void* stream_) {
     p.C[s] = a->seg[s].C;
     p.dil[s] = a->seg[s].taps == 9 ? a->seg[s].dil : 0;
   }
+  p.log_tw = 0;
+  while ((1 << p.log_tw) < p.TW) ++p.log_tw;
+  p.log_th = 0;
+  while ((1 << p.log_th) < p.TH) ++p.log_th;
+  p.Hg = gather ? a->N * a->H : a->H;
+  p.Ng = gather ? 1 : a->N;
+  p.fd_nb = make_fastdiv(p.n_blocks);
+  p.fd_tw = make_fastdiv(p.tiles_w);
+  p.fd_th = make_fastdiv(p.tiles_h);
+  p.fd_cout = make_fastdiv(a->scatter ? a->Cout : a->Ncols);
+  // Staged epilogue (TMA stores) whenever the output is expressible as 32-pixel x 32-channel boxes of a tensor map:
+  // whole 32-column chunks, and for the ConvTranspose pixel shuffle a warp's 32 pixels must be whole rows of the
+  // merged (n, h) axis.  RBU_NO_TMA_STORE=1 forces the per-thread stores (A/B comparisons in the tests).
+  {
+    static int no_tma_store = -1;
+    if (no_tma_store < 0) no_tma_store = getenv("RBU_NO_TMA_STORE") ? 1 : 0;
+    const int rows = 32 / p.TW;   // rows of the h axis in one warp's box when it does not span images
+    bool ok = !no_tma_store && a->Ncols % 32 == 0 && (long long)a->N * a->H * a->W < (1ll << 31);
+    if (a->scatter)
+      ok = ok && a->Cout % 32 == 0 && ((p.TW * p.TH >= 32 && a->H % rows == 0) || p.TH == a->H);
+    p.tma_store = ok ? 1 : 0;
+    p.st_bufs = a->addend ? 3 : 2;
+  }
+  const int staging = p.tma_store ? 1024 + 8 * p.st_bufs * STG_BYTES : 0;
   const int stage_bytes = A_BYTES + p.block_n * 128;
-  p.num_stages = (SMEM_LIMIT - 2048) / stage_bytes;
+  p.num_stages = (SMEM_LIMIT - 1024 - BAR_BYTES - staging) / stage_bytes;
   if (p.num_stages > MAX_STAGES) p.num_stages = MAX_STAGES;
   p.tmem_cols = 32;
   while (p.tmem_cols < 2 * p.block_n) p.tmem_cols <<= 1;
@@ -446,7 +633,36 @@ extern "C" int rbu_conv_gemm(const rbu_conv_gemm_args* a, void* stream_) {
     tmB[1] = tmB[0];
   }
 
-  const int smem_bytes = p.num_stages * stage_bytes + 1024 + 256;
+  // output (and addend) boxes of the staged epilogue: 32 channels x the 32 pixels of one epilogue warp, SWIZZLE_64B
+  CUtensorMap tmY, tmAd;
+  memset(&tmY, 0, sizeof(tmY));
+  memset(&tmAd, 0, sizeof(tmAd));
+  if (p.tma_store) {
+    const int thb = p.TW * p.TH >= 32 ? 32 / p.TW : p.TH;    // h rows per box
+    const int tnb = 32 / (p.TW * thb);                       // images per box (tiny feature maps)
+    int rc;
+    if (a->scatter) {
+      // y is [N, 2H, 2W, ld]; view as (co, j, w, i, n*H + h)
+      const uint64_t dims[5] = {(uint64_t)a->Cout, 2, (uint64_t)a->W, 2, (uint64_t)a->N * a->H};
+      const uint64_t str[4] = {(uint64_t)a->y_ld * 2, (uint64_t)a->y_ld * 4, (uint64_t)a->y_ld * 2 * (2 * a->W),
+                               (uint64_t)a->y_ld * 4 * (2 * a->W)};
+      const uint32_t box[5] = {32, 1, (uint32_t)p.TW, 1, (uint32_t)(32 / p.TW)};
+      rc = rbu_encode_tmap_bf16_sw(&tmY, a->y, 5, dims, str, box, 64);
+    } else {
+      const uint64_t dims[4] = {(uint64_t)a->Ncols, (uint64_t)a->W, (uint64_t)p.Hg, (uint64_t)p.Ng};
+      const uint32_t box[4] = {32, (uint32_t)p.TW, (uint32_t)thb, (uint32_t)tnb};
+      const uint64_t str[3] = {(uint64_t)a->y_ld * 2, (uint64_t)a->y_ld * 2 * a->W, (uint64_t)a->y_ld * 2 * a->W * p.Hg};
+      rc = rbu_encode_tmap_bf16_sw(&tmY, a->y, 4, dims, str, box, 64);
+      if (!rc && a->addend) {
+        const uint64_t astr[3] = {(uint64_t)a->addend_ld * 2, (uint64_t)a->addend_ld * 2 * a->W,
+                                  (uint64_t)a->addend_ld * 2 * a->W * p.Hg};
+        rc = rbu_encode_tmap_bf16_sw(&tmAd, a->addend, 4, dims, astr, box, 64);
+      }
+    }
+    if (rc) return rc;
+  }
+
+  const int smem_bytes = p.num_stages * stage_bytes + 1024 + BAR_BYTES + staging;
   static bool attr_set = false;
   if (!attr_set) {
     RBU_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
@@ -458,7 +674,7 @@ extern "C" int rbu_conv_gemm(const rbu_conv_gemm_args* a, void* stream_) {
                   "rbu_conv_gemm: output statistics are not supported for this shape");
     RBU_CHECK_CUDA(cudaMemsetAsync(a->stats, 0, rbu_conv_stats_floats(a->Ncols) * sizeof(float), stream));
   }
-  conv_gemm_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(tmA[0], tmB[0], tmA[1], tmB[1], p);
+  conv_gemm_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(tmA[0], tmB[0], tmA[1], tmB[1], tmY, tmAd, p);
   RBU_CHECK_LAUNCH();
   return RBU_OK;
 }

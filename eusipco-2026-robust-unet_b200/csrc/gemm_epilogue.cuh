@@ -28,6 +28,29 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
   return v[0];
 }
 
+// Division by a launch-constant divisor without the ~25-instruction integer-division sequence (tile -> coordinate
+// decoding sits on every epilogue warp's per-tile path).  Exact for 0 <= x < 2^31.
+struct FastDiv {
+  uint32_t mul, shr;
+  int d;
+};
+inline FastDiv make_fastdiv(int d) {
+  FastDiv f;
+  f.d = d;
+  f.mul = 0;
+  f.shr = 0;
+  if (d > 1) {
+    int l = 0;
+    while ((1ll << l) < d) ++l;                                   // ceil(log2 d) >= 1
+    f.mul = (uint32_t)(((1ull << (31 + l)) + (uint64_t)d - 1) / (uint64_t)d);
+    f.shr = (uint32_t)(l - 1);
+  }
+  return f;
+}
+__device__ __forceinline__ int fast_div(int x, const FastDiv& f) {
+  return f.d == 1 ? x : (int)(__umulhi((uint32_t)x, f.mul) >> f.shr);
+}
+
 struct EpiOut {
   float* stat_acc;   // this warp's [EPI_STAT_CHUNKS][32][2] shared-memory accumulators, or nullptr (statistics off)
   bf16* y;
@@ -126,4 +149,76 @@ __device__ __forceinline__ void epi_finish(const EpiOut& o, uint32_t taddr, int 
     cur.y += cq;
     *slot = cur;
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Staged variant: the warp writes its 32 pixels x 32 channels (2 KB, SWIZZLE_64B: the 16-byte piece g of pixel row r
+// sits at r*64 + ((g ^ ((r >> 1) & 3)) << 4), conflict-free for 16-byte accesses) into shared memory and one lane
+// hands the box to the TMA store engine.  No per-thread global addresses, no predicates (TMA clips the box at the
+// tensor edge), and no L1 tag traffic (32 rows per st.global.v4 request otherwise).
+// epi_math: accumulator chunk -> scale / bias / addend / ReLU -> four packed 16-byte pieces.
+template <bool ADD, bool BIAS, bool EXTRA>   // EXTRA: per-column scale and / or ReLU (eval-mode folds)
+__device__ __forceinline__ void epi_math(const uint32_t (&r)[32], const float* __restrict__ bias,
+                                         const float* __restrict__ scale, int relu, int cb, const uint4 (&ad)[4],
+                                         uint4 (&out)[4]) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(r[g * 8 + e]);
+    if (EXTRA) {
+      if (scale) {
+        const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + cb + g * 8));
+        const float4 s1 = __ldg(reinterpret_cast<const float4*>(scale + cb + g * 8 + 4));
+        f[0] *= s0.x; f[1] *= s0.y; f[2] *= s0.z; f[3] *= s0.w;
+        f[4] *= s1.x; f[5] *= s1.y; f[6] *= s1.z; f[7] *= s1.w;
+      }
+    }
+    if (BIAS) {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + cb + g * 8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + cb + g * 8 + 4));
+      f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+      f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+    }
+    if (ADD) {
+      float a8[8];
+      bf16x8 t;
+      *reinterpret_cast<uint4*>(&t) = ad[g];
+      unpack8(t, a8);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] += a8[e];
+    }
+    if (EXTRA) {
+      if (cb + g * 8 < relu) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+      }
+    }
+    const bf16x8 packed = pack8(f);
+    out[g] = *reinterpret_cast<const uint4*>(&packed);
+  }
+}
+
+// Per-column sum / sum of squares of the stored (bf16-rounded) chunk over the warp's valid pixels.
+__device__ __forceinline__ void epi_stats(float* stat_acc, int chunk, const uint4 (&out)[4], bool valid) {
+  const int lane = threadIdx.x & 31;
+  float rv[32], sq[32];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    bf16x8 t;
+    *reinterpret_cast<uint4*>(&t) = out[g];
+    unpack8(t, &rv[g * 8]);
+  }
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    rv[i] = valid ? rv[i] : 0.f;
+    sq[i] = rv[i] * rv[i];
+  }
+  const float cs = warp_colsum32(rv, lane);
+  const float cq = warp_colsum32(sq, lane);
+  float2* slot = reinterpret_cast<float2*>(stat_acc) + chunk * 32 + lane;
+  float2 cur = *slot;
+  cur.x += cs;
+  cur.y += cq;
+  *slot = cur;
 }

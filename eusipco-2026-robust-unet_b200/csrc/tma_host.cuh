@@ -11,6 +11,9 @@
 // of dimension i+1 (dimension 0 is contiguous). Returns 0 on success (error text via rbu_set_error).
 int rbu_encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                          const uint64_t* strides_bytes, const uint32_t* box);
+// Same with SWIZZLE_64B (swizzle_bytes == 64; inner box extent <= 64 bytes) or SWIZZLE_128B (128).
+int rbu_encode_tmap_bf16_sw(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                            const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
 
 // conv_halo.cu: halo-reuse variant of the implicit-GEMM convolution (3x3 dilation 1 / 1x1 segments).
 int rbu_conv_halo_supported(const rbu_conv_gemm_args* a);

@@ -25,6 +25,46 @@ SHAPES = [  # name, H=W, Cin, Cout, taps
 ]
 
 
+AUX = [  # name, H=W, Cin, Ncols, mode (plain | addend | scatter)  -- the small-K, epilogue-bound GEMMs of the step
+    ("stem 1x1 32->128", 256, 32, 128, "plain"),
+    ("AG fwd 1x1 64->32", 256, 64, 32, "plain"),
+    ("AG dgrad 1x1 32->64 +add", 256, 32, 64, "addend"),
+    ("AG dgrad 1x1 64->128 +add", 128, 64, 128, "addend"),
+    ("proj 1x1 128->64", 256, 128, 64, "plain"),
+    ("up 128->4x64 scatter", 128, 128, 256, "scatter"),
+    ("up 256->4x128 scatter", 64, 256, 512, "scatter"),
+]
+
+
+def aux(reps, B, dev, flush):
+    for name, S, ci, nc, mode in AUX:
+        x = ops.View(torch.randn((B, S, S, ci), device=dev).to(torch.bfloat16))
+        w = torch.randn((nc, ci, 1, 1), device=dev) * 0.05
+        wp = ops.pack_weight(w, 0)
+        kw = {}
+        if mode == "scatter":
+            co = nc // 4
+            y = ops.View(torch.empty((B, 2 * S, 2 * S, co), dtype=torch.bfloat16, device=dev))
+            kw = dict(scatter=True, Cout=co)
+        else:
+            y = ops.View(torch.zeros((B, S, S, nc), dtype=torch.bfloat16, device=dev))
+            if mode == "addend":
+                kw = dict(addend=y)
+        nbytes = 2.0 * B * S * S * (ci + nc * (2 if mode == "addend" else 1))
+        ms = []
+        for i in range(reps + 2):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ops.conv_gemm(B, S, S, [(x, wp, 1, 0, False)], nc, y, **kw)
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= 2:
+                ms.append(e0.elapsed_time(e1))
+        t = sorted(ms)[len(ms) // 2]
+        print(f"aux   {name:28s} {t:8.3f} ms  {nbytes / t / 1e6:8.1f} GB/s", flush=True)
+
+
 def main():
     reps = int(sys.argv[1]) if len(sys.argv) > 1 else 10
     which = sys.argv[2] if len(sys.argv) > 2 else "all"
@@ -32,6 +72,8 @@ def main():
     dev = torch.device("cuda:0")
     eng = Engine(None)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    if which == "aux":
+        return aux(reps, B, dev, flush)
     for name, S, ci, co, taps in SHAPES:
         x = ops.View(torch.randn((B, S, S, ci), device=dev).to(torch.bfloat16))
         y = ops.View(torch.empty((B, S, S, co), dtype=torch.bfloat16, device=dev))
