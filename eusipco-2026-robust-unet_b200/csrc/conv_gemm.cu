@@ -49,14 +49,15 @@ struct KParams {
   long long addend_ld;
   float* stats;   // [4*SMs][2][Ncols] per-(CTA, lane group) column sum / sum of squares of the stored output, or NULL
   // staged epilogue (TMA stores): see the epilogue branch of the kernel
+  int b_resident;         // 1: this CTA's whole weight operand (all k-blocks of its column block) is loaded once
   int tma_store;          // 1: outputs leave through the y tensor map, 0: per-thread 16-byte stores
-  int st_bufs;            // staging buffers per epilogue warp (2, or 3 when an addend box is prefetched one job ahead)
+  int st_bufs;            // staging buffers per epilogue warp
   int log_tw, log_th;     // TW and TH are powers of two
   int Hg, Ng;             // extent of the (h, n) tile coordinates: (H, N), or (N*H, 1) for merged rows (gather)
   FastDiv fd_nb, fd_tw, fd_th, fd_cout;
 };
 
-constexpr int STG_BYTES = 32 * 32 * 2;   // one staging buffer: 32 pixels x 32 channels bf16
+constexpr int STG_BYTES = 32 * 64 * 2;   // one staging buffer: 32 pixels x 64 channels bf16
 constexpr int BAR_BYTES = 512;           // mbarriers + TMEM slot
 
 __device__ __forceinline__ void decode_tile(const KParams& p, int tile, int& nb, int& w0, int& h0, int& n0) {
@@ -76,16 +77,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                  const __grid_constant__ KParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int stage_bytes = A_BYTES + p.block_n * 128;
+  const int stage_bytes = A_BYTES + (p.b_resident ? 0 : p.block_n * 128);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.num_stages * stage_bytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + MAX_STAGES;
   uint64_t* tfull = bars + 2 * MAX_STAGES;
   uint64_t* tempty = tfull + 2;
   uint64_t* adbar = tempty + 2;            // [8 epilogue warps][3] addend-box arrival barriers
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(adbar + 24);
+  uint64_t* bfull = adbar + 24;            // resident weight operand has landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull + 1);
   uint8_t* stg_base = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(bars) + BAR_BYTES + 1023) & ~uintptr_t(1023));
+  uint8_t* resb = stg_base + (p.tma_store ? 8 * p.st_bufs * STG_BYTES : 0);   // 1024-aligned: STG_BYTES is 4 KB
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -112,9 +115,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tfull[a], 1);
-      ptx::mbar_init(&tempty[a], (p.tma_store && p.block_n <= 32) ? 4 : 8);   // epilogue warps that own columns
+      ptx::mbar_init(&tempty[a], p.tma_store ? 4 : 8);   // staged: one half of the epilogue warps per accumulator
     }
     for (int i = 0; i < 24; ++i) ptx::mbar_init(&adbar[i], 1);
+    ptx::mbar_init(bfull, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
@@ -134,6 +138,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
+      if (p.b_resident && blockIdx.x < p.total_tiles) {
+        // every tile of this CTA has the same column block (grid % n_blocks == 0): fetch its weights once
+        const int nb = blockIdx.x % p.n_blocks;
+        ptx::mbar_arrive_expect_tx(bfull, (uint32_t)(kblocks_total * p.block_n * 128));
+        int kb = 0;
+        for (int seg = 0; seg < p.nseg; ++seg) {
+          const int kch = (p.C[seg] + BLOCK_K - 1) / BLOCK_K;
+          for (int tap = 0; tap < p.taps[seg]; ++tap)
+            for (int kc = 0; kc < kch; ++kc, ++kb)
+              ptx::tma_load_2d(resb + kb * p.block_n * 128, seg ? &tmB1 : &tmB0, bfull, tap * p.C[seg] + kc * BLOCK_K,
+                               nb * p.block_n);
+        }
+      }
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         int nb, w0, h0, n0;
         decode_tile(p, tile, nb, w0, h0, n0);
@@ -156,7 +173,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 ptx::tma_load_5d(a_dst, mA, &full[s], kc * BLOCK_K, tap & 1, w0, tap >> 1, h0);
               else
                 ptx::tma_load_4d(a_dst, mA, &full[s], kc * BLOCK_K, w0 + dw, h0 + dh, n0);
-              ptx::tma_load_2d(b_dst, mB, &full[s], tap * p.C[seg] + kc * BLOCK_K, nb * p.block_n);
+              if (!p.b_resident) ptx::tma_load_2d(b_dst, mB, &full[s], tap * p.C[seg] + kc * BLOCK_K, nb * p.block_n);
               if (++s == p.num_stages) { s = 0; ph ^= 1; }
             }
           }
@@ -171,14 +188,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const uint32_t hi = ptx::desc_hi(1024);
     const uint32_t a_lo0 = ptx::desc_lo(ptx::smem_u32(smem), 16);
     const uint32_t st_step = (uint32_t)stage_bytes >> 4;
+    const uint32_t rb_lo0 = ptx::desc_lo(ptx::smem_u32(resb), 16);
+    const uint32_t rb_step = (uint32_t)(p.block_n * 128) >> 4;
     int s = 0, t = 0;
     uint32_t ph = 0;
+    if (p.b_resident && blockIdx.x < p.total_tiles) ptx::mbar_wait(bfull, 0);
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
       const int a = t & 1;
       ptx::mbar_wait(&tempty[a], ((t >> 1) & 1) ^ 1);
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(a * p.block_n);
       uint32_t accumulate = 0;
+      uint32_t rb_lo = rb_lo0;
       for (int seg = 0; seg < p.nseg; ++seg) {
         const int kch = (p.C[seg] + BLOCK_K - 1) / BLOCK_K;
         for (int tap = 0; tap < p.taps[seg]; ++tap) {
@@ -189,7 +210,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             const int ksteps = rem >= BLOCK_K ? 4 : (rem + 15) / 16;  // channels past C are TMA zero fill
             if (ptx::elect_one()) {
               const uint32_t a_lo = a_lo0 + s * st_step;
-              const uint32_t b_lo = a_lo + (A_BYTES >> 4);
+              const uint32_t b_lo = p.b_resident ? rb_lo : a_lo + (A_BYTES >> 4);
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 if (k < ksteps) {
@@ -200,6 +221,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
               ptx::umma_commit_s(empty_s + s * 8);  // frees the smem stage once these MMAs retire
             }
             accumulate = 1;
+            rb_lo += rb_step;
             __syncwarp();
             if (++s == p.num_stages) { s = 0; ph ^= 1; }
           }
@@ -211,141 +233,126 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   } else if (p.tma_store) {
     // ============================== epilogue, staged (warps 2..9) ==============================
     // Warp (lg, half) owns accumulator rows [32 lg, 32 lg + 32) -- 32 consecutive pixels of the tile in (n, h, w)
-    // order -- and the 32-column chunks c0 = 32 half, 32 half + 64, ...  A "job" is one chunk of one tile:
-    //   tcgen05.ld -> scale / bias / addend / ReLU -> bf16 -> swizzled shared-memory box -> TMA store.
-    // Buffers rotate; `cp.async.bulk.wait_group.read 1` at the top of job k proves the store of job k-2 has drained its
-    // buffer, which is the one job k writes (2 buffers) or the one the addend box of job k+1 is loaded into (3).
+    // order -- of every second tile of this CTA (tiles t = half, half + 2, ...: accumulator buffer `half`), so the two
+    // halves drain two tiles concurrently.  A "job" is one 64-column chunk of one tile:
+    //   2 x tcgen05.ld -> scale / bias / addend / ReLU -> bf16 -> swizzled 4 KB shared-memory box -> one TMA store
+    // (128-byte rows: half as many TMA row requests per byte as 32-column boxes).  Two buffers alternate; with an addend
+    // its box for job k+1 is requested while job k waits for TMEM, into the buffer whose store (job k-1) has drained.
     const int ew = warp - 2;
     const int lg = warp & 3;
     const int half = ew >> 2;
-    if (half * 32 < p.block_n) {
-      const int nbuf = p.st_bufs;
-      uint64_t* abar = adbar + ew * 3;
+    {
+      uint64_t* abar = adbar + ew * 2;
       const int r2g = (lg * 32) >> p.log_tw;                       // first pixel row of the warp's group, in tile rows
       const int hg = p.gather ? r2g : (r2g & (p.TH - 1));
       const int ng = p.gather ? 0 : (r2g >> p.log_th);
-      const int row = lg * 32 + lane;                              // own pixel: only the statistics mask needs it
-      const int wl = row & (p.TW - 1);
-      const int r2 = row >> p.log_tw;
-      const int hl = p.gather ? r2 : (r2 & (p.TH - 1));
-      const int nl = p.gather ? 0 : (r2 >> p.log_th);
       const bool has_add = p.addend != nullptr;
-      uint8_t* stg = stg_base + ew * p.st_bufs * STG_BYTES;
-      const uint32_t my_x = ((uint32_t)lane >> 1) & 3u;
-      // 32-bit shared addresses of this thread's four 16-byte pieces in buffer 0 (SWIZZLE_64B)
-      const uint32_t stg_s = ptx::smem_u32(stg) + (uint32_t)lane * 64u;
-      const uint32_t pc0 = stg_s + ((0u ^ my_x) << 4), pc1 = stg_s + ((1u ^ my_x) << 4);
-      const uint32_t pc2 = stg_s + ((2u ^ my_x) << 4), pc3 = stg_s + ((3u ^ my_x) << 4);
+      uint8_t* stg = stg_base + ew * 2 * STG_BYTES;
+      // 32-bit shared address of this thread's 128-byte row in buffer 0; 16-byte piece g sits at (g ^ (lane & 7)) << 4
+      const uint32_t row_s = ptx::smem_u32(stg) + (uint32_t)lane * 128u;
+      const uint32_t sx = (uint32_t)lane & 7u;
       const int mode = (has_add ? 1 : 0) | (p.bias ? 2 : 0) | ((p.scale || p.relu) ? 4 : 0);
-      float* stat_acc = p.stats ? stat_smem + ew * (EPI_STAT_CHUNKS * 64) : nullptr;
+      const int tstep = 2 * gridDim.x;
+      const uint32_t t_lane = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(half * p.block_n);
 
-      int tile = blockIdx.x, c0 = half * 32;
+      int tile = blockIdx.x + half * gridDim.x, c0 = 0;
       int nb = 0, w0 = 0, h0 = 0, n0 = 0;
       bool live = tile < p.total_tiles;
       if (live) decode_tile(p, tile, nb, w0, h0, n0);
       // box origin of a job in the output (or addend) tensor map
-      auto box = [&](const CUtensorMap* m, bool store, uint8_t* buf, uint64_t* bar, int jnb, int jc0, int jw0, int jh0,
+      auto box = [&](const CUtensorMap* m, bool store, uint32_t buf_s, uint64_t* bar, int jnb, int jc0, int jw0, int jh0,
                      int jn0) {
         const int col = jnb * p.block_n + jc0;
         if (p.scatter) {   // (co, j, w, i, n*H + h) view of the 2x up-sampled tensor; stores only
           const int q = fast_div(col, p.fd_cout);
           if (jh0 + hg < p.H)
-            ptx::tma_store_5d(m, buf, col - q * p.Cout, q & 1, jw0, q >> 1, (jn0 + ng) * p.H + jh0 + hg);
+            ptx::tma_store_5d_s(m, buf_s, col - q * p.Cout, q & 1, jw0, q >> 1, (jn0 + ng) * p.H + jh0 + hg);
         } else if (store) {
-          ptx::tma_store_4d(m, buf, col, jw0, jh0 + hg, jn0 + ng);
+          ptx::tma_store_4d_s(m, buf_s, col, jw0, jh0 + hg, jn0 + ng);
         } else {
           ptx::mbar_arrive_expect_tx(bar, STG_BYTES);
-          ptx::tma_load_4d(buf, m, bar, col, jw0, jh0 + hg, jn0 + ng);
+          ptx::tma_load_4d_s(buf_s, m, bar, col, jw0, jh0 + hg, jn0 + ng);
         }
       };
-      int b = 0, t = 0;
+      int b = 0, u = 0;       // staging buffer of the current job; tiles this warp has started
       uint32_t aphase = 0;
-      if (has_add && live && lane == 0) box(&tmAd, false, stg, &abar[0], nb, c0, w0, h0, n0);
+      const uint32_t stg_s = ptx::smem_u32(stg);
+      if (has_add && live && lane == 0) box(&tmAd, false, stg_s, &abar[0], nb, c0, w0, h0, n0);
       while (live) {
         // next job
         int tile2 = tile, c2 = c0 + 64, nb2 = nb, w2 = w0, h2 = h0, n2 = n0;
         if (c2 >= p.block_n) {
-          c2 = half * 32;
-          tile2 = tile + gridDim.x;
+          c2 = 0;
+          tile2 = tile + tstep;
           if (tile2 < p.total_tiles) decode_tile(p, tile2, nb2, w2, h2, n2);
         }
         const bool live2 = tile2 < p.total_tiles;
-        const int b2 = (b + 1 == nbuf) ? 0 : b + 1;
-        if (lane == 0) {
-          ptx::bulk_wait_read<1>();
-          if (has_add && live2) box(&tmAd, false, stg + b2 * STG_BYTES, &abar[b2], nb2, c2, w2, h2, n2);
-        }
-        __syncwarp();
-        const int a = t & 1;
-        if (c0 == half * 32) {   // first chunk of the tile: the accumulator must be complete
-          ptx::mbar_wait(&tfull[a], (t >> 1) & 1);
+        if (c0 == 0) {   // first chunk of the tile: the accumulator must be complete
+          ptx::mbar_wait(&tfull[half], u & 1);
           ptx::tc_fence_after();
         }
-        uint32_t r[32];
-        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(a * p.block_n + c0), r);
-        uint8_t* buf = stg + b * STG_BYTES;
+        const bool two = c0 + 32 < p.block_n;    // false only for a 32-column GEMM
+        uint32_t r[64];
+        ptx::tmem_ld_32x32(t_lane + (uint32_t)c0, r);
+        if (two) ptx::tmem_ld_32x32(t_lane + (uint32_t)(c0 + 32), r + 32);
         const uint32_t boff = (uint32_t)(b * STG_BYTES);
-        uint4 ad[4];
+        uint4 ad[8];
         if (has_add) {
           ptx::mbar_wait(&abar[b], (aphase >> b) & 1);
           aphase ^= 1u << b;
-          ad[0] = ptx::ld_shared_v4(pc0 + boff);
-          ad[1] = ptx::ld_shared_v4(pc1 + boff);
-          ad[2] = ptx::ld_shared_v4(pc2 + boff);
-          ad[3] = ptx::ld_shared_v4(pc3 + boff);
+#pragma unroll
+          for (int g = 0; g < 8; ++g) ad[g] = ptx::ld_shared_v4(row_s + boff + (((uint32_t)g ^ sx) << 4));
+        }
+        if (lane == 0) {
+          if (has_add) {
+            ptx::bulk_wait_read<0>();    // the previous job's store has drained the other buffer: refill it
+          } else {
+            ptx::bulk_wait_read<1>();    // the store of two jobs ago has drained this buffer
+          }
+          if (has_add && live2) box(&tmAd, false, stg_s + (uint32_t)((b ^ 1) * STG_BYTES), &abar[b ^ 1], nb2, c2, w2, h2, n2);
         }
         ptx::tmem_ld_wait();
-        const bool last = c0 + 64 >= p.block_n;
-        if (last) {   // accumulator drained by this warp: hand it back before the arithmetic
+        if (c0 + 64 >= p.block_n) {   // accumulator drained by this warp: hand it back before the arithmetic
           ptx::tc_fence_before();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&tempty[a]);
-          ++t;
+          if (lane == 0) ptx::mbar_arrive(&tempty[half]);
+          ++u;
         }
         const int col = nb * p.block_n + c0;
         const int cb = p.scatter ? col - fast_div(col, p.fd_cout) * p.Cout : col;
-        uint4 out[4];
-        switch (mode) {   // warp-uniform: one lean arithmetic body per combination
-          case 0: epi_math<false, false, false>(r, p.bias, p.scale, p.relu, cb, ad, out); break;
-          case 1: epi_math<true, false, false>(r, p.bias, p.scale, p.relu, cb, ad, out); break;
-          case 2: epi_math<false, true, false>(r, p.bias, p.scale, p.relu, cb, ad, out); break;
-          case 3: epi_math<true, true, false>(r, p.bias, p.scale, p.relu, cb, ad, out); break;
-          case 4: epi_math<false, false, true>(r, p.bias, p.scale, p.relu, cb, ad, out); break;
-          case 5: epi_math<true, false, true>(r, p.bias, p.scale, p.relu, cb, ad, out); break;
-          case 6: epi_math<false, true, true>(r, p.bias, p.scale, p.relu, cb, ad, out); break;
-          default: epi_math<true, true, true>(r, p.bias, p.scale, p.relu, cb, ad, out); break;
-        }
-        ptx::st_shared_v4(pc0 + boff, out[0]);
-        ptx::st_shared_v4(pc1 + boff, out[1]);
-        ptx::st_shared_v4(pc2 + boff, out[2]);
-        ptx::st_shared_v4(pc3 + boff, out[3]);
-        if (stat_acc) {
-          const bool valid = (w0 + wl < p.W) && (h0 + hl < p.Hg) && (n0 + nl < p.Ng);
-          epi_stats(stat_acc, (c0 - half * 32) >> 6, out, valid);
-        }
+        uint4 out[8];
+        auto arith = [&](const uint32_t (&rr)[32], int cbh, const uint4 (&adh)[4], uint4 (&oh)[4]) {
+          switch (mode) {   // warp-uniform: one lean arithmetic body per combination
+            case 0: epi_math<false, false, false>(rr, p.bias, p.scale, p.relu, cbh, adh, oh); break;
+            case 1: epi_math<true, false, false>(rr, p.bias, p.scale, p.relu, cbh, adh, oh); break;
+            case 2: epi_math<false, true, false>(rr, p.bias, p.scale, p.relu, cbh, adh, oh); break;
+            case 3: epi_math<true, true, false>(rr, p.bias, p.scale, p.relu, cbh, adh, oh); break;
+            case 4: epi_math<false, false, true>(rr, p.bias, p.scale, p.relu, cbh, adh, oh); break;
+            case 5: epi_math<true, false, true>(rr, p.bias, p.scale, p.relu, cbh, adh, oh); break;
+            case 6: epi_math<false, true, true>(rr, p.bias, p.scale, p.relu, cbh, adh, oh); break;
+            default: epi_math<true, true, true>(rr, p.bias, p.scale, p.relu, cbh, adh, oh); break;
+          }
+        };
+        arith(reinterpret_cast<const uint32_t(&)[32]>(r[0]), cb, reinterpret_cast<const uint4(&)[4]>(ad[0]),
+              reinterpret_cast<uint4(&)[4]>(out[0]));
+        if (two)
+          arith(reinterpret_cast<const uint32_t(&)[32]>(r[32]), cb + 32, reinterpret_cast<const uint4(&)[4]>(ad[4]),
+                reinterpret_cast<uint4(&)[4]>(out[4]));
+        __syncwarp();   // lane 0 has seen the last store from this buffer drain
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          if (g < 4 || two) ptx::st_shared_v4(row_s + boff + (((uint32_t)g ^ sx) << 4), out[g]);
         ptx::fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          box(&tmY, true, buf, nullptr, nb, c0, w0, h0, n0);
+          box(&tmY, true, stg_s + boff, nullptr, nb, c0, w0, h0, n0);
           ptx::bulk_commit();
         }
         tile = tile2; c0 = c2; nb = nb2; w0 = w2; h0 = h2; n0 = n2;
         live = live2;
-        b = b2;
+        b ^= 1;
       }
       if (lane == 0) ptx::bulk_wait_read<0>();
-      if (p.stats) {
-        const int nbf = blockIdx.x % p.n_blocks;
-        float* row_out = p.stats + (long long)(blockIdx.x * 4 + lg) * 2 * p.Ncols;
-        for (int cc = half * 32, j = 0; cc < p.block_n; cc += 64, ++j) {
-          const int col = nbf * p.block_n + cc + lane;
-          if (col < p.Ncols) {
-            const float2 v = reinterpret_cast<const float2*>(stat_acc)[j * 32 + lane];
-            row_out[col] = v.x;
-            row_out[p.Ncols + col] = v.y;
-          }
-        }
-      }
     }
   } else {
     // ============================== epilogue, per-thread stores (warps 2..9) ==============================
@@ -577,14 +584,27 @@ extern "C" int rbu_conv_gemm(const rbu_conv_gemm_args* a, void* stream_) {
     static int no_tma_store = -1;
     if (no_tma_store < 0) no_tma_store = getenv("RBU_NO_TMA_STORE") ? 1 : 0;
     const int rows = 32 / p.TW;   // rows of the h axis in one warp's box when it does not span images
-    bool ok = !no_tma_store && a->Ncols % 32 == 0 && (long long)a->N * a->H * a->W < (1ll << 31);
+    bool ok = !no_tma_store && !a->stats && a->Ncols % 32 == 0;
     if (a->scatter)
-      ok = ok && a->Cout % 32 == 0 && ((p.TW * p.TH >= 32 && a->H % rows == 0) || p.TH == a->H);
+      ok = ok && a->Cout % 64 == 0 && ((p.TW * p.TH >= 32 && a->H % rows == 0) || p.TH == a->H);
     p.tma_store = ok ? 1 : 0;
-    p.st_bufs = a->addend ? 3 : 2;
+    p.st_bufs = 2;
   }
-  const int staging = p.tma_store ? 1024 + 8 * p.st_bufs * STG_BYTES : 0;
-  const int stage_bytes = A_BYTES + p.block_n * 128;
+  int grid = p.tiles_w * p.tiles_h * p.tiles_n * p.n_blocks;
+  if (grid > rbu_num_sms()) grid = rbu_num_sms();
+  // Weights resident in shared memory when the CTA's whole operand (its column block, all k-blocks) is at most 64 KB and
+  // every tile of a CTA has the same column block: the small-K GEMMs are bound by L2 -> SM traffic, of which the per-tile
+  // weight reload is 17-40%.  RBU_NO_RESIDENT=1 disables.
+  int kblocks_total = 0;
+  for (int s = 0; s < a->nseg; ++s) kblocks_total += a->seg[s].taps * rbu_cdiv(a->seg[s].C, BLOCK_K);
+  const int resb_bytes = kblocks_total * p.block_n * 128;
+  {
+    static int no_res = -1;
+    if (no_res < 0) no_res = getenv("RBU_NO_RESIDENT") ? 1 : 0;
+    p.b_resident = (!no_res && resb_bytes <= 65536 && grid % p.n_blocks == 0) ? 1 : 0;
+  }
+  const int staging = 1024 + (p.tma_store ? 8 * p.st_bufs * STG_BYTES : 0) + (p.b_resident ? resb_bytes : 0);
+  const int stage_bytes = A_BYTES + (p.b_resident ? 0 : p.block_n * 128);
   p.num_stages = (SMEM_LIMIT - 1024 - BAR_BYTES - staging) / stage_bytes;
   if (p.num_stages > MAX_STAGES) p.num_stages = MAX_STAGES;
   p.tmem_cols = 32;
@@ -633,7 +653,7 @@ extern "C" int rbu_conv_gemm(const rbu_conv_gemm_args* a, void* stream_) {
     tmB[1] = tmB[0];
   }
 
-  // output (and addend) boxes of the staged epilogue: 32 channels x the 32 pixels of one epilogue warp, SWIZZLE_64B
+  // output (and addend) boxes of the staged epilogue: 64 channels x the 32 pixels of one epilogue warp, SWIZZLE_128B
   CUtensorMap tmY, tmAd;
   memset(&tmY, 0, sizeof(tmY));
   memset(&tmAd, 0, sizeof(tmAd));
@@ -646,17 +666,17 @@ extern "C" int rbu_conv_gemm(const rbu_conv_gemm_args* a, void* stream_) {
       const uint64_t dims[5] = {(uint64_t)a->Cout, 2, (uint64_t)a->W, 2, (uint64_t)a->N * a->H};
       const uint64_t str[4] = {(uint64_t)a->y_ld * 2, (uint64_t)a->y_ld * 4, (uint64_t)a->y_ld * 2 * (2 * a->W),
                                (uint64_t)a->y_ld * 4 * (2 * a->W)};
-      const uint32_t box[5] = {32, 1, (uint32_t)p.TW, 1, (uint32_t)(32 / p.TW)};
-      rc = rbu_encode_tmap_bf16_sw(&tmY, a->y, 5, dims, str, box, 64);
+      const uint32_t box[5] = {64, 1, (uint32_t)p.TW, 1, (uint32_t)(32 / p.TW)};
+      rc = rbu_encode_tmap_bf16(&tmY, a->y, 5, dims, str, box);
     } else {
       const uint64_t dims[4] = {(uint64_t)a->Ncols, (uint64_t)a->W, (uint64_t)p.Hg, (uint64_t)p.Ng};
-      const uint32_t box[4] = {32, (uint32_t)p.TW, (uint32_t)thb, (uint32_t)tnb};
+      const uint32_t box[4] = {64, (uint32_t)p.TW, (uint32_t)thb, (uint32_t)tnb};
       const uint64_t str[3] = {(uint64_t)a->y_ld * 2, (uint64_t)a->y_ld * 2 * a->W, (uint64_t)a->y_ld * 2 * a->W * p.Hg};
-      rc = rbu_encode_tmap_bf16_sw(&tmY, a->y, 4, dims, str, box, 64);
+      rc = rbu_encode_tmap_bf16(&tmY, a->y, 4, dims, str, box);
       if (!rc && a->addend) {
         const uint64_t astr[3] = {(uint64_t)a->addend_ld * 2, (uint64_t)a->addend_ld * 2 * a->W,
                                   (uint64_t)a->addend_ld * 2 * a->W * p.Hg};
-        rc = rbu_encode_tmap_bf16_sw(&tmAd, a->addend, 4, dims, astr, box, 64);
+        rc = rbu_encode_tmap_bf16(&tmAd, a->addend, 4, dims, astr, box);
       }
     }
     if (rc) return rc;
@@ -668,7 +688,6 @@ extern "C" int rbu_conv_gemm(const rbu_conv_gemm_args* a, void* stream_) {
     RBU_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     attr_set = true;
   }
-  int grid = p.total_tiles < rbu_num_sms() ? p.total_tiles : rbu_num_sms();
   if (a->stats) {
     RBU_CHECK_ARG(!a->scatter && p.block_n <= 64 * EPI_STAT_CHUNKS && grid % p.n_blocks == 0 && ((uintptr_t)a->stats & 15) == 0,
                   "rbu_conv_gemm: output statistics are not supported for this shape");
