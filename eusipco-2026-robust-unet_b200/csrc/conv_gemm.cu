@@ -47,7 +47,7 @@ struct KParams {
   int relu;
   const bf16* addend;
   long long addend_ld;
-  float* stats;   // [4*SMs][2][Ncols] per-(CTA, lane group) column sum / sum of squares of the stored output, or NULL
+  float* stats;   // [8*SMs][2][Ncols] (rows 4*CTA + lane group) column sum / sum of squares of the stored output, or NULL
   // staged epilogue (TMA stores): see the epilogue branch of the kernel
   int b_resident;         // 1: this CTA's whole weight operand (all k-blocks of its column block) is loaded once
   int tma_store;          // 1: outputs leave through the y tensor map, 0: per-thread 16-byte stores
@@ -444,10 +444,11 @@ int pow2ceil(int v) {
 
 }  // namespace
 
-extern "C" size_t rbu_conv_stats_floats(int Ncols) { return (size_t)4 * rbu_num_sms() * 2 * Ncols; }
+// rows: (CTA, lane group) for the generic kernel, (CTA, half-tile, lane group) for the halo kernel; unused rows stay zero
+extern "C" size_t rbu_conv_stats_floats(int Ncols) { return (size_t)8 * rbu_num_sms() * 2 * Ncols; }
 
 // BatchNorm affine from the per-(CTA, lane group) partial sums written by rbu_conv_gemm(stats != NULL):
-// block = 32 channels x 8 lanes over the 4*SMs rows (lane sums combined in lane order -> deterministic).
+// block = 32 channels x 8 lanes over the 8*SMs rows (lane sums combined in lane order -> deterministic).
 namespace {
 __global__ void __launch_bounds__(256)
 bn_finalize_partials_kernel(const float* __restrict__ part, int rows, int Ncols, int col_off, int C, double M, int training,
@@ -495,7 +496,7 @@ extern "C" int rbu_bn_finalize_partials(const float* part, int Ncols, int col_of
   RBU_CHECK_ARG(part && gamma && beta && scale && shift && Ncols > 0 && C > 0 && col_off >= 0 && col_off + C <= Ncols &&
                     count > 0, "rbu_bn_finalize_partials: bad arguments");
   bn_finalize_partials_kernel<<<rbu_cdiv(C, 32), 256, 0, (cudaStream_t)stream_>>>(
-      part, 4 * rbu_num_sms(), Ncols, col_off, C, (double)count, 1, gamma, beta, running_mean, running_var, momentum, eps,
+      part, 8 * rbu_num_sms(), Ncols, col_off, C, (double)count, 1, gamma, beta, running_mean, running_var, momentum, eps,
       scale, shift, mean_out, rstd_out);
   RBU_CHECK_LAUNCH();
   return RBU_OK;

@@ -1,25 +1,31 @@
 // K1 / K10, halo variant: 3x3 (dilation 1) and 1x1 convolutions and their data gradients as an implicit GEMM on
-// tcgen05 tensor cores where every activation tile is fetched from L2 ONCE and reused by all nine taps.
+// tcgen05 tensor cores where every activation tile is fetched from L2 ONCE and reused by all nine taps, and every
+// weight tile is used for TWO 128-pixel MMA tiles.
 //
 // The generic kernel (conv_gemm.cu) issues one TMA load of the 128-pixel x 64-channel A tile per tap, i.e. nine
-// loads of (almost) the same pixels per 64-channel slab: 24-48 KB of L2->SM traffic per k-block, 44-87 FLOP per
-// byte, which caps the 64/128-channel layers at 540-810 TFLOP/s on the ~12 TB/s L2 (measured 553 on inc.conv2,
-// profiles/r01_a_*).  Here the output tile is 16 rows x 8 columns of one image and the A operand is its
-// 18 x 16(10 used) x 64-channel halo, loaded by ONE 4-D TMA box into a SWIZZLE_128B buffer with a 2048-byte row
-// pitch.  Tap (dy,dx) is then just a different START ADDRESS of the same buffer: the UMMA shared-memory descriptor
-// (K-major, 8-pixel row groups, stride-byte-offset = 2048 = one halo row) starts at pixel (dy, dx) of the halo; the
-// start is a multiple of 128 B, not of 1024 B.  Measured on B200: the tensor core applies the 128-byte swizzle XOR
-// from the ABSOLUTE shared-memory address bits [7:9] of every row it fetches -- exactly what TMA did when it wrote
-// the rows -- so the descriptor's matrix-base-offset field stays 0 (setting it to (start >> 7) & 7 double-counts
-// the phase: every 3x3 parity test failed with it, all pass without).
-// L2->SM traffic per 64-channel slab drops from 9 x 16 KB to 36 KB for A; B (weights) still streams per tap.
+// loads of (almost) the same pixels per 64-channel slab.  Here the output tile is 16 rows x 16 columns of one image
+// and the A operand is its 18 x 24(18 used) x 64-channel halo, loaded by ONE 4-D TMA box into a SWIZZLE_128B buffer with
+// a 3072-byte row pitch.  Tap (dy,dx) of the left / right 8-column half of the tile is then just a different START
+// ADDRESS of the same buffer: the UMMA shared-memory descriptor (K-major, 8-pixel row groups, stride-byte-offset = 3072
+// = one halo row) starts at pixel (dy, dx + 8*half) of the halo; the start is a multiple of 128 B, not of 1024 B.
+// Measured on B200: the tensor core applies the 128-byte swizzle XOR from the ABSOLUTE shared-memory address bits
+// [7:9] of every row it fetches -- exactly what TMA did when it wrote the rows -- so the descriptor's
+// matrix-base-offset field stays 0 (setting it to (start >> 7) & 7 double-counts the phase: every 3x3 parity test
+// failed with it, all pass without).
 //
-// Structure (persistent, warp specialised, 320 threads, 1 CTA / SM), as conv_gemm.cu:
-//   warp 0 lane 0 : TMA producer -- A ring (halo tiles, 2-3 stages) and B ring (one weight tile per tap)
-//   warp 1 lane 0 : MMA issuer   -- per slab 9 taps x 4 tcgen05.mma (K = 16) into one of two TMEM accumulators
-//   warps 2..9    : epilogue     -- tcgen05.ld, bias / addend, bf16 pack, 16-byte stores (gemm_epilogue.cuh)
+// Why 256 pixels per weight tile: with one 128-pixel tile per CTA the >= 128-channel layers re-read K x N x 2 bytes of
+// weights from L2 per tile, and every such layer sat at 42 +- 1 bytes / clk / SM of L2 -> SM traffic (128->128: 1300,
+// 256->256: 1500, 512->512: 1530 TFLOP/s; the chip-wide L2 ceiling of ~6300 B/clk), not at the tensor pipe.  Two
+// accumulators per weight stage halve that traffic.
+//
+// Structure (persistent, warp specialised, 320 threads, 1 CTA / SM):
+//   warp 0 lane 0 : TMA producer -- A ring (halo tiles, 2 stages) and B ring (weight tiles, 1 or 3 taps per stage)
+//   warp 1        : MMA issuer   -- per slab 9 taps x 2 halves x 4 tcgen05.mma (K = 16); accumulators rotate through
+//                                   512 / block_n TMEM slots (4 for block_n <= 128, 2 for 256)
+//   warps 2..9    : epilogue     -- warps 2-5 drain the left half-tile, 6-9 the right one (tcgen05.ld, bias / addend /
+//                                   ReLU, bf16 pack, 16-byte stores; gemm_epilogue.cuh)
 // Two accumulated segments are supported (conv1 3x3 dgrad + shortcut 1x1 dgrad; 1x1 segments use a plain
-// 16 x 8-pixel box with a 1024-byte pitch).
+// 16 x 16-pixel box with a 2048-byte pitch).
 // Replaces aten::convolution / convolution_backward(input) of Main_Final.py:157,159,172,126,131.
 #include "rbu_common.cuh"
 #include "rbu_ptx.cuh"
@@ -31,19 +37,24 @@ namespace {
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
-constexpr int TILE_W = 8, TILE_H = 16;
-constexpr int HALO_W = 16, HALO_H = 18;               // 16 column slots (10 used): row pitch 2048 B = 2 swizzle atoms
-constexpr int A_HALO_BYTES = HALO_H * HALO_W * 128;   // 36864
-constexpr int A_PLAIN_BYTES = BLOCK_M * 128;          // 16384
+constexpr int TILE_W = 16, TILE_H = 16, HALF_W = 8;
+constexpr int HALO_W = 24, HALO_H = 18;               // 24 column slots (18 used): row pitch 3072 B = 3 swizzle atoms
+constexpr int A_HALO_BYTES = HALO_H * HALO_W * 128;   // 55296
+constexpr int A_PLAIN_BYTES = TILE_H * TILE_W * 128;  // 32768
 constexpr int NUM_THREADS = 320;   // TMA warp, MMA warp, 8 epilogue warps
 constexpr int MAX_B_STAGES = 8;
+constexpr int MAX_SLOTS = 4;
 constexpr int SMEM_LIMIT = 232448 - EPI_STAT_FLOATS * 4;   // minus the static statistics accumulators
 constexpr int LOOKAHEAD_TAP = 4;                      // the next slab's A tile is requested after this tap's B tile
+constexpr uint32_t HALF_OFF = (HALF_W * 128) >> 4;    // right half-tile: 8 pixels = 1024 B further (descriptor units)
+constexpr uint32_t ROW_OFF = (HALO_W * 128) >> 4;     // one halo row down
 
 struct HParams {
   int N, H, W;
   int tiles_w, tiles_h;
+  FastDiv fd_nb, fd_tw, fd_th;
   int n_blocks, block_n, Ncols;
+  int slot_mask, slot_shift;   // TMEM accumulator slots: nslots = slot_mask + 1 = 1 << slot_shift
   int nseg;
   int taps[2], C[2];
   int a_stages, b_stages, tmem_cols, total_tiles;
@@ -56,7 +67,7 @@ struct HParams {
   int relu;
   const bf16* addend;
   long long addend_ld;
-  float* stats;   // [4*SMs][2][Ncols] per-(CTA, lane group) column sum / sum of squares of the stored output, or NULL
+  float* stats;   // [8*SMs][2][Ncols] per-(CTA, half-tile, lane group) column sum / sum of squares of the stored output, or NULL
 };
 
 // Enumerates the (tile, segment, 64-channel slab) sequence of this CTA; producer and MMA issuer walk it in lockstep.
@@ -78,12 +89,12 @@ struct SlabIter {
 };
 
 __device__ __forceinline__ void tile_coords(const HParams& p, int tile, int& nb, int& w0, int& h0, int& n) {
-  nb = tile % p.n_blocks;
-  int sp = tile / p.n_blocks;
-  w0 = (sp % p.tiles_w) * TILE_W;
-  sp /= p.tiles_w;
-  h0 = (sp % p.tiles_h) * TILE_H;
-  n = sp / p.tiles_h;
+  const int sp = fast_div(tile, p.fd_nb);
+  nb = tile - sp * p.n_blocks;
+  const int q = fast_div(sp, p.fd_tw);
+  w0 = (sp - q * p.tiles_w) * TILE_W;
+  n = fast_div(q, p.fd_th);
+  h0 = (q - n * p.tiles_h) * TILE_H;
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -101,9 +112,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   uint64_t* emptyA = bars + 4;                 // [4]
   uint64_t* fullB = bars + 8;                  // [MAX_B_STAGES]
   uint64_t* emptyB = bars + 8 + MAX_B_STAGES;  // [MAX_B_STAGES]
-  uint64_t* tfull = bars + 8 + 2 * MAX_B_STAGES;
-  uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* tfull = bars + 8 + 2 * MAX_B_STAGES;   // [MAX_SLOTS]
+  uint64_t* tempty = tfull + MAX_SLOTS;            // [MAX_SLOTS]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + MAX_SLOTS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -128,9 +139,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       ptx::mbar_init(&fullB[s], 1);
       ptx::mbar_init(&emptyB[s], 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < MAX_SLOTS; ++a) {
       ptx::mbar_init(&tfull[a], 1);
-      ptx::mbar_init(&tempty[a], 8);
+      ptx::mbar_init(&tempty[a], 4);   // the four epilogue warps of one half-tile
     }
     ptx::fence_barrier_init();
   }
@@ -158,7 +169,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         int nb, w0, h0, n;
         tile_coords(p, ia.tile, nb, w0, h0, n);
         const bool halo = p.taps[ia.seg] == 9;
-        ptx::mbar_wait(&emptyA[s], ph ^ 1);
+        ptx::mbar_wait_backoff(&emptyA[s], ph ^ 1);
         ptx::mbar_arrive_expect_tx(&fullA[s], halo ? A_HALO_BYTES : A_PLAIN_BYTES);
         const CUtensorMap* mA = ia.seg ? &tmA1 : &tmA0;
         if (halo)
@@ -188,7 +199,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           const int s = sb;
           const uint32_t ph = phb;
           if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
-          ptx::mbar_wait(&emptyB[s], ph ^ 1);
+          ptx::mbar_wait_backoff(&emptyB[s], ph ^ 1);
           ptx::mbar_arrive_expect_tx(&fullB[s], (uint32_t)(b_bytes * tps));
           for (int j = 0; j < tps; ++j)
             ptx::tma_load_2d(smB + s * bs_bytes + j * b_bytes, mB, &fullB[s], (tap0 + j) * p.C[ib.seg] + ib.kc * BLOCK_K,
@@ -216,10 +227,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     uint32_t pha = 0, phb = 0;
     bool bres_ready = false;
     while (it.valid) {
-      const int a = t & 1;
-      ptx::mbar_wait(&tempty[a], ((t >> 1) & 1) ^ 1);
+      // half-tiles 2t (left) and 2t+1 (right) of this CTA's t-th tile: accumulator slots and their use counts
+      const int sl = (2 * t) & p.slot_mask, sr = (2 * t + 1) & p.slot_mask;
+      const uint32_t use_par = (uint32_t)((2 * t) >> p.slot_shift) & 1u;
+      ptx::mbar_wait(&tempty[sl], use_par ^ 1);
+      ptx::mbar_wait(&tempty[sr], use_par ^ 1);
       ptx::tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(a * p.block_n);
+      const uint32_t d_l = tmem_base + (uint32_t)(sl * p.block_n), d_r = tmem_base + (uint32_t)(sr * p.block_n);
       const int cur_tile = it.tile;
       uint32_t accumulate = 0;
       while (it.valid && it.tile == cur_tile) {
@@ -231,9 +245,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const uint32_t a_lo0 = ptx::desc_lo(smA_s + sa * A_HALO_BYTES, 16);
         const int rem = p.C[it.seg] - it.kc * BLOCK_K;
         const int ksteps = rem >= BLOCK_K ? 4 : (rem + 15) / 16;   // channels past C are TMA zero fill
-        // halo origin is pixel (h0-1, w0-1): tap (dy,dx) starts dy halo rows (2048 B) down and dx pixels (128 B) right
+        // halo origin is pixel (h0-1, w0-1): tap (dy,dx) starts dy halo rows (3072 B) down and dx pixels (128 B) right;
+        // the right half-tile starts 8 pixels (1024 B) further
         if (p.resident) {
-          // 36 MMAs per slab straight from the resident weights: one barrier wait (the A tile) per 36 instructions
+          // 72 MMAs per slab straight from the resident weights: one barrier wait (the A tile) per 72 instructions
           if (!bres_ready) {
             ptx::mbar_wait_s(fullB_s, 0);
             ptx::tc_fence_after();
@@ -246,15 +261,18 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll
               for (int dx = 0; dx < 3; ++dx)
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  ptx::umma_bf16(d_tmem, ptx::pack_desc(a_lo0 + dy * ((HALO_W * 128) >> 4) + dx * 8 + 2 * k, a_hi),
-                                 ptx::pack_desc(b_lo + (dy * 3 + dx) * b_step + 2 * k, b_hi), idesc,
-                                 (dy | dx | k) ? 1u : accumulate);
+                for (int k = 0; k < 4; ++k) {
+                  const uint64_t bd = ptx::pack_desc(b_lo + (dy * 3 + dx) * b_step + 2 * k, b_hi);
+                  const uint32_t al = a_lo0 + dy * ROW_OFF + dx * 8 + 2 * k;
+                  const uint32_t acc = (dy | dx | k) ? 1u : accumulate;
+                  ptx::umma_bf16(d_l, ptx::pack_desc(al, a_hi), bd, idesc, acc);
+                  ptx::umma_bf16(d_r, ptx::pack_desc(al + HALF_OFF, a_hi), bd, idesc, acc);
+                }
           }
           accumulate = 1;
           __syncwarp();
         } else if (halo && p.tps == 3 && ksteps == 4) {
-          // one kernel row (3 taps x 4 K-steps = 12 MMAs) per B stage, fully unrolled with immediate offsets
+          // one kernel row (3 taps x 2 halves x 4 K-steps = 24 MMAs) per B stage, fully unrolled with immediate offsets
           uint32_t a_row = a_lo0;
           for (int dy = 0; dy < 3; ++dy) {
             ptx::mbar_wait_s(fullB_s + sb * 8, phb);
@@ -264,16 +282,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll
               for (int dx = 0; dx < 3; ++dx) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  ptx::umma_bf16(d_tmem, ptx::pack_desc(a_row + dx * 8 + 2 * k, a_hi),
-                                 ptx::pack_desc(b_lo + dx * b_step + 2 * k, b_hi), idesc, (dx | k) ? 1u : accumulate);
+                for (int k = 0; k < 4; ++k) {
+                  const uint64_t bd = ptx::pack_desc(b_lo + dx * b_step + 2 * k, b_hi);
+                  const uint32_t acc = (dx | k) ? 1u : accumulate;
+                  ptx::umma_bf16(d_l, ptx::pack_desc(a_row + dx * 8 + 2 * k, a_hi), bd, idesc, acc);
+                  ptx::umma_bf16(d_r, ptx::pack_desc(a_row + HALF_OFF + dx * 8 + 2 * k, a_hi), bd, idesc, acc);
+                }
               }
               ptx::umma_commit_s(emptyB_s + sb * 8);
             }
             accumulate = 1;
             __syncwarp();
             if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
-            a_row += (HALO_W * 128) >> 4;
+            a_row += ROW_OFF;
           }
         } else {
           const int tps = halo ? p.tps : 1;
@@ -289,8 +310,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 if (k < ksteps) {
-                  ptx::umma_bf16(d_tmem, ptx::pack_desc(a_lo + 2 * k, a_hi), ptx::pack_desc(b_lo + 2 * k, b_hi), idesc,
-                                 accumulate);
+                  const uint64_t bd = ptx::pack_desc(b_lo + 2 * k, b_hi);
+                  ptx::umma_bf16(d_l, ptx::pack_desc(a_lo + 2 * k, a_hi), bd, idesc, accumulate);
+                  ptx::umma_bf16(d_r, ptx::pack_desc(a_lo + HALF_OFF + 2 * k, a_hi), bd, idesc, accumulate);
                   accumulate = 1;
                 }
               }
@@ -302,7 +324,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
               j = 0;
               if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
             }
-            if (++dx == 3) { dx = 0; a_row += (HALO_W * 128) >> 4; a_lo = a_row; } else { a_lo += 128 >> 4; }
+            if (++dx == 3) { dx = 0; a_row += ROW_OFF; a_lo = a_row; } else { a_lo += 128 >> 4; }
           }
         }
         if (ptx::elect_one()) ptx::umma_commit_s(emptyA_s + sa * 8);
@@ -310,62 +332,95 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         if (++sa == p.a_stages) { sa = 0; pha ^= 1; }
         it.next(p);
       }
-      if (ptx::elect_one()) ptx::umma_commit(&tfull[a]);
+      if (ptx::elect_one()) {
+        ptx::umma_commit(&tfull[sl]);
+        ptx::umma_commit(&tfull[sr]);
+      }
       __syncwarp();
       ++t;
     }
   } else {
     // ============================== epilogue (warps 2..9) ==============================
+    // Warps 2-5 (half 0) drain the left 16 x 8-pixel half-tile of every tile, warps 6-9 the right one: accumulator row
+    // r = 32 lg + lane is pixel (r >> 3, 8 half + (r & 7)) of the tile, and the warp drains all of its 32-column chunks.
     const int lg = warp & 3;
     const int half = (warp - 2) >> 2;
     const int row = lg * 32 + lane;
+    const int hl = row >> 3, wl = HALF_W * half + (row & 7);
     EpiOut eo;
     eo.stat_acc = p.stats ? stat_smem + (warp - 2) * (EPI_STAT_CHUNKS * 64) : nullptr;
     eo.y = p.y; eo.y_ld = p.y_ld; eo.bias = p.bias; eo.scale = p.scale; eo.relu = p.relu; eo.addend = p.addend; eo.addend_ld = p.addend_ld;
     eo.Ncols = p.Ncols; eo.scatter = 0; eo.Cout = p.Ncols; eo.H = p.H; eo.W = p.W;
+    const int mode = (p.addend ? 1 : 0) | (p.bias ? 2 : 0) | ((p.scale || p.relu) ? 4 : 0);
     auto locate = [&](int tile, int& nb, bool& valid, long long& pix, int& n, int& h, int& w) {
       int w0, h0;
       tile_coords(p, tile, nb, w0, h0, n);
-      h = h0 + row / TILE_W;
-      w = w0 + row % TILE_W;
+      h = h0 + hl;
+      w = w0 + wl;
       valid = h < p.H && w < p.W;
       pix = ((long long)n * p.H + h) * p.W + w;
     };
-    int t = 0;
+    int k = 0;
     int nb, n, h, w;
     bool valid;
     long long pix;
     uint4 ad[4];
     if (blockIdx.x < p.total_tiles) {
       locate(blockIdx.x, nb, valid, pix, n, h, w);
-      epi_prefetch(eo, nb * p.block_n + half * 32, valid, pix, ad);
+      epi_prefetch(eo, nb * p.block_n, valid, pix, ad);
     }
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
-      const int a = t & 1;
-      const uint32_t aph = (t >> 1) & 1;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++k) {
+      const int t = 2 * k + half;                 // half-tile counter of this CTA
+      const int slot = t & p.slot_mask;
+      const uint32_t par = (uint32_t)(t >> p.slot_shift) & 1u;
       int nb2 = 0, n2 = 0, h2 = 0, w2 = 0;
       bool valid2 = false;
       long long pix2 = 0;
       const bool more = tile + gridDim.x < p.total_tiles;
       if (more) locate(tile + gridDim.x, nb2, valid2, pix2, n2, h2, w2);
-      ptx::mbar_wait(&tfull[a], aph);
+      ptx::mbar_wait(&tfull[slot], par);
       ptx::tc_fence_after();
-      const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(a * p.block_n);
-      for (int c0 = half * 32; c0 < p.block_n; c0 += 64) {
-        if (c0 != half * 32) epi_prefetch(eo, nb * p.block_n + c0, valid, pix, ad);
-        epi_finish(eo, t_addr + (uint32_t)c0, nb * p.block_n + c0, valid, pix, n, h, w, ad, (c0 - half * 32) >> 6);
-        if (c0 + 64 >= p.block_n && more) epi_prefetch(eo, nb2 * p.block_n + half * 32, valid2, pix2, ad);   // next tile
+      const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(slot * p.block_n);
+      bf16* yrow = p.y + pix * p.y_ld;
+      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+        const int col = nb * p.block_n + c0;
+        if (p.stats || col + 32 > p.Ncols) {
+          epi_finish(eo, t_addr + (uint32_t)c0, col, valid, pix, n, h, w, ad, c0 >> 5);
+        } else {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(t_addr + (uint32_t)c0, r);
+          ptx::tmem_ld_wait();
+          uint4 out[4];
+          switch (mode) {   // warp-uniform: one lean arithmetic body per combination
+            case 0: epi_math<false, false, false>(r, p.bias, p.scale, p.relu, col, ad, out); break;
+            case 1: epi_math<true, false, false>(r, p.bias, p.scale, p.relu, col, ad, out); break;
+            case 2: epi_math<false, true, false>(r, p.bias, p.scale, p.relu, col, ad, out); break;
+            case 3: epi_math<true, true, false>(r, p.bias, p.scale, p.relu, col, ad, out); break;
+            case 4: epi_math<false, false, true>(r, p.bias, p.scale, p.relu, col, ad, out); break;
+            case 5: epi_math<true, false, true>(r, p.bias, p.scale, p.relu, col, ad, out); break;
+            case 6: epi_math<false, true, true>(r, p.bias, p.scale, p.relu, col, ad, out); break;
+            default: epi_math<true, true, true>(r, p.bias, p.scale, p.relu, col, ad, out); break;
+          }
+          if (valid) {
+            uint4* dst = reinterpret_cast<uint4*>(yrow + col);
+            dst[0] = out[0]; dst[1] = out[1]; dst[2] = out[2]; dst[3] = out[3];
+          }
+        }
+        if (c0 + 32 < p.block_n)
+          epi_prefetch(eo, col + 32, valid, pix, ad);
+        else if (more)
+          epi_prefetch(eo, nb2 * p.block_n, valid2, pix2, ad);   // next tile
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tempty[a]);
+      if (lane == 0) ptx::mbar_arrive(&tempty[slot]);
       nb = nb2; n = n2; h = h2; w = w2; valid = valid2; pix = pix2;
     }
     if (p.stats) {
       // every tile of this CTA has the same column block (grid % n_blocks == 0): flush the warp's accumulators
       const int nbf = blockIdx.x % p.n_blocks;
-      float* row_out = p.stats + (long long)(blockIdx.x * 4 + lg) * 2 * p.Ncols;
-      for (int c0 = half * 32, j = 0; c0 < p.block_n; c0 += 64, ++j) {
+      float* row_out = p.stats + (long long)((blockIdx.x * 2 + half) * 4 + lg) * 2 * p.Ncols;
+      for (int c0 = 0, j = 0; c0 < p.block_n; c0 += 32, ++j) {
         const int col = nbf * p.block_n + c0 + lane;
         if (col < p.Ncols) {
           const float2 v = reinterpret_cast<const float2*>(eo.stat_acc)[j * 32 + lane];
@@ -384,9 +439,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 }  // namespace
 
 // Returns 1 if the halo kernel can run these arguments (3x3 dilation-1 and 1x1 segments on images of at least
-// 16 x 8 pixels, no gather / scatter), else 0.
+// 16 x 16 pixels, no gather / scatter), else 0.
 int rbu_conv_halo_supported(const rbu_conv_gemm_args* a) {
   if (a->scatter || a->H < TILE_H || a->W < TILE_W) return 0;
+  if (a->stats && a->Ncols > 32 * EPI_STAT_CHUNKS) return 0;   // per-warp statistics accumulators cover 128 columns
   int any3x3 = 0;
   for (int s = 0; s < a->nseg; ++s) {
     const rbu_gemm_operand& o = a->seg[s];
@@ -405,8 +461,18 @@ int rbu_conv_halo_launch(const rbu_conv_gemm_args* a, cudaStream_t stream) {
   p.tiles_w = rbu_cdiv(a->W, TILE_W);
   p.tiles_h = rbu_cdiv(a->H, TILE_H);
   p.Ncols = a->Ncols;
-  p.block_n = a->Ncols >= 256 ? 256 : ((a->Ncols + 31) / 32) * 32;
+  // 128-column blocks from 128 output channels up: four accumulator slots (two tiles in flight), so the epilogue of one
+  // tile always overlaps the MMAs of the next -- with 256-column blocks the two half-tiles fill the TMEM and the MMA
+  // issuer waited 40% of the time for the drain (ncu, 256->256 at 64x64: 1438 vs 1480 TFLOP/s).  One-tile images
+  // (16 x 16, 1024 channels) keep 256: half as many activation re-reads per weight block (1503 vs 1393 TFLOP/s).
+  const bool one_tile = p.tiles_w * p.tiles_h == 1;
+  p.block_n = a->Ncols >= 256 ? (one_tile ? 256 : 128) : (a->Ncols >= 128 ? 128 : ((a->Ncols + 31) / 32) * 32);
   p.n_blocks = rbu_cdiv(a->Ncols, p.block_n);
+  p.fd_nb = make_fastdiv(p.n_blocks);
+  p.fd_tw = make_fastdiv(p.tiles_w);
+  p.fd_th = make_fastdiv(p.tiles_h);
+  p.slot_shift = 4 * p.block_n <= 512 ? 2 : 1;
+  p.slot_mask = (1 << p.slot_shift) - 1;
   p.nseg = a->nseg;
   for (int s = 0; s < a->nseg; ++s) {
     p.taps[s] = a->seg[s].taps;
@@ -414,7 +480,7 @@ int rbu_conv_halo_launch(const rbu_conv_gemm_args* a, cudaStream_t stream) {
   }
   const int b_bytes = p.block_n * 128;
   p.tps = p.block_n <= 128 ? 3 : 1;
-  p.a_stages = p.block_n >= 128 ? 2 : 3;
+  p.a_stages = 2;
   p.b_stages = (SMEM_LIMIT - 2048 - p.a_stages * A_HALO_BYTES) / (b_bytes * p.tps);
   if (p.b_stages > MAX_B_STAGES) p.b_stages = MAX_B_STAGES;
   {
@@ -423,8 +489,7 @@ int rbu_conv_halo_launch(const rbu_conv_gemm_args* a, cudaStream_t stream) {
     if (no_res < 0) no_res = getenv("RBU_NO_RESIDENT") ? 1 : 0;
     const long wbytes = (long)(a->seg[0].C / BLOCK_K) * 9 * b_bytes;
     if (!no_res && a->nseg == 1 && a->seg[0].taps == 9 && p.n_blocks == 1 && a->seg[0].C % BLOCK_K == 0) {
-      int as = 3;
-      if (wbytes + as * A_HALO_BYTES > SMEM_LIMIT - 2048) as = 2;
+      const int as = 2;
       if (wbytes + as * A_HALO_BYTES <= SMEM_LIMIT - 2048) {
         p.resident = 1;
         p.a_stages = as;
@@ -434,7 +499,7 @@ int rbu_conv_halo_launch(const rbu_conv_gemm_args* a, cudaStream_t stream) {
     }
   }
   p.tmem_cols = 32;
-  while (p.tmem_cols < 2 * p.block_n) p.tmem_cols <<= 1;
+  while (p.tmem_cols < (p.slot_mask + 1) * p.block_n) p.tmem_cols <<= 1;
   p.total_tiles = p.tiles_w * p.tiles_h * a->N * p.n_blocks;
   p.y = reinterpret_cast<bf16*>(a->y);
   p.y_ld = a->y_ld;
@@ -475,7 +540,7 @@ int rbu_conv_halo_launch(const rbu_conv_gemm_args* a, cudaStream_t stream) {
   }
   const int grid = p.total_tiles < rbu_num_sms() ? p.total_tiles : rbu_num_sms();
   if (a->stats) {
-    RBU_CHECK_ARG(p.block_n <= 64 * EPI_STAT_CHUNKS && grid % p.n_blocks == 0 && ((uintptr_t)a->stats & 15) == 0,
+    RBU_CHECK_ARG(p.block_n <= 32 * EPI_STAT_CHUNKS && grid % p.n_blocks == 0 && ((uintptr_t)a->stats & 15) == 0,
                   "rbu_conv_gemm: output statistics are not supported for this shape");
     RBU_CHECK_CUDA(cudaMemsetAsync(a->stats, 0, rbu_conv_stats_floats(a->Ncols) * sizeof(float), stream));
   }
