@@ -90,11 +90,21 @@ def conv_gemm(N, H, W, segs, Ncols, y: View, scatter=False, Cout=0, bias=None, a
     a.relu = int(relu)
     if flops is None:
         flops = 2.0 * N * H * W * Ncols * sum(t * x.C for (x, _, t, _, _) in segs)
+    nbytes = 0.0
+    if tag == "conv_gemm":
+        # profiler classes: the halo kernel's 3x3 convolutions are tensor-pipe work; everything else that goes through
+        # the generic kernel in this network (1x1, stem, ConvTranspose, 16x16 dilated) is bound by its activation bytes
+        if any(t == 9 and d == 1 for (_, _, t, d, _) in segs) and H >= 16 and W >= 16 and not scatter:
+            tag = "conv3x3"
+        else:
+            tag = "conv_small"
+            nbytes = 2.0 * N * H * W * (sum(x.C for (x, _, _, _, _) in segs) +
+                                        Ncols * (2 if addend is not None else 1))
     label = None
     if _lib.PROFILER is not None:
         label = f"conv {N}x{H}x{W} " + "+".join(f"{x.C}t{t}{'g' if g else ''}d{d}" for (x, _, t, d, g) in segs) + \
             f"->{Ncols}{' scatter' if scatter else ''}"
-    call("rbu_conv_gemm", ctypes.byref(a), stream_ptr(), tag=tag, flops=flops, label=label)
+    call("rbu_conv_gemm", ctypes.byref(a), stream_ptr(), tag=tag, flops=flops, nbytes=nbytes, label=label)
 
 
 def conv_direct_ref(x: View, N, H, W, w, bias, ksz, dil):
