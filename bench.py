@@ -209,10 +209,18 @@ def run_ours(args):
     ms_e2e, _, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2))
 
     # per-kernel-class device times of one extra step (CUDA events around every C-ABI call on the launching stream)
+    # The weight-gradient side stream is switched off for this pass: kernels running concurrently slow each other down and
+    # the per-kernel times (the roofline numerators) would be those of the mix, not of the kernel.
     prof = _lib.Profiler()
+    eng = getattr(model, "engine", None)
+    was_overlap = getattr(eng, "overlap_wgrad", None)
+    if was_overlap:
+        eng.overlap_wgrad = False
     _lib.PROFILER = prof
     step(x_dev, y_dev)
     _lib.PROFILER = None
+    if was_overlap:
+        eng.overlap_wgrad = True
     summ = prof.summary()
     if args.detail and rank == 0:
         with open(args.detail, "w") as f:
