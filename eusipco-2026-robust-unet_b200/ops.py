@@ -155,3 +155,36 @@ def preprocess(img_u8: torch.Tensor, n_channels: int = 3) -> torch.Tensor:
     out = torch.empty((B, n_channels, H, W), dtype=torch.float32, device=img_u8.device)
     call("rbu_preprocess", _p(img_u8), B, H, W, n_channels, _p(out), stream_ptr())
     return out
+
+
+def enhance_image(img: torch.Tensor, enhance_water: bool = True, return_percentiles: bool = False):
+    """tif_to_image.py:139-171 `enhance_image` on the GPU: [H,W,C] or [B,H,W,C] uint8 / uint16 CUDA tensor -> uint8 of the
+    same shape (2-98 percentile stretch per image and band, band-0 darkening).  Bit-exact against the reference."""
+    if not img.is_cuda or img.dtype not in (torch.uint8, torch.uint16) or img.dim() not in (3, 4):
+        raise RuntimeError("rbunet.enhance_image expects a uint8 / uint16 CUDA tensor [H,W,C] or [B,H,W,C] (no CPU fallback)")
+    single = img.dim() == 3
+    x = (img.unsqueeze(0) if single else img).contiguous()
+    B, H, W, C = x.shape
+    bits = 8 if x.dtype == torch.uint8 else 16
+    out = torch.empty((B, H, W, C), dtype=torch.uint8, device=x.device)
+    pct = torch.empty((B, C, 2), dtype=torch.float64, device=x.device)
+    nbytes = int(_lib.lib().rbu_enhance_workspace_bytes(B, C, bits))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    call("rbu_enhance_image", _p(x), bits, B, H, W, C, int(bool(enhance_water)), _p(out), _p(pct), _p(ws), nbytes,
+         stream_ptr(), nbytes=float(x.numel() * x.element_size() * 2 + out.numel()))
+    if single:
+        out, pct = out[0], pct[0]
+    return (out, pct) if return_percentiles else out
+
+
+def coastline_mask(mask: torch.Tensor, ksize: int = 5) -> torch.Tensor:
+    """predict_coastline.py:595-602 on the GPU: cv2.dilate(mask, ellipse(ksize)) - mask for a uint8 CUDA mask [H,W] or
+    [B,H,W].  The contour tracing that follows in the reference stays on the host."""
+    if not mask.is_cuda or mask.dtype != torch.uint8 or mask.dim() not in (2, 3):
+        raise RuntimeError("rbunet.coastline_mask expects a uint8 CUDA tensor [H,W] or [B,H,W] (no CPU fallback)")
+    single = mask.dim() == 2
+    m = (mask.unsqueeze(0) if single else mask).contiguous()
+    B, H, W = m.shape
+    out = torch.empty_like(m)
+    call("rbu_coastline_mask", _p(m), B, H, W, int(ksize), _p(out), stream_ptr(), nbytes=float(2 * m.numel()))
+    return out[0] if single else out

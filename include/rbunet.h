@@ -47,6 +47,23 @@ unsigned long long rbu_launch_count(void);
  * reference has no HSV code).  Bit-identical to the numpy oracle. */
 int rbu_preprocess(const uint8_t* img, int B, int H, int W, int n_channels, float* out, void* stream);
 
+/* ------------------------------------------------------------------ image operations either side of the network
+ * (integer / byte work, bit-exact against the reference's numpy / OpenCV code)
+ *
+ * rbu_enhance_image: tif_to_image.py:139-171 enhance_image (duplicated at train_water_segmentation.py:103-174 and
+ * predict_coastline.py:545-581).  img: [B,H,W,C] interleaved unsigned samples of `bits` (8 or 16) bits, C <= 8 bands.
+ * Per image and band: p2, p98 = np.percentile(band, [2, 98]) (linear method, float64), then
+ * clip((x - p2) / (p98 - p2) * 255, 0, 255); with enhance_water band 0 is multiplied by 0.7 where the stretched value is
+ * below 100; truncation to uint8.  out: [B,H,W,C] uint8.  percentiles_out: optional [B,C,2] float64 device buffer.
+ * A constant band (p98 == p2) yields 0 where the reference's NaN -> integer conversion is undefined. */
+size_t rbu_enhance_workspace_bytes(int B, int C, int bits);
+int rbu_enhance_image(const void* img, int bits, int B, int H, int W, int C, int enhance_water, uint8_t* out,
+                      double* percentiles_out, void* workspace, size_t workspace_bytes, void* stream);
+/* rbu_coastline_mask: predict_coastline.py:595-602 -- cv2.dilate(mask, getStructuringElement(MORPH_ELLIPSE, (k,k)),
+ * iterations=1) - mask on uint8 [B,H,W] masks (any values; uint8 arithmetic), 1 <= ksize <= 64.  Contour tracing
+ * (cv2.findContours / approxPolyDP, :605-616) stays on the host. */
+int rbu_coastline_mask(const uint8_t* mask, int B, int H, int W, int ksize, uint8_t* out, void* stream);
+
 /* ------------------------------------------------------------------ tensor-core implicit GEMM
  * Replaces aten::convolution for 3x3 (dilation 1/2/4), 1x1 and ConvTranspose2d(2, stride 2)
  * (Main_Final.py:157,159,172,126,131,205-208,261-270) and, with re-packed weights, their data

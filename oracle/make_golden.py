@@ -234,6 +234,49 @@ def unet_golden():
     print("unet loss", loss.item(), "eval loss", out["loss_eval"], "acc", out["accuracy_eval"], "iou", out["iou_eval"])
 
 
+def _scene(rng, h, w, c, hi, dtype):
+    """Synthetic satellite-like bands: smooth low-frequency field + speckle, skewed like digital numbers."""
+    low = rng.random((h // 8 + 2, w // 8 + 2, c))
+    up = np.kron(low, np.ones((8, 8, 1)))[:h, :w, :]
+    v = (up ** 2) * hi * 0.6 + rng.gamma(2.0, hi / 40.0, size=(h, w, c))
+    return np.clip(v, 0, hi - 1).astype(dtype)
+
+
+def imageops_golden():
+    """the reference's own enhance_image (tif_to_image.py:139-171, called unbound -- it
+    does not use self) and the OpenCV calls of predict_coastline.py:595-602 on small seeded inputs."""
+    import importlib
+    import cv2
+    T = importlib.import_module("tif_to_image")      # osgeo is stubbed by load_reference()
+    conv = T.TIFToImageConverter.__new__(T.TIFToImageConverter)
+    rng = np.random.default_rng(2026)
+    out = {"cv2_version": np.array(cv2.__version__)}
+    cases = [("u16", np.uint16, 30000, (48, 40, 3)), ("u8", np.uint8, 256, (33, 47, 3)), ("u16full", np.uint16, 65536, (24, 56, 4)),
+             ("tiny", np.uint8, 256, (3, 5, 3))]
+    for tag, dt, hi, shape in cases:
+        rgb = _scene(rng, *shape, hi, dt)
+        out[f"enh_{tag}_in"] = rgb
+        for ew in (0, 1):
+            out[f"enh_{tag}_out{ew}"] = conv.enhance_image(rgb, bool(ew)).astype(np.uint8)
+        out[f"enh_{tag}_pct"] = np.array([[np.percentile(rgb[:, :, i], q) for q in (2, 98)] for i in range(shape[2])])
+    for k in (1, 2, 3, 5, 8, 20, 31):
+        out[f"ellipse_{k}"] = cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (k, k))
+    for tag, shape in (("a", (40, 56)), ("b", (16, 16)), ("c", (5, 70))):
+        blob = _scene(rng, shape[0], shape[1], 1, 256, np.uint8)[:, :, 0]
+        mask = ((blob > np.median(blob)) * 255).astype(np.uint8)
+        mask01 = (mask // 255).astype(np.uint8)
+        out[f"mask_{tag}"] = mask
+        for k in (5, 20, 3):
+            kern = cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (k, k))
+            d = cv2.dilate(mask, kern, iterations=1)
+            out[f"coast_{tag}_k{k}"] = d - mask
+            out[f"coast01_{tag}_k{k}"] = cv2.dilate(mask01, kern, iterations=1) - mask01
+        out[f"gray_{tag}"] = blob
+        out[f"graydil_{tag}_k5"] = cv2.dilate(blob, cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (5, 5)), iterations=1)
+    np.savez_compressed(os.path.join(OUT, "imageops.npz"), **out)
+    print("imageops goldens:", len(out), "arrays")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
@@ -243,6 +286,7 @@ def main():
     module_goldens(MF)
     metric_goldens(MF)
     unet_golden()
+    imageops_golden()
     print("wrote", sorted(os.listdir(OUT)))
 
 
