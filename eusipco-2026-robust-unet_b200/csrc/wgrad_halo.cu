@@ -27,7 +27,7 @@ constexpr int HALO_W = 24, HALO_H = 10;
 constexpr int X_BYTES = HALO_W * HALO_H * 128;   // 30720
 constexpr int DY_BYTES = TILE_W * TILE_H * 128;  // 16384
 constexpr int STAGE_BYTES = X_BYTES + DY_BYTES;  // 47104 (multiple of 1024)
-constexpr int STAGES = 4;
+constexpr int MAX_STAGES = 4;
 constexpr int NUM_THREADS = 192;
 constexpr int SMEM_LIMIT = 232448;
 constexpr int NACC = 5;
@@ -37,6 +37,7 @@ struct HWParams {
   int tiles_w, tiles_h, tiles_total;
   int Cout, Cin;
   int cin_blocks, cout_blocks, ksplit, items;
+  int stages;       // smem ring depth (<= MAX_STAGES)
   float* partial;   // [ksplit][Cout][9][Cin]
 };
 
@@ -51,10 +52,10 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                   const __grid_constant__ HWParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* full = bars;             // [STAGES]
-  uint64_t* empty = bars + STAGES;   // [STAGES]
-  uint64_t* tfull = bars + 2 * STAGES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.stages * STAGE_BYTES);
+  uint64_t* full = bars;             // [MAX_STAGES]
+  uint64_t* empty = bars + MAX_STAGES;   // [MAX_STAGES]
+  uint64_t* tfull = bars + 2 * MAX_STAGES;
   uint64_t* tempty = tfull + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 1);
 
@@ -64,7 +65,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     ptx::prefetch_tmap(&tmDy);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+    for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
     ptx::mbar_init(tfull, 1);
     ptx::mbar_init(tempty, 4);
     ptx::fence_barrier_init();
@@ -96,7 +97,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           uint8_t* dst = smem + s * STAGE_BYTES;
           ptx::tma_load_4d(dst, &tmX, &full[s], cb * 64, tw * TILE_W - 1, th * TILE_H - 1, n);
           ptx::tma_load_4d(dst + X_BYTES, &tmDy, &full[s], ob * 64, tw * TILE_W, th * TILE_H, n);
-          if (++s == STAGES) { s = 0; ph ^= 1; }
+          if (++s == p.stages) { s = 0; ph ^= 1; }
           if (++tw == p.tiles_w) { tw = 0; if (++th == p.tiles_h) { th = 0; ++n; } }
         }
       }
@@ -144,7 +145,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         }
         accumulate = 1;
         __syncwarp();
-        if (++s == STAGES) { s = 0; ph ^= 1; }
+        if (++s == p.stages) { s = 0; ph ^= 1; }
       }
       if (ptx::elect_one()) ptx::umma_commit(tfull);
       __syncwarp();
@@ -259,7 +260,12 @@ int rbu_wgrad_halo_launch(const rbu_wgrad_args* a, void* workspace, cudaStream_t
     int rc = rbu_encode_tmap_bf16(&tmDy, a->a, 4, dims, str, box);
     if (rc) return rc;
   }
-  const int smem_bytes = STAGES * STAGE_BYTES + 1024 + 256;
+  {
+    static int st = -1;   // RBU_WGRAD_STAGES: ring depth experiment (shared memory left for co-resident bandwidth kernels)
+    if (st < 0) { const char* e = getenv("RBU_WGRAD_STAGES"); st = e ? atoi(e) : MAX_STAGES; if (st < 2 || st > MAX_STAGES) st = MAX_STAGES; }
+    p.stages = st;
+  }
+  const int smem_bytes = p.stages * STAGE_BYTES + 1024 + 256;
   static bool attr_set = false;
   if (!attr_set) {
     RBU_CHECK_CUDA(cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));

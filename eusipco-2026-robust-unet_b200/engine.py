@@ -419,6 +419,16 @@ class Engine:
             grads[prefix + ".shortcut.0.weight"] = gst[C:, 4 * nc:5 * nc].reshape(C, nc, 1, 1).contiguous()
             return None
         x = s["x"]
+        # The data gradient goes first: two persistent tensor-core kernels cannot share the SMs, so a weight-gradient kernel
+        # that grabbed them would stall the main stream; enqueued after the data gradient it runs beside the bandwidth-bound
+        # kernels of the next block instead.
+        if need_dx:
+            if dx is None:
+                dx = self.new(N, H, W, x.C, dev)
+            segs = [(dy1, self.pack(blk.conv1.weight, 1), 9, 1, False)]
+            if proj:
+                segs.append((dys, self.pack(blk.shortcut[0].weight, 1), 1, 0, False))
+            conv_gemm(N, H, W, segs, x.C, dx, addend=None if proj else de)
         gW1 = torch.empty_like(blk.conv1.weight)
         self.wgrad(N, H, W, dy1, x, 9, 1, False, gW1)
         grads[prefix + ".conv1.weight"] = gW1
@@ -426,15 +436,7 @@ class Engine:
             gWs = torch.empty_like(blk.shortcut[0].weight)
             self.wgrad(N, H, W, dys, x, 1, 0, False, gWs)
             grads[prefix + ".shortcut.0.weight"] = gWs
-        if not need_dx:
-            return None
-        if dx is None:
-            dx = self.new(N, H, W, x.C, dev)
-        segs = [(dy1, self.pack(blk.conv1.weight, 1), 9, 1, False)]
-        if proj:
-            segs.append((dys, self.pack(blk.shortcut[0].weight, 1), 1, 0, False))
-        conv_gemm(N, H, W, segs, x.C, dx, addend=None if proj else de)
-        return dx
+        return dx if need_dx else None
 
     # ------------------------------------------------------------------ AttentionGate (Main_Final.py:143-148)
     def ag_forward(self, gate, g: View, skip: View, out: View, N, H, W, training):
@@ -492,12 +494,12 @@ class Engine:
         grads[prefix + ".W_x.1.bias"], grads[prefix + ".W_x.1.weight"] = sums_f[F:2 * F], sums_f[3 * F:4 * F]
         grads[prefix + ".W_g.0.bias"] = torch.zeros(F, device=dev)
         grads[prefix + ".W_x.0.bias"] = torch.zeros(F, device=dev)
-        gWg, gWx = torch.empty_like(gate.W_g[0].weight), torch.empty_like(gate.W_x[0].weight)
-        self.wgrad(N, H, W, dyg, s["g"], 1, 0, False, gWg)
-        self.wgrad(N, H, W, dyx, s["skip"], 1, 0, False, gWx)
-        grads[prefix + ".W_g.0.weight"], grads[prefix + ".W_x.0.weight"] = gWg, gWx
         conv_gemm(N, H, W, [(dyg, self.pack(gate.W_g[0].weight, 1), 1, 0, False)], C, dgup, addend=dgup)
         conv_gemm(N, H, W, [(dyx, self.pack(gate.W_x[0].weight, 1), 1, 0, False)], C, dskip, addend=dskip)
+        gWg, gWx = torch.empty_like(gate.W_g[0].weight), torch.empty_like(gate.W_x[0].weight)
+        self.wgrad(N, H, W, dyg, s["g"], 1, 0, False, gWg)        # after the data gradients (see rb_backward)
+        self.wgrad(N, H, W, dyx, s["skip"], 1, 0, False, gWx)
+        grads[prefix + ".W_g.0.weight"], grads[prefix + ".W_x.0.weight"] = gWg, gWx
 
     # ------------------------------------------------------------------ DilatedBlock (Main_Final.py:213-223)
     def dil_forward(self, blk, x: View, N, H, W, training):
@@ -540,15 +542,15 @@ class Engine:
         segs = []
         for i, cv in enumerate(convs):
             taps = 1 if i == 0 else 9
-            d = dycat.slice(i * Cq, Cq)
-            g = torch.empty_like(cv.weight)
-            self.wgrad(N, H, W, d, x, taps, cv.dilation[0], False, g)
-            grads[f"{prefix}.conv{i + 1}.weight"] = g
-            grads[f"{prefix}.conv{i + 1}.bias"] = torch.zeros(Cq, device=dev)   # a bias before a train-mode BN
-            segs.append((d, self.pack(cv.weight, 1), taps, cv.dilation[0], False))
+            segs.append((dycat.slice(i * Cq, Cq), self.pack(cv.weight, 1), taps, cv.dilation[0], False))
         dx = self.new(N, H, W, x.C, dev)
         conv_gemm(N, H, W, segs[:2], x.C, dx)
         conv_gemm(N, H, W, segs[2:], x.C, dx, addend=dx)
+        for i, cv in enumerate(convs):          # weight gradients after the data gradients (see rb_backward)
+            g = torch.empty_like(cv.weight)
+            self.wgrad(N, H, W, segs[i][0], x, segs[i][2], cv.dilation[0], False, g)
+            grads[f"{prefix}.conv{i + 1}.weight"] = g
+            grads[f"{prefix}.conv{i + 1}.bias"] = torch.zeros(Cq, device=dev)   # a bias before a train-mode BN
         return dx
 
     # ------------------------------------------------------------------ whole model
@@ -668,11 +670,11 @@ class Engine:
             gub = torch.empty_like(up.bias)
             ws = self.bwd_ws(N, hk * wk, C, dev)
             call("rbu_chan_sum", _vp(dup), dup.ld, N * hk * wk, C, _p(gub), _p(ws), ws.numel() * 4, stream_ptr())
+            d = self.new(N, su["H"], su["W"], su["x"].C, dev)
+            conv_gemm(N, su["H"], su["W"], [(dup, self.pack(up.weight, 3), 4, 0, True)], su["x"].C, d)
             guw = torch.empty_like(up.weight)
             self.wgrad(N, su["H"], su["W"], su["x"], dup, 4, 0, True, guw)
             grads[f"up{k}.bias"], grads[f"up{k}.weight"] = gub, guw
-            d = self.new(N, su["H"], su["W"], su["x"].C, dev)
-            conv_gemm(N, su["H"], su["W"], [(dup, self.pack(up.weight, 3), 4, 0, True)], su["x"].C, d)
             done(f"dec{k}", f"att{k}", f"up{k}")
         d = self.rb_backward(m.bottleneck[2], S["bott"], d, grads, "bottleneck.2")
         d = self.dil_backward(m.bottleneck[1], S["dil"], d, grads, "bottleneck.1")
