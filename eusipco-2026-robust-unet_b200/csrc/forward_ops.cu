@@ -265,7 +265,7 @@ ca_gate_kernel(const float* __restrict__ nc_mean, const float* __restrict__ nc_m
 // ChannelAttention's max-pool (atomicMin on the pixel index; one hit per (n,c) in general) -- the arg-max that
 // adaptive_max_pool2d_backward routes the gradient to.  grid = (blocks, N); lane li of a TPP-lane group owns the
 // channel groups li, li+TPP, ... (K of them), whose per-(n,c) coefficients stay in registers.
-template <int TPP, int K>
+template <int TPP, int K, bool ARG>   // ARG: also the per-pixel arg-max channel and the ChannelAttention arg-max pixel (training)
 __global__ void __launch_bounds__(NT)
 sa_reduce_kernel(const bf16* __restrict__ y2, long ld, int HW, int C, const float* __restrict__ A2g,
                  const float* __restrict__ B2g, const float* __restrict__ tv, int* __restrict__ nc_arg,
@@ -285,7 +285,7 @@ sa_reduce_kernel(const bf16* __restrict__ y2, long ld, int HW, int C, const floa
       const long o = (long)n * C + cg * 8 + e;
       a[k][e] = cg < G ? A2g[o] : 0.f;
       b[k][e] = cg < G ? B2g[o] : 0.f;
-      t[k][e] = cg < G ? tv[o] : 0.f;
+      t[k][e] = (ARG && cg < G) ? tv[o] : 0.f;
     }
   }
   // bf16 bit patterns of the targets: one packed halfword compare per channel pair finds candidate hits; the exact
@@ -300,16 +300,20 @@ sa_reduce_kernel(const bf16* __restrict__ y2, long ld, int HW, int C, const floa
 #pragma unroll
     for (int e = 0; e < 8; ++e) tz[k] = tz[k] || t[k][e] == 0.f;
   }
-  const bf16* base = y2 + (long)n * HW * ld;
   const float invC = 1.f / (float)C;
-  for (int pb = blockIdx.x * (SLOTS * U); pb < HW; pb += gridDim.x * (SLOTS * U)) {
+  // this thread's pixel pointer walks by a constant stride (no 64-bit multiply per load)
+  const long step_u = (long)SLOTS * ld;
+  const long step_it = (long)gridDim.x * (SLOTS * U) * ld;
+  const bf16* ptr = y2 + ((long)n * HW + (long)blockIdx.x * (SLOTS * U) + slot) * ld + li * 8;
+  const bool lane_live = li < G;
+  for (int pb = blockIdx.x * (SLOTS * U); pb < HW; pb += gridDim.x * (SLOTS * U), ptr += step_it) {
     bf16x8 raw[U][K];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int pp = pb + u * SLOTS + slot;
 #pragma unroll
       for (int k = 0; k < K; ++k)
-        if (pp < HW && li + k * TPP < G) raw[u][k] = ld_bf16x8(base + (long)pp * ld + (li + k * TPP) * 8);
+        if (pp < HW && (K > 1 || lane_live)) raw[u][k] = ld_bf16x8(ptr + u * step_u + k * (TPP * 8));
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -320,22 +324,31 @@ sa_reduce_kernel(const bf16* __restrict__ y2, long ld, int HW, int C, const floa
 #pragma unroll
         for (int k = 0; k < K; ++k) {
           const int cg = li + k * TPP;
-          if (cg < G) {
+          if (K > 1 || lane_live) {
             float v[8];
             unpack8(raw[u][k], v);
+            if (ARG) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float c = a[k][e] * v[e] + b[k][e];
-              sum += c;
-              if (c > best) { best = c; bi = cg * 8 + e; }
-            }
-            const uint4 rw = *reinterpret_cast<const uint4*>(&raw[u][k]);
-            const unsigned hit = __vcmpeq2(rw.x, tp[k].x) | __vcmpeq2(rw.y, tp[k].y) | __vcmpeq2(rw.z, tp[k].z) |
-                                 __vcmpeq2(rw.w, tp[k].w);
-            if (hit != 0u || tz[k]) {
+              for (int e = 0; e < 8; ++e) {
+                const float c = a[k][e] * v[e] + b[k][e];
+                sum += c;
+                if (c > best) { best = c; bi = cg * 8 + e; }
+              }
+              const uint4 rw = *reinterpret_cast<const uint4*>(&raw[u][k]);
+              const unsigned hit = __vcmpeq2(rw.x, tp[k].x) | __vcmpeq2(rw.y, tp[k].y) | __vcmpeq2(rw.z, tp[k].z) |
+                                   __vcmpeq2(rw.w, tp[k].w);
+              if (hit != 0u || tz[k]) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e)
-                if (v[e] == t[k][e]) atomicMin(nc_arg + (long)n * C + cg * 8 + e, pp);
+                for (int e = 0; e < 8; ++e)
+                  if (v[e] == t[k][e]) atomicMin(nc_arg + (long)n * C + cg * 8 + e, pp);
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float c = a[k][e] * v[e] + b[k][e];
+                sum += c;
+                best = fmaxf(best, c);
+              }
             }
           }
         }
@@ -344,12 +357,16 @@ sa_reduce_kernel(const bf16* __restrict__ y2, long ld, int HW, int C, const floa
       for (int o = TPP / 2; o > 0; o >>= 1) {
         sum += __shfl_xor_sync(0xffffffffu, sum, o);
         const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        if (ARG) {
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        } else {
+          best = fmaxf(best, ov);
+        }
       }
       if (li == 0 && pp < HW) {
         s_out[(long)n * HW + pp] = make_float2(sum * invC, best);
-        amax_out[(long)n * HW + pp] = bi;
+        if (ARG) amax_out[(long)n * HW + pp] = bi;
       }
     }
   }
@@ -790,8 +807,10 @@ extern "C" int rbu_ca_gate(const float* nc_mean, const float* nc_max, const floa
 
 extern "C" int rbu_sa_reduce(const void* y2, int64_t ld, int64_t P, int HW, int C, const float* A2g, const float* B2g,
                              const float* tv, int* nc_arg, float* s_out, int* amax_out, void* stream_) {
-  RBU_CHECK_ARG(VIEW_OK(y2, ld) && A2g && B2g && tv && nc_arg && s_out && amax_out && EW_CH_OK(C) && HW > 0 && P > 0 &&
-                    P % HW == 0 && P / HW <= 65535, "rbu_sa_reduce: bad arguments");
+  RBU_CHECK_ARG(VIEW_OK(y2, ld) && A2g && B2g && s_out && EW_CH_OK(C) && HW > 0 && P > 0 && P % HW == 0 && P / HW <= 65535,
+                "rbu_sa_reduce: bad arguments");
+  const bool arg = amax_out != nullptr;     // inference passes NULL: no arg-max bookkeeping
+  RBU_CHECK_ARG(!arg || (tv && nc_arg), "rbu_sa_reduce: the arg-max outputs need tv and nc_arg");
   cudaStream_t st = (cudaStream_t)stream_;
   const int G = C >> 3, N = (int)(P / HW);
   const int tpp = G >= 32 ? 32 : (G < 4 ? 4 : G);
@@ -802,7 +821,15 @@ extern "C" int rbu_sa_reduce(const void* y2, int64_t ld, int64_t P, int HW, int 
   long cap = ((long)rbu_num_sms() * 32 + N - 1) / N;
   if (blocks > cap) blocks = cap;
   const dim3 grid((unsigned)blocks, (unsigned)N);
-#define LAUNCH(T, KK) sa_reduce_kernel<T, KK><<<grid, NT, 0, st>>>((const bf16*)y2, ld, HW, C, A2g, B2g, tv, nc_arg, (float2*)s_out, amax_out)
+#define LAUNCH(T, KK)                                                                                                        \
+  do {                                                                                                                    \
+    if (arg)                                                                                                              \
+      sa_reduce_kernel<T, KK, true><<<grid, NT, 0, st>>>((const bf16*)y2, ld, HW, C, A2g, B2g, tv, nc_arg, (float2*)s_out, \
+                                                         amax_out);                                                       \
+    else                                                                                                                  \
+      sa_reduce_kernel<T, KK, false><<<grid, NT, 0, st>>>((const bf16*)y2, ld, HW, C, A2g, B2g, tv, nc_arg, (float2*)s_out,\
+                                                          amax_out);                                                      \
+  } while (0)
   if (K == 1) { if (tpp == 4) LAUNCH(4, 1); else if (tpp == 8) LAUNCH(8, 1); else if (tpp == 16) LAUNCH(16, 1); else LAUNCH(32, 1); }
   else if (K == 2) LAUNCH(32, 2);
   else if (K == 4) LAUNCH(32, 4);

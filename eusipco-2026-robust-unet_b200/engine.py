@@ -331,9 +331,10 @@ class Engine:
              _p(blk.ca.fc[0].weight), _p(blk.ca.fc[2].weight), N, C, Ch, _p(ca["g"]), _p(ca["A2g"]), _p(ca["B2g"]),
              _p(ca["u_avg"]), _p(ca["u_max"]), _p(ca["h_avg"]), _p(ca["h_max"]), _p(ca["tv"]), _p(ca["nc_arg"]), stream_ptr())
         sa_s = self.f32(P, 2, device=dev)
-        amax_c = torch.empty(P, dtype=torch.int32, device=dev)
+        need_arg = training or self._saving      # the arg-max bookkeeping only feeds the backward pass
+        amax_c = torch.empty(P, dtype=torch.int32, device=dev) if need_arg else None
         call("rbu_sa_reduce", _vp(y2), y2.ld, P, HW, C, _p(ca["A2g"]), _p(ca["B2g"]), _p(ca["tv"]), _p(ca["nc_arg"]),
-             _p(sa_s), _p(amax_c), stream_ptr())
+             _p(sa_s), _p(amax_c) if need_arg else NULL, stream_ptr())
         gs = self.f32(P, device=dev)
         call("rbu_sa_gate", _p(sa_s), N, H, W, _p(blk.sa.conv1.weight), _p(gs), stream_ptr())
         if proj and bns is None:

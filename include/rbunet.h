@@ -211,7 +211,8 @@ int rbu_ca_gate(const float* nc_mean, const float* nc_max, const float* nc_min, 
                 float* B2g, float* u_avg, float* u_max, float* h_avg, float* h_max, float* tv, int* nc_arg,
                 void* stream);
 /* SpatialAttention (Main_Final.py:112-117): channel mean/max (+argmax) of A2g*y2+B2g, then the 7x7 gate.  The same
- * pass records nc_arg[n,c] = first pixel with y2 == tv[n,c] (the AdaptiveMaxPool2d arg-max for the backward). */
+ * pass records nc_arg[n,c] = first pixel with y2 == tv[n,c] (the AdaptiveMaxPool2d arg-max for the backward).
+ * amax_out == NULL (inference) skips both arg-max outputs; tv and nc_arg may then be NULL too. */
 int rbu_sa_reduce(const void* y2, int64_t ld, int64_t P, int HW, int C, const float* A2g, const float* B2g,
                   const float* tv, int* nc_arg, float* s_out /* [P][2] */, int* amax_out, void* stream);
 int rbu_sa_gate(const float* s, int N, int H, int W, const float* k7, float* gs, void* stream);
