@@ -640,31 +640,82 @@ ag_apply_kernel(const bf16* __restrict__ skip, long s_ld, bf16* __restrict__ out
 // Stem: fp32 NCHW image -> bf16 3x3 patches [P][Kp], k = tap*nc + c (zero padded), so that inc.conv1
 // (3x3, Cin=3|4) and inc.shortcut (1x1) run as ONE tensor-core GEMM with K = Kp (Main_Final.py:157,172,233).
 // ------------------------------------------------------------------------------------------------
+// Generic channel count: one thread per 16-byte piece of a patch row, reads through L1.
 __global__ void __launch_bounds__(NT)
-stem_im2col_kernel(const float* __restrict__ x, int N, int nc, int H, int W, int Kp, bf16* __restrict__ out) {
-  // one thread per pixel: the reads of a warp are 32 consecutive pixels of one (tap, channel) plane (coalesced),
-  // the writes are the thread's own contiguous Kp*2-byte patch row in 16-byte pieces
-  const long P = (long)N * H * W;
+stem_im2col_any_kernel(const float* __restrict__ x, int N, int nc, int H, int W, int Kp, bf16* __restrict__ out) {
   const int KG = Kp >> 3;
-  for (long p = blockIdx.x * (long)NT + threadIdx.x; p < P; p += (long)gridDim.x * NT) {
-    const int w = (int)(p % W);
-    const int h = (int)((p / W) % H);
-    const int n = (int)(p / ((long)W * H));
-    const float* xn = x + (long)n * nc * H * W;
-    for (int kg = 0; kg < KG; ++kg) {
-      float v[8];
+  const long total = (long)N * H * W * KG;
+  const int HW = H * W;
+  for (long i = blockIdx.x * (long)NT + threadIdx.x; i < total; i += (long)gridDim.x * NT) {
+    const int kg = (int)(i % KG);
+    const long p = i / KG;
+    const int n = (int)(p / HW);
+    const int pl = (int)(p - (long)n * HW);
+    const int h = pl / W, w = pl - h * W;
+    const float* xn = x + (long)n * nc * HW;
+    float v[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int k = kg * 8 + e;
-        float t = 0.f;
-        if (k < 9 * nc) {
-          const int tap = k / nc, c = k - tap * nc;
-          const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
-          if (hh >= 0 && hh < H && ww >= 0 && ww < W) t = __ldg(xn + ((long)c * H + hh) * W + ww);
-        }
-        v[e] = t;
+    for (int e = 0; e < 8; ++e) {
+      const int k = kg * 8 + e;
+      float t = 0.f;
+      if (k < 9 * nc) {
+        const int tap = k / nc, c = k - tap * nc;
+        const int dy = tap / 3;
+        const int hh = h + dy - 1, ww = w + (tap - dy * 3) - 1;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) t = __ldg(xn + (long)c * HW + hh * W + ww);
       }
-      st_bf16x8(out + p * Kp + kg * 8, pack8(v));
+      v[e] = t;
+    }
+    st_bf16x8(out + i * 8, pack8(v));
+  }
+}
+
+// NC = 3 / 4 input channels (the reference's models): a block stages the three input rows of a run of pixels in shared
+// memory (coalesced reads, zero padding resolved once) and every thread assembles one 16-byte piece of a patch row with
+// compile-time tap / channel offsets; a warp writes 512 contiguous bytes.
+template <int NC, int KG>
+__global__ void __launch_bounds__(NT)
+stem_im2col_kernel(const float* __restrict__ x, int N, int H, int W, bf16* __restrict__ out) {
+  constexpr int TP = NT / KG;            // pixels per tile row
+  constexpr int TR = 4;                  // output rows per tile (TR + 2 input rows staged: 1.5 reads per output row)
+  constexpr int TWD = TP + 2;
+  __shared__ float t[NC][TR + 2][TWD];
+  const int tiles_w = (W + TP - 1) / TP, tiles_h = (H + TR - 1) / TR;
+  const long tiles = (long)N * tiles_h * tiles_w;
+  const int px = threadIdx.x / KG, kg = threadIdx.x - px * KG;
+  for (long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int tw = (int)(tile % tiles_w);
+    const long nh = tile / tiles_w;
+    const int h0 = (int)(nh % tiles_h) * TR;
+    const int n = (int)(nh / tiles_h);
+    const int w0 = tw * TP;
+    __syncthreads();
+    for (int i = threadIdx.x; i < NC * (TR + 2) * TWD; i += NT) {
+      const int c = i / ((TR + 2) * TWD), rem = i - c * (TR + 2) * TWD;
+      const int r = rem / TWD, j = rem - r * TWD;
+      const int hh = h0 + r - 1, ww = w0 + j - 1;
+      (&t[0][0][0])[i] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(x + (((long)n * NC + c) * H + hh) * W + ww) : 0.f;
+    }
+    __syncthreads();
+    const int w = w0 + px;
+    if (px < TP && w < W) {
+#pragma unroll
+      for (int r = 0; r < TR; ++r) {
+        if (h0 + r < H) {
+          float v[8];
+#pragma unroll
+          for (int q = 0; q < KG; ++q) {
+            if (kg == q) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int k = q * 8 + e;               // compile-time after unrolling
+                v[e] = k < 9 * NC ? t[k % NC][r + (k / NC) / 3][px + (k / NC) % 3] : 0.f;
+              }
+            }
+          }
+          st_bf16x8(out + (((long)n * H + h0 + r) * W + w) * (KG * 8) + kg * 8, pack8(v));
+        }
+      }
     }
   }
 }
@@ -678,6 +729,41 @@ head_fwd_kernel(const bf16* __restrict__ x, long ld, long P, int C, const float*
   const int li = threadIdx.x % TPP;
   const int slot = threadIdx.x / TPP;
   constexpr int SLOTS = NT / TPP;
+  if (G <= TPP) {
+    // one channel group per lane: weights in registers, four pixels (independent 16-byte loads) per iteration
+    constexpr int U = 4;
+    float wr[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) wr[e] = li < G ? w[li * 8 + e] : 0.f;
+    const float b0 = b[0];
+    for (long p0 = blockIdx.x * (long)(SLOTS * U) + slot; p0 < P; p0 += (long)gridDim.x * (SLOTS * U)) {
+      bf16x8 raw[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long pp = p0 + u * SLOTS;
+        if (pp < P && li < G) raw[u] = ld_bf16x8_stream(x + pp * ld + li * 8);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long pp = p0 + u * SLOTS;
+        float acc = 0.f;
+        if (pp < P && li < G) {
+          float v[8];
+          unpack8(raw[u], v);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc += wr[e] * v[e];
+        }
+#pragma unroll
+        for (int o = TPP / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (li == 0 && pp < P) {
+          const float z = acc + b0;
+          probs[pp] = sigmoidf_acc(z);
+          if (logits) logits[pp] = z;
+        }
+      }
+    }
+    return;
+  }
   for (long p = blockIdx.x * (long)SLOTS + slot; p < P; p += (long)gridDim.x * SLOTS) {
     float acc = 0.f;
     for (int cg = li; cg < G; cg += TPP) {
@@ -924,7 +1010,18 @@ extern "C" int rbu_ag_apply(const void* skip, int64_t s_ld, void* out, int64_t o
 extern "C" int rbu_stem_im2col(const float* x, int N, int nc, int H, int W, int Kp, void* out, void* stream_) {
   RBU_CHECK_ARG(x && out && N > 0 && nc > 0 && H > 0 && W > 0 && Kp % 8 == 0 && Kp >= 9 * nc && ((uintptr_t)out & 15) == 0,
                 "rbu_stem_im2col: bad arguments");
-  stem_im2col_kernel<<<grid_for((long)N * H * W, NT), NT, 0, (cudaStream_t)stream_>>>(x, N, nc, H, W, Kp, (bf16*)out);
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (nc == 3 && Kp == 32) {
+    const long tiles = (long)N * rbu_cdiv(H, 4) * rbu_cdiv(W, NT / 4);
+    stem_im2col_kernel<3, 4><<<(unsigned)(tiles < (long)rbu_num_sms() * 16 ? tiles : (long)rbu_num_sms() * 16), NT, 0, st>>>(
+        x, N, H, W, (bf16*)out);
+  } else if (nc == 4 && Kp == 40) {
+    const long tiles = (long)N * rbu_cdiv(H, 4) * rbu_cdiv(W, NT / 5);
+    stem_im2col_kernel<4, 5><<<(unsigned)(tiles < (long)rbu_num_sms() * 16 ? tiles : (long)rbu_num_sms() * 16), NT, 0, st>>>(
+        x, N, H, W, (bf16*)out);
+  } else {
+    stem_im2col_any_kernel<<<grid_for((long)N * H * W * (Kp / 8), NT), NT, 0, st>>>(x, N, nc, H, W, Kp, (bf16*)out);
+  }
   RBU_CHECK_LAUNCH();
   return RBU_OK;
 }
