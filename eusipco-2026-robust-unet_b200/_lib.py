@@ -22,7 +22,7 @@ class ConvGemmArgs(Structure):
     _fields_ = [("N", c_int), ("H", c_int), ("W", c_int), ("nseg", c_int), ("seg", GemmOperand * 2),
                 ("Ncols", c_int), ("y", c_void_p), ("y_ld", c_int64), ("scatter", c_int), ("Cout", c_int),
                 ("bias", c_void_p), ("addend", c_void_p), ("addend_ld", c_int64), ("scale", c_void_p), ("relu", c_int),
-                ("stats", c_void_p)]
+                ("stats", c_void_p), ("tile_stats", c_void_p)]
 
 
 class WgradArgs(Structure):

@@ -444,6 +444,12 @@ int pow2ceil(int v) {
 
 }  // namespace
 
+// Per-image tile statistics of the halo kernel: two 16x8-pixel half-tiles per 16x16 tile.
+extern "C" int rbu_conv_tile_stats_chunks(int H, int W) { return rbu_cdiv(H, 16) * rbu_cdiv(W, 16) * 2; }
+extern "C" size_t rbu_conv_tile_stats_floats(int N, int H, int W, int Ncols) {
+  return (size_t)N * rbu_conv_tile_stats_chunks(H, W) * 4 * Ncols;
+}
+
 // rows: (CTA, lane group) for the generic kernel, (CTA, half-tile, lane group) for the halo kernel; unused rows stay zero
 extern "C" size_t rbu_conv_stats_floats(int Ncols) { return (size_t)8 * rbu_num_sms() * 2 * Ncols; }
 
@@ -539,6 +545,7 @@ extern "C" int rbu_conv_gemm(const rbu_conv_gemm_args* a, void* stream_) {
     if (no_halo < 0) no_halo = getenv("RBU_NO_HALO") ? 1 : 0;
     if (!no_halo && rbu_conv_halo_supported(a)) return rbu_conv_halo_launch(a, stream);
   }
+  RBU_CHECK_ARG(a->tile_stats == nullptr, "rbu_conv_gemm: tile statistics are produced by the 3x3 halo kernel only");
 
   KParams p;
   memset(&p, 0, sizeof(p));

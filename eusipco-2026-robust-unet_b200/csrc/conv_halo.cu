@@ -67,6 +67,7 @@ struct HParams {
   int relu;
   const bf16* addend;
   long long addend_ld;
+  float* tile_stats;   // [N][tiles_h*tiles_w*2][4][Ncols]: per image and half-tile column sum / sum of squares / max / min
   float* stats;   // [8*SMs][2][Ncols] per-(CTA, half-tile, lane group) column sum / sum of squares of the stored output, or NULL
 };
 
@@ -121,6 +122,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   __shared__ __align__(16) float stat_smem[EPI_STAT_FLOATS];
   if (p.stats)
     for (int i = threadIdx.x; i < EPI_STAT_FLOATS; i += NUM_THREADS) stat_smem[i] = 0.f;
+  static_assert(EPI_STAT_FLOATS >= 2 * 2 * 4 * 4 * 32, "tile statistics exchange buffer");
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA0);
@@ -361,6 +363,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       pix = ((long long)n * p.H + h) * p.W + w;
     };
     int k = 0;
+    int jc = 0;      // tile-statistics exchanges so far (buffer parity)
     int nb, n, h, w;
     bool valid;
     long long pix;
@@ -382,6 +385,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       ptx::tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(slot * p.block_n);
       bf16* yrow = p.y + pix * p.y_ld;
+      // statistics chunk of this half-tile inside its image
+      const int chunks_img = p.tiles_w * p.tiles_h * 2;
+      const int tchunk = ((h - hl) / TILE_H * p.tiles_w + (w - wl) / TILE_W) * 2 + half;
       for (int c0 = 0; c0 < p.block_n; c0 += 32) {
         const int col = nb * p.block_n + c0;
         if (p.stats || col + 32 > p.Ncols) {
@@ -404,6 +410,51 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           if (valid) {
             uint4* dst = reinterpret_cast<uint4*>(yrow + col);
             dst[0] = out[0]; dst[1] = out[1]; dst[2] = out[2]; dst[3] = out[3];
+          }
+          if (p.tile_stats) {
+            // per-image statistics of the stored values: the warp reduces its 32 pixels per column (lane l ends up with
+            // column l), the four lane-group warps of this half-tile exchange through shared memory and warp lg == 0
+            // writes one row per statistic -- in the [n][chunk][4][C] layout rbu_bn_stats' second stage consumes
+            float rv[32], tmp[32];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              bf16x8 t8;
+              *reinterpret_cast<uint4*>(&t8) = out[g];
+              unpack8(t8, &rv[g * 8]);
+            }
+            float red[4];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) tmp[i] = valid ? rv[i] : 0.f;
+            red[0] = warp_colsum32(tmp, lane);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) tmp[i] = valid ? rv[i] * rv[i] : 0.f;
+            red[1] = warp_colsum32(tmp, lane);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) tmp[i] = valid ? rv[i] : -INFINITY;
+            red[2] = warp_colext32<true>(tmp, lane);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) tmp[i] = valid ? rv[i] : INFINITY;
+            red[3] = warp_colext32<false>(tmp, lane);
+            float* xb = stat_smem + ((jc & 1) * 2 + half) * (4 * 4 * 32);     // [parity][half][lg][q][32]
+            ++jc;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) xb[(lg * 4 + q) * 32 + lane] = red[q];
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+            if (lg == 0) {
+              float acc[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) acc[q] = xb[q * 32 + lane];
+#pragma unroll
+              for (int g2 = 1; g2 < 4; ++g2) {
+                acc[0] += xb[(g2 * 4 + 0) * 32 + lane];
+                acc[1] += xb[(g2 * 4 + 1) * 32 + lane];
+                acc[2] = fmaxf(acc[2], xb[(g2 * 4 + 2) * 32 + lane]);
+                acc[3] = fminf(acc[3], xb[(g2 * 4 + 3) * 32 + lane]);
+              }
+              float* dstp = p.tile_stats + (((long long)n * chunks_img + tchunk) * 4) * p.Ncols + col + lane;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) dstp[(long long)q * p.Ncols] = acc[q];
+            }
           }
         }
         if (c0 + 32 < p.block_n)
@@ -509,6 +560,10 @@ int rbu_conv_halo_launch(const rbu_conv_gemm_args* a, cudaStream_t stream) {
   p.addend = reinterpret_cast<const bf16*>(a->addend);
   p.addend_ld = a->addend_ld;
   p.stats = a->stats;
+  p.tile_stats = a->tile_stats;
+  if (a->tile_stats)
+    RBU_CHECK_ARG(!a->stats && a->Ncols % 32 == 0 && ((uintptr_t)a->tile_stats & 15) == 0,
+                  "rbu_conv_gemm: tile statistics need Ncols %% 32 == 0 and exclude the per-CTA statistics");
 
   CUtensorMap tmA[2], tmB[2];
   memset(tmA, 0, sizeof(tmA));

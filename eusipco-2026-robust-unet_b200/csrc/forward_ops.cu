@@ -103,6 +103,46 @@ __global__ void bn_reduce_nc_kernel(const float* __restrict__ part_f, int chunks
   }
 }
 
+// Stage 2 for many chunks (the per-half-tile partials written by the 3x3 convolution's epilogue: up to 512 chunks per
+// image): block = 32 channels x 8 parts of one image; part j combines chunks j, j+8, ... in order, the 8 parts are then
+// combined in part order (fixed order -> deterministic).
+__global__ void __launch_bounds__(256)
+bn_reduce_nc_wide_kernel(const float* __restrict__ part_f, int chunks, int HW, int C, int pool,
+                         double* __restrict__ nsum /* [N][2][C] */, float* __restrict__ nc_mean,
+                         float* __restrict__ nc_max, float* __restrict__ nc_min) {
+  __shared__ double shs[2][8][32];
+  __shared__ float shm[2][8][32];
+  const int cx = threadIdx.x & 31, j = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  const int n = blockIdx.y;
+  double s = 0.0, q = 0.0;
+  float bmx = -INFINITY, bmn = INFINITY;
+  if (c < C)
+    for (int k = j; k < chunks; k += 8) {
+      const long o = ((long)n * chunks + k) * 4;
+      s += (double)part_f[(o + 0) * C + c];
+      q += (double)part_f[(o + 1) * C + c];
+      if (pool) {
+        bmx = fmaxf(bmx, part_f[(o + 2) * C + c]);
+        bmn = fminf(bmn, part_f[(o + 3) * C + c]);
+      }
+    }
+  shs[0][j][cx] = s; shs[1][j][cx] = q; shm[0][j][cx] = bmx; shm[1][j][cx] = bmn;
+  __syncthreads();
+  if (j != 0 || c >= C) return;
+  for (int r = 1; r < 8; ++r) {
+    s += shs[0][r][cx]; q += shs[1][r][cx];
+    bmx = fmaxf(bmx, shm[0][r][cx]); bmn = fminf(bmn, shm[1][r][cx]);
+  }
+  nsum[((long)n * 2 + 0) * C + c] = s;
+  nsum[((long)n * 2 + 1) * C + c] = q;
+  if (pool) {
+    nc_mean[(long)n * C + c] = (float)(s / (double)HW);
+    nc_max[(long)n * C + c] = bmx;
+    nc_min[(long)n * C + c] = bmn;
+  }
+}
+
 // Stage 3: block = 32 channels x 8 lanes; lane j adds images j, j+8, ... and the 8 lane sums are combined in lane
 // order (fixed order -> deterministic).  BN affine (train: batch statistics + running update; eval: running stats).
 __global__ void __launch_bounds__(256)
@@ -860,6 +900,32 @@ extern "C" int rbu_bn_stats(const void* x, int64_t ld, int N, int HW, int C, int
   double* nsum = (double*)(((uintptr_t)(part_f + (size_t)N * chunks * 4 * C) + 15) & ~(uintptr_t)15);
   bn_reduce_nc_kernel<<<dim3(rbu_cdiv(C, 128), N), 128, 0, stream>>>(part_f, chunks, HW, C, pool, nsum, nc_mean, nc_max,
                                                                       nc_min);
+  RBU_CHECK_LAUNCH();
+  bn_finalize_kernel<<<rbu_cdiv(C, 32), 256, 0, stream>>>(nsum, N, HW, C, training, gamma, beta, running_mean, running_var,
+                                                           momentum, eps, scale, shift, mean_out, rstd_out);
+  RBU_CHECK_LAUNCH();
+  return RBU_OK;
+}
+
+// BatchNorm statistics (+ pooled per-image statistics) from partials that another kernel already produced in the
+// [N][chunks][4][C] layout of rbu_bn_stats' first stage -- the 3x3 convolution epilogue (rbu_conv_gemm tile_stats):
+// no pass over the activation tensor.  workspace: N*2*C doubles.
+extern "C" int rbu_bn_stats_from_partials(const float* partials, int chunks, int N, int HW, int C, int pool, int training,
+                                          const float* gamma, const float* beta, float* running_mean, float* running_var,
+                                          float momentum, float eps, float* scale, float* shift, float* mean_out,
+                                          float* rstd_out, float* nc_mean, float* nc_max, float* nc_min, void* workspace,
+                                          size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  RBU_CHECK_ARG(partials && chunks > 0 && N > 0 && N <= 65535 && HW > 0 && C >= 8 && C <= 2048,
+                "rbu_bn_stats_from_partials: bad shape");
+  RBU_CHECK_ARG(gamma && beta && scale && shift, "rbu_bn_stats_from_partials: null parameter pointer");
+  RBU_CHECK_ARG(training || (running_mean && running_var), "rbu_bn_stats_from_partials: eval mode needs running statistics");
+  RBU_CHECK_ARG(!pool || (nc_mean && nc_max && nc_min), "rbu_bn_stats_from_partials: pool outputs missing");
+  RBU_CHECK_ARG(workspace && ((uintptr_t)workspace & 15) == 0 && workspace_bytes >= (size_t)N * 2 * C * sizeof(double),
+                "rbu_bn_stats_from_partials: workspace too small");
+  double* nsum = (double*)workspace;
+  bn_reduce_nc_wide_kernel<<<dim3(rbu_cdiv(C, 32), N), 256, 0, stream>>>(partials, chunks, HW, C, pool, nsum, nc_mean, nc_max,
+                                                                        nc_min);
   RBU_CHECK_LAUNCH();
   bn_finalize_kernel<<<rbu_cdiv(C, 32), 256, 0, stream>>>(nsum, N, HW, C, training, gamma, beta, running_mean, running_var,
                                                            momentum, eps, scale, shift, mean_out, rstd_out);

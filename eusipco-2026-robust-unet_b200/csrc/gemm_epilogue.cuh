@@ -51,6 +51,24 @@ __device__ __forceinline__ int fast_div(int x, const FastDiv& f) {
   return f.d == 1 ? x : (int)(__umulhi((uint32_t)x, f.mul) >> f.shr);
 }
 
+// Same recursive halving for max / min (per-image pooled statistics of ChannelAttention).
+template <bool MAX>
+__device__ __forceinline__ float warp_colext32(float (&v)[32], int lane) {
+#define RBU_HALVE(OFF, HALF)                                                        \
+  {                                                                                 \
+    const bool up = (lane & (OFF)) != 0;                                            \
+    _Pragma("unroll") for (int i = 0; i < (HALF); ++i) {                            \
+      const float send = up ? v[i] : v[i + (HALF)];                                 \
+      const float keep = up ? v[i + (HALF)] : v[i];                                 \
+      const float got = __shfl_xor_sync(0xffffffffu, send, (OFF));                  \
+      v[i] = MAX ? fmaxf(keep, got) : fminf(keep, got);                             \
+    }                                                                               \
+  }
+  RBU_HALVE(16, 16) RBU_HALVE(8, 8) RBU_HALVE(4, 4) RBU_HALVE(2, 2) RBU_HALVE(1, 1)
+#undef RBU_HALVE
+  return v[0];
+}
+
 struct EpiOut {
   float* stat_acc;   // this warp's [EPI_STAT_CHUNKS][32][2] shared-memory accumulators, or nullptr (statistics off)
   bf16* y;

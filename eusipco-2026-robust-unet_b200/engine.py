@@ -58,6 +58,12 @@ class Engine:
         # over the activations less, but the warp-transpose reduction slows the epilogue-sensitive small-N GEMMs by
         # about as much (measured on B200: 44.9 vs 45.0 ms/step) -- off by default, exercised by the tests.
         self.fuse_bn_stats = os.environ.get("RBU_FUSE_BN_STATS") == "1"
+        # Per-image statistics (sum, sum of squares, max, min per half-tile) from the 3x3 halo kernel's epilogue: BatchNorm
+        # batch statistics and ChannelAttention's pooled inputs without re-reading the conv output.  Measured on B200: in
+        # the training step (batch 64, 256^2) the 18 statistics passes it replaces cost 1.34 ms, the longer epilogues 0.4 ms
+        # and the reduction of the partials 0.35 ms; in inference at 1024^2 the 64-channel convolutions become
+        # epilogue-bound (+6 ms against -3.5 ms), so it is used in training mode only.  RBU_NO_TILE_STATS=1 disables it.
+        self.fuse_tile_stats = os.environ.get("RBU_NO_TILE_STATS") is None
         self._ws = None
         self.drop_mask_fn = None     # optional callable(name, N, C) -> float32 [N,C] device tensor (tests)
         self.kernel_launches = 0
@@ -183,6 +189,32 @@ class Engine:
             bn.num_batches_tracked += 1
         return out
 
+    def tile_stats_ok(self, H, W, C):
+        """The 3x3 halo kernel can emit the per-image statistics of its output (see bn_stats_tiles)."""
+        return self.fuse_tile_stats and H >= 16 and W >= 16 and C % 32 == 0 and 8 <= C <= 2048
+
+    def tile_stats_buf(self, N, H, W, C, device):
+        return torch.empty(_lib.lib().rbu_conv_tile_stats_floats(N, H, W, C), dtype=torch.float32, device=device)
+
+    def bn_stats_tiles(self, part, N, H, W, C, bn: nn.BatchNorm2d, training, pool=False):
+        """bn_stats() without the pass over the tensor: the producing 3x3 convolution wrote per-image, per-half-tile
+        partial sums / extremes of what it stored (rbu_conv_gemm tile_stats)."""
+        dev = part.device
+        out = {"scale": self.f32(C, device=dev), "shift": self.f32(C, device=dev),
+               "mean": self.f32(C, device=dev), "rstd": self.f32(C, device=dev)}
+        if pool:
+            out.update(nc_mean=self.f32(N, C, device=dev), nc_max=self.f32(N, C, device=dev),
+                       nc_min=self.f32(N, C, device=dev))
+        ws = self.ws(N * 2 * C * 8 + 16, dev)
+        chunks = int(_lib.lib().rbu_conv_tile_stats_chunks(H, W))
+        call("rbu_bn_stats_from_partials", _p(part), chunks, N, H * W, C, int(pool), int(training), _p(bn.weight),
+             _p(bn.bias), _p(bn.running_mean), _p(bn.running_var), float(bn.momentum), float(bn.eps), _p(out["scale"]),
+             _p(out["shift"]), _p(out["mean"]), _p(out["rstd"]), _p(out.get("nc_mean")), _p(out.get("nc_max")),
+             _p(out.get("nc_min")), _p(ws), ws.numel() * 4, stream_ptr())
+        if training:
+            bn.num_batches_tracked += 1
+        return out
+
     def bn_eval_affine(self, bn: nn.BatchNorm2d, any_view: View, conv_bias=None):
         """Eval-mode BatchNorm as a per-channel (scale, shift) pair from the running statistics, with the producing
         convolution's bias folded in: BN(acc + b) = scale*acc + (shift + scale*b).  Feeds the conv epilogue."""
@@ -278,7 +310,7 @@ class Engine:
         HW, P = H * W, N * H * W
         proj = not isinstance(blk.shortcut, nn.Identity)
         s = {"name": name, "x": x, "N": N, "H": H, "W": W, "C": C, "proj": proj, "patches": stem_patches}
-        bns = None
+        bns = bn1 = None
         fuse = training and self.fuse_bn_stats
         if stem_patches is not None:
             y12 = self.new(N, H, W, 2 * C, dev)
@@ -300,7 +332,10 @@ class Engine:
                 conv_gemm(N, H, W, [(x, self.pack(blk.conv1.weight, 0), 9, 1, False)], C, a1, scale=bn1["scale"],
                           bias=bn1["shift"], relu=C)
             else:
-                conv_gemm(N, H, W, [(x, self.pack(blk.conv1.weight, 0), 9, 1, False)], C, y1, stats=st1)
+                ts1 = self.tile_stats_buf(N, H, W, C, dev) if (training and not fuse and self.tile_stats_ok(H, W, C)) else None
+                conv_gemm(N, H, W, [(x, self.pack(blk.conv1.weight, 0), 9, 1, False)], C, y1, stats=st1, tile_stats=ts1)
+                if ts1 is not None:
+                    bn1 = self.bn_stats_tiles(ts1, N, H, W, C, blk.bn1, training)
             if fuse:
                 bn1 = self.bn_from_conv(st1, C, 0, C, P, blk.bn1)
             ys = None
@@ -313,7 +348,7 @@ class Engine:
         if fuse:
             for b_ in ((blk.bn1, blk.shortcut[1]) if proj else (blk.bn1,)):
                 b_.num_batches_tracked += 1
-        elif y1 is not None:
+        elif y1 is not None and bn1 is None:
             bn1 = self.bn_stats(y1, N, HW, blk.bn1, training)
         drop = self.drop_mask(name, N, C, blk.dropout.p, dev) if training and blk.dropout.p > 0 else None
         if y1 is not None:
@@ -321,8 +356,12 @@ class Engine:
             call("rbu_affine_act", _vp(y1), y1.ld, _vp(a1), a1.ld, P, HW, C, _p(bn1["scale"]), _p(bn1["shift"]), _p(drop), 1,
                  stream_ptr())
         y2 = self.new(N, H, W, C, dev)
-        conv_gemm(N, H, W, [(a1, self.pack(blk.conv2.weight, 0), 9, 1, False)], C, y2)
-        bn2 = self.bn_stats(y2, N, HW, blk.bn2, training, pool=True)
+        ts2 = self.tile_stats_buf(N, H, W, C, dev) if (training and self.tile_stats_ok(H, W, C)) else None
+        conv_gemm(N, H, W, [(a1, self.pack(blk.conv2.weight, 0), 9, 1, False)], C, y2, tile_stats=ts2)
+        if ts2 is not None:
+            bn2 = self.bn_stats_tiles(ts2, N, H, W, C, blk.bn2, training, pool=True)
+        else:
+            bn2 = self.bn_stats(y2, N, HW, blk.bn2, training, pool=True)
         Ch = blk.ca.fc[0].out_channels
         ca = {k: self.f32(N, C, device=dev) for k in ("g", "A2g", "B2g", "u_avg", "u_max", "tv")}
         ca["nc_arg"] = torch.empty((N, C), dtype=torch.int32, device=dev)

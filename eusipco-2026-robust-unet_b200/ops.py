@@ -62,7 +62,8 @@ def pack_weight(w: torch.Tensor, mode: int) -> torch.Tensor:
 
 
 def conv_gemm(N, H, W, segs, Ncols, y: View, scatter=False, Cout=0, bias=None, addend: View = None, tag="conv_gemm",
-              flops=None, stats: torch.Tensor = None, scale: torch.Tensor = None, relu: int = 0):
+              flops=None, stats: torch.Tensor = None, scale: torch.Tensor = None, relu: int = 0,
+              tile_stats: torch.Tensor = None):
     """segs: list of (x: View, w_packed, taps, dil, gather).  `flops`: algorithmic FLOPs of the call when they
     differ from the GEMM's own 2*M*N*K (e.g. the zero-padded stem)."""
     a = ConvGemmArgs()
@@ -86,6 +87,7 @@ def conv_gemm(N, H, W, segs, Ncols, y: View, scatter=False, Cout=0, bias=None, a
     a.addend = addend.ptr if addend is not None else None
     a.addend_ld = addend.ld if addend is not None else 0
     a.stats = stats.data_ptr() if stats is not None else None
+    a.tile_stats = tile_stats.data_ptr() if tile_stats is not None else None
     a.scale = scale.data_ptr() if scale is not None else None
     a.relu = int(relu)
     if flops is None:

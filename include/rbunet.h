@@ -96,10 +96,16 @@ typedef struct {
   float* stats;             /* optional: rbu_conv_stats_floats(Ncols) floats receiving per-(CTA, lane group)  */
                             /* partial sum / sum of squares per output column of the STORED (bf16) result --  */
                             /* the BatchNorm batch statistics, fused into the epilogue (scatter=0 only)        */
+  float* tile_stats;        /* optional (3x3 dilation-1 convs on >= 16x16 images, Ncols % 32 == 0):            */
+                            /* rbu_conv_tile_stats_floats() floats receiving, per image and 16x8-pixel          */
+                            /* half-tile, the column sum / sum of squares / max / min of the STORED result:     */
+                            /* [N][chunks][4][Ncols] with chunks = rbu_conv_tile_stats_chunks(H, W)             */
 } rbu_conv_gemm_args;
 
 int rbu_conv_gemm(const rbu_conv_gemm_args* args, void* stream);
 size_t rbu_conv_stats_floats(int Ncols);
+int rbu_conv_tile_stats_chunks(int H, int W);
+size_t rbu_conv_tile_stats_floats(int N, int H, int W, int Ncols);
 /* nn.BatchNorm2d train-mode affine (Main_Final.py:158,173,127,132,210) from the partials above: columns
  * [col_off, col_off + C) of a conv whose GEMM had Ncols columns, `count` = N*H*W values per channel.  Updates the
  * running statistics (momentum, unbiased variance) when running_mean != NULL. */
@@ -202,6 +208,14 @@ int rbu_bn_stats(const void* x, int64_t ld, int N, int HW, int C, int pool, int 
                  float* scale, float* shift, float* mean_out, float* rstd_out, float* nc_mean, float* nc_max,
                  float* nc_min, void* workspace, size_t workspace_bytes, void* stream);
 /* y = [relu](scale[c]*x + shift[c]) * drop[n,c]   (BN apply + ReLU + Dropout2d; Main_Final.py:182-184,220-221) */
+/* The same outputs as rbu_bn_stats from partials in the [N][chunks][4][C] layout (sum, sum of squares, max, min per
+ * chunk) that the 3x3 convolution epilogue writes (rbu_conv_gemm_args.tile_stats; chunks =
+ * rbu_conv_tile_stats_chunks(H, W)): no pass over the activation tensor.  workspace: N*2*C doubles. */
+int rbu_bn_stats_from_partials(const float* partials, int chunks, int N, int HW, int C, int pool, int training,
+                               const float* gamma, const float* beta, float* running_mean, float* running_var,
+                               float momentum, float eps, float* scale, float* shift, float* mean_out, float* rstd_out,
+                               float* nc_mean, float* nc_max, float* nc_min, void* workspace, size_t workspace_bytes,
+                               void* stream);
 int rbu_affine_act(const void* x, int64_t x_ld, void* y, int64_t y_ld, int64_t P, int HW, int C, const float* scale,
                    const float* shift, const float* drop, int relu, void* stream);
 /* ChannelAttention gate (Main_Final.py:97-101) from the pooled statistics; also A2g = scale*g, B2g = shift*g,
