@@ -240,6 +240,17 @@ def run_ours(args):
             "all_gemm_tflops": gemm_flops / gemm_ms / 1e9 if gemm_ms else None}
     if roof["achieved"]:
         roof["frac"] = roof["achieved"] / peak_tf
+    # DRAM bytes per launch of the dominant kernel from the committed ncu capture (dram__bytes_read/write.sum) of the same step
+    # (tools/ncu_traffic.py -> profiles/traffic.json: {class: {"dram_bytes_per_launch": ..., "launches": ..., "source": ...}})
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tr = json.load(f).get(top[0])
+        if tr and not infer and not unet and B == 64 and S == 256:
+            roof["traffic"] = tr["dram_bytes_per_launch"]
+            roof["traffic_source"] = tr["source"]
+            roof["algorithmic_bytes_per_launch"] = top[1]["bytes"] / max(1, top[1]["calls"]) if top[1].get("bytes") else None
+    except (OSError, ValueError):
+        pass
     classes = {k: {"calls": v["calls"], "ms": round(v["ms"], 3), "share": round(v["ms"] / lib_ms, 4) if lib_ms else None,
                    **({"tflops": round(v["flops"] / v["ms"] / 1e9, 1),
                        "tensor_frac": round(v["flops"] / v["ms"] / 1e9 / peak_tf, 3)} if v["flops"] and v["ms"] else {}),

@@ -92,7 +92,9 @@ def conv_gemm(N, H, W, segs, Ncols, y: View, scatter=False, Cout=0, bias=None, a
     a.relu = int(relu)
     if flops is None:
         flops = 2.0 * N * H * W * Ncols * sum(t * x.C for (x, _, t, _, _) in segs)
-    nbytes = 0.0
+    # algorithmic bytes: every input / output activation once, plus the packed weights
+    nbytes = 2.0 * N * H * W * (sum(x.C for (x, _, _, _, _) in segs) + Ncols * (2 if addend is not None else 1)) + \
+        2.0 * Ncols * sum(t * x.C for (x, _, t, _, _) in segs)
     if tag == "conv_gemm":
         # profiler classes: the halo kernel's 3x3 convolutions are tensor-pipe work; everything else that goes through
         # the generic kernel in this network (1x1, stem, ConvTranspose, 16x16 dilated) is bound by its activation bytes
@@ -100,8 +102,6 @@ def conv_gemm(N, H, W, segs, Ncols, y: View, scatter=False, Cout=0, bias=None, a
             tag = "conv3x3"
         else:
             tag = "conv_small"
-            nbytes = 2.0 * N * H * W * (sum(x.C for (x, _, _, _, _) in segs) +
-                                        Ncols * (2 if addend is not None else 1))
     label = None
     if _lib.PROFILER is not None:
         label = f"conv {N}x{H}x{W} " + "+".join(f"{x.C}t{t}{'g' if g else ''}d{d}" for (x, _, t, d, g) in segs) + \
