@@ -61,6 +61,8 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        self.recording = False     # the thread polls from before the warm-up (first NVML queries are slow and hold a
+                                   # driver lock); samples and throttle reasons count only inside the timed region
 
     def run(self):
         nv = ClockSampler._nv
@@ -75,14 +77,16 @@ class ClockSampler(threading.Thread):
                      nv.nvmlClocksEventReasonSwThermalSlowdown: "sw_thermal_slowdown",
                      nv.nvmlClocksEventReasonSwPowerCap: "sw_power_cap"}
             while not self.stop_flag:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                mhz = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
                 try:
                     r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
                 except Exception:
                     r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for bit, nm in names.items():
-                    if r & bit:
-                        self.reasons.add(nm)
+                if self.recording:
+                    self.samples.append(mhz)
+                    for bit, nm in names.items():
+                        if r & bit:
+                            self.reasons.add(nm)
                 time.sleep(0.1)
         except Exception as e:   # NVML trouble: report that instead of failing the bench
             self.reasons.add(f"nvml_error:{type(e).__name__}")
@@ -153,6 +157,8 @@ def run_ours(args):
         return xs, ys
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+    flush.zero_()      # first use loads torch's fill-kernel module (lazy CUDA module loading: 200-400 ms); the inference
+                       # workload has no other fill before the timed region and its first timed step used to absorb that
 
     def step(x, y):
         if infer:
@@ -182,21 +188,31 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def timed(fn, steps, warmup):
+        sampler = ClockSampler(local)
+        sampler.start()
         for _ in range(warmup):
             fn()
         barrier()
-        sampler = ClockSampler(local)
-        sampler.start()
+        sampler.recording = True
         l0 = _lib.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        marks = []
         for _ in range(steps):
             if not args.no_flush:
                 flush.zero_()               # L2 flush between timed iterations
             fn()
+            m = torch.cuda.Event(enable_timing=True)
+            m.record()
+            marks.append(m)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
+        prev, per = e0, []
+        for m in marks:                     # per-step durations (diagnostic: outliers show up here, not in the mean)
+            per.append(prev.elapsed_time(m))
+            prev = m
+        timed.per_step = [round(v, 2) for v in per]
         launches = _lib.launch_count() - l0
         clocks = sampler.result()
         if world > 1:
@@ -206,6 +222,7 @@ def run_ours(args):
         return ms, launches, clocks
 
     ms, launches, clocks = timed(lambda: step(x_dev, y_dev), args.steps, args.warmup)
+    per_step_value = list(timed.per_step)
     ms_e2e, _, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2))
 
     # per-kernel-class device times of one extra step (CUDA events around every C-ABI call on the launching stream)
@@ -278,7 +295,7 @@ def run_ours(args):
                           "global_batch": B * world, "image": [nc, S, S], "parallelism": f"dp{world}",
                           "l2": "256 MiB flush buffer written between timed steps; per-step activations exceed L2",
                           "weights": "reference init (seed 0), random", "optimizer": "rbunet.FusedAdam (= torch.optim.Adam, coupled L2) lr 1e-4 wd 1e-4"},
-               "clocks": clocks,
+               "clocks": clocks, "ms_each_step": per_step_value,
                "e2e": {"value": round(imgs / (ms_e2e / 1e3), 2), "unit": "img/s", "h2d_bytes_per_step": h2d,
                        "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_e2e / args.steps, 3)},
                "gpu_launches": int(launches),

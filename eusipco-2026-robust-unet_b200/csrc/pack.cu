@@ -33,21 +33,76 @@ __device__ __forceinline__ long pack_src_index(int mode, int Nn, int T, int K, i
 }
 
 // All weight operands of the network in ONE launch: a block looks its job up in the table by binary search over the
-// jobs' first-block prefix and converts 1024 consecutive destination elements.
-//   mode 0-3: as pack_weight_kernel;  mode 4: stem operand [2C][Kp] -- rows 0..C-1 the 3x3 conv1 weights as
-//   (tap-major, channel) columns, rows C..2C-1 the 1x1 shortcut weights in the centre-tap columns, zero elsewhere
-//   (Nn = 2C, K = Kp, T = number of input channels, src = conv1 weight, src2 = shortcut weight).
+// jobs' first-block prefix.  Work units (pack_job_blocks() tells the host how many a job has):
+//   mode 0 (conv fwd):   one unit = (n, 128 input channels): 128*T consecutive source floats are staged in shared memory
+//                        and written as T rows of 128 bf16 -- both sides coalesced (the element-wise version read one
+//                        float per 32-byte sector: the kernel was bound by L2 sector traffic, 0.5 ms per step)
+//   mode 1 (conv dgrad): one unit = (32 output channels, 32 input channels): per output channel 32*T consecutive source
+//                        floats; written as 64-byte runs of the transposed, tap-reversed operand
+//   mode 2, 3, 4, 5:     1024 consecutive destination elements (small tensors)
+//   mode 4: stem operand [2C][Kp] -- rows 0..C-1 the 3x3 conv1 weights as (tap-major, channel) columns, rows C..2C-1 the
+//   1x1 shortcut weights in the centre-tap columns, zero elsewhere (Nn = 2C, K = Kp, T = number of input channels, src =
+//   conv1 weight, src2 = shortcut weight); mode 5: the same without the shortcut rows.
+constexpr int PK0 = 128;          // mode 0: channels per unit
+constexpr int PK1 = 32;           // mode 1: tile edge
+constexpr int PACK_MAX_T = 9;
+
+__host__ __device__ inline long long pack_job_blocks(int Nn, int T, int K, int mode) {
+  if (mode == 0 && T <= PACK_MAX_T) return (long long)Nn * ((K + PK0 - 1) / PK0);
+  if (mode == 1 && T <= PACK_MAX_T) return (long long)((K + PK1 - 1) / PK1) * ((Nn + PK1 - 1) / PK1);
+  const long long total = (mode == 4 || mode == 5) ? (long long)Nn * K : (long long)Nn * T * K;
+  return (total + 1023) / 1024;
+}
+
 __global__ void __launch_bounds__(256)
 pack_multi_kernel(const rbu_pack_job* __restrict__ jobs, int njobs) {
-  int lo = 0, hi = njobs - 1;
+  __shared__ float tile[PK1 * PK1 * PACK_MAX_T];      // 36 KB (mode 1); mode 0 uses the first 128*T floats
+  // job lookup: every thread tests one table entry (one global-load latency instead of a 7-deep dependent binary search)
+  __shared__ int job_idx;
   const long long b = blockIdx.x;
-  while (lo < hi) {
-    const int mid = (lo + hi + 1) >> 1;
-    if (jobs[mid].first_block <= b) lo = mid; else hi = mid - 1;
+  for (int i = threadIdx.x; i < njobs; i += 256) {
+    const long long fb = jobs[i].first_block;
+    const long long nb = i + 1 < njobs ? jobs[i + 1].first_block : 0x7fffffffffffffffLL;
+    if (fb <= b && b < nb) job_idx = i;
   }
-  const rbu_pack_job j = jobs[lo];
+  __syncthreads();
+  const rbu_pack_job j = jobs[job_idx];
   bf16* dst = reinterpret_cast<bf16*>(j.dst);
-  const long long base = (b - j.first_block) * 1024;
+  const long long lb = b - j.first_block;
+  const int T = j.T, K = j.K, Nn = j.Nn;
+  if (j.mode == 0 && T <= PACK_MAX_T) {
+    const int kchunks = (K + PK0 - 1) / PK0;
+    const int n = (int)(lb / kchunks), k0 = (int)(lb - (long long)n * kchunks) * PK0;
+    const int kw = min(PK0, K - k0);
+    const float* sp = j.src + ((long long)n * K + k0) * T;
+    for (int i = threadIdx.x; i < kw * T; i += 256) tile[i] = sp[i];          // [k][t], contiguous in the source
+    __syncthreads();
+    for (int i = threadIdx.x; i < kw * T; i += 256) {
+      const int t = i / kw, k = i - t * kw;
+      dst[((long long)n * T + t) * K + k0 + k] = __float2bfloat16_rn(tile[k * T + t]);
+    }
+    return;
+  }
+  if (j.mode == 1 && T <= PACK_MAX_T) {
+    // src [K][Nn][T] -> dst[n][T-1-t][k]
+    const int nchunks = (Nn + PK1 - 1) / PK1;
+    const int kc = (int)(lb / nchunks), k0 = kc * PK1, n0 = (int)(lb - (long long)kc * nchunks) * PK1;
+    const int kw = min(PK1, K - k0), nw = min(PK1, Nn - n0);
+    const int row = nw * T;                                                   // contiguous source floats per k
+    for (int i = threadIdx.x; i < kw * row; i += 256) {
+      const int kk = i / row, r = i - kk * row;
+      tile[kk * (PK1 * PACK_MAX_T) + r] = j.src[((long long)(k0 + kk) * Nn + n0) * T + r];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kw * row; i += 256) {
+      const int kk = i % kw, r = i / kw;                                       // r = nn * T + t'
+      const int nn = r / T, tp = r - nn * T;
+      dst[((long long)(n0 + nn) * T + tp) * K + k0 + kk] =
+          __float2bfloat16_rn(tile[kk * (PK1 * PACK_MAX_T) + nn * T + (T - 1 - tp)]);
+    }
+    return;
+  }
+  const long long base = lb * 1024;
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
     const long long i = base + u * 256 + threadIdx.x;
@@ -116,6 +171,8 @@ extern "C" int rbu_pack_weight(const float* src, void* dst, int Nn, int T, int K
   RBU_CHECK_LAUNCH();
   return RBU_OK;
 }
+
+extern "C" long long rbu_pack_job_blocks(int Nn, int T, int K, int mode) { return pack_job_blocks(Nn, T, K, mode); }
 
 extern "C" int rbu_pack_weights_multi(const rbu_pack_job* jobs_device, int njobs, long long total_blocks, void* stream) {
   RBU_CHECK_ARG(jobs_device && njobs > 0 && total_blocks > 0 && total_blocks < (1LL << 31), "rbu_pack_weights_multi: bad arguments");

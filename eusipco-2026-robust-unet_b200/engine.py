@@ -158,7 +158,7 @@ class Engine:
                 total = Nn * K if mode in (4, 5) else Nn * T * K   # the stem operands' T carries the channel count
                 tab[i] = (src.data_ptr(), src2.data_ptr() if src2 is not None else 0, dst.data_ptr(), first, total, Nn, T, K,
                           mode, cout, 0)
-                first += (total + 1023) // 1024
+                first += int(_lib.lib().rbu_pack_job_blocks(Nn, T, K, mode))
             dev_tab = torch.from_numpy(tab.view(np.uint8).copy()).to(dev)
             self._pack_table = (sig, dev_tab, len(plan), first)
         _, dev_tab, njobs, blocks = self._pack_table

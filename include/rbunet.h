@@ -122,7 +122,7 @@ int rbu_bn_finalize_partials(const float* part, int Ncols, int col_off, int C, i
 int rbu_pack_weight(const float* src, void* dst, int Nn, int T, int K, int mode, int Cout, void* stream);
 
 /* Every weight operand of a model in one launch.  `jobs_device` is a DEVICE array of njobs descriptors sorted by
- * first_block (job i owns blocks [first_block_i, first_block_{i+1}), 1024 destination elements per block; total =
+ * first_block (job i owns blocks [first_block_i, first_block_i + rbu_pack_job_blocks(Nn, T, K, mode)); total =
  * Nn*T*K destination elements).  mode 0-3 as rbu_pack_weight; mode 4 builds the stem operand [2C][Kp] from the 3x3
  * conv1 weight (src) and the 1x1 shortcut weight (src2): Nn = 2C, K = Kp, T = input channels. */
 typedef struct {
@@ -133,6 +133,7 @@ typedef struct {
   long long total;
   int Nn, T, K, mode, Cout, reserved;
 } rbu_pack_job;
+long long rbu_pack_job_blocks(int Nn, int T, int K, int mode);
 int rbu_pack_weights_multi(const rbu_pack_job* jobs_device, int njobs, long long total_blocks, void* stream);
 
 /* Fused multi-tensor Adam with coupled L2 weight decay = torch.optim.Adam(params, lr, betas, eps, weight_decay) as used
