@@ -224,6 +224,12 @@ def run_ours(args):
     ms, launches, clocks = timed(lambda: step(x_dev, y_dev), args.steps, args.warmup)
     per_step_value = list(timed.per_step)
     ms_e2e, _, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+    # host time to ENQUEUE one step (no synchronisation inside): how close the launching thread is to being the bottleneck
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    step(x_dev, y_dev)
+    host_enqueue_ms = (time.perf_counter() - t0) * 1e3
+    torch.cuda.synchronize()
 
     # per-kernel-class device times of one extra step (CUDA events around every C-ABI call on the launching stream)
     # The weight-gradient side stream is switched off for this pass: kernels running concurrently slow each other down and
@@ -295,7 +301,7 @@ def run_ours(args):
                           "global_batch": B * world, "image": [nc, S, S], "parallelism": f"dp{world}",
                           "l2": "256 MiB flush buffer written between timed steps; per-step activations exceed L2",
                           "weights": "reference init (seed 0), random", "optimizer": "rbunet.FusedAdam (= torch.optim.Adam, coupled L2) lr 1e-4 wd 1e-4"},
-               "clocks": clocks, "ms_each_step": per_step_value,
+               "clocks": clocks, "ms_each_step": per_step_value, "host_enqueue_ms_per_step": round(host_enqueue_ms, 2),
                "e2e": {"value": round(imgs / (ms_e2e / 1e3), 2), "unit": "img/s", "h2d_bytes_per_step": h2d,
                        "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_e2e / args.steps, 3)},
                "gpu_launches": int(launches),
