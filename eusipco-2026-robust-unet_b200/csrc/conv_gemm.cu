@@ -51,7 +51,6 @@ struct KParams {
   // staged epilogue (TMA stores): see the epilogue branch of the kernel
   int b_resident;         // 1: this CTA's whole weight operand (all k-blocks of its column block) is loaded once
   int tma_store;          // 1: outputs leave through the y tensor map, 0: per-thread 16-byte stores
-  int st_bufs;            // staging buffers per epilogue warp
   int log_tw, log_th;     // TW and TH are powers of two
   int Hg, Ng;             // extent of the (h, n) tile coordinates: (H, N), or (N*H, 1) for merged rows (gather)
   FastDiv fd_nb, fd_tw, fd_th, fd_cout;
@@ -59,6 +58,7 @@ struct KParams {
 
 constexpr int STG_BYTES = 32 * 64 * 2;   // one staging buffer: 32 pixels x 64 channels bf16
 constexpr int BAR_BYTES = 512;           // mbarriers + TMEM slot
+constexpr int ST_BUFS = 2;               // staging buffers per epilogue warp
 
 __device__ __forceinline__ void decode_tile(const KParams& p, int tile, int& nb, int& w0, int& h0, int& n0) {
   const int sp = fast_div(tile, p.fd_nb);
@@ -88,7 +88,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull + 1);
   uint8_t* stg_base = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(bars) + BAR_BYTES + 1023) & ~uintptr_t(1023));
-  uint8_t* resb = stg_base + (p.tma_store ? 8 * p.st_bufs * STG_BYTES : 0);   // 1024-aligned: STG_BYTES is 4 KB
+  uint8_t* resb = stg_base + (p.tma_store ? 8 * ST_BUFS * STG_BYTES : 0);   // 1024-aligned: STG_BYTES is 4 KB
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -596,7 +596,6 @@ extern "C" int rbu_conv_gemm(const rbu_conv_gemm_args* a, void* stream_) {
     if (a->scatter)
       ok = ok && a->Cout % 64 == 0 && ((p.TW * p.TH >= 32 && a->H % rows == 0) || p.TH == a->H);
     p.tma_store = ok ? 1 : 0;
-    p.st_bufs = 2;
   }
   int grid = p.tiles_w * p.tiles_h * p.tiles_n * p.n_blocks;
   if (grid > rbu_num_sms()) grid = rbu_num_sms();
@@ -611,7 +610,7 @@ extern "C" int rbu_conv_gemm(const rbu_conv_gemm_args* a, void* stream_) {
     if (no_res < 0) no_res = getenv("RBU_NO_RESIDENT") ? 1 : 0;
     p.b_resident = (!no_res && resb_bytes <= 65536 && grid % p.n_blocks == 0) ? 1 : 0;
   }
-  const int staging = 1024 + (p.tma_store ? 8 * p.st_bufs * STG_BYTES : 0) + (p.b_resident ? resb_bytes : 0);
+  const int staging = 1024 + (p.tma_store ? 8 * ST_BUFS * STG_BYTES : 0) + (p.b_resident ? resb_bytes : 0);
   const int stage_bytes = A_BYTES + (p.b_resident ? 0 : p.block_n * 128);
   p.num_stages = (SMEM_LIMIT - 1024 - BAR_BYTES - staging) / stage_bytes;
   if (p.num_stages > MAX_STAGES) p.num_stages = MAX_STAGES;

@@ -216,27 +216,3 @@ __device__ __forceinline__ void epi_math(const uint32_t (&r)[32], const float* _
     out[g] = *reinterpret_cast<const uint4*>(&packed);
   }
 }
-
-// Per-column sum / sum of squares of the stored (bf16-rounded) chunk over the warp's valid pixels.
-__device__ __forceinline__ void epi_stats(float* stat_acc, int chunk, const uint4 (&out)[4], bool valid) {
-  const int lane = threadIdx.x & 31;
-  float rv[32], sq[32];
-#pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    bf16x8 t;
-    *reinterpret_cast<uint4*>(&t) = out[g];
-    unpack8(t, &rv[g * 8]);
-  }
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    rv[i] = valid ? rv[i] : 0.f;
-    sq[i] = rv[i] * rv[i];
-  }
-  const float cs = warp_colsum32(rv, lane);
-  const float cq = warp_colsum32(sq, lane);
-  float2* slot = reinterpret_cast<float2*>(stat_acc) + chunk * 32 + lane;
-  float2 cur = *slot;
-  cur.x += cs;
-  cur.y += cq;
-  *slot = cur;
-}

@@ -38,6 +38,15 @@ CASES = [
     ("1x1_cin32", 2, 8, 8, 32, 32, 1, 1, 32, 0, 32, 0, True, False),
     ("3x3_multi_tile", 4, 64, 64, 256, 512, 3, 1, 256, 0, 512, 0, False, False),
     ("3x3_1x1spatial", 130, 1, 1, 64, 64, 3, 1, 64, 0, 64, 0, False, False),
+    # halo kernel (16x16 tiles, two accumulators per weight stage): ragged tile edges, channel slices, partial column
+    # blocks, a one-tile image with a 256-column block, resident weights
+    ("3x3_halo_ragged", 2, 20, 36, 64, 96, 3, 1, 64, 0, 96, 0, True, True),
+    ("3x3_halo_slice", 2, 32, 48, 128, 160, 3, 1, 192, 64, 256, 32, True, False),
+    ("3x3_one_tile_n256", 3, 16, 16, 128, 256, 3, 1, 128, 0, 256, 0, False, True),
+    ("3x3_halo_resident", 2, 48, 32, 64, 64, 3, 1, 64, 0, 64, 0, True, False),
+    # generic kernel, staged epilogue: weights streamed (operand > 64 KB) with bias and addend; 32-column GEMM
+    ("1x1_wide_k", 2, 32, 32, 512, 256, 1, 1, 512, 0, 256, 0, True, True),
+    ("1x1_n32_slice", 3, 24, 40, 64, 32, 1, 1, 128, 32, 96, 64, True, False),
 ]
 
 
