@@ -245,6 +245,51 @@ coastline_kernel(const uint8_t* __restrict__ mask, int H, int W, const __grid_co
   }
 }
 
+// Fast path (W % 4 == 0, 4-byte aligned images): four horizontally adjacent pixels per thread as one packed word.  The
+// tile (128 x 8 outputs + margins) sits in shared memory as aligned 32-bit words; the window byte at offset o of a row is
+// the funnel shift of words o/4 and o/4 + 1, and the running maximum is a per-byte __vmaxu4.
+constexpr int CT_W = 128, CT_H = 8;
+__global__ void __launch_bounds__(256)
+coastline_vec_kernel(const uint8_t* __restrict__ mask, int H, int W, const __grid_constant__ Spans sp,
+                     uint8_t* __restrict__ out) {
+  extern __shared__ uint32_t wt[];
+  const int k = sp.k;
+  const int L4 = (sp.ax + 3) & ~3;                       // left margin rounded up to whole words
+  const int R4 = ((k - 1 - sp.ax + 3) & ~3) + 4;         // right margin + one word for the funnel shift
+  const int roww = (L4 + CT_W + R4) >> 2;                // words per tile row
+  const int rows = CT_H + k - 1;
+  const long img = (long)blockIdx.z * H * W;
+  const int y0 = blockIdx.y * CT_H, x0 = blockIdx.x * CT_W;
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(mask + img);
+  const int Ww = W >> 2;
+  for (int i = threadIdx.x; i < roww * rows; i += 256) {
+    const int ty = i / roww, tx = i - ty * roww;
+    const int y = y0 + ty - sp.ay;
+    const int xw = ((x0 - L4) >> 2) + tx;                // word column in the image (x0, L4 multiples of 4)
+    wt[i] = (y >= 0 && y < H && xw >= 0 && xw < Ww) ? __ldg(src + (long)y * Ww + xw) : 0u;
+  }
+  __syncthreads();
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int x = x0 + 4 * tx, y = y0 + ty;
+  if (x >= W || y >= H) return;
+  uint32_t m = 0;
+  for (int i = 0; i < k; ++i) {
+    const int j1 = sp.j1[i], j2 = sp.j2[i];
+    if (j1 >= j2) continue;
+    const uint32_t* rowp = wt + (ty + i) * roww;
+    int o = 4 * tx + L4 - sp.ax + j1;                    // byte offset of the first window position
+    int wi = o >> 2;
+    uint32_t lo = rowp[wi], hi = rowp[wi + 1];
+    for (int j = j1; j < j2; ++j, ++o) {
+      const int sh = (o & 3) * 8;
+      if (sh == 0 && j != j1) { ++wi; lo = hi; hi = rowp[wi + 1]; }
+      m = __vmaxu4(m, __funnelshift_r(lo, hi, sh));
+    }
+  }
+  const uint32_t center = wt[(ty + sp.ay) * roww + tx + (L4 >> 2)];
+  reinterpret_cast<uint32_t*>(out + img)[(long)y * Ww + (x >> 2)] = __vsub4(m, center);   // per-byte wrapping subtraction
+}
+
 int nearbyint_even(double x) { return (int)nearbyint(x); }   // cvRound under the default rounding mode
 
 }  // namespace
@@ -373,6 +418,14 @@ extern "C" int rbu_coastline_mask(const uint8_t* mask, int B, int H, int W, int 
     }
     sp.j1[i] = (signed char)j1;
     sp.j2[i] = (signed char)j2;
+  }
+  if (ksize <= 8 && W % 4 == 0 && (((uintptr_t)mask | (uintptr_t)out) & 3) == 0) {
+    const int L4 = (sp.ax + 3) & ~3, R4 = ((ksize - 1 - sp.ax + 3) & ~3) + 4;
+    const int smem = ((L4 + CT_W + R4) >> 2) * (CT_H + ksize - 1) * 4;
+    const dim3 grid((unsigned)rbu_cdiv(W, CT_W), (unsigned)rbu_cdiv(H, CT_H), (unsigned)B);
+    coastline_vec_kernel<<<grid, 256, smem, (cudaStream_t)stream_>>>(mask, H, W, sp, out);
+    RBU_CHECK_LAUNCH();
+    return RBU_OK;
   }
   const int tw = DT + ksize - 1;
   const dim3 grid((unsigned)rbu_cdiv(W, DT), (unsigned)rbu_cdiv(H, DT), (unsigned)B);

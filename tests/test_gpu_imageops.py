@@ -66,13 +66,14 @@ def test_coastline_fixture(tag):
         assert np.array_equal(rbunet.coastline_mask(_dev(mask // 255), k).cpu().numpy(), GOLD[f"coast01_{tag}_k{k}"])
 
 
+@pytest.mark.parametrize("shape", [(3, 70, 45), (2, 37, 64), (1, 9, 260)])   # byte-wise path / packed-word path (W % 4 == 0)
 @pytest.mark.parametrize("k", [1, 2, 5, 20, 33, 64])
-def test_coastline_random_batch(k):
+def test_coastline_random_batch(k, shape):
     rng = np.random.default_rng(k)
-    m = rng.integers(0, 256, size=(3, 70, 45)).astype(np.uint8)          # general uint8 values, ragged tile edges
+    m = rng.integers(0, 256, size=shape).astype(np.uint8)          # general uint8 values, ragged tile edges
     m[0] = (m[0] > 200) * 255
     got = rbunet.coastline_mask(_dev(m), k).cpu().numpy()
-    for b in range(3):
+    for b in range(shape[0]):
         assert np.array_equal(got[b], I.coastline_mask(m[b], k)), (k, b)
 
 
