@@ -290,6 +290,71 @@ coastline_vec_kernel(const uint8_t* __restrict__ mask, int H, int W, const __gri
   reinterpret_cast<uint32_t*>(out + img)[(long)y * Ww + (x >> 2)] = __vsub4(m, center);   // per-byte wrapping subtraction
 }
 
+// Larger structuring elements: horizontal window maxima by doubling.  Level l of a tile row holds, at every byte, the
+// maximum over the 2^l bytes starting there (level 0 = the tile); a window [a, a + len) is then the maximum of two level
+// floor(log2 len) entries at a and a + len - 2^l -- two funnel-shifted words per kernel row instead of len bytes.
+__device__ __forceinline__ uint32_t word_at(const uint32_t* rowp, int o) {      // 4 bytes starting at byte offset o
+  const int wi = o >> 2;
+  return __funnelshift_r(rowp[wi], rowp[wi + 1], (o & 3) * 8);
+}
+
+__global__ void __launch_bounds__(256)
+coastline_lvl_kernel(const uint8_t* __restrict__ mask, int H, int W, const __grid_constant__ Spans sp, int levels,
+                     uint8_t* __restrict__ out) {
+  extern __shared__ uint32_t wt[];      // [levels][rows][roww]
+  const int k = sp.k;
+  const int L4 = (sp.ax + 3) & ~3;
+  const int R4 = ((k - 1 - sp.ax + 3) & ~3) + 4;
+  const int roww = (L4 + CT_W + R4) >> 2;
+  const int rows = CT_H + k - 1;
+  const int lsz = roww * rows;
+  const long img = (long)blockIdx.z * H * W;
+  const int y0 = blockIdx.y * CT_H, x0 = blockIdx.x * CT_W;
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(mask + img);
+  const int Ww = W >> 2;
+  for (int i = threadIdx.x; i < lsz; i += 256) {
+    const int ty = i / roww, tx = i - ty * roww;
+    const int y = y0 + ty - sp.ay;
+    const int xw = ((x0 - L4) >> 2) + tx;
+    wt[i] = (y >= 0 && y < H && xw >= 0 && xw < Ww) ? __ldg(src + (long)y * Ww + xw) : 0u;
+  }
+  __syncthreads();
+  for (int l = 1; l < levels; ++l) {
+    const uint32_t* prev = wt + (l - 1) * lsz;
+    uint32_t* cur = wt + l * lsz;
+    const int sb = 1 << (l - 1);                         // byte shift between the two halves of the window
+    for (int i = threadIdx.x; i < lsz; i += 256) {
+      const int tx = i % roww;
+      const uint32_t a = prev[i];
+      uint32_t b;
+      if (sb < 4) {
+        const uint32_t nx = tx + 1 < roww ? prev[i + 1] : 0u;
+        b = __funnelshift_r(a, nx, sb * 8);
+      } else {
+        const int dw = sb >> 2;
+        b = tx + dw < roww ? prev[i + dw] : 0u;
+      }
+      cur[i] = __vmaxu4(a, b);
+    }
+    __syncthreads();
+  }
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int x = x0 + 4 * tx, y = y0 + ty;
+  if (x >= W || y >= H) return;
+  uint32_t m = 0;
+  const int o0 = 4 * tx + L4 - sp.ax;
+  for (int i = 0; i < k; ++i) {
+    const int j1 = sp.j1[i], len = sp.j2[i] - j1;
+    if (len <= 0) continue;
+    const int l = 31 - __clz(len);
+    const uint32_t* rowp = wt + l * lsz + (ty + i) * roww;
+    m = __vmaxu4(m, word_at(rowp, o0 + j1));
+    m = __vmaxu4(m, word_at(rowp, o0 + j1 + len - (1 << l)));
+  }
+  const uint32_t center = wt[(ty + sp.ay) * roww + tx + (L4 >> 2)];
+  reinterpret_cast<uint32_t*>(out + img)[(long)y * Ww + (x >> 2)] = __vsub4(m, center);
+}
+
 int nearbyint_even(double x) { return (int)nearbyint(x); }   // cvRound under the default rounding mode
 
 }  // namespace
@@ -426,6 +491,25 @@ extern "C" int rbu_coastline_mask(const uint8_t* mask, int B, int H, int W, int 
     coastline_vec_kernel<<<grid, 256, smem, (cudaStream_t)stream_>>>(mask, H, W, sp, out);
     RBU_CHECK_LAUNCH();
     return RBU_OK;
+  }
+  if (W % 4 == 0 && (((uintptr_t)mask | (uintptr_t)out) & 3) == 0) {
+    int maxlen = 1;
+    for (int i = 0; i < ksize; ++i) maxlen = sp.j2[i] - sp.j1[i] > maxlen ? sp.j2[i] - sp.j1[i] : maxlen;
+    int levels = 1;
+    while ((2 << (levels - 1)) <= maxlen) ++levels;           // levels = floor(log2(maxlen)) + 1
+    const int L4 = (sp.ax + 3) & ~3, R4 = ((ksize - 1 - sp.ax + 3) & ~3) + 4;
+    const size_t smem = (size_t)levels * ((L4 + CT_W + R4) >> 2) * (CT_H + ksize - 1) * 4;
+    if (smem <= 200 * 1024) {
+      static size_t attr = 0;
+      if (smem > 48 * 1024 && smem > attr) {
+        RBU_CHECK_CUDA(cudaFuncSetAttribute(coastline_lvl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr = 200 * 1024;
+      }
+      const dim3 grid((unsigned)rbu_cdiv(W, CT_W), (unsigned)rbu_cdiv(H, CT_H), (unsigned)B);
+      coastline_lvl_kernel<<<grid, 256, smem, (cudaStream_t)stream_>>>(mask, H, W, sp, levels, out);
+      RBU_CHECK_LAUNCH();
+      return RBU_OK;
+    }
   }
   const int tw = DT + ksize - 1;
   const dim3 grid((unsigned)rbu_cdiv(W, DT), (unsigned)rbu_cdiv(H, DT), (unsigned)B);
