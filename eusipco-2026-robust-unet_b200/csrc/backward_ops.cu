@@ -491,29 +491,35 @@ ca_bwd_n_kernel(const double* __restrict__ D, const float* __restrict__ scale2, 
     du_max[(long)n * C + c] = m;
   }
 }
-// weight gradients of the shared MLP: thread per weight, sum over images
-__global__ void ca_bwd_w_kernel(const float* __restrict__ dt, const float* __restrict__ dh_avg,
-                                const float* __restrict__ dh_max, const float* __restrict__ h_avg,
-                                const float* __restrict__ h_max, const float* __restrict__ u_avg,
-                                const float* __restrict__ u_max, int N, int C, int Ch, float* __restrict__ dV1,
-                                float* __restrict__ dV2) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= C * Ch) return;
-  {  // dV1[j][c]
-    const int j = i / C, c = i % C;
-    float s = 0.f;
-#pragma unroll 8
-    for (int n = 0; n < N; ++n)
-      s += dh_avg[(long)n * Ch + j] * u_avg[(long)n * C + c] + dh_max[(long)n * Ch + j] * u_max[(long)n * C + c];
-    dV1[i] = s;
+// weight gradients of the shared MLP: block = 32 weights x 8 image lanes (lane j adds images j, j+8, ...; the lane sums
+// are combined in lane order -> deterministic).  A thread per weight walking all N images was a 2 x 64-deep chain of
+// dependent loads: 44 us per call for a few thousand values.
+__global__ void __launch_bounds__(256)
+ca_bwd_w_kernel(const float* __restrict__ dt, const float* __restrict__ dh_avg,
+                const float* __restrict__ dh_max, const float* __restrict__ h_avg,
+                const float* __restrict__ h_max, const float* __restrict__ u_avg,
+                const float* __restrict__ u_max, int N, int C, int Ch, float* __restrict__ dV1,
+                float* __restrict__ dV2) {
+  __shared__ float sh[2][8][33];
+  const int wx = threadIdx.x & 31, ln = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + wx;
+  float s1 = 0.f, s2 = 0.f;
+  if (i < C * Ch) {
+    const int j1 = i / C, c1 = i - j1 * C;      // dV1[j][c]
+    const int c2 = i / Ch, j2 = i - c2 * Ch;    // dV2[c][j]
+    for (int n = ln; n < N; n += 8) {
+      s1 += dh_avg[(long)n * Ch + j1] * u_avg[(long)n * C + c1] + dh_max[(long)n * Ch + j1] * u_max[(long)n * C + c1];
+      s2 += dt[(long)n * C + c2] * (fmaxf(h_avg[(long)n * Ch + j2], 0.f) + fmaxf(h_max[(long)n * Ch + j2], 0.f));
+    }
   }
-  {  // dV2[c][j]
-    const int c = i / Ch, j = i % Ch;
-    float s = 0.f;
-#pragma unroll 8
-    for (int n = 0; n < N; ++n)
-      s += dt[(long)n * C + c] * (fmaxf(h_avg[(long)n * Ch + j], 0.f) + fmaxf(h_max[(long)n * Ch + j], 0.f));
-    dV2[i] = s;
+  sh[0][ln][wx] = s1;
+  sh[1][ln][wx] = s2;
+  __syncthreads();
+  if (ln == 0 && i < C * Ch) {
+    float a = sh[0][0][wx], b = sh[1][0][wx];
+    for (int r = 1; r < 8; ++r) { a += sh[0][r][wx]; b += sh[1][r][wx]; }
+    dV1[i] = a;
+    dV2[i] = b;
   }
 }
 
@@ -1184,8 +1190,8 @@ extern "C" int rbu_rb_mid(const double* D, const float* g, const float* h_avg, c
   ca_bwd_n_kernel<<<N, NT, (C + 2 * Ch) * sizeof(float), st>>>(D, scale2, shift2, g, h_avg, h_max, V1, V2, C, Ch, dt, dh_avg,
                                                                dh_max, du_avg, du_max);
   RBU_CHECK_LAUNCH();
-  ca_bwd_w_kernel<<<rbu_cdiv((long)C * Ch, 128), 128, 0, st>>>(dt, dh_avg, dh_max, h_avg, h_max, u_avg, u_max, N, C, Ch,
-                                                               dV1, dV2);
+  ca_bwd_w_kernel<<<rbu_cdiv((long)C * Ch, 32), 256, 0, st>>>(dt, dh_avg, dh_max, h_avg, h_max, u_avg, u_max, N, C, Ch,
+                                                              dV1, dV2);
   RBU_CHECK_LAUNCH();
   float* c1 = coef;
   float* c0 = c1 + (size_t)N * C;

@@ -138,7 +138,7 @@ class UNetEngine(Engine):
         return dx
 
     # ------------------------------------------------------------------ whole model (:262-288)
-    def forward(self, x: torch.Tensor, training: bool, save: bool):
+    def _forward_impl(self, x: torch.Tensor, training: bool, save: bool):
         m = self.model
         if not x.is_cuda:
             raise RuntimeError("rbunet.UNet runs on CUDA tensors only (no CPU fallback)")
