@@ -62,8 +62,10 @@ class Engine:
         # batch statistics and ChannelAttention's pooled inputs without re-reading the conv output.  Measured on B200: in
         # the training step (batch 64, 256^2) the 18 statistics passes it replaces cost 1.34 ms, the longer epilogues 0.4 ms
         # and the reduction of the partials 0.35 ms; in inference at 1024^2 the 64-channel convolutions become
-        # epilogue-bound (+6 ms against -3.5 ms), so it is used in training mode only.  RBU_NO_TILE_STATS=1 disables it.
+        # epilogue-bound (+6 ms against -3.5 ms), so it is used in training mode only, and only from 128 output channels up
+        # (at 64 channels the longer epilogue costs what the saved pass gains).  RBU_NO_TILE_STATS=1 disables it.
         self.fuse_tile_stats = os.environ.get("RBU_NO_TILE_STATS") is None
+        self.tile_stats_min_c = int(os.environ.get("RBU_TILE_STATS_MIN_C", "128"))   # 64-channel convs (K = 576): epilogue-bound with it
         self._ws = None
         self._defer_counters = False     # whole-model forward: the 39 num_batches_tracked increments become one launch
         self._pending_counters = []
@@ -206,7 +208,7 @@ class Engine:
 
     def tile_stats_ok(self, H, W, C):
         """The 3x3 halo kernel can emit the per-image statistics of its output (see bn_stats_tiles)."""
-        return self.fuse_tile_stats and H >= 16 and W >= 16 and C % 32 == 0 and 8 <= C <= 2048
+        return self.fuse_tile_stats and H >= 16 and W >= 16 and C % 32 == 0 and self.tile_stats_min_c <= C <= 2048
 
     def tile_stats_buf(self, N, H, W, C, device):
         return torch.empty(_lib.lib().rbu_conv_tile_stats_floats(N, H, W, C), dtype=torch.float32, device=device)
