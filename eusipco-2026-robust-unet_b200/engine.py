@@ -65,6 +65,7 @@ class Engine:
         # epilogue-bound (+6 ms against -3.5 ms), so it is used in training mode only, and only from 128 output channels up
         # (at 64 channels the longer epilogue costs what the saved pass gains).  RBU_NO_TILE_STATS=1 disables it.
         self.fuse_tile_stats = os.environ.get("RBU_NO_TILE_STATS") is None
+        self.tile_stats_eval = os.environ.get("RBU_TILE_STATS_EVAL") == "1"
         self.tile_stats_min_c = int(os.environ.get("RBU_TILE_STATS_MIN_C", "128"))   # 64-channel convs (K = 576): epilogue-bound with it
         self._ws = None
         self._defer_counters = False     # whole-model forward: the 39 num_batches_tracked increments become one launch
@@ -373,7 +374,7 @@ class Engine:
             call("rbu_affine_act", _vp(y1), y1.ld, _vp(a1), a1.ld, P, HW, C, _p(bn1["scale"]), _p(bn1["shift"]), _p(drop), 1,
                  stream_ptr())
         y2 = self.new(N, H, W, C, dev)
-        ts2 = self.tile_stats_buf(N, H, W, C, dev) if (training and self.tile_stats_ok(H, W, C)) else None
+        ts2 = self.tile_stats_buf(N, H, W, C, dev) if ((training or self.tile_stats_eval) and self.tile_stats_ok(H, W, C)) else None
         conv_gemm(N, H, W, [(a1, self.pack(blk.conv2.weight, 0), 9, 1, False)], C, y2, tile_stats=ts2)
         if ts2 is not None:
             bn2 = self.bn_stats_tiles(ts2, N, H, W, C, blk.bn2, training, pool=True)
