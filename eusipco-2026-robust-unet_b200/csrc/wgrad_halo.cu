@@ -38,6 +38,8 @@ struct HWParams {
   int Cout, Cin;
   int cin_blocks, cout_blocks, ksplit, items;
   int stages;       // smem ring depth (<= MAX_STAGES)
+  int NB;           // output channels per work item: 64 (all nine taps, 5 accumulators) or 128 (taps 0-7, 4 accumulators of
+                    // 128 columns = the whole TMEM; tap 8 is left to the generic kernel)
   float* partial;   // [ksplit][Cout][9][Cin]
 };
 
@@ -52,7 +54,9 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                   const __grid_constant__ HWParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.stages * STAGE_BYTES);
+  const int nbox = p.NB >> 6;                           // 64-channel dy boxes per stage
+  const int stage_bytes = X_BYTES + nbox * DY_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
   uint64_t* full = bars;             // [MAX_STAGES]
   uint64_t* empty = bars + MAX_STAGES;   // [MAX_STAGES]
   uint64_t* tfull = bars + 2 * MAX_STAGES;
@@ -93,10 +97,11 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         int th = t2 % p.tiles_h, n = t2 / p.tiles_h;
         for (int tile = tile0; tile < tile1; ++tile) {
           ptx::mbar_wait(&empty[s], ph ^ 1);
-          ptx::mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
-          uint8_t* dst = smem + s * STAGE_BYTES;
+          ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)stage_bytes);
+          uint8_t* dst = smem + s * stage_bytes;
           ptx::tma_load_4d(dst, &tmX, &full[s], cb * 64, tw * TILE_W - 1, th * TILE_H - 1, n);
-          ptx::tma_load_4d(dst + X_BYTES, &tmDy, &full[s], ob * 64, tw * TILE_W, th * TILE_H, n);
+          for (int j = 0; j < nbox; ++j)
+            ptx::tma_load_4d(dst + X_BYTES + j * DY_BYTES, &tmDy, &full[s], ob * p.NB + j * 64, tw * TILE_W, th * TILE_H, n);
           if (++s == p.stages) { s = 0; ph ^= 1; }
           if (++tw == p.tiles_w) { tw = 0; if (++th == p.tiles_h) { th = 0; ++n; } }
         }
@@ -104,8 +109,11 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     }
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
-    const uint32_t idesc128 = ptx::make_idesc_bf16(128, 64, 1, 1);
+    const uint32_t idesc128 = ptx::make_idesc_bf16(128, p.NB, 1, 1);
     const uint32_t idesc64 = ptx::make_idesc_bf16(64, 64, 1, 1);
+    const bool wide = p.NB == 128;
+    const uint32_t nb_cols = (uint32_t)p.NB;
+    const uint32_t dy_lbo = ((uint32_t)(wide ? DY_BYTES : 1024) >> 4) << 16;   // distance between the two 64-channel dy boxes
     const uint32_t full_s = ptx::smem_u32(full), empty_s = ptx::smem_u32(empty);
     const uint32_t hi = ptx::desc_hi(1024);
     const uint32_t base_lo = (ptx::smem_u32(smem) & 0x3FFFFu) >> 4;
@@ -126,20 +134,21 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         ptx::mbar_wait_s(full_s + s * 8, ph);
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
-          const uint32_t x_lo = base_lo + s * (STAGE_BYTES >> 4);
+          const uint32_t x_lo = base_lo + s * ((uint32_t)stage_bytes >> 4);
           const uint32_t y_lo = x_lo + (X_BYTES >> 4);
 #pragma unroll
           for (int kk = 0; kk < TILE_H; ++kk) {      // K step = one tile row of 16 pixels
             const uint32_t acc = kk ? 1u : accumulate;
             const uint32_t b = y_lo + kk * ((TILE_W * 128) >> 4);
-            const uint64_t db = ptx::pack_desc(b | ((1024u >> 4) << 16), hi);
+            const uint64_t db = ptx::pack_desc(b | dy_lbo, hi);
             const uint32_t xr = x_lo + kk * ROW;     // halo pixel (kk, 0): tap (dy,dx) starts at (kk+dy, dx)
             // accumulators: 0 = taps (0,1), 1 = taps (3,4), 2 = taps (6,7), 3 = taps (2,5), 4 = tap 8
-            ptx::umma_bf16(tmem_base + 0 * 64, ptx::pack_desc((xr + 0 * ROW + 0 * 8) | LBO_DX, hi), db, idesc128, acc);
-            ptx::umma_bf16(tmem_base + 1 * 64, ptx::pack_desc((xr + 1 * ROW + 0 * 8) | LBO_DX, hi), db, idesc128, acc);
-            ptx::umma_bf16(tmem_base + 2 * 64, ptx::pack_desc((xr + 2 * ROW + 0 * 8) | LBO_DX, hi), db, idesc128, acc);
-            ptx::umma_bf16(tmem_base + 3 * 64, ptx::pack_desc((xr + 0 * ROW + 2 * 8) | LBO_DY, hi), db, idesc128, acc);
-            ptx::umma_bf16(tmem_base + 4 * 64, ptx::pack_desc((xr + 2 * ROW + 2 * 8) | LBO_DX, hi), db, idesc64, acc);
+            ptx::umma_bf16(tmem_base + 0 * nb_cols, ptx::pack_desc((xr + 0 * ROW + 0 * 8) | LBO_DX, hi), db, idesc128, acc);
+            ptx::umma_bf16(tmem_base + 1 * nb_cols, ptx::pack_desc((xr + 1 * ROW + 0 * 8) | LBO_DX, hi), db, idesc128, acc);
+            ptx::umma_bf16(tmem_base + 2 * nb_cols, ptx::pack_desc((xr + 2 * ROW + 0 * 8) | LBO_DX, hi), db, idesc128, acc);
+            ptx::umma_bf16(tmem_base + 3 * nb_cols, ptx::pack_desc((xr + 0 * ROW + 2 * 8) | LBO_DY, hi), db, idesc128, acc);
+            if (!wide)
+              ptx::umma_bf16(tmem_base + 4 * 64, ptx::pack_desc((xr + 2 * ROW + 2 * 8) | LBO_DX, hi), db, idesc64, acc);
           }
           ptx::umma_commit_s(empty_s + s * 8);
         }
@@ -160,7 +169,8 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       ptx::mbar_wait(tfull, it & 1);
       ptx::tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
-      for (int a = 0; a < NACC; ++a) {
+      const int nacc = p.NB == 128 ? 4 : NACC;
+      for (int a = 0; a < nacc; ++a) {
         // which (tap, cin) does this thread's TMEM lane hold?
         int tap, cl;
         bool ok = true;
@@ -175,14 +185,14 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         }
         const int cin = cb * 64 + cl;
         ok = ok && cin < p.Cin;
-        for (int c0 = 0; c0 < 64; c0 += 32) {
+        for (int c0 = 0; c0 < p.NB; c0 += 32) {
           uint32_t r[32];
-          ptx::tmem_ld_32x32(t_addr + (uint32_t)(a * 64 + c0), r);
+          ptx::tmem_ld_32x32(t_addr + (uint32_t)(a * p.NB + c0), r);
           ptx::tmem_ld_wait();
           if (ok) {
 #pragma unroll
             for (int e = 0; e < 32; ++e) {
-              const int cout = ob * 64 + c0 + e;
+              const int cout = ob * p.NB + c0 + e;
               if (cout < p.Cout) p.partial[(((long)ks * p.Cout + cout) * 9 + tap) * p.Cin + cin] = __uint_as_float(r[e]);
             }
           }
@@ -206,8 +216,17 @@ void plan(const rbu_wgrad_args* a, HWParams* p) {
   p->tiles_total = p->tiles_w * p->tiles_h * a->N;
   p->Cout = a->Ca;
   p->Cin = a->Cb;
+  {
+    // Optional (RBU_WGRAD_NB128=1): 128 output channels per item -- the dy operand is then as wide as the x operand
+    // (balanced shared-memory fetch per MMA) but the 512-column TMEM holds only eight taps, and tap 8 needs a second pass
+    // over both activation tensors (generic kernel).  Measured on B200: the 8-tap kernel is 1.2-1.34x faster per tap, the
+    // extra pass costs more than that except for Cin >= 2 Cout -- off by default.
+    static int nb128 = -1;
+    if (nb128 < 0) nb128 = getenv("RBU_WGRAD_NB128") ? 1 : 0;
+    p->NB = (nb128 && a->Ca % 128 == 0) ? 128 : 64;
+  }
   p->cin_blocks = rbu_cdiv(a->Cb, 64);
-  p->cout_blocks = rbu_cdiv(a->Ca, 64);
+  p->cout_blocks = rbu_cdiv(a->Ca, p->NB);
   const int base_items = p->cin_blocks * p->cout_blocks;
   // split-K factor: the smallest one that fills the machine with at most ~15 % of the last wave idle (every item
   // pays an un-overlapped epilogue and a partial-sum round trip, so fewer, longer items win), else the best found
@@ -234,11 +253,10 @@ int rbu_wgrad_halo_supported(const rbu_wgrad_args* a) {
 size_t rbu_wgrad_halo_workspace_bytes(const rbu_wgrad_args* a) {
   HWParams p;
   plan(a, &p);
-  return (size_t)p.ksplit * a->Ca * 9 * a->Cb * sizeof(float);
+  size_t own = (size_t)p.ksplit * a->Ca * 9 * a->Cb * sizeof(float);
+  own = (own + 255) & ~(size_t)255;
+  return own + (p.NB == 128 ? rbu_wgrad_generic_workspace_bytes(a, 8, 9) : 0);
 }
-
-void rbu_wgrad_reduce_launch(const float* partial, int ksplit, int Mtot, int taps, int Ntot, float* out, int accumulate,
-                             cudaStream_t stream);
 
 // Argument validation is done by the caller (rbu_wgrad_gemm).
 int rbu_wgrad_halo_launch(const rbu_wgrad_args* a, void* workspace, cudaStream_t stream) {
@@ -265,7 +283,9 @@ int rbu_wgrad_halo_launch(const rbu_wgrad_args* a, void* workspace, cudaStream_t
     if (st < 0) { const char* e = getenv("RBU_WGRAD_STAGES"); st = e ? atoi(e) : MAX_STAGES; if (st < 2 || st > MAX_STAGES) st = MAX_STAGES; }
     p.stages = st;
   }
-  const int smem_bytes = p.stages * STAGE_BYTES + 1024 + 256;
+  const int stage_bytes = X_BYTES + (p.NB >> 6) * DY_BYTES;
+  if (p.stages * stage_bytes + 1024 + 256 > SMEM_LIMIT) p.stages = (SMEM_LIMIT - 1024 - 256) / stage_bytes;
+  const int smem_bytes = p.stages * stage_bytes + 1024 + 256;
   static bool attr_set = false;
   if (!attr_set) {
     RBU_CHECK_CUDA(cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
@@ -274,6 +294,15 @@ int rbu_wgrad_halo_launch(const rbu_wgrad_args* a, void* workspace, cudaStream_t
   const int grid = p.items < rbu_num_sms() ? p.items : rbu_num_sms();
   wgrad_halo_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(tmX, tmDy, p);
   RBU_CHECK_LAUNCH();
+  if (p.NB == 128) {
+    // taps 0-7 from this kernel, tap 8 from the generic kernel (its own partials behind ours)
+    rbu_wgrad_reduce_launch(p.partial, p.ksplit, a->Ca, 9, a->Cb, a->out, a->accumulate, stream, 0, 8);
+    RBU_CHECK_LAUNCH();
+    size_t own = (size_t)p.ksplit * a->Ca * 9 * a->Cb * sizeof(float);
+    own = (own + 255) & ~(size_t)255;
+    return rbu_wgrad_generic_launch(a, 8, 9, static_cast<uint8_t*>(workspace) + own, rbu_wgrad_generic_workspace_bytes(a, 8, 9),
+                                    stream);
+  }
   rbu_wgrad_reduce_launch(p.partial, p.ksplit, a->Ca, 9, a->Cb, a->out, a->accumulate, stream);
   RBU_CHECK_LAUNCH();
   return RBU_OK;

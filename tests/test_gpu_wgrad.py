@@ -79,3 +79,17 @@ def test_wgrad_is_deterministic():
     eng.wgrad(4, 32, 32, dy, x, 9, 1, False, b)
     torch.cuda.synchronize()
     assert torch.equal(a, b)
+
+
+def test_128_channel_items_variant_in_subprocess():
+    """RBU_WGRAD_NB128=1 (read once per process): taps 0-7 from the halo kernel with 128-output-channel items, tap 8 from
+    the generic kernel -- the same parity cases must pass."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("RBU_WGRAD_NB128"):
+        pytest.skip("already inside the variant run")
+    env = dict(os.environ, RBU_WGRAD_NB128="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k", "3x3 and not subprocess"],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
