@@ -44,19 +44,20 @@ __device__ __forceinline__ long pack_src_index(int mode, int Nn, int T, int K, i
 //   1x1 shortcut weights in the centre-tap columns, zero elsewhere (Nn = 2C, K = Kp, T = number of input channels, src =
 //   conv1 weight, src2 = shortcut weight); mode 5: the same without the shortcut rows.
 constexpr int PK0 = 128;          // mode 0: channels per unit
-constexpr int PK1 = 32;           // mode 1: tile edge
+constexpr int PK1 = 32;           // mode 1: output channels (k) per unit
+constexpr int PK1N = 16;          // mode 1: input channels (n) per unit (18 KB of shared memory: 8 blocks per SM)
 constexpr int PACK_MAX_T = 9;
 
 __host__ __device__ inline long long pack_job_blocks(int Nn, int T, int K, int mode) {
   if (mode == 0 && T <= PACK_MAX_T) return (long long)Nn * ((K + PK0 - 1) / PK0);
-  if (mode == 1 && T <= PACK_MAX_T) return (long long)((K + PK1 - 1) / PK1) * ((Nn + PK1 - 1) / PK1);
+  if (mode == 1 && T <= PACK_MAX_T) return (long long)((K + PK1 - 1) / PK1) * ((Nn + PK1N - 1) / PK1N);
   const long long total = (mode == 4 || mode == 5) ? (long long)Nn * K : (long long)Nn * T * K;
   return (total + 1023) / 1024;
 }
 
 __global__ void __launch_bounds__(256)
 pack_multi_kernel(const rbu_pack_job* __restrict__ jobs, int njobs) {
-  __shared__ float tile[PK1 * PK1 * PACK_MAX_T];      // 36 KB (mode 1); mode 0 uses the first 128*T floats
+  __shared__ float tile[PK1 * PK1N * PACK_MAX_T];     // 18 KB (mode 1); mode 0 uses the first 128*T floats
   // job lookup: every thread tests one table entry (one global-load latency instead of a 7-deep dependent binary search)
   __shared__ int job_idx;
   const long long b = blockIdx.x;
@@ -75,7 +76,20 @@ pack_multi_kernel(const rbu_pack_job* __restrict__ jobs, int njobs) {
     const int n = (int)(lb / kchunks), k0 = (int)(lb - (long long)n * kchunks) * PK0;
     const int kw = min(PK0, K - k0);
     const float* sp = j.src + ((long long)n * K + k0) * T;
-    for (int i = threadIdx.x; i < kw * T; i += 256) tile[i] = sp[i];          // [k][t], contiguous in the source
+    {
+      // [k][t], contiguous in the source; all loads of a thread are issued before the first shared-memory store
+      float v[5];
+#pragma unroll
+      for (int u = 0; u < 5; ++u) {
+        const int i = threadIdx.x + u * 256;
+        v[u] = i < kw * T ? __ldg(sp + i) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 5; ++u) {
+        const int i = threadIdx.x + u * 256;
+        if (i < kw * T) tile[i] = v[u];
+      }
+    }
     __syncthreads();
     for (int i = threadIdx.x; i < kw * T; i += 256) {
       const int t = i / kw, k = i - t * kw;
@@ -85,20 +99,37 @@ pack_multi_kernel(const rbu_pack_job* __restrict__ jobs, int njobs) {
   }
   if (j.mode == 1 && T <= PACK_MAX_T) {
     // src [K][Nn][T] -> dst[n][T-1-t][k]
-    const int nchunks = (Nn + PK1 - 1) / PK1;
-    const int kc = (int)(lb / nchunks), k0 = kc * PK1, n0 = (int)(lb - (long long)kc * nchunks) * PK1;
-    const int kw = min(PK1, K - k0), nw = min(PK1, Nn - n0);
+    const int nchunks = (Nn + PK1N - 1) / PK1N;
+    const int kc = (int)(lb / nchunks), k0 = kc * PK1, n0 = (int)(lb - (long long)kc * nchunks) * PK1N;
+    const int kw = min(PK1, K - k0), nw = min(PK1N, Nn - n0);
     const int row = nw * T;                                                   // contiguous source floats per k
-    for (int i = threadIdx.x; i < kw * row; i += 256) {
-      const int kk = i / row, r = i - kk * row;
-      tile[kk * (PK1 * PACK_MAX_T) + r] = j.src[((long long)(k0 + kk) * Nn + n0) * T + r];
+    for (int base = 0; base < kw * row; base += 256 * 6) {
+      float v[6];
+#pragma unroll
+      for (int u = 0; u < 6; ++u) {
+        const int i = base + threadIdx.x + u * 256;
+        float x = 0.f;
+        if (i < kw * row) {
+          const int kk = i / row, r = i - kk * row;
+          x = __ldg(j.src + ((long long)(k0 + kk) * Nn + n0) * T + r);
+        }
+        v[u] = x;
+      }
+#pragma unroll
+      for (int u = 0; u < 6; ++u) {
+        const int i = base + threadIdx.x + u * 256;
+        if (i < kw * row) {
+          const int kk = i / row, r = i - kk * row;
+          tile[kk * (PK1N * PACK_MAX_T) + r] = v[u];
+        }
+      }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < kw * row; i += 256) {
       const int kk = i % kw, r = i / kw;                                       // r = nn * T + t'
       const int nn = r / T, tp = r - nn * T;
       dst[((long long)(n0 + nn) * T + tp) * K + k0 + kk] =
-          __float2bfloat16_rn(tile[kk * (PK1 * PACK_MAX_T) + nn * T + (T - 1 - tp)]);
+          __float2bfloat16_rn(tile[kk * (PK1N * PACK_MAX_T) + nn * T + (T - 1 - tp)]);
     }
     return;
   }
