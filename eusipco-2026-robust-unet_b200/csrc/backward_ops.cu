@@ -237,9 +237,10 @@ rb_bwd1_kernel(const bf16* __restrict__ dout, long dout_ld, const bf16* __restri
 // SpatialAttention backward (Main_Final.py:112-117), one shared-memory tiled kernel: dq = dG * gs (1-gs);
 //   ds[k][h,w]   = sum_{r,q} K7[k][r][q] * dq[h-r+3, w-q+3]      (data gradient wrt [s_avg, s_max])
 //   dK7[k][r][q] = sum_p dq[p] * s_k[p + (r-3, q-3)]             (98 per-thread accumulators, block partials)
-// A block walks 32 x 8 tiles (grid-stride) holding the 38 x 14 halos of dq and s in shared memory.
-constexpr int SB_TX = 32, SB_TY = 4, SB_HX = SB_TX + 6, SB_HY = SB_TY + 6;
-__global__ void __launch_bounds__(SB_TX * SB_TY)
+// A block walks 32 x 16 tiles (grid-stride) holding the 38 x 22 halos of dq and s in shared memory; a thread owns four
+// horizontally adjacent pixels, so one 10-wide window per halo row serves 4 x 7 taps (35 loads per pixel instead of 98).
+constexpr int SB_TX = 32, SB_TY = 16, SB_HX = SB_TX + 6, SB_HY = SB_TY + 6, SB_NT = (SB_TX / 4) * SB_TY;
+__global__ void __launch_bounds__(SB_NT)
 sa_bwd_kernel(const float* __restrict__ dG, const float* __restrict__ gs, const float2* __restrict__ s, int N, int H, int W,
               const float* __restrict__ k7, float2* __restrict__ ds, float* __restrict__ partials) {
   __shared__ float wk[98];
@@ -252,13 +253,13 @@ sa_bwd_kernel(const float* __restrict__ dG, const float* __restrict__ gs, const 
   for (int i = 0; i < 98; ++i) acc[i] = 0.f;
   const int tiles_x = (W + SB_TX - 1) / SB_TX, tiles_y = (H + SB_TY - 1) / SB_TY;
   const int tiles = tiles_x * tiles_y * N;
-  const int tx = tid % SB_TX, ty = tid / SB_TX;
+  const int tx = (tid % (SB_TX / 4)) * 4, ty = tid / (SB_TX / 4);
   for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
     const int bx = t % tiles_x, by = (t / tiles_x) % tiles_y, n = t / (tiles_x * tiles_y);
     const int x0 = bx * SB_TX, y0 = by * SB_TY;
     const long nb = (long)n * H * W;
     __syncthreads();
-    for (int i = tid; i < SB_HX * SB_HY; i += SB_TX * SB_TY) {
+    for (int i = tid; i < SB_HX * SB_HY; i += SB_NT) {
       const int hy = i / SB_HX, hx = i - hy * SB_HX;
       const int yy = y0 + hy - 3, xx = x0 + hx - 3;
       float q = 0.f;
@@ -275,23 +276,39 @@ sa_bwd_kernel(const float* __restrict__ dG, const float* __restrict__ gs, const 
     __syncthreads();
     const int x = x0 + tx, y = y0 + ty;
     if (x < W && y < H) {
-      const float dq = tq[ty + 3][tx + 3];
-      float a0 = 0.f, a1 = 0.f;
+      // dq of this thread's pixels (0 outside the image, so those pixels add nothing to the weight gradient)
+      float dqc[4];
 #pragma unroll
-      for (int r = 0; r < 7; ++r)
+      for (int e = 0; e < 4; ++e) dqc[e] = tq[ty + 3][tx + 3 + e];
+      float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int r = 0; r < 7; ++r) {
+        float2 sw[10];      // s at (y + r - 3, x + j - 3)
+        float dw[10];       // dq at (y - r + 3, x + j - 3)
+#pragma unroll
+        for (int j = 0; j < 10; ++j) {
+          sw[j] = tsv[ty + r][tx + j];
+          dw[j] = tq[ty + 6 - r][tx + j];
+        }
 #pragma unroll
         for (int q = 0; q < 7; ++q) {
-          const float2 v = tsv[ty + r][tx + q];                 // s at (y + r - 3, x + q - 3)
-          acc[r * 7 + q] += dq * v.x;
-          acc[49 + r * 7 + q] += dq * v.y;
-          const float dqq = tq[ty + 6 - r][tx + 6 - q];          // dq at (y - r + 3, x - q + 3)
-          a0 += wk[r * 7 + q] * dqq;
-          a1 += wk[49 + r * 7 + q] * dqq;
+          const float w0 = wk[r * 7 + q], w1 = wk[49 + r * 7 + q];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            acc[r * 7 + q] += dqc[e] * sw[q + e].x;
+            acc[49 + r * 7 + q] += dqc[e] * sw[q + e].y;
+            const float dqq = dw[e + 6 - q];              // dq at (y - r + 3, x + e - q + 3)
+            a0[e] += w0 * dqq;
+            a1[e] += w1 * dqq;
+          }
         }
-      ds[nb + (long)y * W + x] = make_float2(a0, a1);
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (x + e < W) ds[nb + (long)y * W + x + e] = make_float2(a0[e], a1[e]);
     }
   }
-  __shared__ float sm[98][SB_TX * SB_TY / 32];
+  __shared__ float sm[98][SB_NT / 32];
   const int warp = tid >> 5, lane = tid & 31;
 #pragma unroll
   for (int i = 0; i < 98; ++i) {
@@ -301,7 +318,7 @@ sa_bwd_kernel(const float* __restrict__ dG, const float* __restrict__ gs, const 
   __syncthreads();
   if (tid < 98) {
     float tsum = 0.f;
-    for (int wq = 0; wq < SB_TX * SB_TY / 32; ++wq) tsum += sm[tid][wq];
+    for (int wq = 0; wq < SB_NT / 32; ++wq) tsum += sm[tid][wq];
     partials[(long)blockIdx.x * 98 + tid] = tsum;
   }
 }
@@ -1139,7 +1156,7 @@ extern "C" int rbu_sa_bwd(const float* dG, const float* gs, const float* s, int 
   const long cap = (long)rbu_num_sms() * 6;
   const int blocks = (int)(tiles < cap ? tiles : cap);
   RBU_CHECK_ARG(workspace && workspace_bytes >= (size_t)blocks * 98 * sizeof(float), "rbu_sa_bwd: workspace too small");
-  sa_bwd_kernel<<<blocks, SB_TX * SB_TY, 0, st>>>(dG, gs, (const float2*)s, N, H, W, k7, (float2*)ds, (float*)workspace);
+  sa_bwd_kernel<<<blocks, SB_NT, 0, st>>>(dG, gs, (const float2*)s, N, H, W, k7, (float2*)ds, (float*)workspace);
   RBU_CHECK_LAUNCH();
   const float* pp = (const float*)workspace;
   int nb2 = blocks;
