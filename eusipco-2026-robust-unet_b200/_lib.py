@@ -179,5 +179,8 @@ def launch_count() -> int:
 
 
 def stream_ptr():
+    """torch's current stream of the CURRENT device.  One device per process is the supported deployment (torchrun);
+    Engine.forward/backward and the functional ops enter `torch.cuda.device(tensor.device)` first, so a model living
+    on a device other than the current one still launches on its own device's stream."""
     import torch
     return c_void_p(torch.cuda.current_stream().cuda_stream)

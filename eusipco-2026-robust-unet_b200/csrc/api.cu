@@ -6,12 +6,20 @@
 
 namespace {
 thread_local char g_err[1024] = "";
-int g_sms = 0;
+constexpr int MAX_DEVICES = 64;
+std::atomic<int> g_sms[MAX_DEVICES];          // per device ordinal; 0 = not queried yet
 }  // namespace
 
-unsigned long long g_rbu_launches = 0;
+std::atomic<unsigned long long> g_rbu_launches{0};
 
-extern "C" unsigned long long rbu_launch_count(void) { return g_rbu_launches; }
+extern "C" unsigned long long rbu_launch_count(void) { return g_rbu_launches.load(std::memory_order_relaxed); }
+
+bool rbu_first_use_on_device(std::atomic<unsigned long long>* done_mask) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) return true;   // unknown: set the attribute again
+  const unsigned long long bit = 1ull << dev;
+  return (done_mask->fetch_or(bit, std::memory_order_acq_rel) & bit) == 0;
+}
 
 void rbu_set_error(const char* fmt, ...) {
   va_list ap;
@@ -21,15 +29,14 @@ void rbu_set_error(const char* fmt, ...) {
 }
 
 int rbu_num_sms() {
-  if (g_sms == 0) {
-    int dev = 0;
-    cudaDeviceProp prop;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess)
-      g_sms = prop.multiProcessorCount;
-    else
-      g_sms = 148;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) return 148;
+  int n = g_sms[dev].load(std::memory_order_relaxed);
+  if (n == 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    g_sms[dev].store(n, std::memory_order_relaxed);
   }
-  return g_sms;
+  return n;
 }
 
 extern "C" int rbu_version(void) { return 100; }

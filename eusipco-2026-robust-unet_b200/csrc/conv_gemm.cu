@@ -690,11 +690,9 @@ extern "C" int rbu_conv_gemm(const rbu_conv_gemm_args* a, void* stream_) {
   }
 
   const int smem_bytes = p.num_stages * stage_bytes + 1024 + BAR_BYTES + staging;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<unsigned long long> attr_set{0};      // one bit per device ordinal
+  if (rbu_first_use_on_device(&attr_set))
     RBU_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    attr_set = true;
-  }
   if (a->stats) {
     RBU_CHECK_ARG(!a->scatter && p.block_n <= 64 * EPI_STAT_CHUNKS && grid % p.n_blocks == 0 && ((uintptr_t)a->stats & 15) == 0,
                   "rbu_conv_gemm: output statistics are not supported for this shape");

@@ -588,11 +588,9 @@ int rbu_conv_halo_launch(const rbu_conv_gemm_args* a, cudaStream_t stream) {
     tmB[1] = tmB[0];
   }
   const int smem_bytes = p.a_stages * A_HALO_BYTES + p.b_stages * b_bytes * p.tps + 1024 + 512;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<unsigned long long> attr_set{0};      // one bit per device ordinal
+  if (rbu_first_use_on_device(&attr_set))
     RBU_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    attr_set = true;
-  }
   const int grid = p.total_tiles < rbu_num_sms() ? p.total_tiles : rbu_num_sms();
   if (a->stats) {
     RBU_CHECK_ARG(p.block_n <= 32 * EPI_STAT_CHUNKS && grid % p.n_blocks == 0 && ((uintptr_t)a->stats & 15) == 0,

@@ -34,14 +34,19 @@ void rbu_set_error(const char* fmt, ...);
   } while (0)
 
 // every kernel launch of the library goes through this macro: it also feeds rbu_launch_count()
-extern unsigned long long g_rbu_launches;
-#define RBU_CHECK_LAUNCH()                  \
-  do {                                      \
-    ++g_rbu_launches;                       \
-    RBU_CHECK_CUDA(cudaGetLastError());     \
+#include <atomic>
+extern std::atomic<unsigned long long> g_rbu_launches;
+#define RBU_CHECK_LAUNCH()                                        \
+  do {                                                            \
+    g_rbu_launches.fetch_add(1, std::memory_order_relaxed);       \
+    RBU_CHECK_CUDA(cudaGetLastError());                           \
   } while (0)
 
-int rbu_num_sms();
+int rbu_num_sms();          // SM count of the CURRENT device (cached per device ordinal)
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: one bit per device ordinal, set once.
+// Usage:  static std::atomic<unsigned long long> done{0};  if (rbu_first_use_on_device(&done)) cudaFuncSetAttribute(...)
+bool rbu_first_use_on_device(std::atomic<unsigned long long>* done_mask);
 
 static inline int rbu_cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 

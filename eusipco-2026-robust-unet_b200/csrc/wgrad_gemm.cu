@@ -443,11 +443,9 @@ int rbu_wgrad_generic_launch(const rbu_wgrad_args* a, int tap_first, int tap_end
 
   const int a_bytes = ((p.BM + 63) / 64) * BOX_BYTES, b_bytes = ((p.BN + 63) / 64) * BOX_BYTES;
   const int smem_bytes = A_STAGES * a_bytes + p.b_stages * b_bytes + 1024 + 256;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<unsigned long long> attr_set{0};      // one bit per device ordinal
+  if (rbu_first_use_on_device(&attr_set))
     RBU_CHECK_CUDA(cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    attr_set = true;
-  }
   const int grid = p.items < rbu_num_sms() ? p.items : rbu_num_sms();
   wgrad_gemm_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(tmA, tmB, p);
   RBU_CHECK_LAUNCH();

@@ -286,11 +286,9 @@ int rbu_wgrad_halo_launch(const rbu_wgrad_args* a, void* workspace, cudaStream_t
   const int stage_bytes = X_BYTES + (p.NB >> 6) * DY_BYTES;
   if (p.stages * stage_bytes + 1024 + 256 > SMEM_LIMIT) p.stages = (SMEM_LIMIT - 1024 - 256) / stage_bytes;
   const int smem_bytes = p.stages * stage_bytes + 1024 + 256;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<unsigned long long> attr_set{0};      // one bit per device ordinal
+  if (rbu_first_use_on_device(&attr_set))
     RBU_CHECK_CUDA(cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    attr_set = true;
-  }
   const int grid = p.items < rbu_num_sms() ? p.items : rbu_num_sms();
   wgrad_halo_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(tmX, tmDy, p);
   RBU_CHECK_LAUNCH();

@@ -51,7 +51,9 @@ class Engine:
         self._side_stream = None
         self._side_ws = None
         self._side_dirty = False
-        self._side_keep = []
+        self._side_keep = []          # [(event recorded behind a side-stream kernel, tensors it reads / writes)]
+        self.grad_alloc = None        # optional callable(name, shape) -> fp32 tensor to receive that parameter's gradient
+                                      # (parallel.DataParallel: a slice of a flat all-reduce bucket), or None
         self._saving = False
         self.overlap_wgrad = os.environ.get("RBU_NO_OVERLAP") is None
         # BatchNorm batch statistics fused into the producing convolution's epilogue (rbu_conv_gemm stats=...): one pass
@@ -275,7 +277,8 @@ class Engine:
     def _side(self, device):
         if self._side_stream is None or self._side_stream.device != device:
             self._side_stream = torch.cuda.Stream(device=device)
-            self._side_ws = Workspace(device)
+            with torch.cuda.stream(self._side_stream):      # the caching allocator ties a block to the stream it was
+                self._side_ws = Workspace(device)           # allocated under: this buffer is only ever used on the side stream
         return self._side_stream
 
     def join_side(self, device):
@@ -285,15 +288,38 @@ class Engine:
             self._side_dirty = False
             self._side_keep.clear()      # operands may be recycled now: later main-stream work is ordered after the join
 
+    def side_event(self):
+        """An event behind everything enqueued on the weight-gradient stream so far (None if nothing is pending)."""
+        if self._side_stream is None or not self._side_dirty:
+            return None
+        ev = torch.cuda.Event()
+        ev.record(self._side_stream)
+        return ev
+
+    def gbuf(self, name, like: torch.Tensor):
+        """Destination of a parameter gradient: the data-parallel bucket slice when one is registered, else fresh memory."""
+        if self.grad_alloc is not None:
+            t = self.grad_alloc(name, like.shape)
+            if t is not None:
+                return t
+        return torch.empty_like(like)
+
     def wgrad(self, N, H, W, a: View, b: View, taps, dil, gather, out: torch.Tensor):
         if self.overlap_wgrad:
             dev = out.device
             main = torch.cuda.current_stream(dev)
             side = self._side(dev)
             side.wait_stream(main)                       # operands were produced on the main stream
-            self._side_keep.extend((a.base, b.base, out))    # keep their memory alive until the next join
+            # operands were allocated under the main stream: keep them referenced until the side-stream kernel that reads
+            # them has finished (polled, never waited for), so the allocator cannot hand their memory to later main-stream work
+            keep = self._side_keep
+            while keep and keep[0][0].query():
+                keep.pop(0)
             with torch.cuda.stream(side):
                 self._wgrad(N, H, W, a, b, taps, dil, gather, out, self._side_ws)
+                ev = torch.cuda.Event()
+                ev.record(side)
+            keep.append((ev, (a.base, b.base, out)))
             self._side_dirty = True
         else:
             self._wgrad(N, H, W, a, b, taps, dil, gather, out, None)
@@ -457,7 +483,7 @@ class Engine:
         a1 = s["a1"]
         da1 = self.new(N, H, W, C, dev)
         conv_gemm(N, H, W, [(dy2, self.pack(blk.conv2.weight, 1), 9, 1, False)], C, da1)
-        gW2 = torch.empty_like(blk.conv2.weight)
+        gW2 = self.gbuf(prefix + ".conv2.weight", blk.conv2.weight)
         self.wgrad(N, H, W, dy2, a1, 9, 1, False, gW2)
         grads[prefix + ".conv2.weight"] = gW2
         # bn1 + relu + dropout
@@ -487,11 +513,11 @@ class Engine:
             if proj:
                 segs.append((dys, self.pack(blk.shortcut[0].weight, 1), 1, 0, False))
             conv_gemm(N, H, W, segs, x.C, dx, addend=None if proj else de)
-        gW1 = torch.empty_like(blk.conv1.weight)
+        gW1 = self.gbuf(prefix + ".conv1.weight", blk.conv1.weight)
         self.wgrad(N, H, W, dy1, x, 9, 1, False, gW1)
         grads[prefix + ".conv1.weight"] = gW1
         if proj:
-            gWs = torch.empty_like(blk.shortcut[0].weight)
+            gWs = self.gbuf(prefix + ".shortcut.0.weight", blk.shortcut[0].weight)
             self.wgrad(N, H, W, dys, x, 1, 0, False, gWs)
             grads[prefix + ".shortcut.0.weight"] = gWs
         return dx if need_dx else None
@@ -549,12 +575,15 @@ class Engine:
         grads[prefix + ".psi.0.bias"] = torch.zeros(1, device=dev)          # BN removes the mean: exactly zero
         grads[prefix + ".psi.1.bias"], grads[prefix + ".psi.1.weight"] = sums_psi[0:1], sums_psi[1:2]
         grads[prefix + ".W_g.1.bias"], grads[prefix + ".W_g.1.weight"] = sums_f[F:2 * F], sums_f[2 * F:3 * F]
-        grads[prefix + ".W_x.1.bias"], grads[prefix + ".W_x.1.weight"] = sums_f[F:2 * F], sums_f[3 * F:4 * F]
+        # d(beta) of the two BatchNorms is the same sum (both see dt); every parameter still gets its OWN storage: autograd
+        # adopts these tensors as .grad, and in-place users (clip_grad_norm_, gradient accumulation) must not see aliases
+        grads[prefix + ".W_x.1.bias"], grads[prefix + ".W_x.1.weight"] = sums_f[F:2 * F].clone(), sums_f[3 * F:4 * F]
         grads[prefix + ".W_g.0.bias"] = torch.zeros(F, device=dev)
         grads[prefix + ".W_x.0.bias"] = torch.zeros(F, device=dev)
         conv_gemm(N, H, W, [(dyg, self.pack(gate.W_g[0].weight, 1), 1, 0, False)], C, dgup, addend=dgup)
         conv_gemm(N, H, W, [(dyx, self.pack(gate.W_x[0].weight, 1), 1, 0, False)], C, dskip, addend=dskip)
-        gWg, gWx = torch.empty_like(gate.W_g[0].weight), torch.empty_like(gate.W_x[0].weight)
+        gWg = self.gbuf(prefix + ".W_g.0.weight", gate.W_g[0].weight)
+        gWx = self.gbuf(prefix + ".W_x.0.weight", gate.W_x[0].weight)
         self.wgrad(N, H, W, dyg, s["g"], 1, 0, False, gWg)        # after the data gradients (see rb_backward)
         self.wgrad(N, H, W, dyx, s["skip"], 1, 0, False, gWx)
         grads[prefix + ".W_g.0.weight"], grads[prefix + ".W_x.0.weight"] = gWg, gWx
@@ -605,7 +634,7 @@ class Engine:
         conv_gemm(N, H, W, segs[:2], x.C, dx)
         conv_gemm(N, H, W, segs[2:], x.C, dx, addend=dx)
         for i, cv in enumerate(convs):          # weight gradients after the data gradients (see rb_backward)
-            g = torch.empty_like(cv.weight)
+            g = self.gbuf(f"{prefix}.conv{i + 1}.weight", cv.weight)
             self.wgrad(N, H, W, segs[i][0], x, segs[i][2], cv.dilation[0], False, g)
             grads[f"{prefix}.conv{i + 1}.weight"] = g
             grads[f"{prefix}.conv{i + 1}.bias"] = torch.zeros(Cq, device=dev)   # a bias before a train-mode BN
@@ -613,10 +642,13 @@ class Engine:
 
     # ------------------------------------------------------------------ whole model
     def forward(self, x: torch.Tensor, training: bool, save: bool):
+        if not x.is_cuda:
+            raise RuntimeError("rbunet.RobustUNet runs on CUDA tensors only (no CPU fallback)")
         self._pending_counters = []
         self._defer_counters = True
         try:
-            return self._forward_impl(x, training, save)
+            with torch.cuda.device(x.device):        # stream_ptr() and the library's per-device state follow the tensors
+                return self._forward_impl(x, training, save)
         finally:
             self.flush_counters()
 
@@ -700,6 +732,10 @@ class Engine:
     def backward(self, S, dprobs: torch.Tensor, allreduce_hook=None):
         """Returns {param_name: fp32 gradient}.  `allreduce_hook(names, grads)` is called as soon as the gradients
         of a top-level child are complete (reverse execution order) so data-parallel buckets can overlap."""
+        with torch.cuda.device(dprobs.device):
+            return self._backward_impl(S, dprobs, allreduce_hook)
+
+    def _backward_impl(self, S, dprobs: torch.Tensor, allreduce_hook=None):
         m = self.model
         grads = {}
         N, H, W = S["N"], S["H"], S["W"]
@@ -715,9 +751,11 @@ class Engine:
         grads["outc.0.weight"], grads["outc.0.bias"] = gw, gb
 
         def done(*prefixes):
+            # the hook gets an event behind the stage's weight-gradient kernels (side stream): the all-reduce waits for it
+            # on the communication stream, the compute stream never does
             if allreduce_hook is not None:
-                self.join_side(dev)
-                allreduce_hook([k for k in grads if any(k == p or k.startswith(p + ".") for p in prefixes)], grads)
+                allreduce_hook([k for k in grads if any(k == p or k.startswith(p + ".") for p in prefixes)], grads,
+                               self.side_event())
 
         done("outc")
         enc = S["enc"]
@@ -738,7 +776,7 @@ class Engine:
             call("rbu_chan_sum", _vp(dup), dup.ld, N * hk * wk, C, _p(gub), _p(ws), ws.numel() * 4, stream_ptr())
             d = self.new(N, su["H"], su["W"], su["x"].C, dev)
             conv_gemm(N, su["H"], su["W"], [(dup, self.pack(up.weight, 3), 4, 0, True)], su["x"].C, d)
-            guw = torch.empty_like(up.weight)
+            guw = self.gbuf(f"up{k}.weight", up.weight)
             self.wgrad(N, su["H"], su["W"], su["x"], dup, 4, 0, True, guw)
             grads[f"up{k}.bias"], grads[f"up{k}.weight"] = gub, guw
             done(f"dec{k}", f"att{k}", f"up{k}")

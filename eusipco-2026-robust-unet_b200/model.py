@@ -112,8 +112,14 @@ class _Graph(torch.autograd.Function):
     def backward(ctx, dprobs):
         model, state = ctx.model, ctx.state
         if state is None:
-            raise RuntimeError("backward through rbunet.RobustUNet without a saved forward state")
+            raise RuntimeError(
+                "rbunet.RobustUNet: backward needs a train-mode forward with gradients enabled.  Backward through an "
+                "eval-mode forward (running-statistics BatchNorm) is not implemented: the backward kernels apply the "
+                "batch-statistics BatchNorm formulas of Main_Final.py:573-582's training loop and would return wrong "
+                "gradients, so this raises instead")
         ctx.state = None
+        if model._grad_begin_hook is not None:
+            model._grad_begin_hook(model._engine)
         grads = model._engine.backward(state, dprobs, allreduce_hook=model._grad_ready_hook)
         if model._grad_transform is not None:
             grads = model._grad_transform(grads)
@@ -147,6 +153,7 @@ class RobustUNet(nn.Module):
         self.outc = nn.Sequential(nn.Conv2d(b, n_classes, 1), _Slot())
         self._initialize_weights()
         self._engine = Engine(self)
+        self._grad_begin_hook = None      # set by parallel.DataParallel: called with the engine when a backward starts
         self._grad_ready_hook = None      # set by parallel.DataParallel: called with the names of finished grads
         self._grad_transform = None       # set by parallel.DataParallel: swaps in the all-reduced gradients
 
@@ -166,6 +173,10 @@ class RobustUNet(nn.Module):
 
     def forward(self, x):
         params = tuple(self.parameters())
-        # grad mode is off inside autograd.Function.forward, so decide here whether to keep the backward state
-        save = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        if torch.is_grad_enabled() and x.requires_grad:
+            raise RuntimeError("rbunet.RobustUNet does not produce a gradient for its input (the first layer's data "
+                               "gradient is never computed); detach the input")
+        # grad mode is off inside autograd.Function.forward, so decide here whether to keep the backward state.  Only a
+        # train-mode forward keeps it: the backward kernels implement batch-statistics BatchNorm (see _Graph.backward)
+        save = self.training and torch.is_grad_enabled() and any(p.requires_grad for p in params)
         return _Graph.apply(self, save, x, *params)

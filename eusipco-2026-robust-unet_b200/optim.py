@@ -36,6 +36,7 @@ class FusedAdam(torch.optim.Optimizer):
             tab = np.zeros(len(ps), dtype=_JOB)
             first = 0
             step = None
+            keep = []                      # contiguous copies of strided gradients: alive until the launch is enqueued
             for i, p in enumerate(ps):
                 if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
                     raise RuntimeError("rbunet.FusedAdam needs contiguous fp32 CUDA parameters (no CPU fallback)")
@@ -48,7 +49,12 @@ class FusedAdam(torch.optim.Optimizer):
                 step = st["step"] if step is None else step
                 if st["step"] != step:
                     raise RuntimeError("rbunet.FusedAdam: parameters of one group must share the step count")
-                g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+                g = p.grad
+                if not g.is_contiguous():
+                    g = g.contiguous()
+                    keep.append(g)
+                if g.dtype != torch.float32 or g.device != p.device:
+                    raise RuntimeError("rbunet.FusedAdam needs fp32 gradients on the parameter's device")
                 tab[i] = (p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), first, p.numel())
                 first += (p.numel() + 1023) // 1024
             dev = ps[0].device
@@ -56,5 +62,7 @@ class FusedAdam(torch.optim.Optimizer):
             b1, b2 = group["betas"]
             call("rbu_adam_step", _p(dev_tab), len(ps), first, float(group["lr"]), float(b1), float(b2), float(group["eps"]),
                  float(group["weight_decay"]), int(step), stream_ptr())
-            self._keep = dev_tab        # the table must outlive the asynchronous launch
+            # the job table and the gradient copies must outlive the asynchronous launch: torch's caching allocator only
+            # hands their blocks to later allocations of the SAME stream, which are ordered behind the launch
+            self._keep = (dev_tab, keep)
         return loss

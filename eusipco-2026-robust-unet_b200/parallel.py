@@ -7,9 +7,11 @@ SyncBN), so the only exchange per step is the gradient all-reduce:
 
   * parameters are grouped into flat fp32 buckets in the order the engine finishes their gradients
     (outc, dec1/att1/up1, ..., dec4/att4/up4, bottleneck, down3, down2, down1, inc);
-  * when the engine reports a stage finished (`Engine.backward(..., allreduce_hook=...)`), its gradients are copied
-    into their bucket slices; a bucket whose members are all present is all-reduced (average) on a dedicated
-    communication stream while the compute stream carries on with the next stage's kernels;
+  * the weight-gradient GEMMs write straight into their bucket slices (`Engine.grad_alloc`); when the engine reports a
+    stage finished (`Engine.backward(..., allreduce_hook=...)`) only the small per-channel gradients are copied (one
+    multi-tensor launch per stage).  A bucket whose members are all present is all-reduced (average) on a dedicated
+    communication stream, which waits for the compute stream AND for the weight-gradient side stream through events --
+    the compute stream itself never waits and carries on with the next stage's kernels;
   * at the end of the backward the compute stream waits for the communication stream and the parameters receive
     views of the reduced buckets as `.grad`.
 
@@ -68,18 +70,46 @@ class GradBucketer:
         self.pending = [set(m) for m in self.bucket_members]
         self.works = []
         self.launched = [False] * len(self.flat)
+        self.side_events = [None] * len(self.flat)
+
+    def slot_view(self, name: str, shape=None):
+        """The bucket slice that holds `name`'s gradient, shaped like the parameter (the engine's weight-gradient kernels
+        write into it directly); None for a parameter outside the buckets."""
+        ent = self.slots.get(name)
+        if ent is None:
+            return None
+        b, off, numel = ent
+        shp = self.shapes[name] if shape is None else shape
+        if int(torch.Size(shp).numel()) != numel:
+            return None
+        return self.flat[b][off:off + numel].view(shp)
 
     # -- called by the engine hook -------------------------------------------------------------
-    def ready(self, names: Iterable[str], grads: Dict[str, torch.Tensor]):
+    def ready(self, names: Iterable[str], grads: Dict[str, torch.Tensor], side_event=None):
+        """`grads[n]` is complete for every n in names (on the current stream, or -- for tensors written by kernels of
+        another stream -- behind `side_event`).  Gradients that already live in their bucket slice are not copied."""
         touched = set()
+        dsts, srcs = [], []
         for n in names:
             if n not in self.slots:
                 continue
             b, off, numel = self.slots[n]
-            self.flat[b][off:off + numel].copy_(grads[n].reshape(-1))
+            g = grads[n]
+            dst = self.flat[b][off:off + numel]
+            if g.data_ptr() != dst.data_ptr():
+                dsts.append(dst)
+                srcs.append(g.reshape(-1))
             self.pending[b].discard(n)
             touched.add(b)
+        if dsts:
+            if self.cuda:
+                torch._foreach_copy_(dsts, srcs)           # one multi-tensor launch for the stage's small gradients
+            else:
+                for d, s_ in zip(dsts, srcs):
+                    d.copy_(s_)
         for b in sorted(touched):
+            if side_event is not None:
+                self.side_events[b] = side_event            # the side stream is in-order: the latest event covers the rest
             if not self.pending[b] and not self.launched[b]:
                 self._launch(b)
 
@@ -93,6 +123,8 @@ class GradBucketer:
             ev.record(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(self.comm_stream):
                 self.comm_stream.wait_event(ev)
+                if self.side_events[b] is not None:
+                    self.comm_stream.wait_event(self.side_events[b])
                 self.works.append(dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=self.pg, async_op=True))
         else:  # gloo has no AVG
             self.works.append((dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.pg, async_op=True), buf))
@@ -131,8 +163,30 @@ class DataParallel(nn.Module):
             dist.broadcast(t.data, src=0, group=process_group)
         self.bucketer = GradBucketer([(n, p.shape) for n, p in module.named_parameters() if p.requires_grad], dev,
                                      process_group, bucket_bytes)
+        self._params = [p for p in module.parameters() if p.requires_grad]
+        module._grad_begin_hook = self._begin
         module._grad_ready_hook = self.bucketer.ready
-        module._grad_transform = lambda grads: self.bucketer.finish()
+        module._grad_transform = self._finish
+
+    def _detach_surviving_grads(self):
+        """The gradients handed to autograd are views of the flat buckets, which the next backward overwrites.  A .grad
+        that survived (zero_grad(set_to_none=False), gradient accumulation) would be overwritten and then accumulated
+        into itself (2x): give such a .grad its own storage before the buckets are touched."""
+        lo_hi = [(b.data_ptr(), b.data_ptr() + b.numel() * 4) for b in self.bucketer.flat]
+        for p in self._params:
+            g = p.grad
+            if g is not None and any(lo <= g.data_ptr() < hi for lo, hi in lo_hi):
+                p.grad = g.clone()
+
+    def _begin(self, engine):
+        """Start of a backward pass: surviving .grad views leave the buckets, then the engine's weight-gradient kernels
+        are pointed at the bucket slices."""
+        self._detach_surviving_grads()
+        engine.grad_alloc = self.bucketer.slot_view
+
+    def _finish(self, grads):
+        self.module._engine.grad_alloc = None
+        return self.bucketer.finish()
 
     def forward(self, x):
         if self.broadcast_buffers and self.training:

@@ -138,7 +138,8 @@ int rbu_pack_weights_multi(const rbu_pack_job* jobs_device, int njobs, long long
 
 /* Fused multi-tensor Adam with coupled L2 weight decay = torch.optim.Adam(params, lr, betas, eps, weight_decay) as used
  * by the reference (Main_Final.py:552,582), one launch for all parameter tensors.  `jobs_device`: DEVICE array sorted by
- * first_block (1024 elements per block); step is the 1-based step count of the bias corrections. */
+ * first_block (1024 elements per block); step is the 1-based step count of the bias corrections.  Hyper-parameters are
+ * doubles: torch evaluates 1-beta^t, lr/(1-beta1^t) and sqrt(1-beta2^t) in Python doubles and only then rounds to fp32. */
 typedef struct {
   float* param;
   const float* grad;
@@ -147,8 +148,8 @@ typedef struct {
   long long first_block;
   long long numel;
 } rbu_adam_job;
-int rbu_adam_step(const rbu_adam_job* jobs_device, int njobs, long long total_blocks, float lr, float beta1, float beta2,
-                  float eps, float weight_decay, int step, void* stream);
+int rbu_adam_step(const rbu_adam_job* jobs_device, int njobs, long long total_blocks, double lr, double beta1, double beta2,
+                  double eps, double weight_decay, int step, void* stream);
 
 /* TEST-ONLY device reference: direct (CUDA-core) convolution, bf16 NHWC in, fp32 torch-layout weights
  * (rounded to bf16 on the fly), fp32 dense NHWC out.  Used by the parity tests at sizes where the CPU

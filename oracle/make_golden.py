@@ -277,10 +277,21 @@ def imageops_golden():
     print("imageops goldens:", len(out), "arrays")
 
 
+def base64_goldens(MF):
+    """The reference's own width (base 64, up to 1024 channels, Main_Final.py:229) at sizes whose fixtures stay small:
+    probabilities in full, gradients as per-tensor (norm, sum, first 8 values) summaries of all 173 parameters."""
+    model_golden(MF, "c3_b64_64x64", 3, 64, 2, 64, 64)
+    model_golden(MF, "c4_b64_64x96", 4, 64, 2, 64, 96, w_dice=0.5)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
     MF = load_reference()
+    if sys.argv[1:] == ["base64"]:          # only the base-64 fixtures (the others are unchanged)
+        base64_goldens(MF)
+        return
+    base64_goldens(MF)
     model_golden(MF, "c3_b16_32x32", 3, 16, 2, 32, 32)
     model_golden(MF, "c4_b16_32x48", 4, 16, 2, 32, 48, w_dice=0.5)
     module_goldens(MF)

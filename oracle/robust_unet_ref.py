@@ -195,9 +195,11 @@ def attention_gate(sd, prefix, g, x, training, new_buffers=None, st=FP32):
 
 
 def robust_unet_forward(sd, x, training=False, drop_masks: Optional[dict] = None,
-                        new_buffers: Optional[dict] = None, return_logits=False, st=FP32):
+                        new_buffers: Optional[dict] = None, return_logits=False, st=FP32, fp32_head=False):
     """RobustUNet.forward (Main_Final.py:290-321).  Concat order is [gated skip, upsampled]
-    (:303,308,313,318).  Returns probabilities [B,1,H,W] (sigmoid inside `outc`, :274-277)."""
+    (:303,308,313,318).  Returns probabilities [B,1,H,W] (sigmoid inside `outc`, :274-277).
+    `fp32_head`: evaluate `outc` + sigmoid in fp32 outside any enclosing torch.autocast region (the bf16-autocast
+    yardstick of SURVEY.md §8c: bf16-rounded logits saturate the BCE, so the head stays fp32 as on the device)."""
     dm = drop_masks or {}
 
     def rb(prefix, t):
@@ -214,6 +216,10 @@ def robust_unet_forward(sd, x, training=False, drop_masks: Optional[dict] = None
         t = st.act(F.conv_transpose2d(t, st.weight(sd[f"up{k}.weight"]), sd[f"up{k}.bias"], stride=2))
         att = attention_gate(sd, f"att{k}", t, skip, training, new_buffers, st)
         t = rb(f"dec{k}", torch.cat([att, t], dim=1))
+    if fp32_head:
+        with torch.autocast(device_type=t.device.type, enabled=False):
+            z = F.conv2d(t.float(), sd["outc.0.weight"].float(), sd["outc.0.bias"].float())
+            return z if return_logits else torch.sigmoid(z)
     z = F.conv2d(t, sd["outc.0.weight"], sd["outc.0.bias"])
     return z if return_logits else torch.sigmoid(z)
 

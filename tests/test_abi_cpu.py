@@ -62,3 +62,20 @@ def test_state_dict_schema_and_init_match_the_reference_schema():
         for k, v in sd.items():
             assert tuple(v.shape) == tuple(shapes[k]), k
     assert sum(p.numel() for p in rbunet.RobustUNet(3).parameters()) == 40872223
+
+
+def test_bench_input_generator_matches_the_oracle_generator():
+    """bench.py's product arm uses tools/synthetic.py (no oracle import); it must produce the oracle's tensors."""
+    import torch
+    from oracle import robust_unet_ref as R
+    from tools.synthetic import synthetic_batch
+    for (b, c, h, w, seed) in ((2, 3, 32, 48, 123), (1, 4, 16, 16, 7)):
+        x, y = synthetic_batch(b, c, h, w, seed=seed)
+        xo, yo = R.synthetic_inputs(b, c, h, w, seed=seed, blobby=True)
+        assert torch.equal(x, xo) and torch.equal(y, yo)
+
+
+def test_bench_product_arm_does_not_import_the_oracle():
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    own = src[src.index("class Env"):src.index("def load_reference_module")]
+    assert "oracle" not in own

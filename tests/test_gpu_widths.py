@@ -1,0 +1,255 @@
+"""GPU parity at the widths and tile counts the product configuration actually runs (base 64: 64 ... 1024 channels,
+K = 9 * 1024 = 9 216, many tiles per persistent CTA), plus the routing / RNG details the reference inherits from torch:
+first-maximum routing of MaxPool2d / AdaptiveMaxPool2d / torch.max on ties, and nn.Dropout2d's RNG stream.
+
+Every residual-block case is compared with the oracle run with the device's bf16 storage points (logic check, tight)
+and the convolution / weight-gradient cases with torch CPU fp32 on the same bf16-rounded operands."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from gpu_util import Report, bf16r, from_view, rel_l2, to_view
+from oracle import robust_unet_ref as R
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(shape, generator=g) * scale
+
+
+# ----------------------------------------------------------------------------------------------- residual blocks
+def _rb_shapes(cin, cout):
+    s = {"conv1.weight": (cout, cin, 3, 3), "conv2.weight": (cout, cout, 3, 3),
+         "ca.fc.0.weight": (cout // 16, cout, 1, 1), "ca.fc.2.weight": (cout, cout // 16, 1, 1),
+         "sa.conv1.weight": (1, 2, 7, 7)}
+    for bn in ("bn1", "bn2") + (("shortcut.1",) if cin != cout else ()):
+        s.update({f"{bn}.weight": (cout,), f"{bn}.bias": (cout,), f"{bn}.running_mean": (cout,),
+                  f"{bn}.running_var": (cout,), f"{bn}.num_batches_tracked": ()})
+    if cin != cout:
+        s["shortcut.0.weight"] = (cout, cin, 1, 1)
+    return s
+
+
+RB_CASES = [
+    # name, N, Cin, Cout, H, W, p      what it reaches
+    ("64_128_at128", 2, 64, 128, 128, 128, 0.1),      # epilogue tile statistics, block_n 128, projection shortcut
+    ("1024_1024_at16", 2, 1024, 1024, 16, 16, 0.3),   # bottleneck.2: K = 9 216, identity shortcut, one tile per image
+    ("1024_512_at32", 2, 1024, 512, 32, 32, 0.2),     # dec4: concat-wide input, K = 9 216 -> 512
+    ("64_64_at256_b8", 8, 64, 64, 256, 256, 0.1),     # resident weights, 2 048 tiles: ~14 tiles per persistent CTA
+    ("128_64_at64_ragged", 3, 128, 64, 48, 80, 0.1),  # dec1-like, H and W not multiples of the 16 x 16 tile pair
+]
+
+
+@pytest.mark.parametrize("case", RB_CASES, ids=[c[0] for c in RB_CASES])
+def test_residual_block_at_product_widths(case):
+    from rbunet.engine import Engine
+    from rbunet.model import ResidualBlock
+    name, N, Cin, Cout, H, W, pdrop = case
+    dev = torch.device(DEV)
+    sd = R.synthetic_state_dict(_rb_shapes(Cin, Cout), seed=11)
+    blk = ResidualBlock(Cin, Cout, pdrop)
+    blk.load_state_dict(sd)
+    blk.to(dev).train()
+    eng = Engine(None)
+    u = torch.from_numpy(R._hash_uniform(N * Cout, 41)).float().reshape(N, Cout, 1, 1)
+    mask = (u >= pdrop).float() / (1.0 - pdrop)
+    eng.drop_mask_fn = lambda nm, n_, c_: mask
+    x = F.relu(_rand((N, Cin, H, W), 5))              # block inputs are post-ReLU tensors in the network
+    gout = _rand((N, Cout, H, W), 6, scale=1e-3)
+    out, st = eng.rb_forward("b", blk, to_view(x, dev), N, H, W, True)
+    grads = {}
+    dx = eng.rb_backward(blk, st, to_view(gout, dev), grads, "b")
+    torch.cuda.synchronize()
+    qsd = {"b." + k: v.clone() for k, v in sd.items()}
+    for k, v in qsd.items():
+        if v.is_floating_point() and "running" not in k:
+            v.requires_grad_(True)
+    xq = bf16r(x).requires_grad_(True)
+    nb = {}
+    oq = R.residual_block(qsd, "b", R.BF16.act(xq), True, mask, nb, st=R.BF16)
+    oq.backward(bf16r(gout))
+    rep = Report()
+    rep.check("out vs bf16-storage oracle", from_view(out), oq.detach(), 5e-3)
+    rep.check("dx vs bf16-storage oracle", from_view(dx), xq.grad, 2e-2)
+    for k, v in grads.items():
+        rep.check(k + " vs bf16-storage oracle", v.cpu(), qsd[k].grad, 2e-2)
+    # forward against plain fp32 arithmetic: the north-star bf16 tolerance
+    of = R.residual_block({k: v.detach() for k, v in qsd.items()}, "b", x, True, mask)
+    rep.check("out vs fp32 oracle (rel-L2 <= 1e-2)", from_view(out), of, 1e-2)
+    for k, v in nb.items():
+        got = dict(blk.state_dict())[k[2:]].cpu()
+        if v.dtype == torch.int64:
+            assert int(got) == int(v), k
+        else:
+            rep.check(k, got, v, 5e-3)
+    rep.finish()
+
+
+# ----------------------------------------------------------------------------------------------- K = 9 216 GEMMs
+CONV_CASES = [
+    # name, N, H, W, Cin, Cout, ksz, dil
+    ("3x3_1024_1024_at16", 2, 16, 16, 1024, 1024, 3, 1),
+    ("3x3_1024_512_at32", 2, 32, 32, 1024, 512, 3, 1),
+    ("3x3_512_256_d4_at16", 2, 16, 16, 512, 256, 3, 4),
+    ("1x1_1024_512", 2, 32, 32, 1024, 512, 1, 1),
+    ("3x3_64_64_at256_many_tiles", 6, 256, 256, 64, 64, 3, 1),
+    ("3x3_128_128_at128", 4, 128, 128, 128, 128, 3, 1),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+def test_conv_forward_dgrad_wgrad_at_product_widths(case):
+    from rbunet import ops
+    from rbunet.engine import Engine
+    name, N, H, W, Cin, Cout, ksz, dil = case
+    dev = torch.device(DEV)
+    pad = dil * (ksz // 2)
+    x = bf16r(_rand((N, Cin, H, W), 1)).requires_grad_(True)
+    w = bf16r(_rand((Cout, Cin, ksz, ksz), 2, scale=(1.0 / (Cin * ksz * ksz)) ** 0.5)).requires_grad_(True)
+    dy = bf16r(_rand((N, Cout, H, W), 3))
+    y = F.conv2d(x, w, padding=pad, dilation=dil)
+    y.backward(dy)
+    xv, dyv = to_view(x.detach(), dev), to_view(dy, dev)
+    wd = w.detach().to(dev).contiguous()
+    yo = ops.View(torch.empty((N, H, W, Cout), dtype=torch.bfloat16, device=dev))
+    ops.conv_gemm(N, H, W, [(xv, ops.pack_weight(wd, 0), ksz * ksz, dil if ksz == 3 else 0, False)], Cout, yo)
+    dxo = ops.View(torch.empty((N, H, W, Cin), dtype=torch.bfloat16, device=dev))
+    ops.conv_gemm(N, H, W, [(dyv, ops.pack_weight(wd, 1), ksz * ksz, dil if ksz == 3 else 0, False)], Cin, dxo)
+    gw = torch.empty((Cout, Cin, ksz, ksz), device=dev)
+    eng = Engine(None)
+    eng.wgrad(N, H, W, dyv, xv, ksz * ksz, dil if ksz == 3 else 0, False, gw)
+    torch.cuda.synchronize()
+    assert rel_l2(from_view(yo), y.detach()) < 4e-3, name              # one bf16 rounding of the output
+    assert rel_l2(from_view(dxo), x.grad) < 4e-3, name
+    assert rel_l2(gw, w.grad) < 1e-4, name                             # fp32 out: accumulation order only
+
+
+def test_conv_transpose_1024_512():
+    from rbunet import ops
+    from rbunet.engine import Engine
+    dev = torch.device(DEV)
+    N, H, W, Cin, Cout = 2, 16, 16, 1024, 512
+    x = bf16r(_rand((N, Cin, H, W), 7)).requires_grad_(True)
+    w = bf16r(_rand((Cin, Cout, 2, 2), 8, scale=0.03)).requires_grad_(True)
+    b = _rand((Cout,), 9)
+    dout = bf16r(_rand((N, Cout, 2 * H, 2 * W), 10))
+    F.conv_transpose2d(x, w, b, stride=2).backward(dout)
+    ref = F.conv_transpose2d(x, w, b, stride=2).detach()
+    cat = torch.zeros((N, 2 * H, 2 * W, 2 * Cout), dtype=torch.bfloat16, device=dev)
+    wd = w.detach().to(dev).contiguous()
+    ops.conv_gemm(N, H, W, [(to_view(x.detach(), dev), ops.pack_weight(wd, 2), 1, 0, False)], 4 * Cout,
+                  ops.View(cat, Cout, Cout), scatter=True, Cout=Cout, bias=b.to(dev))
+    dcat = to_view(dout, dev, ld=2 * Cout, off=Cout)
+    dx = ops.View(torch.empty((N, H, W, Cin), dtype=torch.bfloat16, device=dev))
+    ops.conv_gemm(N, H, W, [(dcat, ops.pack_weight(wd, 3), 4, 0, True)], Cin, dx)
+    gw = torch.empty((Cin, Cout, 2, 2), device=dev)
+    Engine(None).wgrad(N, H, W, to_view(x.detach(), dev), dcat, 4, 0, True, gw)
+    torch.cuda.synchronize()
+    assert rel_l2(from_view(ops.View(cat, Cout, Cout)), ref) < 4e-3
+    assert rel_l2(from_view(dx), x.grad) < 4e-3
+    assert rel_l2(gw, w.grad) < 1e-4
+
+
+# ----------------------------------------------------------------------------------------------- tie routing
+def test_maxpool_routes_to_the_first_maximum_on_ties():
+    """nn.MaxPool2d(2) backward (Main_Final.py:235-249): ties inside a 2 x 2 window send the gradient to the first
+    maximal element in row-major order, as torch does; values drawn from {0, 1, 2} make ties the rule."""
+    from rbunet._lib import call, stream_ptr
+    from ctypes import c_void_p
+    dev = torch.device(DEV)
+    N, C, Ho, Wo = 2, 16, 6, 10
+    g = torch.Generator().manual_seed(3)
+    x = torch.randint(0, 3, (N, C, 2 * Ho, 2 * Wo), generator=g).float().requires_grad_(True)
+    dy = bf16r(torch.randn((N, C, Ho, Wo), generator=g))
+    F.max_pool2d(x, 2).backward(dy)
+    xv, dyv = to_view(x.detach(), dev), to_view(dy, dev)
+    yv = to_view(torch.zeros((N, C, Ho, Wo)), dev)
+    call("rbu_maxpool2x2", c_void_p(xv.ptr), xv.ld, c_void_p(yv.ptr), yv.ld, N, Ho, Wo, C, stream_ptr())
+    assert torch.equal(from_view(yv), F.max_pool2d(x.detach(), 2))
+    base = bf16r(torch.randn((N, C, 2 * Ho, 2 * Wo), generator=g))
+    for accumulate in (0, 1):
+        dxv = to_view(base, dev)
+        call("rbu_maxpool2x2_bwd", c_void_p(xv.ptr), xv.ld, c_void_p(dyv.ptr), dyv.ld, c_void_p(dxv.ptr), dxv.ld, N, Ho, Wo, C,
+             accumulate, stream_ptr())
+        torch.cuda.synchronize()
+        want = x.grad + base if accumulate else x.grad
+        assert torch.equal(from_view(dxv), bf16r(want)), accumulate
+
+
+def test_attention_max_routing_on_exact_ties():
+    """ChannelAttention's AdaptiveMaxPool2d(1) and SpatialAttention's torch.max(dim=1) (Main_Final.py:99,114) route
+    the gradient to the FIRST maximal pixel / LOWEST maximal channel on exact ties.  Duplicated output channels of conv2
+    (identical weights and BatchNorm parameters => bit-identical columns) create exact channel ties at every pixel and a
+    spatially periodic input creates exact pixel ties; a wrong tie rule moves O(1) of the conv2 weight gradient."""
+    from rbunet.engine import Engine
+    from rbunet.model import ResidualBlock
+    dev = torch.device(DEV)
+    N, C, H, W = 2, 32, 16, 16
+    sd = R.synthetic_state_dict(_rb_shapes(C, C), seed=13)
+    sd["bn2.weight"] = sd["bn2.weight"].abs()
+    for k in ("conv2.weight", "bn2.weight", "bn2.bias", "ca.fc.2.weight"):      # channel c+16 := channel c
+        sd[k][16:] = sd[k][:16]
+    sd["ca.fc.0.weight"][:, 16:] = sd["ca.fc.0.weight"][:, :16]
+    blk = ResidualBlock(C, C, 0.0)
+    blk.load_state_dict(sd)
+    blk.to(dev).train()
+    eng = Engine(None)
+    tile = F.relu(_rand((N, C, 4, 4), 21))
+    x = bf16r(tile.repeat(1, 1, 4, 4))                  # period 4 in both directions: interior pixels repeat exactly
+    gout = bf16r(_rand((N, C, H, W), 22, scale=1e-2))
+    out, st = eng.rb_forward("b", blk, to_view(x, dev), N, H, W, True)
+    grads = {}
+    dx = eng.rb_backward(blk, st, to_view(gout, dev), grads, "b")
+    torch.cuda.synchronize()
+    qsd = {"b." + k: v.clone() for k, v in sd.items()}
+    for k, v in qsd.items():
+        if v.is_floating_point() and "running" not in k:
+            v.requires_grad_(True)
+    xq = x.clone().requires_grad_(True)
+    oq = R.residual_block(qsd, "b", R.BF16.act(xq), True, None, st=R.BF16)
+    oq.backward(gout)
+    # the construction really produces exact ties in the oracle arithmetic: ~6 tied maximal pixels per (n,c) for the
+    # AdaptiveMaxPool2d and exactly two tied maximal channels at every pixel for torch.max(dim=1)
+    with torch.no_grad():
+        q0 = {k: v.detach() for k, v in qsd.items()}
+        a1 = R.BF16.act(F.relu(R.batch_norm(q0, "b.bn1", R.BF16.act(F.conv2d(x, R.BF16.weight(q0["b.conv1.weight"]), padding=1)), True)))
+        y2 = R.BF16.act(F.conv2d(a1, R.BF16.weight(q0["b.conv2.weight"]), padding=1))
+        bq = R.batch_norm(q0, "b.bn2", y2, True)
+        cq = R.channel_attention(q0, "b.ca", bq)
+        assert ((y2.flatten(2) == y2.flatten(2).max(2, keepdim=True).values).sum(2) >= 2).float().mean() > 0.9
+        assert ((cq == cq.max(1, keepdim=True).values).sum(1) == 2).all()
+    rep = Report()
+    rep.check("out", from_view(out), oq.detach(), 5e-3)
+    rep.check("dx", from_view(dx), xq.grad, 2e-2)
+    for k in ("b.conv2.weight", "b.bn2.weight", "b.bn2.bias", "b.conv1.weight", "b.ca.fc.2.weight"):
+        rep.check(k, grads[k].cpu(), qsd[k].grad, 2e-2)
+    rep.finish()
+
+
+# ----------------------------------------------------------------------------------------------- dropout RNG stream
+def test_dropout_masks_follow_the_dropout2d_rng_stream():
+    """Without injected masks the engine draws the nine Dropout2d channel masks exactly as nn.Dropout2d does on CUDA
+    (Main_Final.py:162,184: one [N,C,1,1] Bernoulli(1-p) noise tensor per block from the default CUDA generator, scaled
+    by 1/(1-p)), in the reference's module execution order -- so a seeded training run consumes the same RNG stream."""
+    import rbunet
+    dev = torch.device(DEV)
+    torch.manual_seed(0)
+    model = rbunet.RobustUNet(3, 1, 64).to(dev).train()
+    N = 3
+    x, _ = R.synthetic_inputs(N, 3, 32, 32, seed=9)
+    torch.manual_seed(1234)
+    eng = model.engine
+    probs, S = eng.forward(x.to(dev), True, True)
+    torch.cuda.synchronize()
+    order = [("inc", "inc", 64), ("down1", "down1.1", 128), ("down2", "down2.1", 256), ("down3", "down3.1", 512),
+             ("bott", "bottleneck.2", 1024), ("dec4", "dec4", 512), ("dec3", "dec3", 256), ("dec2", "dec2", 128),
+             ("dec1", "dec1", 64)]
+    torch.manual_seed(1234)
+    for key, name, C in order:
+        drop = torch.nn.Dropout2d(R.DROPOUT_P[name]).train()
+        want = drop(torch.ones((N, C, 2, 2), device=dev))[:, :, 0, 0]          # the reference module itself
+        got = S[key]["drop"]
+        assert torch.equal(got, want), name

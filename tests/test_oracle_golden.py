@@ -21,7 +21,8 @@ def _run_model(g, training):
     return sd, x, y, masks, base
 
 
-@pytest.mark.parametrize("name", ["model_c3_b16_32x32.npz", "model_c4_b16_32x48.npz"])
+@pytest.mark.parametrize("name", ["model_c3_b16_32x32.npz", "model_c4_b16_32x48.npz", "model_c3_b64_64x64.npz",
+                                  "model_c4_b64_64x96.npz"])
 def test_model_eval_matches_reference_golden(golden_dir, name):
     g = _load(golden_dir, name)
     sd, x, y, _, _ = _run_model(g, False)
@@ -38,7 +39,8 @@ def test_model_eval_matches_reference_golden(golden_dir, name):
             assert abs(m[str(k)] - g["metrics_eval"][i, j]) < 1e-12
 
 
-@pytest.mark.parametrize("name", ["model_c3_b16_32x32.npz", "model_c4_b16_32x48.npz"])
+@pytest.mark.parametrize("name", ["model_c3_b16_32x32.npz", "model_c4_b16_32x48.npz", "model_c3_b64_64x64.npz",
+                                  "model_c4_b64_64x96.npz"])
 def test_model_train_step_matches_reference_golden(golden_dir, name):
     g = _load(golden_dir, name)
     sd, x, y, masks, _ = _run_model(g, True)
