@@ -51,7 +51,8 @@ class Engine:
         self._side_stream = None
         self._side_ws = None
         self._side_dirty = False
-        self._side_keep = []          # [(event recorded behind a side-stream kernel, tensors it reads / writes)]
+        self._side_keep = []          # tensors read / written by side-stream kernels the compute stream is not yet ordered behind
+        self._side_mark = None        # (event, len(_side_keep)) of the previous stage boundary
         self.grad_alloc = None        # optional callable(name, shape) -> fp32 tensor to receive that parameter's gradient
                                       # (parallel.DataParallel: a slice of a flat all-reduce bucket), or None
         self._saving = False
@@ -73,6 +74,8 @@ class Engine:
         self._defer_counters = False     # whole-model forward: the 39 num_batches_tracked increments become one launch
         self._pending_counters = []
         self.drop_mask_fn = None     # optional callable(name, N, C) -> float32 [N,C] device tensor (tests)
+        self.keep_logits = False     # tests: also keep the fp32 logits of the head in self.last_logits
+        self.last_logits = None
         self.kernel_launches = 0
 
     # ------------------------------------------------------------------ helpers
@@ -286,14 +289,25 @@ class Engine:
         if self._side_stream is not None and self._side_dirty:
             torch.cuda.current_stream(device).wait_stream(self._side_stream)
             self._side_dirty = False
-            self._side_keep.clear()      # operands may be recycled now: later main-stream work is ordered after the join
+        self._side_keep.clear()      # operands may be recycled now: later main-stream work is ordered after the join
+        self._side_mark = None
 
-    def side_event(self):
-        """An event behind everything enqueued on the weight-gradient stream so far (None if nothing is pending)."""
+    def stage_boundary(self, device):
+        """End of a backward stage.  Returns an event behind the weight-gradient kernels enqueued so far (None if there
+        are none) -- the data-parallel all-reduce of the stage waits for it on the communication stream.  Operand
+        memory is released with a lag of ONE stage: the compute stream waits for the event of the PREVIOUS boundary
+        (normally long complete: the side stream trails by a few kernels) and drops the references held up to there.
+        Release points are fixed in program order, so the caching allocator sees the same request sequence every step
+        (releasing on event polls made cudaMalloc calls appear in random steps)."""
         if self._side_stream is None or not self._side_dirty:
             return None
         ev = torch.cuda.Event()
         ev.record(self._side_stream)
+        if self._side_mark is not None:
+            prev_ev, count = self._side_mark
+            torch.cuda.current_stream(device).wait_event(prev_ev)
+            del self._side_keep[:count]
+        self._side_mark = (ev, len(self._side_keep))
         return ev
 
     def gbuf(self, name, like: torch.Tensor):
@@ -310,16 +324,11 @@ class Engine:
             main = torch.cuda.current_stream(dev)
             side = self._side(dev)
             side.wait_stream(main)                       # operands were produced on the main stream
-            # operands were allocated under the main stream: keep them referenced until the side-stream kernel that reads
-            # them has finished (polled, never waited for), so the allocator cannot hand their memory to later main-stream work
-            keep = self._side_keep
-            while keep and keep[0][0].query():
-                keep.pop(0)
+            # operands were allocated under the main stream: they stay referenced until a stage boundary has ordered the
+            # compute stream behind this kernel (stage_boundary / join_side), so their memory cannot be recycled early
+            self._side_keep.extend((a.base, b.base, out))
             with torch.cuda.stream(side):
                 self._wgrad(N, H, W, a, b, taps, dil, gather, out, self._side_ws)
-                ev = torch.cuda.Event()
-                ev.record(side)
-            keep.append((ev, (a.base, b.base, out)))
             self._side_dirty = True
         else:
             self._wgrad(N, H, W, a, b, taps, dil, gather, out, None)
@@ -724,7 +733,9 @@ class Engine:
         P = N * H * W
         probs = torch.empty((N, 1, H, W), dtype=torch.float32, device=dev)
         hc = m.outc[0]
-        call("rbu_head_forward", _vp(cur), cur.ld, P, cur.C, _p(hc.weight), _p(hc.bias), _p(probs), NULL, stream_ptr())
+        logits = torch.empty_like(probs) if self.keep_logits else None
+        call("rbu_head_forward", _vp(cur), cur.ld, P, cur.C, _p(hc.weight), _p(hc.bias), _p(probs), _p(logits), stream_ptr())
+        self.last_logits = logits
         S["head_x"] = cur
         S["probs"] = probs
         return probs, (S if save else None)
@@ -752,10 +763,10 @@ class Engine:
 
         def done(*prefixes):
             # the hook gets an event behind the stage's weight-gradient kernels (side stream): the all-reduce waits for it
-            # on the communication stream, the compute stream never does
+            # on the communication stream; the compute stream only ever waits for the PREVIOUS stage's event
+            ev = self.stage_boundary(dev)
             if allreduce_hook is not None:
-                allreduce_hook([k for k in grads if any(k == p or k.startswith(p + ".") for p in prefixes)], grads,
-                               self.side_event())
+                allreduce_hook([k for k in grads if any(k == p or k.startswith(p + ".") for p in prefixes)], grads, ev)
 
         done("outc")
         enc = S["enc"]

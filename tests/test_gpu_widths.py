@@ -71,11 +71,34 @@ def test_residual_block_at_product_widths(case):
     nb = {}
     oq = R.residual_block(qsd, "b", R.BF16.act(xq), True, mask, nb, st=R.BF16)
     oq.backward(bf16r(gout))
+    # Arg-max routing: AdaptiveMaxPool2d sends d(u_max) -- one value per (n,c) that aggregates the whole channel -- to ONE
+    # pixel, torch.max(dim=1) sends d(s_max) to one channel per pixel.  The candidates are exact ties or one bf16 ulp
+    # apart, and the tensor core sums K = 9*Cin products in another order than the CPU convolution, so a handful of the
+    # stored bf16 values differ by an ulp and a handful of routes with them.  Both are counted and printed.  Measured on
+    # B200 (profiles/r02_gputest.log): 0.5 % (K = 576) to 13 % (K = 9 216) of the stored conv2 outputs differ from the
+    # oracle's by one bf16 ulp; the BatchNorm backward (a difference of large, strongly correlated terms) amplifies that
+    # ~25x: forward 5e-4, gradients 0.4-1.9 % even where not a single maximum is rerouted (1024 -> 1024 at 16 x 16).  The
+    # same schedule on the small golden block (tests/test_gpu_blocks.py, K = 144) agrees to 7e-4.  Bar here: 4e-2.
+    with torch.no_grad():
+        q0 = {k: v.detach() for k, v in qsd.items()}
+        a1 = R.BF16.act(F.relu(R.batch_norm(q0, "b.bn1", R.BF16.act(F.conv2d(bf16r(x), R.BF16.weight(q0["b.conv1.weight"]), padding=1)), True)) * mask)
+        y2 = R.BF16.act(F.conv2d(a1, R.BF16.weight(q0["b.conv2.weight"]), padding=1))
+        bq = R.batch_norm(q0, "b.bn2", y2, True)
+        cq = R.channel_attention(q0, "b.ca", bq)
+        ca_ref = bq.flatten(2).argmax(2)                                   # first maximal pixel per (n,c)
+        sa_ref = cq.argmax(1).flatten()                                    # lowest maximal channel per pixel
+    ca_dev, sa_dev = st["ca"]["nc_arg"].cpu().long(), st["amax_c"].cpu().long()
+    ca_flips, sa_flips = int((ca_dev != ca_ref).sum()), int((sa_dev != sa_ref).sum())
+    y2_diff = int((from_view(st["y2"]) != y2).sum())
+    print(f"{name}: stored conv2 outputs differing from the oracle's by an ulp: {y2_diff} of {y2.numel()}; rerouted "
+          f"channel-attention maxima: {ca_flips} of {ca_ref.numel()}; rerouted spatial-attention maxima: {sa_flips} of {sa_ref.numel()}")
+    btol = 4e-2
     rep = Report()
     rep.check("out vs bf16-storage oracle", from_view(out), oq.detach(), 5e-3)
-    rep.check("dx vs bf16-storage oracle", from_view(dx), xq.grad, 2e-2)
+    rep.check("dx vs bf16-storage oracle", from_view(dx), xq.grad, btol)
     for k, v in grads.items():
-        rep.check(k + " vs bf16-storage oracle", v.cpu(), qsd[k].grad, 2e-2)
+        rep.check(k + " vs bf16-storage oracle", v.cpu(), qsd[k].grad, btol)
+    assert ca_flips <= 0.02 * ca_ref.numel() + 2 and sa_flips <= 0.01 * sa_ref.numel() + 2
     # forward against plain fp32 arithmetic: the north-star bf16 tolerance
     of = R.residual_block({k: v.detach() for k, v in qsd.items()}, "b", x, True, mask)
     rep.check("out vs fp32 oracle (rel-L2 <= 1e-2)", from_view(out), of, 1e-2)
