@@ -107,6 +107,10 @@ __device__ __forceinline__ uint64_t pack_desc(uint32_t lo, uint32_t hi) {
 __device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) {
   return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
 }
+// same for SWIZZLE_64B operands (layout type 4; MN-major: 64 B = 32 bf16 of M/N per K-row, 8-row atoms of 512 B)
+__device__ __forceinline__ uint32_t desc_hi_sw64(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (4u << 29);
+}
 __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
   return ((saddr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
 }

@@ -16,6 +16,17 @@
 // Per tile: 46 KB from L2 for 9.4 MFLOP (205 FLOP/B), 40 MMAs per barrier round trip.
 // Split-K over tile ranges with fp32 partials and the ordered reduction of wgrad_gemm.cu (deterministic).
 // Replaces aten::convolution_backward(weight) of Main_Final.py:157,159,205-206.
+//
+// Second form (wgrad_halo2_kernel, used whenever Cout is a multiple of 128): the roles of the operands are swapped.
+// The form above runs M = 128 x N = 64 MMAs, which read 6 KB of operands from shared memory per 32 tensor-pipe cycles
+// (192 B/clk against the 128 B/clk the SM delivers: ncu l1tex__data_pipe_tc_wavefronts_mem_shared 81 %, tensor pipe
+// 50-61 %), and the 9 x 64 = 576 fp32 columns of a 64 x 64 x 9 block rule out N = 128 in the 512-column TMEM.  With
+//   * dy as the M side (128 output channels = two 64-channel boxes, leading-byte-offset = one box) and
+//   * the x halo as the N side, loaded with 32 channels per pixel (SWIZZLE_64B, 64-byte pixel pitch) so that the THREE
+//     taps of a kernel row are three 32-channel MN-atoms 64 bytes apart: N = 96 with leading-byte-offset = 64 B,
+// a work item is 128 output channels x 32 input channels x 9 taps = 3 accumulators x 96 columns (288 of 512), every MMA
+// is M128 x N96 x K16 (7 KB per 48 cycles = 146 B/clk) and the L2 traffic per FLOP is unchanged (47 KB per 9.4 MFLOP).
+// The epilogue thread (= output channel) reads, per tap, 32 consecutive input channels = one 128-byte run of the partials.
 #include "rbu_common.cuh"
 #include "rbu_ptx.cuh"
 #include "tma_host.cuh"
@@ -38,8 +49,7 @@ struct HWParams {
   int Cout, Cin;
   int cin_blocks, cout_blocks, ksplit, items;
   int stages;       // smem ring depth (<= MAX_STAGES)
-  int NB;           // output channels per work item: 64 (all nine taps, 5 accumulators) or 128 (taps 0-7, 4 accumulators of
-                    // 128 columns = the whole TMEM; tap 8 is left to the generic kernel)
+  int CB, OB;       // input / output channels per work item: 64 x 64 (wgrad_halo_kernel) or 32 x 128 (wgrad_halo2_kernel)
   float* partial;   // [ksplit][Cout][9][Cin]
 };
 
@@ -54,8 +64,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                   const __grid_constant__ HWParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int nbox = p.NB >> 6;                           // 64-channel dy boxes per stage
-  const int stage_bytes = X_BYTES + nbox * DY_BYTES;
+  constexpr int stage_bytes = STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
   uint64_t* full = bars;             // [MAX_STAGES]
   uint64_t* empty = bars + MAX_STAGES;   // [MAX_STAGES]
@@ -100,8 +109,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)stage_bytes);
           uint8_t* dst = smem + s * stage_bytes;
           ptx::tma_load_4d(dst, &tmX, &full[s], cb * 64, tw * TILE_W - 1, th * TILE_H - 1, n);
-          for (int j = 0; j < nbox; ++j)
-            ptx::tma_load_4d(dst + X_BYTES + j * DY_BYTES, &tmDy, &full[s], ob * p.NB + j * 64, tw * TILE_W, th * TILE_H, n);
+          ptx::tma_load_4d(dst + X_BYTES, &tmDy, &full[s], ob * 64, tw * TILE_W, th * TILE_H, n);
           if (++s == p.stages) { s = 0; ph ^= 1; }
           if (++tw == p.tiles_w) { tw = 0; if (++th == p.tiles_h) { th = 0; ++n; } }
         }
@@ -109,11 +117,10 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     }
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
-    const uint32_t idesc128 = ptx::make_idesc_bf16(128, p.NB, 1, 1);
+    const uint32_t idesc128 = ptx::make_idesc_bf16(128, 64, 1, 1);
     const uint32_t idesc64 = ptx::make_idesc_bf16(64, 64, 1, 1);
-    const bool wide = p.NB == 128;
-    const uint32_t nb_cols = (uint32_t)p.NB;
-    const uint32_t dy_lbo = ((uint32_t)(wide ? DY_BYTES : 1024) >> 4) << 16;   // distance between the two 64-channel dy boxes
+    constexpr uint32_t nb_cols = 64;
+    constexpr uint32_t dy_lbo = (1024u >> 4) << 16;              // unused for N = 64 (one 64-channel block)
     const uint32_t full_s = ptx::smem_u32(full), empty_s = ptx::smem_u32(empty);
     const uint32_t hi = ptx::desc_hi(1024);
     const uint32_t base_lo = (ptx::smem_u32(smem) & 0x3FFFFu) >> 4;
@@ -147,8 +154,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             ptx::umma_bf16(tmem_base + 1 * nb_cols, ptx::pack_desc((xr + 1 * ROW + 0 * 8) | LBO_DX, hi), db, idesc128, acc);
             ptx::umma_bf16(tmem_base + 2 * nb_cols, ptx::pack_desc((xr + 2 * ROW + 0 * 8) | LBO_DX, hi), db, idesc128, acc);
             ptx::umma_bf16(tmem_base + 3 * nb_cols, ptx::pack_desc((xr + 0 * ROW + 2 * 8) | LBO_DY, hi), db, idesc128, acc);
-            if (!wide)
-              ptx::umma_bf16(tmem_base + 4 * 64, ptx::pack_desc((xr + 2 * ROW + 2 * 8) | LBO_DX, hi), db, idesc64, acc);
+            ptx::umma_bf16(tmem_base + 4 * 64, ptx::pack_desc((xr + 2 * ROW + 2 * 8) | LBO_DX, hi), db, idesc64, acc);
           }
           ptx::umma_commit_s(empty_s + s * 8);
         }
@@ -169,8 +175,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       ptx::mbar_wait(tfull, it & 1);
       ptx::tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
-      const int nacc = p.NB == 128 ? 4 : NACC;
-      for (int a = 0; a < nacc; ++a) {
+      for (int a = 0; a < NACC; ++a) {
         // which (tap, cin) does this thread's TMEM lane hold?
         int tap, cl;
         bool ok = true;
@@ -185,17 +190,161 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         }
         const int cin = cb * 64 + cl;
         ok = ok && cin < p.Cin;
-        for (int c0 = 0; c0 < p.NB; c0 += 32) {
+        for (int c0 = 0; c0 < 64; c0 += 32) {
           uint32_t r[32];
-          ptx::tmem_ld_32x32(t_addr + (uint32_t)(a * p.NB + c0), r);
+          ptx::tmem_ld_32x32(t_addr + (uint32_t)(a * 64 + c0), r);
           ptx::tmem_ld_wait();
           if (ok) {
 #pragma unroll
             for (int e = 0; e < 32; ++e) {
-              const int cout = ob * p.NB + c0 + e;
+              const int cout = ob * 64 + c0 + e;
               if (cout < p.Cout) p.partial[(((long)ks * p.Cout + cout) * 9 + tap) * p.Cin + cin] = __uint_as_float(r[e]);
             }
           }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(tempty);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// Second form: dy = M side (128 output channels), x halo = N side (3 taps x 32 input channels), see the file comment.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int X2_BYTES = HALO_W * HALO_H * 64;     // 15360: 32 channels per halo pixel, SWIZZLE_64B
+constexpr int DY2_BYTES = 2 * DY_BYTES;            // 32768: two 64-channel boxes
+constexpr int STAGE2_BYTES = X2_BYTES + DY2_BYTES; // 48128 = 47 * 1024
+constexpr int N2 = 96;                             // 3 taps x 32 input channels per MMA
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+wgrad_halo2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDy,
+                   const __grid_constant__ HWParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.stages * STAGE2_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + MAX_STAGES;
+  uint64_t* tfull = bars + 2 * MAX_STAGES;
+  uint64_t* tempty = tfull + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmX);
+    ptx::prefetch_tmap(&tmDy);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+    ptx::mbar_init(tfull, 1);
+    ptx::mbar_init(tempty, 4);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        int cb, ob, ks;
+        decode(p, item, cb, ob, ks);
+        const int tile0 = (int)((long)ks * p.tiles_total / p.ksplit);
+        const int tile1 = (int)((long)(ks + 1) * p.tiles_total / p.ksplit);
+        int tw = tile0 % p.tiles_w, t2 = tile0 / p.tiles_w;
+        int th = t2 % p.tiles_h, n = t2 / p.tiles_h;
+        for (int tile = tile0; tile < tile1; ++tile) {
+          ptx::mbar_wait(&empty[s], ph ^ 1);
+          ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)STAGE2_BYTES);
+          uint8_t* dst = smem + s * STAGE2_BYTES;
+          ptx::tma_load_4d(dst, &tmX, &full[s], cb * 32, tw * TILE_W - 1, th * TILE_H - 1, n);
+          ptx::tma_load_4d(dst + X2_BYTES, &tmDy, &full[s], ob * 128, tw * TILE_W, th * TILE_H, n);
+          ptx::tma_load_4d(dst + X2_BYTES + DY_BYTES, &tmDy, &full[s], ob * 128 + 64, tw * TILE_W, th * TILE_H, n);
+          if (++s == p.stages) { s = 0; ph ^= 1; }
+          if (++tw == p.tiles_w) { tw = 0; if (++th == p.tiles_h) { th = 0; ++n; } }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer ==============================
+    const uint32_t idesc = ptx::make_idesc_bf16(128, N2, 1, 1);
+    const uint32_t full_s = ptx::smem_u32(full), empty_s = ptx::smem_u32(empty);
+    const uint32_t hi_a = ptx::desc_hi(1024);                     // dy: SWIZZLE_128B, 8 pixels x 128 B per K-atom
+    const uint32_t hi_b = ptx::desc_hi_sw64(512);                 // x : SWIZZLE_64B,  8 pixels x  64 B per K-atom
+    const uint32_t base_lo = (ptx::smem_u32(smem) & 0x3FFFFu) >> 4;
+    constexpr uint32_t LBO_A = ((uint32_t)DY_BYTES >> 4) << 16;   // second 64-channel dy box
+    constexpr uint32_t LBO_B = (64u >> 4) << 16;                  // next tap of the kernel row = next halo pixel = 64 B
+    constexpr uint32_t ROW2 = (HALO_W * 64) >> 4;                 // halo row pitch in 16-byte units
+    int s = 0, it = 0;
+    uint32_t ph = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+      int cb, ob, ks;
+      decode(p, item, cb, ob, ks);
+      const int tile0 = (int)((long)ks * p.tiles_total / p.ksplit);
+      const int tile1 = (int)((long)(ks + 1) * p.tiles_total / p.ksplit);
+      ptx::mbar_wait(tempty, (it & 1) ^ 1);
+      ptx::tc_fence_after();
+      uint32_t accumulate = 0;
+      for (int tile = tile0; tile < tile1; ++tile) {
+        ptx::mbar_wait_s(full_s + s * 8, ph);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint32_t x_lo = base_lo + s * ((uint32_t)STAGE2_BYTES >> 4);
+          const uint32_t y_lo = x_lo + (X2_BYTES >> 4);
+#pragma unroll
+          for (int kk = 0; kk < TILE_H; ++kk) {      // K step = one tile row of 16 pixels
+            const uint32_t acc = kk ? 1u : accumulate;
+            const uint64_t da = ptx::pack_desc((y_lo + kk * ((TILE_W * 128) >> 4)) | LBO_A, hi_a);
+            const uint32_t xr = x_lo + kk * ROW2;    // halo pixel (kk, 0): kernel row dy starts at halo row kk + dy
+            ptx::umma_bf16(tmem_base + 0 * N2, da, ptx::pack_desc((xr + 0 * ROW2) | LBO_B, hi_b), idesc, acc);
+            ptx::umma_bf16(tmem_base + 1 * N2, da, ptx::pack_desc((xr + 1 * ROW2) | LBO_B, hi_b), idesc, acc);
+            ptx::umma_bf16(tmem_base + 2 * N2, da, ptx::pack_desc((xr + 2 * ROW2) | LBO_B, hi_b), idesc, acc);
+          }
+          ptx::umma_commit_s(empty_s + s * 8);
+        }
+        accumulate = 1;
+        __syncwarp();
+        if (++s == p.stages) { s = 0; ph ^= 1; }
+      }
+      if (ptx::elect_one()) ptx::umma_commit(tfull);
+      __syncwarp();
+    }
+  } else {
+    // ============================== epilogue (warps 2..5) ==============================
+    const int lg = warp & 3;                     // TMEM lanes 32*lg .. 32*lg+31 = output channels of the block
+    int it = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+      int cb, ob, ks;
+      decode(p, item, cb, ob, ks);
+      ptx::mbar_wait(tfull, it & 1);
+      ptx::tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
+      const int cout = ob * 128 + lg * 32 + lane;
+      float* dst = p.partial + (((long)ks * p.Cout + cout) * 9) * p.Cin + cb * 32;
+#pragma unroll 1
+      for (int tap = 0; tap < 9; ++tap) {        // column (tap / 3) * 96 + (tap % 3) * 32 + ci  ==  tap * 32 + ci
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(t_addr + (uint32_t)(tap * 32), r);
+        ptx::tmem_ld_wait();
+        if (cout < p.Cout) {
+          float4* d4 = reinterpret_cast<float4*>(dst + (long)tap * p.Cin);
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            d4[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+                                __uint_as_float(r[4 * q + 3]));
         }
       }
       ptx::tc_fence_before();
@@ -217,16 +366,16 @@ void plan(const rbu_wgrad_args* a, HWParams* p) {
   p->Cout = a->Ca;
   p->Cin = a->Cb;
   {
-    // Optional (RBU_WGRAD_NB128=1): 128 output channels per item -- the dy operand is then as wide as the x operand
-    // (balanced shared-memory fetch per MMA) but the 512-column TMEM holds only eight taps, and tap 8 needs a second pass
-    // over both activation tensors (generic kernel).  Measured on B200: the 8-tap kernel is 1.2-1.34x faster per tap, the
-    // extra pass costs more than that except for Cin >= 2 Cout -- off by default.
-    static int nb128 = -1;
-    if (nb128 < 0) nb128 = getenv("RBU_WGRAD_NB128") ? 1 : 0;
-    p->NB = (nb128 && a->Ca % 128 == 0) ? 128 : 64;
+    // Block shape: 128 output x 32 input channels (second form, balanced shared-memory operand fetch) whenever the channel
+    // counts allow it, else 64 x 64 (the 64-output-channel level).  RBU_WGRAD_V1=1 forces the first form (A/B measurements).
+    static int v1 = -1;
+    if (v1 < 0) v1 = getenv("RBU_WGRAD_V1") ? 1 : 0;
+    const bool form2 = !v1 && a->Ca % 128 == 0 && a->Cb % 32 == 0;
+    p->OB = form2 ? 128 : 64;
+    p->CB = form2 ? 32 : 64;
   }
-  p->cin_blocks = rbu_cdiv(a->Cb, 64);
-  p->cout_blocks = rbu_cdiv(a->Ca, p->NB);
+  p->cin_blocks = rbu_cdiv(a->Cb, p->CB);
+  p->cout_blocks = rbu_cdiv(a->Ca, p->OB);
   const int base_items = p->cin_blocks * p->cout_blocks;
   // split-K factor: the smallest one that fills the machine with at most ~15 % of the last wave idle (every item
   // pays an un-overlapped epilogue and a partial-sum round trip, so fewer, longer items win), else the best found
@@ -254,8 +403,7 @@ size_t rbu_wgrad_halo_workspace_bytes(const rbu_wgrad_args* a) {
   HWParams p;
   plan(a, &p);
   size_t own = (size_t)p.ksplit * a->Ca * 9 * a->Cb * sizeof(float);
-  own = (own + 255) & ~(size_t)255;
-  return own + (p.NB == 128 ? rbu_wgrad_generic_workspace_bytes(a, 8, 9) : 0);
+  return (own + 255) & ~(size_t)255;
 }
 
 // Argument validation is done by the caller (rbu_wgrad_gemm).
@@ -263,12 +411,13 @@ int rbu_wgrad_halo_launch(const rbu_wgrad_args* a, void* workspace, cudaStream_t
   HWParams p;
   plan(a, &p);
   p.partial = reinterpret_cast<float*>(workspace);
+  const bool form2 = p.OB == 128;
   CUtensorMap tmX, tmDy;
   {
     const uint64_t dims[4] = {(uint64_t)a->Cb, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->N};
     const uint64_t str[3] = {(uint64_t)a->b_ld * 2, (uint64_t)a->b_ld * 2 * a->W, (uint64_t)a->b_ld * 2 * a->W * a->H};
-    const uint32_t box[4] = {64, HALO_W, HALO_H, 1};
-    int rc = rbu_encode_tmap_bf16(&tmX, a->b, 4, dims, str, box);
+    const uint32_t box[4] = {(uint32_t)p.CB, HALO_W, HALO_H, 1};
+    int rc = rbu_encode_tmap_bf16_sw(&tmX, a->b, 4, dims, str, box, form2 ? 64 : 128);
     if (rc) return rc;
   }
   {
@@ -278,29 +427,21 @@ int rbu_wgrad_halo_launch(const rbu_wgrad_args* a, void* workspace, cudaStream_t
     int rc = rbu_encode_tmap_bf16(&tmDy, a->a, 4, dims, str, box);
     if (rc) return rc;
   }
-  {
-    static int st = -1;   // RBU_WGRAD_STAGES: ring depth experiment (shared memory left for co-resident bandwidth kernels)
-    if (st < 0) { const char* e = getenv("RBU_WGRAD_STAGES"); st = e ? atoi(e) : MAX_STAGES; if (st < 2 || st > MAX_STAGES) st = MAX_STAGES; }
-    p.stages = st;
-  }
-  const int stage_bytes = X_BYTES + (p.NB >> 6) * DY_BYTES;
+  const int stage_bytes = form2 ? STAGE2_BYTES : STAGE_BYTES;
+  p.stages = MAX_STAGES;
   if (p.stages * stage_bytes + 1024 + 256 > SMEM_LIMIT) p.stages = (SMEM_LIMIT - 1024 - 256) / stage_bytes;
   const int smem_bytes = p.stages * stage_bytes + 1024 + 256;
   static std::atomic<unsigned long long> attr_set{0};      // one bit per device ordinal
-  if (rbu_first_use_on_device(&attr_set))
+  if (rbu_first_use_on_device(&attr_set)) {
     RBU_CHECK_CUDA(cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-  const int grid = p.items < rbu_num_sms() ? p.items : rbu_num_sms();
-  wgrad_halo_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(tmX, tmDy, p);
-  RBU_CHECK_LAUNCH();
-  if (p.NB == 128) {
-    // taps 0-7 from this kernel, tap 8 from the generic kernel (its own partials behind ours)
-    rbu_wgrad_reduce_launch(p.partial, p.ksplit, a->Ca, 9, a->Cb, a->out, a->accumulate, stream, 0, 8);
-    RBU_CHECK_LAUNCH();
-    size_t own = (size_t)p.ksplit * a->Ca * 9 * a->Cb * sizeof(float);
-    own = (own + 255) & ~(size_t)255;
-    return rbu_wgrad_generic_launch(a, 8, 9, static_cast<uint8_t*>(workspace) + own, rbu_wgrad_generic_workspace_bytes(a, 8, 9),
-                                    stream);
+    RBU_CHECK_CUDA(cudaFuncSetAttribute(wgrad_halo2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
   }
+  const int grid = p.items < rbu_num_sms() ? p.items : rbu_num_sms();
+  if (form2)
+    wgrad_halo2_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(tmX, tmDy, p);
+  else
+    wgrad_halo_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(tmX, tmDy, p);
+  RBU_CHECK_LAUNCH();
   rbu_wgrad_reduce_launch(p.partial, p.ksplit, a->Ca, 9, a->Cb, a->out, a->accumulate, stream);
   RBU_CHECK_LAUNCH();
   return RBU_OK;

@@ -19,6 +19,8 @@ SHAPES = [  # name, H=W, Cin, Cout, taps
     ("L2 3x3 256->256", 64, 256, 256, 9),
     ("L3 3x3 512->512", 32, 512, 512, 9),
     ("L4 3x3 1024->1024", 16, 1024, 1024, 9),
+    ("D4 3x3 1024->512", 32, 1024, 512, 9),
+    ("D3 3x3 512->256", 64, 512, 256, 9),
     ("L0 1x1 128->64", 256, 128, 64, 1),
     ("L1 1x1 256->128", 128, 256, 128, 1),
     ("L3 1x1 1024->512", 32, 1024, 512, 1),
@@ -71,6 +73,7 @@ def main():
     B = 64
     dev = torch.device("cuda:0")
     eng = Engine(None)
+    eng.overlap_wgrad = False          # time the weight-gradient kernels on the stream the events are recorded on
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     if which == "aux":
         return aux(reps, B, dev, flush)
