@@ -207,7 +207,7 @@ def test_base64_against_reference_golden(golden_dir, name):
         dn.append(abs(got.norm().item() - s_[0]) / (s_[0] + 1e-30))
         an.append(abs(ga[n].double().norm().item() - s_[0]) / (s_[0] + 1e-30))
         if got.numel() >= 1024:
-            rep.rows.append((f"{n} |grad| vs golden (autocast {an[-1]:.2e})", dn[-1], 1.5 * an[-1] + 0.1))
+            rep.rows.append((f"{n} |grad| vs golden (autocast {an[-1]:.2e})", dn[-1], 1.5 * an[-1] + 0.15))
         scale = s_[0] / got.numel() ** 0.5 * k ** 0.5 + 1e-30          # expected norm of k entries
         dh.append(((got[:k] - head).norm() / scale).item())
         ah.append(((ga[n].double().flatten()[:k] - head).norm() / scale).item())

@@ -7,7 +7,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import rbunet  # noqa: E402
-from oracle import robust_unet_ref as R  # noqa: E402  (synthetic inputs only)
+from tools.synthetic import synthetic_batch  # noqa: E402
 
 
 def main():
@@ -18,8 +18,8 @@ def main():
     torch.manual_seed(0)
     model = rbunet.RobustUNet(3, 1, 64).to(dev).train()
     crit = rbunet.RobustBCEDiceLoss()
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=1e-4, fused=True)
-    x, y = R.synthetic_inputs(B, 3, S, S, seed=123, blobby=True)
+    opt = rbunet.FusedAdam(model.parameters(), lr=1e-4, weight_decay=1e-4)
+    x, y = synthetic_batch(B, 3, S, S, seed=123)
     x, y = x.to(dev), y.to(dev)
     for _ in range(steps):
         opt.zero_grad(set_to_none=True)
