@@ -377,17 +377,24 @@ void plan(const rbu_wgrad_args* a, HWParams* p) {
   p->cin_blocks = rbu_cdiv(a->Cb, p->CB);
   p->cout_blocks = rbu_cdiv(a->Ca, p->OB);
   const int base_items = p->cin_blocks * p->cout_blocks;
-  // split-K factor: the smallest one that fills the machine with at most ~15 % of the last wave idle (every item
-  // pays an un-overlapped epilogue and a partial-sum round trip, so fewer, longer items win), else the best found
+  // Split-K factor from a cost model instead of a utilisation threshold (ncu on the first build of the second form:
+  // 256 items on 148 SMs = 86.5 % of the SM-time busy, tensor pipe 72 % while busy but 59 % of the launch).  Every CTA
+  // walks ceil(items / SMs) items of tiles_total / k tiles each; an item ends with an un-overlapped epilogue (147 KB of
+  // partial sums) and every extra split adds one partial tensor for the ordered reduction kernel to read back.
   const int sms = rbu_num_sms();
+  const double t_tile = p->OB == 128 ? 1550.0 : 1900.0;       // cycles per 8x16-pixel tile at the measured MMA efficiency
+  const double t_epi = 6000.0;                                // TMEM -> global drain of one item
+  const double out_bytes = (double)a->Ca * 9.0 * a->Cb * 4.0;
+  const double t_red = out_bytes / (3.0e12 / 1.8e9);          // cycles per split: one more partial tensor for the reduction kernel
   int ks = 1;
-  double best = -1.0;
-  for (int k = 1; k <= p->tiles_total && (long)k * base_items <= 8L * sms; ++k) {
+  double best = 1e300;
+  for (int k = 1; k <= p->tiles_total && (long)k * base_items <= 16L * sms; ++k) {
     const long items = (long)k * base_items;
-    const double util = (double)items / (double)(((items + sms - 1) / sms) * sms);
-    if (items >= sms && util >= 0.85) { ks = k; break; }
-    const double score = items >= sms ? util : util - 1.0;      // a full machine always beats a partially filled one
-    if (score > best + 1e-9) { best = score; ks = k; }
+    const long waves = (items + sms - 1) / sms;
+    const double tiles_per_item = (double)p->tiles_total / k;
+    if (k > 1 && tiles_per_item < 8.0) break;                 // items shorter than the 4-stage pipeline fill
+    const double cost = (double)waves * (tiles_per_item * t_tile + t_epi) + (double)k * t_red;
+    if (cost < best * (1.0 - 1e-9)) { best = cost; ks = k; }
   }
   p->ksplit = ks;
   p->items = base_items * ks;
