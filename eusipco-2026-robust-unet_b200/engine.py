@@ -48,6 +48,8 @@ class Engine:
         self.model = model
         self._packs = {}
         self._pack_table = None
+        self._pack_srcs = None
+        self._pack_plan_cache = None
         self._side_stream = None
         self._side_ws = None
         self._side_dirty = False
@@ -160,12 +162,34 @@ class Engine:
             jobs.append(((id(w), 3), w, None, (w.shape[0], 4, w.shape[1]), w.shape[0], 4, w.shape[1], 3, 0))
         return jobs
 
+    def _pack_src_params(self):
+        """The Parameter objects behind the packed operands, in a fixed order (identity check for the plan cache)."""
+        m = self.model
+        out = [m.inc.conv1.weight, m.inc.shortcut[0].weight]
+        for blk in (m.inc, m.down1[1], m.down2[1], m.down3[1], m.bottleneck[2], m.dec4, m.dec3, m.dec2, m.dec1):
+            out += [blk.conv1.weight, blk.conv2.weight]
+            if not isinstance(blk.shortcut, nn.Identity):
+                out.append(blk.shortcut[0].weight)
+        d = m.bottleneck[1]
+        out += [d.conv1.weight, d.conv2.weight, d.conv3.weight, d.conv4.weight]
+        for k in (4, 3, 2, 1):
+            g = getattr(m, f"att{k}")
+            out += [g.W_g[0].weight, g.W_x[0].weight, getattr(m, f"up{k}").weight]
+        return out
+
     def refresh_packs(self):
         """Rebuild every bf16 weight operand from the fp32 masters with ONE kernel launch.  Done at the start of every
         forward: optimizers that update parameters through fused multi-tensor kernels (torch.optim.Adam(fused=True))
         do not bump tensor version counters, so staleness cannot be detected -- it is simply never allowed."""
         import numpy as np
-        plan = self._pack_plan()
+        # the job list only depends on which Parameter objects the modules hold: rebuilt when one of them is replaced
+        # (model.to(), load_state_dict(assign=True)), otherwise reused -- this runs on the launching thread before the
+        # first kernel of every forward, i.e. while the GPU idles whenever the caller synchronised on the previous step
+        srcs = self._pack_srcs
+        if srcs is None or any(a is not b for a, b in zip(srcs, self._pack_src_params())):
+            self._pack_plan_cache = self._pack_plan()
+            self._pack_srcs = tuple(self._pack_src_params())
+        plan = self._pack_plan_cache
         sig = tuple(j[1].data_ptr() for j in plan)
         if self._pack_table is None or self._pack_table[0] != sig:
             dev = plan[0][1].device

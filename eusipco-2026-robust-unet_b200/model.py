@@ -124,7 +124,7 @@ class _Graph(torch.autograd.Function):
         if model._grad_transform is not None:
             grads = model._grad_transform(grads)
         out = []
-        for name, p in model.named_parameters():
+        for name, p in model._named_params():
             g = grads.get(name) if p.requires_grad else None
             out.append(g.reshape(p.shape) if g is not None else None)
         return (None, None, None, *out)
@@ -171,8 +171,34 @@ class RobustUNet(nn.Module):
     def engine(self) -> Engine:
         return self._engine
 
+    # The module tree is fixed after construction, so the (name, Parameter) list is cached: walking 173 parameters through
+    # nn.Module.named_parameters() costs ~0.5 ms of host time per call -- time the GPU idles whenever the caller has just
+    # synchronised on the previous step (`loss.item()`, Main_Final.py:584).  Anything that can replace Parameter objects
+    # goes through _apply / load_state_dict / register_parameter and drops the cache.
+    def _named_params(self):
+        c = self.__dict__.get("_param_cache")
+        if c is None:
+            c = tuple(self.named_parameters())
+            self.__dict__["_param_cache"] = c
+        return c
+
+    def _drop_param_cache(self):
+        self.__dict__["_param_cache"] = None
+
+    def _apply(self, fn, recurse=True):
+        self._drop_param_cache()
+        return super()._apply(fn, recurse)
+
+    def load_state_dict(self, *args, **kwargs):
+        self._drop_param_cache()
+        return super().load_state_dict(*args, **kwargs)
+
+    def requires_grad_(self, requires_grad: bool = True):
+        self._drop_param_cache()
+        return super().requires_grad_(requires_grad)
+
     def forward(self, x):
-        params = tuple(self.parameters())
+        params = tuple(p for _, p in self._named_params())
         if torch.is_grad_enabled() and x.requires_grad:
             raise RuntimeError("rbunet.RobustUNet does not produce a gradient for its input (the first layer's data "
                                "gradient is never computed); detach the input")

@@ -33,8 +33,10 @@ def test_reference_init_is_bit_identical_and_state_dict_loads(MF):
 
 
 def test_oracle_equals_reference_at_base64_train_and_eval(MF):
-    """Bit-identical probabilities and gradients (same torch CPU kernels in the same order) at base 64, 3 x 128 x 128,
-    reference initialisation, Dropout2d masks injected into both."""
+    """Same torch CPU kernels in the same order at base 64, 3 x 128 x 128, reference initialisation, Dropout2d masks
+    injected into both: bit-identical probabilities; gradients bit-identical when the test runs alone and within 1e-6
+    (rel-L2) always -- oneDNN's backward kernels split their reductions over however many threads the process has at
+    that moment, which other tests of the suite change."""
     import torch.nn as nn
     torch.manual_seed(0)
     ref = MF.RobustUNet(3, 1)
@@ -57,7 +59,8 @@ def test_oracle_equals_reference_at_base64_train_and_eval(MF):
     R.bce_loss(p, y).backward()
     assert torch.equal(p.detach(), p_ref.detach())
     for n, prm in ref.named_parameters():
-        assert torch.equal(sd[n].grad, prm.grad), n
+        a, b = sd[n].grad.double(), prm.grad.double()
+        assert (a - b).norm() <= 1e-6 * b.norm() + 1e-12, n
     ref.eval()
     with torch.no_grad():
         pe_ref = ref(x)
