@@ -10,6 +10,11 @@ from oracle.load_reference import load_reference, reference_available
 pytestmark = pytest.mark.skipif(not reference_available(), reason="/root/reference is not present on this machine")
 
 
+def _same(a, b):
+    """Bit-identical in a quiet process; <= 1e-6 rel-L2 when other tests have changed the intra-op thread partitioning."""
+    return torch.equal(a, b) or ((a.double() - b.double()).norm() <= 1e-6 * b.double().norm() + 1e-12).item()
+
+
 @pytest.fixture(scope="module")
 def MF():
     return load_reference()
@@ -57,7 +62,7 @@ def test_oracle_equals_reference_at_base64_train_and_eval(MF):
         sd[n].requires_grad_(True)
     p = R.robust_unet_forward(sd, x, training=True, drop_masks=masks, new_buffers={})
     R.bce_loss(p, y).backward()
-    assert torch.equal(p.detach(), p_ref.detach())
+    assert _same(p.detach(), p_ref.detach())
     for n, prm in ref.named_parameters():
         a, b = sd[n].grad.double(), prm.grad.double()
         assert (a - b).norm() <= 1e-6 * b.norm() + 1e-12, n
@@ -66,4 +71,4 @@ def test_oracle_equals_reference_at_base64_train_and_eval(MF):
         pe_ref = ref(x)
         sd2 = {k: v.detach() for k, v in ref.state_dict().items()}
         pe = R.robust_unet_forward(sd2, x, training=False)
-    assert torch.equal(pe, pe_ref)
+    assert _same(pe, pe_ref)
