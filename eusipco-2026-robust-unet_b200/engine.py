@@ -58,20 +58,22 @@ class Engine:
         self.grad_alloc = None        # optional callable(name, shape) -> fp32 tensor to receive that parameter's gradient
                                       # (parallel.DataParallel: a slice of a flat all-reduce bucket), or None
         self._saving = False
+        # Weight gradients on a side stream (see wgrad()).  RBU_NO_OVERLAP=1 keeps them on the compute stream: used by the
+        # profiling tools, which need per-kernel times that are not inflated by a co-running kernel.
         self.overlap_wgrad = os.environ.get("RBU_NO_OVERLAP") is None
-        # BatchNorm batch statistics fused into the producing convolution's epilogue (rbu_conv_gemm stats=...): one pass
-        # over the activations less, but the warp-transpose reduction slows the epilogue-sensitive small-N GEMMs by
-        # about as much (measured on B200: 44.9 vs 45.0 ms/step) -- off by default, exercised by the tests.
-        self.fuse_bn_stats = os.environ.get("RBU_FUSE_BN_STATS") == "1"
+        # BatchNorm batch statistics fused into the generic convolution's epilogue (rbu_conv_gemm stats=...): one pass over
+        # the activations less, but the warp-transpose reduction slows the epilogue-sensitive small-N GEMMs by about as
+        # much (measured on B200: 44.9 vs 45.0 ms/step) -- off; kept as an attribute because the parity tests exercise it.
+        self.fuse_bn_stats = False
         # Per-image statistics (sum, sum of squares, max, min per half-tile) from the 3x3 halo kernel's epilogue: BatchNorm
         # batch statistics and ChannelAttention's pooled inputs without re-reading the conv output.  Measured on B200: in
         # the training step (batch 64, 256^2) the 18 statistics passes it replaces cost 1.34 ms, the longer epilogues 0.4 ms
-        # and the reduction of the partials 0.35 ms; in inference at 1024^2 the 64-channel convolutions become
-        # epilogue-bound (+6 ms against -3.5 ms), so it is used in training mode only, and only from 128 output channels up
-        # (at 64 channels the longer epilogue costs what the saved pass gains).  RBU_NO_TILE_STATS=1 disables it.
-        self.fuse_tile_stats = os.environ.get("RBU_NO_TILE_STATS") is None
-        self.tile_stats_eval = os.environ.get("RBU_TILE_STATS_EVAL") == "1"
-        self.tile_stats_min_c = int(os.environ.get("RBU_TILE_STATS_MIN_C", "128"))   # 64-channel convs (K = 576): epilogue-bound with it
+        # and the reduction of the partials 0.35 ms.  Used from 128 output channels up (at 64 channels, K = 576, the longer
+        # epilogue costs what the saved pass gains) and in training mode only (inference at 1024^2, round 2: statistics
+        # pass -1.9 ms, convolutions +1.7 ms -- no gain).
+        self.fuse_tile_stats = True
+        self.tile_stats_eval = False
+        self.tile_stats_min_c = 128
         self._ws = None
         self._defer_counters = False     # whole-model forward: the 39 num_batches_tracked increments become one launch
         self._pending_counters = []
@@ -163,8 +165,11 @@ class Engine:
         return jobs
 
     def _pack_src_params(self):
-        """The Parameter objects behind the packed operands, in a fixed order (identity check for the plan cache)."""
+        """The Parameter objects behind the packed operands, in a fixed order (identity check for the plan cache); None when
+        the model is not a RobustUNet."""
         m = self.model
+        if not hasattr(m, "bottleneck"):
+            return None
         out = [m.inc.conv1.weight, m.inc.shortcut[0].weight]
         for blk in (m.inc, m.down1[1], m.down2[1], m.down3[1], m.bottleneck[2], m.dec4, m.dec3, m.dec2, m.dec1):
             out += [blk.conv1.weight, blk.conv2.weight]
@@ -185,11 +190,15 @@ class Engine:
         # the job list only depends on which Parameter objects the modules hold: rebuilt when one of them is replaced
         # (model.to(), load_state_dict(assign=True)), otherwise reused -- this runs on the launching thread before the
         # first kernel of every forward, i.e. while the GPU idles whenever the caller synchronised on the previous step
-        srcs = self._pack_srcs
-        if srcs is None or any(a is not b for a, b in zip(srcs, self._pack_src_params())):
-            self._pack_plan_cache = self._pack_plan()
-            self._pack_srcs = tuple(self._pack_src_params())
-        plan = self._pack_plan_cache
+        cur = self._pack_src_params()
+        if cur is None:                          # an engine without a cheap identity list (UNetEngine): rebuild every time
+            plan = self._pack_plan()
+        else:
+            srcs = self._pack_srcs
+            if srcs is None or len(srcs) != len(cur) or any(a is not b for a, b in zip(srcs, cur)):
+                self._pack_plan_cache = self._pack_plan()
+                self._pack_srcs = tuple(cur)
+            plan = self._pack_plan_cache
         sig = tuple(j[1].data_ptr() for j in plan)
         if self._pack_table is None or self._pack_table[0] != sig:
             dev = plan[0][1].device

@@ -62,6 +62,17 @@ def main():
         print(f"stream {sid}: {len(ks)} kernels, span {span / 1e3:.2f} ms, busy {busy / 1e3:.2f} ms, gaps {sum(gaps) / 1e3:.2f} ms "
               f"(gaps < 20 us: n={len(small)}, sum {sum(small) / 1e3:.2f} ms, median {small[len(small) // 2] if small else 0:.2f} us); "
               f"largest gaps: {[round(g, 1) for g in sorted(gaps)[-6:]]}")
+    import collections
+    import re
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for e in ev:
+        nm = e["name"].replace("(anonymous namespace)::", "").replace("void ", "")
+        nm = re.sub(r"\(.*", "", nm)[:40]
+        agg[nm][0] += 1
+        agg[nm][1] += e["dur"]
+    print("per-kernel busy time per step (us), 3 steps averaged:")
+    for nm, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:28]:
+        print(f"   {nm:40s} {n // 3:4d} launches {us / 3:9.1f} us")
     os.remove(path)
 
 
