@@ -1233,9 +1233,7 @@ extern "C" int rbu_rb_bwd3(const void* de, int64_t de_ld, const void* y2, int64_
   int lg = 0;
   while ((1 << (lg + 1)) <= (C >> 3)) ++lg;
   const long items = (long)HW << lg;
-  long blocks = (items + NT * 2 - 1) / (NT * 2);
-  long cap = ((long)rbu_num_sms() * 32 + N - 1) / N;
-  if (blocks > cap) blocks = cap;
+  const long blocks = rbu_stream_blocks(items, NT * 2, N);
   const float* c1 = coef;
   const float* c0 = c1 + (size_t)N * C;
   const float* cm = c0 + (size_t)N * C;
@@ -1282,9 +1280,7 @@ extern "C" int rbu_bn_bwd(const void* dy, int64_t dy_ld, const void* y, int64_t 
   int lg = 0;
   while ((1 << (lg + 1)) <= (C >> 3)) ++lg;
   const long items = (long)HW << lg;
-  long blocks = (items + NT * 4 - 1) / (NT * 4);
-  long cap = ((long)rbu_num_sms() * 32 + N - 1) / N;
-  if (blocks > cap) blocks = cap;
+  const long blocks = rbu_stream_blocks(items, NT * 4, N);
   bn_bwd_apply_kernel<<<dim3((unsigned)blocks, N), NT, 0, st>>>((const bf16*)dy, dy_ld, (const bf16*)y, y_ld, (bf16*)dx, dx_ld,
                                                                 HW, C, lg, scale, shift, drop, relu, coef);
   RBU_CHECK_LAUNCH();
@@ -1344,9 +1340,7 @@ extern "C" int rbu_ag_bwd(const void* da, int64_t da_ld, const void* skip, int64
     int lg = 0;
     while ((1 << (lg + 1)) <= (F >> 3)) ++lg;
     const long items = (long)HW << lg;
-    long blocks = (items + NT * 2 - 1) / (NT * 2);
-    long cap = ((long)rbu_num_sms() * 32 + N - 1) / N;
-    if (blocks > cap) blocks = cap;
+    const long blocks = rbu_stream_blocks(items, NT * 2, N);
     ag_bwd3_kernel<<<dim3((unsigned)blocks, N), NT, 0, st>>>((const bf16*)yg, yg_ld, (const bf16*)yx, yx_ld, (bf16*)dyg, dyg_ld,
                                                              (bf16*)dyx, dyx_ld, HW, F, lg, Ag, Bg, Ax, Bx, wpsi, dq, q0, stats,
                                                              sums_psi, invM, coef);

@@ -845,12 +845,7 @@ int ilog2(int v) {
 
 // grid.x for the streaming skeleton: enough blocks for ~32 resident warps per SM over >= 4 waves, at most one
 // block per NT*EW_U items
-int ew_blocks(long items_per_image, int images) {
-  long b = (items_per_image + NT * EW_U - 1) / (NT * EW_U);
-  long cap = ((long)rbu_num_sms() * 32 + images - 1) / images;
-  if (cap < 1) cap = 1;
-  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
-}
+int ew_blocks(long items_per_image, int images) { return rbu_stream_blocks(items_per_image, NT * EW_U, images); }
 
 int pick_tpp(int C) {
   const int G = C >> 3;
@@ -978,9 +973,7 @@ extern "C" int rbu_sa_reduce(const void* y2, int64_t ld, int64_t P, int HW, int 
   const int K = G > 32 ? G / 32 : 1;
   const int U = K == 1 ? 4 : (K == 2 ? 2 : 1);
   const int per_block = NT / tpp * U;
-  long blocks = (HW + per_block - 1) / per_block;
-  long cap = ((long)rbu_num_sms() * 32 + N - 1) / N;
-  if (blocks > cap) blocks = cap;
+  const long blocks = rbu_stream_blocks(HW, per_block, N);
   const dim3 grid((unsigned)blocks, (unsigned)N);
 #define LAUNCH(T, KK)                                                                                                        \
   do {                                                                                                                    \

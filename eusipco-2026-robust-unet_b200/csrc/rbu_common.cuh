@@ -50,6 +50,12 @@ bool rbu_first_use_on_device(std::atomic<unsigned long long>* done_mask);
 
 static inline int rbu_cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 
+// grid.x (blocks per image, grid.y = images) of a streaming kernel whose threads keep per-(image, channel) coefficients in
+// registers: every block pays a prologue of 24-64 scalar loads per thread before its first 16-byte load, so a thread
+// should stream at least `min_iters` x U vectors -- as long as ~3 blocks per SM remain in flight -- and at most ~32
+// resident warps per SM over a few waves are useful.  `per_iter` = items one block covers per loop iteration (threads x U).
+int rbu_stream_blocks(long items_per_image, int per_iter, int images);
+
 // ---------------------------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------------------------

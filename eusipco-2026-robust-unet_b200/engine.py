@@ -168,7 +168,7 @@ class Engine:
         """The Parameter objects behind the packed operands, in a fixed order (identity check for the plan cache); None when
         the model is not a RobustUNet."""
         m = self.model
-        if not hasattr(m, "bottleneck"):
+        if not (hasattr(m, "inc") and hasattr(m, "att4")):
             return None
         out = [m.inc.conv1.weight, m.inc.shortcut[0].weight]
         for blk in (m.inc, m.down1[1], m.down2[1], m.down3[1], m.bottleneck[2], m.dec4, m.dec3, m.dec2, m.dec1):
