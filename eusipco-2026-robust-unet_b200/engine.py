@@ -228,7 +228,15 @@ class Engine:
     def f32(*shape, device):
         return torch.empty(shape, dtype=torch.float32, device=device)
 
+    @staticmethod
+    def _check_bn_population(N, HW, C, training):
+        """torch.nn.functional.batch_norm refuses a one-value population in training mode (the reference raises there,
+        e.g. batch 1 at 16 x 16 reaches the bottleneck with 1 x 1 pixels): same error, not a silent zero variance."""
+        if training and N * HW <= 1:
+            raise ValueError(f"Expected more than 1 value per channel when training, got input size {[N, C, 1, 1]}")
+
     def bn_stats(self, x: View, N, HW, bn: nn.BatchNorm2d, training, pool=False):
+        self._check_bn_population(N, HW, x.C, training)
         C, dev = x.C, x.base.device
         out = {"scale": self.f32(C, device=dev), "shift": self.f32(C, device=dev),
                "mean": self.f32(C, device=dev), "rstd": self.f32(C, device=dev)}
@@ -255,6 +263,7 @@ class Engine:
     def bn_stats_tiles(self, part, N, H, W, C, bn: nn.BatchNorm2d, training, pool=False):
         """bn_stats() without the pass over the tensor: the producing 3x3 convolution wrote per-image, per-half-tile
         partial sums / extremes of what it stored (rbu_conv_gemm tile_stats)."""
+        self._check_bn_population(N, H * W, C, training)
         dev = part.device
         out = {"scale": self.f32(C, device=dev), "shift": self.f32(C, device=dev),
                "mean": self.f32(C, device=dev), "rstd": self.f32(C, device=dev)}
@@ -295,6 +304,7 @@ class Engine:
     def bn_from_conv(self, part, Ncols, col_off, C, count, bn: nn.BatchNorm2d, off=0, out=None):
         """Train-mode BatchNorm affine from the statistics fused into the producing convolution's epilogue.  `off`
         selects a channel range of a wider BatchNorm (DilatedBlock: four convolutions feed one BN)."""
+        self._check_bn_population(count, 1, C, True)
         dev = part.device
         if out is None:
             nC = bn.num_features
@@ -583,6 +593,7 @@ class Engine:
         else:
             bg = self.bn_stats(yg, N, HW, gate.W_g[1], training)
             bx = self.bn_stats(yx, N, HW, gate.W_x[1], training)
+        self._check_bn_population(P, 1, 1, training)
         q0 = self.f32(P, device=dev)
         stats = self.f32(4, device=dev)
         nblk = _lib.lib().rbu_ag_psi_blocks(P, F)

@@ -6,10 +6,12 @@ shapes / dtypes and the `forward(x) -> probabilities [B,1,H,W]` contract of the 
 (Main_Final.py:226-321), so reference checkpoints load unchanged and an unmodified
 `torch.optim.Adam(model.parameters())` + `loss.backward()` loop (Main_Final.py:552,573-582) trains it.
 
-The sub-modules below are *parameter schemas only*: they own the fp32 master parameters and buffers in
-torch layouts, but none of them executes a torch op.  `RobustUNet.forward` hands the whole graph to
-`engine.Engine`, which schedules the sm_100a kernels of librbunet.so; the backward pass is one
-`torch.autograd.Function` whose gradients come from the same library.  There is no CPU fallback.
+The sub-modules below own the fp32 master parameters and buffers in torch layouts; none of them executes a torch op.
+`RobustUNet.forward` hands the whole graph to `engine.Engine`, which schedules the sm_100a kernels of librbunet.so; the
+backward pass is one `torch.autograd.Function` whose gradients come from the same library.  `ResidualBlock`,
+`AttentionGate` and `DilatedBlock` are also callable on their own like the reference's modules (NCHW fp32 at the
+boundary, the same block schedules inside); `ChannelAttention` / `SpatialAttention` exist only fused into the residual
+block.  There is no CPU fallback.
 """
 from __future__ import annotations
 
@@ -24,8 +26,87 @@ class _Slot(nn.Identity):
 
 
 def _no_standalone(self, *a, **k):
-    raise RuntimeError(f"{type(self).__name__} is a parameter schema; it only runs inside rbunet.RobustUNet "
-                       "(the CUDA engine schedules the whole network)")
+    raise RuntimeError(f"{type(self).__name__} has no kernel of its own: its arithmetic is fused into the ResidualBlock "
+                       "schedule (channel statistics come from the convolution epilogue, the gates are applied in the "
+                       "block's output pass); call the enclosing rbunet.ResidualBlock or rbunet.RobustUNet")
+
+
+def _nhwc(t: torch.Tensor):
+    """NCHW float CUDA tensor -> engine View (NHWC bf16)."""
+    from .ops import View
+    return View(t.detach().permute(0, 2, 3, 1).contiguous().to(torch.bfloat16))
+
+
+def _nchw(v) -> torch.Tensor:
+    return v.dense().permute(0, 3, 1, 2).float().contiguous()
+
+
+class _Block(torch.autograd.Function):
+    """One block-level module (ResidualBlock / AttentionGate / DilatedBlock) called on its own, as the reference's
+    modules can be (Main_Final.py:143-148,178-196,213-223): NCHW fp32 at the boundary, the engine's block schedule inside."""
+
+    @staticmethod
+    def forward(ctx, mod, n_in, save, *tensors):
+        xs = tensors[:n_in]
+        eng = mod.__dict__.setdefault("_engine", Engine(None))
+        eng._packs.clear()                      # the fp32 masters may have changed since the last call
+        eng._saving = bool(save)
+        for t in xs:
+            if not t.is_cuda:
+                raise RuntimeError(f"rbunet.{type(mod).__name__} runs on CUDA tensors only (no CPU fallback)")
+        N, C, H, W = xs[0].shape
+        with torch.cuda.device(xs[0].device):
+            if isinstance(mod, ResidualBlock):
+                if C != mod.conv1.in_channels or C % 8:
+                    raise RuntimeError(f"rbunet.ResidualBlock({mod.conv1.in_channels}, ...) got {C} input channels; standalone "
+                                       "calls need a multiple of 8 (the 3/4-channel stem block runs inside rbunet.RobustUNet)")
+                out, st = eng.rb_forward("block", mod, _nhwc(xs[0]), N, H, W, mod.training)
+            elif isinstance(mod, DilatedBlock):
+                out, st = eng.dil_forward(mod, _nhwc(xs[0]), N, H, W, mod.training)
+            else:                                # AttentionGate(g, x) -> x * psi
+                g, x = xs
+                if g.shape != x.shape:
+                    raise RuntimeError("rbunet.AttentionGate: g and x must have the same shape")
+                from .ops import View
+                out = View(torch.empty((N, H, W, C), dtype=torch.bfloat16, device=x.device))
+                st = eng.ag_forward(mod, _nhwc(g), _nhwc(x), out, N, H, W, mod.training)
+            ctx.mod, ctx.st, ctx.n_in = mod, (st if save else None), n_in
+            return _nchw(out)
+
+    @staticmethod
+    def backward(ctx, dout):
+        mod, st = ctx.mod, ctx.st
+        if st is None:
+            raise RuntimeError(f"rbunet.{type(mod).__name__}: backward needs a train-mode forward with gradients enabled "
+                               "(the backward kernels implement batch-statistics BatchNorm)")
+        ctx.st = None
+        eng = mod._engine
+        grads = {}
+        with torch.cuda.device(dout.device):
+            d = _nhwc(dout)
+            if isinstance(mod, ResidualBlock):
+                dxs = (eng.rb_backward(mod, st, d, grads, "m"),)
+            elif isinstance(mod, DilatedBlock):
+                dxs = (eng.dil_backward(mod, st, d, grads, "m"),)
+            else:
+                from .ops import View
+                N, H, W, C = st["N"], st["H"], st["W"], st["C"]
+                dskip = View(torch.empty((N, H, W, C), dtype=torch.bfloat16, device=dout.device))
+                dg = View(torch.zeros((N, H, W, C), dtype=torch.bfloat16, device=dout.device))
+                eng.ag_backward(mod, st, d, dskip, dg, grads, "m")
+                dxs = (dg, dskip)
+            eng.join_side(dout.device)
+            outs = [_nchw(v) for v in dxs]
+        for name, p in mod.named_parameters():
+            g = grads.get("m." + name) if p.requires_grad else None
+            outs.append(g.reshape(p.shape).clone() if g is not None else None)
+        return (None, None, None, *outs)
+
+
+def _standalone(self, *xs):
+    params = tuple(self.parameters())
+    save = self.training and torch.is_grad_enabled() and (any(p.requires_grad for p in params) or any(x.requires_grad for x in xs))
+    return _Block.apply(self, len(xs), save, *xs, *params)
 
 
 class ChannelAttention(nn.Module):
@@ -60,7 +141,9 @@ class AttentionGate(nn.Module):
         self.W_x = nn.Sequential(nn.Conv2d(F_l, F_int, 1), nn.BatchNorm2d(F_int))
         self.psi = nn.Sequential(nn.Conv2d(F_int, 1, 1), nn.BatchNorm2d(1), _Slot())
 
-    forward = _no_standalone
+    def forward(self, g, x):
+        """x * sigmoid(BN(psi(relu(BN(W_g g) + BN(W_x x)))))  (Main_Final.py:143-148), standalone call."""
+        return _standalone(self, g, x)
 
 
 class ResidualBlock(nn.Module):
@@ -81,7 +164,9 @@ class ResidualBlock(nn.Module):
         else:
             self.shortcut = nn.Identity()
 
-    forward = _no_standalone
+    def forward(self, x):
+        """Main_Final.py:178-196, standalone call (inside RobustUNet the engine schedules the block directly)."""
+        return _standalone(self, x)
 
 
 class DilatedBlock(nn.Module):
@@ -95,7 +180,9 @@ class DilatedBlock(nn.Module):
             setattr(self, f"conv{i}", nn.Conv2d(in_channels, q, 3, padding=d, dilation=d))
         self.bn = nn.BatchNorm2d(out_channels)
 
-    forward = _no_standalone
+    def forward(self, x):
+        """Main_Final.py:213-223, standalone call."""
+        return _standalone(self, x)
 
 
 class _Graph(torch.autograd.Function):

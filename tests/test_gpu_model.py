@@ -214,3 +214,54 @@ def test_weights_are_repacked_after_a_fused_optimizer_step():
         pref = R.robust_unet_forward({k: v.cpu() for k, v in model.state_dict().items()}, x.cpu(), training=False, st=R.BF16)
     assert (p1 - p0).abs().max().item() > 1e-3                  # the update is visible
     assert rel_l2(p1, pref) < 5e-2                              # and it is the update the masters hold
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 16, 16), (3, 16, 32), (1, 48, 16)])
+def test_minimum_and_ragged_input_sizes(B, H, W):
+    """Smallest legal inputs (H, W multiples of 16: the bottleneck sees 1 x 1 and 1 x 2 pixels, below every halo-kernel
+    tile, so each convolution takes its fallback path), odd batch sizes, and inputs that are not contiguous fp32 NCHW
+    (channels_last memory format, float64) -- forward and backward against the bf16-storage oracle."""
+    import rbunet
+    dev = torch.device("cuda:0")
+    base = 16
+    sd = R.synthetic_state_dict(R.robust_unet_shapes(3, 1, base), seed=0)
+    x, y = R.synthetic_inputs(B, 3, H, W, seed=31, blobby=True)
+    masks = R.synthetic_drop_masks(B, base, seed=7)
+    model = rbunet.RobustUNet(3, 1, base)
+    model.load_state_dict(sd)
+    model.to(dev).train()
+    model.engine.drop_mask_fn = lambda nm, N, C: masks[nm]
+    xin = x.to(dev).double().contiguous(memory_format=torch.channels_last)      # converted by the module, not rejected
+    if B * (H // 16) * (W // 16) == 1:
+        # one value per channel at the bottleneck: torch's batch_norm (hence the reference) raises in training mode
+        with pytest.raises(ValueError, match="Expected more than 1 value per channel"):
+            model(xin)
+        with pytest.raises(ValueError, match="Expected more than 1 value per channel"):
+            R.robust_unet_forward(sd, x, training=True, drop_masks=masks)
+        model.load_state_dict(sd)           # the aborted forward had already updated the encoder's running statistics
+        model.eval()
+        with torch.no_grad():
+            pe = model(xin)
+            pr = R.robust_unet_forward(sd, x, training=False, st=R.BF16)
+        assert rel_l2(pe, pr) < 5e-2
+        return
+    p = model(xin)
+    loss = rbunet.RobustBCEDiceLoss()(p, y.to(dev))
+    loss.backward()
+    torch.cuda.synchronize()
+    names = [n for n, _ in model.named_parameters()]
+    pq, lq, gq, _ = _oracle_train(sd, x, y, masks, 0.0, R.BF16, names)
+    pf, lf, gf, _ = _oracle_train(sd, x, y, masks, 0.0, R.FP32, names)
+    assert p.shape == (B, 1, H, W) and torch.isfinite(p).all()
+    assert rel_l2(p.detach(), pf) < 1.5 * rel_l2(pq, pf) + 2e-2
+    a = torch.cat([prm.grad.flatten().cpu().double() for _, prm in model.named_parameters()])
+    b = torch.cat([gq[n].flatten().double() for n in names])
+    assert torch.isfinite(a).all()
+    cos = (a @ b / (a.norm() * b.norm() + 1e-30)).item()
+    assert cos > 0.8, cos          # tiny BatchNorm populations (3-6 values per channel at the bottleneck): chaotic; sign and scale must hold
+    model.load_state_dict(sd)      # the training forward updated the running statistics
+    model.eval()
+    with torch.no_grad():
+        pe = model(x.to(dev))
+        pr = R.robust_unet_forward(sd, x, training=False, st=R.BF16)
+    assert rel_l2(pe, pr) < 5e-2
