@@ -34,7 +34,7 @@ def main():
             "issue%": "smsp__issue_active.avg.pct_of_peak_sustained_active",
             "occ%": "sm__warps_active.avg.pct_of_peak_sustained_active",
             "L2%": "lts__throughput.avg.pct_of_peak_sustained_elapsed",
-            "smemTC%": "l1tex__data_pipe_tc_wavefronts_mem_shared.avg.pct_of_peak_sustained_elapsed"}
+            "smemTC%": "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"}
     agg = collections.OrderedDict()
     for d in step:
         name = re.sub(r"\(.*", "", d["name"])
