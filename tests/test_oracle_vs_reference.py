@@ -65,7 +65,7 @@ def test_oracle_equals_reference_at_base64_train_and_eval(MF):
     assert _same(p.detach(), p_ref.detach())
     for n, prm in ref.named_parameters():
         a, b = sd[n].grad.double(), prm.grad.double()
-        assert (a - b).norm() <= 1e-5 * b.norm() + 1e-12, n
+        assert (a - b).norm() <= 1e-5 * b.norm() + 1e-7, n          # floor: biases in front of a train-mode BN have pure round-off gradients
     ref.eval()
     with torch.no_grad():
         pe_ref = ref(x)
