@@ -265,3 +265,31 @@ def test_minimum_and_ragged_input_sizes(B, H, W):
         pe = model(x.to(dev))
         pr = R.robust_unet_forward(sd, x, training=False, st=R.BF16)
     assert rel_l2(pe, pr) < 5e-2
+
+
+@pytest.mark.parametrize("nc", [1, 6])
+def test_other_input_channel_counts(nc):
+    """n_channels other than 3 / 4 (1 = single band, 6 = RGB + the three HSV planes of rbunet.preprocess): the stem takes
+    the generic im2col path; forward and backward against the bf16-storage oracle."""
+    import rbunet
+    dev = torch.device("cuda:0")
+    base, B, H, W = 16, 2, 32, 32
+    sd = R.synthetic_state_dict(R.robust_unet_shapes(nc, 1, base), seed=0)
+    x, y = R.synthetic_inputs(B, nc, H, W, seed=17, blobby=True)
+    masks = R.synthetic_drop_masks(B, base, seed=7)
+    model = rbunet.RobustUNet(nc, 1, base)
+    model.load_state_dict(sd)
+    model.to(dev).train()
+    model.engine.drop_mask_fn = lambda nm, N, C: masks[nm]
+    p = model(x.to(dev))
+    rbunet.RobustBCEDiceLoss()(p, y.to(dev)).backward()
+    torch.cuda.synchronize()
+    names = [n for n, _ in model.named_parameters()]
+    pq, _, gq, _ = _oracle_train(sd, x, y, masks, 0.0, R.BF16, names)
+    pq2, _, _, _ = _oracle_train(sd, x, y, masks, 0.0, R.BF16, names, perturb=1e-6)
+    assert rel_l2(p.detach(), pq) < 1.5 * rel_l2(pq2, pq) + 2e-2
+    g1 = dict(model.named_parameters())["inc.conv1.weight"].grad.cpu()
+    assert g1.shape == (base, nc, 3, 3) and torch.isfinite(g1).all()
+    a = torch.cat([prm.grad.flatten().cpu().double() for _, prm in model.named_parameters()])
+    b = torch.cat([gq[n].flatten().double() for n in names])
+    assert (a @ b / (a.norm() * b.norm())).item() > 0.85
