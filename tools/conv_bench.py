@@ -24,6 +24,10 @@ SHAPES = [  # name, H=W, Cin, Cout, taps
     ("L0 1x1 128->64", 256, 128, 64, 1),
     ("L1 1x1 256->128", 128, 256, 128, 1),
     ("L3 1x1 1024->512", 32, 1024, 512, 1),
+    ("A4 1x1 512->256", 32, 512, 256, 1),
+    ("D3 1x1 512->256", 64, 512, 256, 1),
+    ("A3 1x1 256->128", 64, 256, 128, 1),
+    ("dil 1x1 512->256", 16, 512, 256, 1),
 ]
 
 
