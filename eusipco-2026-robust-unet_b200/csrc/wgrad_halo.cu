@@ -357,6 +357,170 @@ wgrad_halo2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Third form: the second form on a CTA PAIR (thread-block cluster of 2, tcgen05 cta_group::2), for Cout % 256 == 0.
+// One MMA is M = 256 (each CTA's 128 output channels from its own dy tile) x N = 96, and the B operand is SPLIT between
+// the two CTAs: each CTA loads the x halo for 16 of the pair's 32 input channels (SWIZZLE_32B, 32-byte pixel pitch; the
+// three taps of a kernel row are three 16-channel MN-atoms 32 bytes apart) and supplies 48 of the 96 columns -- per MMA a
+// CTA reads 4 KB (A) + 1.5 KB (B half) from shared memory per 48 tensor-pipe cycles = 115 B/clk (second form: 146), and
+// 40 KB instead of 47 KB from L2 per stage.  Only the leader CTA (cluster rank 0) issues MMAs; both CTAs run a TMA
+// producer whose bytes are counted on the leader's full barrier, the leader's commit frees the stage in both CTAs
+// (multicast arrive), both CTAs drain their own 128 TMEM lanes and arrive on the leader's TMEM-empty barrier.
+// Accumulator columns of kernel row dy: dy*96 + n, n = half*48 + dx*16 + c  <->  tap (dy, dx), input channel half*16 + c.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int XP_BYTES = HALO_W * HALO_H * 32;         // 7680: 16 channels per halo pixel, SWIZZLE_32B
+constexpr int STAGEP_BYTES = 40 * 1024;                // dy (32768, first: 1024-aligned) + x (7680) padded to 40 KB
+constexpr int STAGEP_TX = DY2_BYTES + XP_BYTES;        // bytes ONE CTA's loads deliver per stage
+constexpr int PAIR_STAGES = 5;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDy,
+                  const __grid_constant__ HWParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PAIR_STAGES * STAGEP_BYTES);
+  uint64_t* full = bars;                      // [PAIR_STAGES]  used in the leader only
+  uint64_t* empty = bars + 8;                 // [PAIR_STAGES]  one per CTA, arrived by the leader's multicast commit
+  uint64_t* tfull = bars + 16;                // one per CTA (multicast commit)
+  uint64_t* tempty = bars + 17;               // leader's: 8 arrivals (4 epilogue warps x 2 CTAs)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmX);
+    ptx::prefetch_tmap(&tmDy);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < PAIR_STAGES; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+    ptx::mbar_init(tfull, 1);
+    ptx::mbar_init(tempty, 8);
+    ptx::fence_barrier_init();
+  }
+  ptx::cluster_sync_all();                    // both CTAs' barriers exist before anything arrives on them remotely
+  if (warp == 2) {
+    ptx::tmem_alloc_pair(tmem_slot, 512);
+    ptx::tmem_relinquish_pair();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ============================== TMA producer (both CTAs) ==============================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int item = pair; item < p.items; item += npairs) {
+        int cb, ob, ks;
+        decode(p, item, cb, ob, ks);
+        const int tile0 = (int)((long)ks * p.tiles_total / p.ksplit);
+        const int tile1 = (int)((long)(ks + 1) * p.tiles_total / p.ksplit);
+        int tw = tile0 % p.tiles_w, t2 = tile0 / p.tiles_w;
+        int th = t2 % p.tiles_h, n = t2 / p.tiles_h;
+        for (int tile = tile0; tile < tile1; ++tile) {
+          ptx::mbar_wait_cluster(&empty[s], ph ^ 1);
+          if (rank == 0) ptx::mbar_arrive_expect_tx(&full[s], 2u * STAGEP_TX);     // both CTAs' bytes land on this barrier
+          uint8_t* dst = smem + s * STAGEP_BYTES;
+          const int co = ob * 256 + (int)rank * 128;
+          ptx::tma_load_4d_pair(dst, &tmDy, &full[s], co, tw * TILE_W, th * TILE_H, n);
+          ptx::tma_load_4d_pair(dst + DY_BYTES, &tmDy, &full[s], co + 64, tw * TILE_W, th * TILE_H, n);
+          ptx::tma_load_4d_pair(dst + DY2_BYTES, &tmX, &full[s], cb * 32 + (int)rank * 16, tw * TILE_W - 1, th * TILE_H - 1, n);
+          if (++s == PAIR_STAGES) { s = 0; ph ^= 1; }
+          if (++tw == p.tiles_w) { tw = 0; if (++th == p.tiles_h) { th = 0; ++n; } }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer (leader CTA only) ==============================
+    if (rank == 0) {
+      const uint32_t idesc = ptx::make_idesc_bf16(256, N2, 1, 1);
+      const uint32_t full_s = ptx::smem_u32(full), empty_s = ptx::smem_u32(empty);
+      const uint32_t hi_a = ptx::desc_hi(1024);                    // dy: SWIZZLE_128B
+      const uint32_t hi_b = ptx::desc_hi_sw32(256);                // x : SWIZZLE_32B, 8 pixels x 32 B per K-atom
+      const uint32_t base_lo = (ptx::smem_u32(smem) & 0x3FFFFu) >> 4;
+      constexpr uint32_t LBO_A = ((uint32_t)DY_BYTES >> 4) << 16;  // second 64-channel dy box
+      constexpr uint32_t LBO_B = (32u >> 4) << 16;                 // next tap of the kernel row = next halo pixel = 32 B
+      constexpr uint32_t ROWP = (HALO_W * 32) >> 4;                // halo row pitch in 16-byte units
+      int s = 0, it = 0;
+      uint32_t ph = 0;
+      for (int item = pair; item < p.items; item += npairs, ++it) {
+        int cb, ob, ks;
+        decode(p, item, cb, ob, ks);
+        const int tile0 = (int)((long)ks * p.tiles_total / p.ksplit);
+        const int tile1 = (int)((long)(ks + 1) * p.tiles_total / p.ksplit);
+        ptx::mbar_wait_cluster(tempty, (it & 1) ^ 1);
+        ptx::tc_fence_after();
+        uint32_t accumulate = 0;
+        for (int tile = tile0; tile < tile1; ++tile) {
+          ptx::mbar_wait_cluster(&full[s], ph);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            const uint32_t y_lo = base_lo + s * ((uint32_t)STAGEP_BYTES >> 4);
+            const uint32_t x_lo = y_lo + (DY2_BYTES >> 4);
+#pragma unroll
+            for (int kk = 0; kk < TILE_H; ++kk) {
+              const uint32_t acc = kk ? 1u : accumulate;
+              const uint64_t da = ptx::pack_desc((y_lo + kk * ((TILE_W * 128) >> 4)) | LBO_A, hi_a);
+              const uint32_t xr = x_lo + kk * ROWP;
+              ptx::umma_bf16_pair(tmem_base + 0 * N2, da, ptx::pack_desc((xr + 0 * ROWP) | LBO_B, hi_b), idesc, acc);
+              ptx::umma_bf16_pair(tmem_base + 1 * N2, da, ptx::pack_desc((xr + 1 * ROWP) | LBO_B, hi_b), idesc, acc);
+              ptx::umma_bf16_pair(tmem_base + 2 * N2, da, ptx::pack_desc((xr + 2 * ROWP) | LBO_B, hi_b), idesc, acc);
+            }
+            ptx::umma_commit_pair(empty_s + s * 8, 3);             // frees stage s in BOTH CTAs
+          }
+          accumulate = 1;
+          __syncwarp();
+          if (++s == PAIR_STAGES) { s = 0; ph ^= 1; }
+        }
+        if (ptx::elect_one()) ptx::umma_commit_pair(ptx::smem_u32(tfull), 3);
+        __syncwarp();
+      }
+    }
+  } else {
+    // ============================== epilogue (warps 2..5, both CTAs) ==============================
+    const int lg = warp & 3;
+    int it = 0;
+    for (int item = pair; item < p.items; item += npairs, ++it) {
+      int cb, ob, ks;
+      decode(p, item, cb, ob, ks);
+      ptx::mbar_wait_cluster(tfull, it & 1);
+      ptx::tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
+      const int cout = ob * 256 + (int)rank * 128 + lg * 32 + lane;
+      float* dst = p.partial + (((long)ks * p.Cout + cout) * 9) * p.Cin + cb * 32;
+#pragma unroll 1
+      for (int j = 0; j < 9; ++j) {              // 32-column chunk j of the 288 accumulator columns
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(t_addr + (uint32_t)(j * 32), r);
+        ptx::tmem_ld_wait();
+        if (cout < p.Cout) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {          // 16-column run: column c16 = 2*j + h of 18 runs
+            const int run = 2 * j + h;
+            const int dyk = run / 6, rr = run - dyk * 6;          // kernel row, run within the row's 96 columns
+            const int half = rr / 3, dxk = rr - half * 3;         // which CTA's channels, tap within the row
+            float4* d4 = reinterpret_cast<float4*>(dst + (long)(dyk * 3 + dxk) * p.Cin + half * 16);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              d4[q] = make_float4(__uint_as_float(r[h * 16 + 4 * q]), __uint_as_float(r[h * 16 + 4 * q + 1]),
+                                  __uint_as_float(r[h * 16 + 4 * q + 2]), __uint_as_float(r[h * 16 + 4 * q + 3]));
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(tempty, 0);          // the LEADER's barrier
+    }
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();                       // neither CTA may leave (or free TMEM) while its peer still uses the pair
+  if (warp == 2) ptx::tmem_dealloc_pair(tmem_base, 512);
+}
+
 void plan(const rbu_wgrad_args* a, HWParams* p) {
   memset(p, 0, sizeof(*p));
   p->N = a->N; p->H = a->H; p->W = a->W;
@@ -373,6 +537,9 @@ void plan(const rbu_wgrad_args* a, HWParams* p) {
     const bool form2 = !v1 && a->Ca % 128 == 0 && a->Cb % 32 == 0;
     p->OB = form2 ? 128 : 64;
     p->CB = form2 ? 32 : 64;
+    static int pair = -1;
+    if (pair < 0) pair = getenv("RBU_WGRAD_NOPAIR") ? 0 : 1;     // RBU_WGRAD_NOPAIR=1: second form everywhere (A/B measurements)
+    if (form2 && pair && a->Ca % 256 == 0) p->OB = 256;          // third form: a CTA pair per item
   }
   p->cin_blocks = rbu_cdiv(a->Cb, p->CB);
   p->cout_blocks = rbu_cdiv(a->Ca, p->OB);
@@ -381,8 +548,8 @@ void plan(const rbu_wgrad_args* a, HWParams* p) {
   // 256 items on 148 SMs = 86.5 % of the SM-time busy, tensor pipe 72 % while busy but 59 % of the launch).  Every CTA
   // walks ceil(items / SMs) items of tiles_total / k tiles each; an item ends with an un-overlapped epilogue (147 KB of
   // partial sums) and every extra split adds one partial tensor for the ordered reduction kernel to read back.
-  const int sms = rbu_num_sms();
-  const double t_tile = p->OB == 128 ? 1550.0 : 1900.0;       // cycles per 8x16-pixel tile at the measured MMA efficiency
+  const int sms = p->OB == 256 ? rbu_num_sms() / 2 : rbu_num_sms();      // work items run on CTAs or on CTA pairs
+  const double t_tile = p->OB == 128 ? 1550.0 : (p->OB == 256 ? 1400.0 : 1900.0);       // cycles per 8x16-pixel tile at the measured MMA efficiency
   const double t_epi = 6000.0;                                // TMEM -> global drain of one item
   const double out_bytes = (double)a->Ca * 9.0 * a->Cb * 4.0;
   const double t_red = out_bytes / (3.0e12 / 1.8e9);          // cycles per split: one more partial tensor for the reduction kernel
@@ -418,13 +585,13 @@ int rbu_wgrad_halo_launch(const rbu_wgrad_args* a, void* workspace, cudaStream_t
   HWParams p;
   plan(a, &p);
   p.partial = reinterpret_cast<float*>(workspace);
-  const bool form2 = p.OB == 128;
+  const bool form2 = p.OB == 128, pairf = p.OB == 256;
   CUtensorMap tmX, tmDy;
   {
     const uint64_t dims[4] = {(uint64_t)a->Cb, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->N};
     const uint64_t str[3] = {(uint64_t)a->b_ld * 2, (uint64_t)a->b_ld * 2 * a->W, (uint64_t)a->b_ld * 2 * a->W * a->H};
-    const uint32_t box[4] = {(uint32_t)p.CB, HALO_W, HALO_H, 1};
-    int rc = rbu_encode_tmap_bf16_sw(&tmX, a->b, 4, dims, str, box, form2 ? 64 : 128);
+    const uint32_t box[4] = {pairf ? 16u : (uint32_t)p.CB, HALO_W, HALO_H, 1};
+    int rc = rbu_encode_tmap_bf16_sw(&tmX, a->b, 4, dims, str, box, pairf ? 32 : (form2 ? 64 : 128));
     if (rc) return rc;
   }
   {
@@ -442,6 +609,19 @@ int rbu_wgrad_halo_launch(const rbu_wgrad_args* a, void* workspace, cudaStream_t
   if (rbu_first_use_on_device(&attr_set)) {
     RBU_CHECK_CUDA(cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     RBU_CHECK_CUDA(cudaFuncSetAttribute(wgrad_halo2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+  }
+  if (pairf) {
+    static std::atomic<unsigned long long> attr_pair{0};
+    if (rbu_first_use_on_device(&attr_pair))
+      RBU_CHECK_CUDA(cudaFuncSetAttribute(wgrad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    const int pairs = rbu_num_sms() / 2;
+    const int gridp = 2 * (p.items < pairs ? p.items : pairs);
+    p.stages = PAIR_STAGES;
+    wgrad_pair_kernel<<<gridp, NUM_THREADS, PAIR_STAGES * STAGEP_BYTES + 1024 + 256, stream>>>(tmX, tmDy, p);
+    RBU_CHECK_LAUNCH();
+    rbu_wgrad_reduce_launch(p.partial, p.ksplit, a->Ca, 9, a->Cb, a->out, a->accumulate, stream);
+    RBU_CHECK_LAUNCH();
+    return RBU_OK;
   }
   const int grid = p.items < rbu_num_sms() ? p.items : rbu_num_sms();
   if (form2)
