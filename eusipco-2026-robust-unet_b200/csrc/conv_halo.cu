@@ -58,6 +58,7 @@ struct HParams {
   int nseg;
   int taps[2], C[2];
   int a_stages, b_stages, tmem_cols, total_tiles;
+  int sp_total;   // spatial tiles (tiles_w * tiles_h * N); a CTA pair's work unit is two of them times one column block
   int tps;   // taps per B stage for a 3x3 segment (3 = one kernel row per stage when block_n <= 128, else 1)
   int resident;   // 1: the whole weight operand (slabs x 9 taps) stays in shared memory for the life of the CTA
   bf16* y;
@@ -73,10 +74,10 @@ struct HParams {
 
 // Enumerates the (tile, segment, 64-channel slab) sequence of this CTA; producer and MMA issuer walk it in lockstep.
 struct SlabIter {
-  int tile, seg, kc;
+  int tile, seg, kc, stride;
   bool valid;
-  __device__ __forceinline__ void init(const HParams& p) {
-    tile = blockIdx.x; seg = 0; kc = 0;
+  __device__ __forceinline__ void init(const HParams& p, int first, int step) {
+    tile = first; seg = 0; kc = 0; stride = step;
     valid = tile < p.total_tiles;
   }
   __device__ __forceinline__ void next(const HParams& p) {
@@ -84,27 +85,65 @@ struct SlabIter {
     kc = 0;
     if (++seg < p.nseg) return;
     seg = 0;
-    tile += gridDim.x;
+    tile += stride;
     valid = tile < p.total_tiles;
   }
 };
 
-__device__ __forceinline__ void tile_coords(const HParams& p, int tile, int& nb, int& w0, int& h0, int& n) {
-  const int sp = fast_div(tile, p.fd_nb);
+// PAIR: work unit `tile` = (two horizontally consecutive spatial tiles, one column block); CTA `rank` of the pair owns
+// spatial tile 2 * (tile / n_blocks) + rank, which may lie past the end (odd tile count): the CTA still walks the
+// schedule (its TMA boxes are out of bounds = zero fill) but stores nothing.
+template <bool PAIR>
+__device__ __forceinline__ bool tile_coords(const HParams& p, int tile, int rank, int& nb, int& w0, int& h0, int& n) {
+  int sp = fast_div(tile, p.fd_nb);
   nb = tile - sp * p.n_blocks;
+  if (PAIR) sp = 2 * sp + rank;
   const int q = fast_div(sp, p.fd_tw);
   w0 = (sp - q * p.tiles_w) * TILE_W;
   n = fast_div(q, p.fd_th);
   h0 = (q - n * p.tiles_h) * TILE_H;
+  return !PAIR || sp < p.sp_total;
 }
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
-                 const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
-                 const __grid_constant__ HParams p) {
+// barrier / TMA / MMA primitives of the single-CTA and the CTA-pair (cta_group::2) instantiation
+template <bool PAIR> __device__ __forceinline__ void bar_wait(uint64_t* b, uint32_t par) {
+  if (PAIR) ptx::mbar_wait_cluster(b, par); else ptx::mbar_wait(b, par);
+}
+template <bool PAIR> __device__ __forceinline__ void bar_wait_s(uint32_t b, uint32_t par) {
+  if (PAIR) ptx::mbar_wait_cluster_s(b, par); else ptx::mbar_wait_s(b, par);
+}
+template <bool PAIR> __device__ __forceinline__ void bar_wait_backoff(uint64_t* b, uint32_t par) {
+  if (PAIR) ptx::mbar_wait_cluster_backoff(b, par); else ptx::mbar_wait_backoff(b, par);
+}
+template <bool PAIR> __device__ __forceinline__ void load_4d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  if (PAIR) ptx::tma_load_4d_pair(dst, m, bar, c0, c1, c2, c3); else ptx::tma_load_4d(dst, m, bar, c0, c1, c2, c3);
+}
+template <bool PAIR> __device__ __forceinline__ void load_2d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  if (PAIR) ptx::tma_load_2d_pair(dst, m, bar, c0, c1); else ptx::tma_load_2d(dst, m, bar, c0, c1);
+}
+template <bool PAIR> __device__ __forceinline__ void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  if (PAIR) ptx::umma_bf16_pair(d, a, b, idesc, acc); else ptx::umma_bf16(d, a, b, idesc, acc);
+}
+template <bool PAIR> __device__ __forceinline__ void commit_s(uint32_t bar) {
+  if (PAIR) ptx::umma_commit_pair(bar, 3); else ptx::umma_commit_s(bar);
+}
+
+// PAIR = true: the kernel runs as thread-block clusters of two CTAs (cta_group::2).  Each CTA owns its own spatial tile
+// (halo in its own shared memory = 128 + 128 of the M = 256 rows of every MMA) and HALF of the weight tile (block_n / 2
+// output channels: the B operand of a pair MMA is split along N between the two CTAs' shared memory), so the weight
+// bytes per SM -- L2 -> SM traffic and shared-memory operand fetch -- halve.  Only the leader (cluster rank 0) issues
+// MMAs; its commits are multicast to both CTAs' empty / accumulator-full barriers, both CTAs' TMA loads count on the
+// leader's full barriers, and both epilogues arrive on the leader's accumulator-empty barriers.
+template <bool PAIR>
+__device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CUtensorMap& tmB0, const CUtensorMap& tmA1,
+                                               const CUtensorMap& tmB1, const HParams& p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int b_bytes = p.block_n * 128;          // one tap's weight tile
+  const int rank = PAIR ? (int)ptx::cluster_ctarank() : 0;
+  const int cta0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;        // first work unit and stride of this CTA (pair)
+  const int cta_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int bn_cta = PAIR ? p.block_n >> 1 : p.block_n;   // weight rows (output channels) in this CTA's shared memory
+  const int b_bytes = bn_cta * 128;             // one tap's weight tile
   const int bs_bytes = b_bytes * p.tps;         // one B stage
   uint8_t* smA = smem;
   uint8_t* smB = smem + p.a_stages * A_HALO_BYTES;
@@ -143,13 +182,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
     for (int a = 0; a < MAX_SLOTS; ++a) {
       ptx::mbar_init(&tfull[a], 1);
-      ptx::mbar_init(&tempty[a], 4);   // the four epilogue warps of one half-tile
+      ptx::mbar_init(&tempty[a], PAIR ? 8 : 4);   // the four epilogue warps of one half-tile (of both CTAs)
     }
     ptx::fence_barrier_init();
   }
+  if (PAIR) ptx::cluster_sync_all();             // both CTAs' barriers exist before anything arrives on them remotely
   if (warp == 2) {
-    ptx::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
-    ptx::tmem_relinquish();
+    if (PAIR) {
+      ptx::tmem_alloc_pair(tmem_slot, (uint32_t)p.tmem_cols);
+      ptx::tmem_relinquish_pair();
+    } else {
+      ptx::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -160,8 +205,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     // ============================== TMA producer ==============================
     if (lane == 0) {
       SlabIter ia, ib;
-      ia.init(p);
-      ib.init(p);
+      ia.init(p, cta0, cta_step);
+      ib.init(p, cta0, cta_step);
+      const uint32_t txm = PAIR ? 2u : 1u;       // both CTAs' bytes land on the leader's barrier
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
       auto issue_a = [&]() {
@@ -169,30 +215,30 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const uint32_t ph = pha;
         if (++sa == p.a_stages) { sa = 0; pha ^= 1; }
         int nb, w0, h0, n;
-        tile_coords(p, ia.tile, nb, w0, h0, n);
+        tile_coords<PAIR>(p, ia.tile, rank, nb, w0, h0, n);
         const bool halo = p.taps[ia.seg] == 9;
-        ptx::mbar_wait_backoff(&emptyA[s], ph ^ 1);
-        ptx::mbar_arrive_expect_tx(&fullA[s], halo ? A_HALO_BYTES : A_PLAIN_BYTES);
+        bar_wait_backoff<PAIR>(&emptyA[s], ph ^ 1);
+        if (rank == 0) ptx::mbar_arrive_expect_tx(&fullA[s], txm * (halo ? A_HALO_BYTES : A_PLAIN_BYTES));
         const CUtensorMap* mA = ia.seg ? &tmA1 : &tmA0;
         if (halo)
-          ptx::tma_load_4d(smA + s * A_HALO_BYTES, mA, &fullA[s], ia.kc * BLOCK_K, w0 - 1, h0 - 1, n);
+          load_4d<PAIR>(smA + s * A_HALO_BYTES, mA, &fullA[s], ia.kc * BLOCK_K, w0 - 1, h0 - 1, n);
         else
-          ptx::tma_load_4d(smA + s * A_HALO_BYTES, mA, &fullA[s], ia.kc * BLOCK_K, w0, h0, n);
+          load_4d<PAIR>(smA + s * A_HALO_BYTES, mA, &fullA[s], ia.kc * BLOCK_K, w0, h0, n);
         ia.next(p);
       };
       if (p.resident) {
         // the weights of a 64-output-channel layer fit in shared memory: fetch them once, then stream only A tiles
         const int slabs = p.C[0] / BLOCK_K;
-        ptx::mbar_arrive_expect_tx(&fullB[0], (uint32_t)(slabs * 9 * b_bytes));
+        if (rank == 0) ptx::mbar_arrive_expect_tx(&fullB[0], txm * (uint32_t)(slabs * 9 * b_bytes));
         for (int kc = 0; kc < slabs; ++kc)
           for (int tap = 0; tap < 9; ++tap)
-            ptx::tma_load_2d(smB + (kc * 9 + tap) * b_bytes, &tmB0, &fullB[0], tap * p.C[0] + kc * BLOCK_K, 0);
+            load_2d<PAIR>(smB + (kc * 9 + tap) * b_bytes, &tmB0, &fullB[0], tap * p.C[0] + kc * BLOCK_K, rank * bn_cta);
         while (ia.valid) issue_a();
       }
       if (!p.resident && ia.valid) issue_a();
       while (!p.resident && ib.valid) {
         int nb, w0, h0, n;
-        tile_coords(p, ib.tile, nb, w0, h0, n);
+        tile_coords<PAIR>(p, ib.tile, rank, nb, w0, h0, n);
         const int taps = p.taps[ib.seg];
         const int tps = taps == 9 ? p.tps : 1;
         const int look = taps - 1 < LOOKAHEAD_TAP ? taps - 1 : LOOKAHEAD_TAP;
@@ -201,30 +247,30 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           const int s = sb;
           const uint32_t ph = phb;
           if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
-          ptx::mbar_wait_backoff(&emptyB[s], ph ^ 1);
-          ptx::mbar_arrive_expect_tx(&fullB[s], (uint32_t)(b_bytes * tps));
+          bar_wait_backoff<PAIR>(&emptyB[s], ph ^ 1);
+          if (rank == 0) ptx::mbar_arrive_expect_tx(&fullB[s], txm * (uint32_t)(b_bytes * tps));
           for (int j = 0; j < tps; ++j)
-            ptx::tma_load_2d(smB + s * bs_bytes + j * b_bytes, mB, &fullB[s], (tap0 + j) * p.C[ib.seg] + ib.kc * BLOCK_K,
-                             nb * p.block_n);
+            load_2d<PAIR>(smB + s * bs_bytes + j * b_bytes, mB, &fullB[s], (tap0 + j) * p.C[ib.seg] + ib.kc * BLOCK_K,
+                          nb * p.block_n + rank * bn_cta);
           if (tap0 <= look && look < tap0 + tps && ia.valid) issue_a();
         }
         ib.next(p);
       }
     }
-  } else if (warp == 1) {
-    // ============================== MMA issuer ==============================
+  } else if (warp == 1 && rank == 0) {
+    // ============================== MMA issuer (PAIR: the leader CTA only) ==============================
     // The whole warp walks the schedule (uniform control flow, barrier waits by all lanes); one elected lane issues
     // the tcgen05 instructions.  The per-tap body is kept to a few dozen instructions: descriptor halves are
     // precomputed, ring indices wrap by compare instead of modulo -- the issuing thread, not the tensor pipe, was the
     // bottleneck of the first version (ncu: ~1190 cycles of scalar code per tap, profiles/r01_b_*).
-    const uint32_t idesc = ptx::make_idesc_bf16(BLOCK_M, p.block_n, 0, 0);
+    const uint32_t idesc = ptx::make_idesc_bf16(PAIR ? 2 * BLOCK_M : BLOCK_M, p.block_n, 0, 0);
     const uint32_t fullA_s = ptx::smem_u32(fullA), emptyA_s = ptx::smem_u32(emptyA);
     const uint32_t fullB_s = ptx::smem_u32(fullB), emptyB_s = ptx::smem_u32(emptyB);
     const uint32_t smA_s = ptx::smem_u32(smA), smB_s = ptx::smem_u32(smB);
     const uint32_t b_hi = ptx::desc_hi(1024);
     const uint32_t b_step = (uint32_t)b_bytes >> 4;
     SlabIter it;
-    it.init(p);
+    it.init(p, cta0, cta_step);
     int sa = 0, sb = 0, t = 0;
     uint32_t pha = 0, phb = 0;
     bool bres_ready = false;
@@ -232,14 +278,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       // half-tiles 2t (left) and 2t+1 (right) of this CTA's t-th tile: accumulator slots and their use counts
       const int sl = (2 * t) & p.slot_mask, sr = (2 * t + 1) & p.slot_mask;
       const uint32_t use_par = (uint32_t)((2 * t) >> p.slot_shift) & 1u;
-      ptx::mbar_wait(&tempty[sl], use_par ^ 1);
-      ptx::mbar_wait(&tempty[sr], use_par ^ 1);
+      bar_wait<PAIR>(&tempty[sl], use_par ^ 1);
+      bar_wait<PAIR>(&tempty[sr], use_par ^ 1);
       ptx::tc_fence_after();
       const uint32_t d_l = tmem_base + (uint32_t)(sl * p.block_n), d_r = tmem_base + (uint32_t)(sr * p.block_n);
       const int cur_tile = it.tile;
       uint32_t accumulate = 0;
       while (it.valid && it.tile == cur_tile) {
-        ptx::mbar_wait_s(fullA_s + sa * 8, pha);
+        bar_wait_s<PAIR>(fullA_s + sa * 8, pha);
         ptx::tc_fence_after();
         const int taps = p.taps[it.seg];
         const bool halo = taps == 9;
@@ -252,7 +298,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         if (p.resident) {
           // 72 MMAs per slab straight from the resident weights: one barrier wait (the A tile) per 72 instructions
           if (!bres_ready) {
-            ptx::mbar_wait_s(fullB_s, 0);
+            bar_wait_s<PAIR>(fullB_s, 0);
             ptx::tc_fence_after();
             bres_ready = true;
           }
@@ -267,8 +313,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                   const uint64_t bd = ptx::pack_desc(b_lo + (dy * 3 + dx) * b_step + 2 * k, b_hi);
                   const uint32_t al = a_lo0 + dy * ROW_OFF + dx * 8 + 2 * k;
                   const uint32_t acc = (dy | dx | k) ? 1u : accumulate;
-                  ptx::umma_bf16(d_l, ptx::pack_desc(al, a_hi), bd, idesc, acc);
-                  ptx::umma_bf16(d_r, ptx::pack_desc(al + HALF_OFF, a_hi), bd, idesc, acc);
+                  mma<PAIR>(d_l, ptx::pack_desc(al, a_hi), bd, idesc, acc);
+                  mma<PAIR>(d_r, ptx::pack_desc(al + HALF_OFF, a_hi), bd, idesc, acc);
                 }
           }
           accumulate = 1;
@@ -277,7 +323,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           // one kernel row (3 taps x 2 halves x 4 K-steps = 24 MMAs) per B stage, fully unrolled with immediate offsets
           uint32_t a_row = a_lo0;
           for (int dy = 0; dy < 3; ++dy) {
-            ptx::mbar_wait_s(fullB_s + sb * 8, phb);
+            bar_wait_s<PAIR>(fullB_s + sb * 8, phb);
             ptx::tc_fence_after();
             if (ptx::elect_one()) {
               const uint32_t b_lo = ptx::desc_lo(smB_s, 16) + sb * (3 * b_step);
@@ -287,11 +333,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 for (int k = 0; k < 4; ++k) {
                   const uint64_t bd = ptx::pack_desc(b_lo + dx * b_step + 2 * k, b_hi);
                   const uint32_t acc = (dx | k) ? 1u : accumulate;
-                  ptx::umma_bf16(d_l, ptx::pack_desc(a_row + dx * 8 + 2 * k, a_hi), bd, idesc, acc);
-                  ptx::umma_bf16(d_r, ptx::pack_desc(a_row + HALF_OFF + dx * 8 + 2 * k, a_hi), bd, idesc, acc);
+                  mma<PAIR>(d_l, ptx::pack_desc(a_row + dx * 8 + 2 * k, a_hi), bd, idesc, acc);
+                  mma<PAIR>(d_r, ptx::pack_desc(a_row + HALF_OFF + dx * 8 + 2 * k, a_hi), bd, idesc, acc);
                 }
               }
-              ptx::umma_commit_s(emptyB_s + sb * 8);
+              commit_s<PAIR>(emptyB_s + sb * 8);
             }
             accumulate = 1;
             __syncwarp();
@@ -304,7 +350,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           int dx = 0, j = 0;
           for (int tap = 0; tap < taps; ++tap) {
             if (j == 0) {
-              ptx::mbar_wait_s(fullB_s + sb * 8, phb);
+              bar_wait_s<PAIR>(fullB_s + sb * 8, phb);
               ptx::tc_fence_after();
             }
             if (ptx::elect_one()) {
@@ -313,12 +359,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
               for (int k = 0; k < 4; ++k) {
                 if (k < ksteps) {
                   const uint64_t bd = ptx::pack_desc(b_lo + 2 * k, b_hi);
-                  ptx::umma_bf16(d_l, ptx::pack_desc(a_lo + 2 * k, a_hi), bd, idesc, accumulate);
-                  ptx::umma_bf16(d_r, ptx::pack_desc(a_lo + HALF_OFF + 2 * k, a_hi), bd, idesc, accumulate);
+                  mma<PAIR>(d_l, ptx::pack_desc(a_lo + 2 * k, a_hi), bd, idesc, accumulate);
+                  mma<PAIR>(d_r, ptx::pack_desc(a_lo + HALF_OFF + 2 * k, a_hi), bd, idesc, accumulate);
                   accumulate = 1;
                 }
               }
-              if (j == tps - 1) ptx::umma_commit_s(emptyB_s + sb * 8);
+              if (j == tps - 1) commit_s<PAIR>(emptyB_s + sb * 8);
             }
             accumulate = 1;
             __syncwarp();
@@ -329,19 +375,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             if (++dx == 3) { dx = 0; a_row += ROW_OFF; a_lo = a_row; } else { a_lo += 128 >> 4; }
           }
         }
-        if (ptx::elect_one()) ptx::umma_commit_s(emptyA_s + sa * 8);
+        if (ptx::elect_one()) commit_s<PAIR>(emptyA_s + sa * 8);
         __syncwarp();
         if (++sa == p.a_stages) { sa = 0; pha ^= 1; }
         it.next(p);
       }
       if (ptx::elect_one()) {
-        ptx::umma_commit(&tfull[sl]);
-        ptx::umma_commit(&tfull[sr]);
+        commit_s<PAIR>(ptx::smem_u32(&tfull[sl]));
+        commit_s<PAIR>(ptx::smem_u32(&tfull[sr]));
       }
       __syncwarp();
       ++t;
     }
-  } else {
+  } else if (warp >= 2) {
     // ============================== epilogue (warps 2..9) ==============================
     // Warps 2-5 (half 0) drain the left 16 x 8-pixel half-tile of every tile, warps 6-9 the right one: accumulator row
     // r = 32 lg + lane is pixel (r >> 3, 8 half + (r & 7)) of the tile, and the warp drains all of its 32-column chunks.
@@ -356,10 +402,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const int mode = (p.addend ? 1 : 0) | (p.bias ? 2 : 0) | ((p.scale || p.relu) ? 4 : 0);
     auto locate = [&](int tile, int& nb, bool& valid, long long& pix, int& n, int& h, int& w) {
       int w0, h0;
-      tile_coords(p, tile, nb, w0, h0, n);
+      const bool ok = tile_coords<PAIR>(p, tile, rank, nb, w0, h0, n);
       h = h0 + hl;
       w = w0 + wl;
-      valid = h < p.H && w < p.W;
+      valid = ok && h < p.H && w < p.W;
       pix = ((long long)n * p.H + h) * p.W + w;
     };
     int k = 0;
@@ -368,20 +414,20 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     bool valid;
     long long pix;
     uint4 ad[4];
-    if (blockIdx.x < p.total_tiles) {
-      locate(blockIdx.x, nb, valid, pix, n, h, w);
+    if (cta0 < p.total_tiles) {
+      locate(cta0, nb, valid, pix, n, h, w);
       epi_prefetch(eo, nb * p.block_n, valid, pix, ad);
     }
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++k) {
+    for (int tile = cta0; tile < p.total_tiles; tile += cta_step, ++k) {
       const int t = 2 * k + half;                 // half-tile counter of this CTA
       const int slot = t & p.slot_mask;
       const uint32_t par = (uint32_t)(t >> p.slot_shift) & 1u;
       int nb2 = 0, n2 = 0, h2 = 0, w2 = 0;
       bool valid2 = false;
       long long pix2 = 0;
-      const bool more = tile + gridDim.x < p.total_tiles;
-      if (more) locate(tile + gridDim.x, nb2, valid2, pix2, n2, h2, w2);
-      ptx::mbar_wait(&tfull[slot], par);
+      const bool more = tile + cta_step < p.total_tiles;
+      if (more) locate(tile + cta_step, nb2, valid2, pix2, n2, h2, w2);
+      bar_wait<PAIR>(&tfull[slot], par);
       ptx::tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(slot * p.block_n);
       bf16* yrow = p.y + pix * p.y_ld;
@@ -440,7 +486,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll
             for (int q = 0; q < 4; ++q) xb[(lg * 4 + q) * 32 + lane] = red[q];
             asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
-            if (lg == 0) {
+            if (lg == 0 && (!PAIR || n < p.N)) {
               float acc[4];
 #pragma unroll
               for (int q = 0; q < 4; ++q) acc[q] = xb[q * 32 + lane];
@@ -464,7 +510,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tempty[slot]);
+      if (lane == 0) {
+        if (PAIR) ptx::mbar_arrive_cluster(&tempty[slot], 0); else ptx::mbar_arrive(&tempty[slot]);
+      }
       nb = nb2; n = n2; h = h2; w = w2; valid = valid2; pix = pix2;
     }
     if (p.stats) {
@@ -483,8 +531,28 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == 2) ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  if (PAIR) {
+    __syncwarp();
+    ptx::cluster_sync_all();                     // neither CTA may leave (or free TMEM) while its peer still uses the pair
+    if (warp == 2) ptx::tmem_dealloc_pair(tmem_base, (uint32_t)p.tmem_cols);
+  } else {
+    __syncthreads();
+    if (warp == 2) ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
+                 const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
+                 const __grid_constant__ HParams p) {
+  conv_halo_body<false>(tmA0, tmB0, tmA1, tmB1, p);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+conv_halo_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
+                      const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
+                      const __grid_constant__ HParams p) {
+  conv_halo_body<true>(tmA0, tmB0, tmA1, tmB1, p);
 }
 
 }  // namespace
@@ -529,7 +597,12 @@ int rbu_conv_halo_launch(const rbu_conv_gemm_args* a, cudaStream_t stream) {
     p.taps[s] = a->seg[s].taps;
     p.C[s] = a->seg[s].C;
   }
-  const int b_bytes = p.block_n * 128;
+  // CTA pairs (cta_group::2): every shape except the per-CTA output statistics (unused by the engine) and column blocks
+  // whose halves are not whole 8-row swizzle groups; RBU_CONV_NOPAIR=1 selects the single-CTA kernel for A/B runs
+  static int no_pair = -1;
+  if (no_pair < 0) no_pair = getenv("RBU_CONV_NOPAIR") ? 1 : (getenv("RBU_CONV_PAIR") ? 0 : 1);
+  const bool pair = !no_pair && !a->stats && p.block_n % 32 == 0 && rbu_num_sms() >= 2;
+  const int b_bytes = (pair ? p.block_n / 2 : p.block_n) * 128;     // one tap's weight tile in ONE CTA's shared memory
   p.tps = p.block_n <= 128 ? 3 : 1;
   p.a_stages = 2;
   p.b_stages = (SMEM_LIMIT - 2048 - p.a_stages * A_HALO_BYTES) / (b_bytes * p.tps);
@@ -540,7 +613,9 @@ int rbu_conv_halo_launch(const rbu_conv_gemm_args* a, cudaStream_t stream) {
     if (no_res < 0) no_res = getenv("RBU_NO_RESIDENT") ? 1 : 0;
     const long wbytes = (long)(a->seg[0].C / BLOCK_K) * 9 * b_bytes;
     if (!no_res && a->nseg == 1 && a->seg[0].taps == 9 && p.n_blocks == 1 && a->seg[0].C % BLOCK_K == 0) {
-      const int as = 2;
+      static int a3 = -1;
+      if (a3 < 0) a3 = getenv("RBU_CONV_PAIR_A3") ? 1 : 0;
+      const int as = (pair && a3 && wbytes + 3 * A_HALO_BYTES <= SMEM_LIMIT - 2048) ? 3 : 2;
       if (wbytes + as * A_HALO_BYTES <= SMEM_LIMIT - 2048) {
         p.resident = 1;
         p.a_stages = as;
@@ -551,7 +626,8 @@ int rbu_conv_halo_launch(const rbu_conv_gemm_args* a, cudaStream_t stream) {
   }
   p.tmem_cols = 32;
   while (p.tmem_cols < (p.slot_mask + 1) * p.block_n) p.tmem_cols <<= 1;
-  p.total_tiles = p.tiles_w * p.tiles_h * a->N * p.n_blocks;
+  p.sp_total = p.tiles_w * p.tiles_h * a->N;
+  p.total_tiles = (pair ? (p.sp_total + 1) / 2 : p.sp_total) * p.n_blocks;
   p.y = reinterpret_cast<bf16*>(a->y);
   p.y_ld = a->y_ld;
   p.bias = a->bias;
@@ -579,7 +655,7 @@ int rbu_conv_halo_launch(const rbu_conv_gemm_args* a, cudaStream_t stream) {
     const uint64_t ktot = (uint64_t)o.taps * o.C;
     const uint64_t bdims[2] = {ktot, (uint64_t)a->Ncols};
     const uint64_t bstr[1] = {ktot * 2};
-    const uint32_t bbox[2] = {BLOCK_K, (uint32_t)p.block_n};
+    const uint32_t bbox[2] = {BLOCK_K, (uint32_t)(pair ? p.block_n / 2 : p.block_n)};
     rc = rbu_encode_tmap_bf16(&tmB[s], o.w, 2, bdims, bstr, bbox);
     if (rc) return rc;
   }
@@ -591,6 +667,16 @@ int rbu_conv_halo_launch(const rbu_conv_gemm_args* a, cudaStream_t stream) {
   static std::atomic<unsigned long long> attr_set{0};      // one bit per device ordinal
   if (rbu_first_use_on_device(&attr_set))
     RBU_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+  if (pair) {
+    static std::atomic<unsigned long long> attr_pair{0};
+    if (rbu_first_use_on_device(&attr_pair))
+      RBU_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    const int pairs = rbu_num_sms() / 2;
+    const int gridp = 2 * (p.total_tiles < pairs ? p.total_tiles : pairs);
+    conv_halo_pair_kernel<<<gridp, NUM_THREADS, smem_bytes, stream>>>(tmA[0], tmB[0], tmA[1], tmB[1], p);
+    RBU_CHECK_LAUNCH();
+    return RBU_OK;
+  }
   const int grid = p.total_tiles < rbu_num_sms() ? p.total_tiles : rbu_num_sms();
   if (a->stats) {
     RBU_CHECK_ARG(p.block_n <= 32 * EPI_STAT_CHUNKS && grid % p.n_blocks == 0 && ((uintptr_t)a->stats & 15) == 0,

@@ -266,6 +266,22 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
     if (++spins > (1u << 26)) mbar_timeout();
   }
 }
+__device__ __forceinline__ void mbar_wait_cluster_s(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (++spins > (1u << 26)) mbar_timeout();
+  }
+}
+__device__ __forceinline__ void mbar_wait_cluster_backoff(uint64_t* bar, uint32_t parity) {
+  const uint32_t b = smem_u32(bar);
+  if (mbar_try_wait_cluster(b, parity)) return;
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cluster(b, parity)) {
+    __nanosleep(64);
+    if (++spins > (1u << 24)) mbar_timeout();
+  }
+}
 // TMA load issued by either CTA of a pair into its OWN shared memory; the bytes are counted on the LEADER's mbarrier
 // (the barrier at the same offset in the even CTA: peer bit 24 of the shared::cluster address cleared)
 __device__ __forceinline__ void tma_load_4d_pair(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
@@ -273,6 +289,12 @@ __device__ __forceinline__ void tma_load_4d_pair(void* dst, const CUtensorMap* m
       "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2),
       "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
       : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {

@@ -44,6 +44,12 @@ CASES = [
     ("3x3_halo_slice", 2, 32, 48, 128, 160, 3, 1, 192, 64, 256, 32, True, False),
     ("3x3_one_tile_n256", 3, 16, 16, 128, 256, 3, 1, 128, 0, 256, 0, False, True),
     ("3x3_halo_resident", 2, 48, 32, 64, 64, 3, 1, 64, 0, 64, 0, True, False),
+    # odd numbers of spatial tiles: the second CTA of the last CTA pair has no tile (streamed and resident weights,
+    # a 96-column block whose halves are 48 weight rows per CTA, four column blocks)
+    ("3x3_odd_tiles", 3, 16, 48, 128, 128, 3, 1, 128, 0, 128, 0, True, True),
+    ("3x3_odd_resident", 1, 48, 16, 64, 64, 3, 1, 64, 0, 64, 0, False, False),
+    ("3x3_odd_n96", 1, 40, 56, 64, 96, 3, 1, 64, 0, 96, 0, True, False),
+    ("3x3_odd_4blocks", 1, 16, 16, 256, 1024, 3, 1, 256, 0, 1024, 0, False, False),
     # generic kernel, staged epilogue: weights streamed (operand > 64 KB) with bias and addend; 32-column GEMM
     ("1x1_wide_k", 2, 32, 32, 512, 256, 1, 1, 512, 0, 256, 0, True, True),
     ("1x1_n32_slice", 3, 24, 40, 64, 32, 1, 1, 128, 32, 96, 64, True, False),
