@@ -106,14 +106,11 @@ __device__ __forceinline__ bool tile_coords(const HParams& p, int tile, int rank
 }
 
 // barrier / TMA / MMA primitives of the single-CTA and the CTA-pair (cta_group::2) instantiation
-template <bool PAIR> __device__ __forceinline__ void bar_wait(uint64_t* b, uint32_t par) {
+// Barriers completed by tcgen05.commit or TMA complete_tx are polled with the CTA-scope wait in both instantiations (the
+// data they guard travels through the async proxy / TMEM); only the accumulator-empty barriers, which collect
+// release.cluster arrivals from the peer CTA's epilogue threads, need the cluster-scope acquire.
+template <bool PAIR> __device__ __forceinline__ void bar_wait_remote(uint64_t* b, uint32_t par) {
   if (PAIR) ptx::mbar_wait_cluster(b, par); else ptx::mbar_wait(b, par);
-}
-template <bool PAIR> __device__ __forceinline__ void bar_wait_s(uint32_t b, uint32_t par) {
-  if (PAIR) ptx::mbar_wait_cluster_s(b, par); else ptx::mbar_wait_s(b, par);
-}
-template <bool PAIR> __device__ __forceinline__ void bar_wait_backoff(uint64_t* b, uint32_t par) {
-  if (PAIR) ptx::mbar_wait_cluster_backoff(b, par); else ptx::mbar_wait_backoff(b, par);
 }
 template <bool PAIR> __device__ __forceinline__ void load_4d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
   if (PAIR) ptx::tma_load_4d_pair(dst, m, bar, c0, c1, c2, c3); else ptx::tma_load_4d(dst, m, bar, c0, c1, c2, c3);
@@ -217,7 +214,7 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
         int nb, w0, h0, n;
         tile_coords<PAIR>(p, ia.tile, rank, nb, w0, h0, n);
         const bool halo = p.taps[ia.seg] == 9;
-        bar_wait_backoff<PAIR>(&emptyA[s], ph ^ 1);
+        ptx::mbar_wait_backoff(&emptyA[s], ph ^ 1);
         if (rank == 0) ptx::mbar_arrive_expect_tx(&fullA[s], txm * (halo ? A_HALO_BYTES : A_PLAIN_BYTES));
         const CUtensorMap* mA = ia.seg ? &tmA1 : &tmA0;
         if (halo)
@@ -247,7 +244,7 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
           const int s = sb;
           const uint32_t ph = phb;
           if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
-          bar_wait_backoff<PAIR>(&emptyB[s], ph ^ 1);
+          ptx::mbar_wait_backoff(&emptyB[s], ph ^ 1);
           if (rank == 0) ptx::mbar_arrive_expect_tx(&fullB[s], txm * (uint32_t)(b_bytes * tps));
           for (int j = 0; j < tps; ++j)
             load_2d<PAIR>(smB + s * bs_bytes + j * b_bytes, mB, &fullB[s], (tap0 + j) * p.C[ib.seg] + ib.kc * BLOCK_K,
@@ -278,14 +275,14 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
       // half-tiles 2t (left) and 2t+1 (right) of this CTA's t-th tile: accumulator slots and their use counts
       const int sl = (2 * t) & p.slot_mask, sr = (2 * t + 1) & p.slot_mask;
       const uint32_t use_par = (uint32_t)((2 * t) >> p.slot_shift) & 1u;
-      bar_wait<PAIR>(&tempty[sl], use_par ^ 1);
-      bar_wait<PAIR>(&tempty[sr], use_par ^ 1);
+      bar_wait_remote<PAIR>(&tempty[sl], use_par ^ 1);
+      bar_wait_remote<PAIR>(&tempty[sr], use_par ^ 1);
       ptx::tc_fence_after();
       const uint32_t d_l = tmem_base + (uint32_t)(sl * p.block_n), d_r = tmem_base + (uint32_t)(sr * p.block_n);
       const int cur_tile = it.tile;
       uint32_t accumulate = 0;
       while (it.valid && it.tile == cur_tile) {
-        bar_wait_s<PAIR>(fullA_s + sa * 8, pha);
+        ptx::mbar_wait_s(fullA_s + sa * 8, pha);
         ptx::tc_fence_after();
         const int taps = p.taps[it.seg];
         const bool halo = taps == 9;
@@ -298,7 +295,7 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
         if (p.resident) {
           // 72 MMAs per slab straight from the resident weights: one barrier wait (the A tile) per 72 instructions
           if (!bres_ready) {
-            bar_wait_s<PAIR>(fullB_s, 0);
+            ptx::mbar_wait_s(fullB_s, 0);
             ptx::tc_fence_after();
             bres_ready = true;
           }
@@ -323,7 +320,7 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
           // one kernel row (3 taps x 2 halves x 4 K-steps = 24 MMAs) per B stage, fully unrolled with immediate offsets
           uint32_t a_row = a_lo0;
           for (int dy = 0; dy < 3; ++dy) {
-            bar_wait_s<PAIR>(fullB_s + sb * 8, phb);
+            ptx::mbar_wait_s(fullB_s + sb * 8, phb);
             ptx::tc_fence_after();
             if (ptx::elect_one()) {
               const uint32_t b_lo = ptx::desc_lo(smB_s, 16) + sb * (3 * b_step);
@@ -350,7 +347,7 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
           int dx = 0, j = 0;
           for (int tap = 0; tap < taps; ++tap) {
             if (j == 0) {
-              bar_wait_s<PAIR>(fullB_s + sb * 8, phb);
+              ptx::mbar_wait_s(fullB_s + sb * 8, phb);
               ptx::tc_fence_after();
             }
             if (ptx::elect_one()) {
@@ -427,7 +424,7 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
       long long pix2 = 0;
       const bool more = tile + cta_step < p.total_tiles;
       if (more) locate(tile + cta_step, nb2, valid2, pix2, n2, h2, w2);
-      bar_wait<PAIR>(&tfull[slot], par);
+      ptx::mbar_wait(&tfull[slot], par);
       ptx::tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(slot * p.block_n);
       bf16* yrow = p.y + pix * p.y_ld;
@@ -597,11 +594,19 @@ int rbu_conv_halo_launch(const rbu_conv_gemm_args* a, cudaStream_t stream) {
     p.taps[s] = a->seg[s].taps;
     p.C[s] = a->seg[s].C;
   }
-  // CTA pairs (cta_group::2): every shape except the per-CTA output statistics (unused by the engine) and column blocks
-  // whose halves are not whole 8-row swizzle groups; RBU_CONV_NOPAIR=1 selects the single-CTA kernel for A/B runs
-  static int no_pair = -1;
-  if (no_pair < 0) no_pair = getenv("RBU_CONV_NOPAIR") ? 1 : (getenv("RBU_CONV_PAIR") ? 0 : 1);
-  const bool pair = !no_pair && !a->stats && p.block_n % 32 == 0 && rbu_num_sms() >= 2;
+  // CTA pairs (cta_group::2) halve the weight bytes every SM pulls from L2 -- what bounded the >= 128-channel layers --
+  // and make the 128->64 layer's weights resident (72 KB per CTA).  Not used where a single CTA already keeps the whole
+  // weight operand resident (64->64: nothing left to halve, and the pair's lock step costs 10 %; measured 918 vs 1020
+  // TFLOP/s), with the per-CTA output statistics (unused by the engine), or for column blocks whose halves are not whole
+  // 8-row swizzle groups.  RBU_CONV_NOPAIR=1 selects the single-CTA kernel everywhere (A/B runs), RBU_CONV_PAIR=1 the
+  // pair kernel wherever it can run.
+  static int pair_mode = -1;     // 0 never, 1 by shape, 2 always
+  if (pair_mode < 0) pair_mode = getenv("RBU_CONV_NOPAIR") ? 0 : (getenv("RBU_CONV_PAIR") ? 2 : 1);
+  const bool single_resident = !getenv("RBU_NO_RESIDENT") && a->nseg == 1 && a->seg[0].taps == 9 && p.n_blocks == 1 &&
+                               a->seg[0].C % BLOCK_K == 0 &&
+                               (long)(a->seg[0].C / BLOCK_K) * 9 * p.block_n * 128 + 2 * A_HALO_BYTES <= SMEM_LIMIT - 2048;
+  const bool pair = pair_mode && (pair_mode == 2 || !single_resident) && !a->stats && p.block_n % 32 == 0 &&
+                    rbu_num_sms() >= 2;
   const int b_bytes = (pair ? p.block_n / 2 : p.block_n) * 128;     // one tap's weight tile in ONE CTA's shared memory
   p.tps = p.block_n <= 128 ? 3 : 1;
   p.a_stages = 2;
@@ -613,9 +618,7 @@ int rbu_conv_halo_launch(const rbu_conv_gemm_args* a, cudaStream_t stream) {
     if (no_res < 0) no_res = getenv("RBU_NO_RESIDENT") ? 1 : 0;
     const long wbytes = (long)(a->seg[0].C / BLOCK_K) * 9 * b_bytes;
     if (!no_res && a->nseg == 1 && a->seg[0].taps == 9 && p.n_blocks == 1 && a->seg[0].C % BLOCK_K == 0) {
-      static int a3 = -1;
-      if (a3 < 0) a3 = getenv("RBU_CONV_PAIR_A3") ? 1 : 0;
-      const int as = (pair && a3 && wbytes + 3 * A_HALO_BYTES <= SMEM_LIMIT - 2048) ? 3 : 2;
+      const int as = 2;   // a third stage does not help (pair 64->64: 759 vs 918 TFLOP/s)
       if (wbytes + as * A_HALO_BYTES <= SMEM_LIMIT - 2048) {
         p.resident = 1;
         p.a_stages = as;

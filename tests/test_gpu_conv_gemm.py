@@ -50,6 +50,8 @@ CASES = [
     ("3x3_odd_resident", 1, 48, 16, 64, 64, 3, 1, 64, 0, 64, 0, False, False),
     ("3x3_odd_n96", 1, 40, 56, 64, 96, 3, 1, 64, 0, 96, 0, True, False),
     ("3x3_odd_4blocks", 1, 16, 16, 256, 1024, 3, 1, 256, 0, 1024, 0, False, False),
+    # 128 -> 64: resident weights in the CTA-pair kernel (72 KB per CTA), two 64-channel slabs per tile
+    ("3x3_pair_resident", 2, 32, 48, 128, 64, 3, 1, 128, 0, 64, 0, True, True),
     # generic kernel, staged epilogue: weights streamed (operand > 64 KB) with bias and addend; 32-column GEMM
     ("1x1_wide_k", 2, 32, 32, 512, 256, 1, 1, 512, 0, 256, 0, True, True),
     ("1x1_n32_slice", 3, 24, 40, 64, 32, 1, 1, 128, 32, 96, 64, True, False),
@@ -176,3 +178,24 @@ def test_invalid_arguments_raise():
         ops.conv_gemm(1, 4, 4, [(ops.View(x), w, 5, 1, False)], 64, ops.View(y))   # taps must be 1 or 9
     with pytest.raises(RuntimeError):
         ops.conv_gemm(1, 4, 4, [(ops.View(x), w, 1, 1, False)], 60, ops.View(y))   # Ncols % 8
+
+
+@pytest.mark.parametrize("switch", ["RBU_CONV_PAIR", "RBU_CONV_NOPAIR"])
+def test_halo_kernel_forced_variants(switch):
+    """The library picks the single-CTA or the CTA-pair 3x3 kernel by shape; the switches are read once per process, so
+    the 3x3 cases, the data-gradient and the two-segment case are repeated in a child process with each variant forced."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("RBU_CONV_CHILD"):
+        pytest.skip("child run")
+    env = dict(os.environ, RBU_CONV_CHILD="1")
+    env.pop("RBU_CONV_PAIR", None)
+    env.pop("RBU_CONV_NOPAIR", None)
+    env[switch] = "1"
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-m", "gpu", "-x",
+                        "-k", "3x3 or dgrad or two_segment", "-p", "no:cacheprovider"],
+                       env=env, capture_output=True, text=True, timeout=600,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout
