@@ -44,6 +44,7 @@ constexpr int A_PLAIN_BYTES = TILE_H * TILE_W * 128;  // 32768
 constexpr int NUM_THREADS = 320;   // TMA warp, MMA warp, 8 epilogue warps
 constexpr int MAX_B_STAGES = 8;
 constexpr int MAX_SLOTS = 4;
+constexpr int STG_BYTES = 32 * 64 * 2;   // staging buffer of one epilogue warp: its 32 pixels x 64 channels (one TMA store box)
 constexpr int SMEM_LIMIT = 232448 - EPI_STAT_FLOATS * 4;   // minus the static statistics accumulators
 constexpr int LOOKAHEAD_TAP = 4;                      // the next slab's A tile is requested after this tap's B tile
 constexpr uint32_t HALF_OFF = (HALF_W * 128) >> 4;    // right half-tile: 8 pixels = 1024 B further (descriptor units)
@@ -60,6 +61,8 @@ struct HParams {
   int a_stages, b_stages, tmem_cols, total_tiles;
   int sp_total;   // spatial tiles (tiles_w * tiles_h * N); a CTA pair's work unit is two of them times one column block
   int tps;   // taps per B stage for a 3x3 segment (3 = one kernel row per stage when block_n <= 128, else 1)
+  int tma_store;  // 1: outputs leave through the y tensor map (8 x 4-pixel x 64-channel boxes staged in shared memory)
+  int st_bufs;    // staging buffers per epilogue warp (1 or 2)
   int resident;   // 1: the whole weight operand (slabs x 9 taps) stays in shared memory for the life of the CTA
   bf16* y;
   long long y_ld;
@@ -133,7 +136,7 @@ template <bool PAIR> __device__ __forceinline__ void commit_s(uint32_t bar) {
 // leader's full barriers, and both epilogues arrive on the leader's accumulator-empty barriers.
 template <bool PAIR>
 __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CUtensorMap& tmB0, const CUtensorMap& tmA1,
-                                               const CUtensorMap& tmB1, const HParams& p) {
+                                               const CUtensorMap& tmB1, const CUtensorMap& tmY, const HParams& p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int rank = PAIR ? (int)ptx::cluster_ctarank() : 0;
@@ -144,7 +147,8 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
   const int bs_bytes = b_bytes * p.tps;         // one B stage
   uint8_t* smA = smem;
   uint8_t* smB = smem + p.a_stages * A_HALO_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smB + p.b_stages * bs_bytes);
+  uint8_t* stg_base = smB + p.b_stages * bs_bytes;                          // 1024-aligned: all regions are multiples of 2 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_base + (p.tma_store ? 8 * p.st_bufs * STG_BYTES : 0));
   uint64_t* fullA = bars;                      // [4]
   uint64_t* emptyA = bars + 4;                 // [4]
   uint64_t* fullB = bars + 8;                  // [MAX_B_STAGES]
@@ -163,6 +167,7 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA0);
     ptx::prefetch_tmap(&tmB0);
+    if (p.tma_store) ptx::prefetch_tmap(&tmY);
     if (p.nseg > 1) {
       ptx::prefetch_tmap(&tmA1);
       ptx::prefetch_tmap(&tmB1);
@@ -397,6 +402,15 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
     eo.y = p.y; eo.y_ld = p.y_ld; eo.bias = p.bias; eo.scale = p.scale; eo.relu = p.relu; eo.addend = p.addend; eo.addend_ld = p.addend_ld;
     eo.Ncols = p.Ncols; eo.scatter = 0; eo.Cout = p.Ncols; eo.H = p.H; eo.W = p.W;
     const int mode = (p.addend ? 1 : 0) | (p.bias ? 2 : 0) | ((p.scale || p.relu) ? 4 : 0);
+    // Staged stores: the warp's 32 accumulator rows are the 4 x 8 pixels (h0 + 4 lg .., w0 + 8 half ..) of the tile.  A
+    // 64-column "job" (two 32-column chunks) is written to a SWIZZLE_128B buffer -- row = lane, 16-byte piece g at
+    // (g ^ (lane & 7)) -- and leaves as ONE TMA box, which also clips ragged image edges.  The per-thread path stores
+    // 16 bytes per lane at a 2 * y_ld byte pitch: 32 L1 wavefronts per instruction on the data pipe the tensor core
+    // fetches its operands through (ncu: LSU wavefronts 25-46 % next to 63-73 % operand wavefronts).
+    const uint32_t stg_s = ptx::smem_u32(stg_base + (warp - 2) * p.st_bufs * STG_BYTES);
+    const uint32_t row_s = stg_s + (uint32_t)lane * 128u;
+    const uint32_t sx = (uint32_t)lane & 7u;
+    uint32_t job = 0;     // stores issued by this warp (staging buffer parity)
     auto locate = [&](int tile, int& nb, bool& valid, long long& pix, int& n, int& h, int& w) {
       int w0, h0;
       const bool ok = tile_coords<PAIR>(p, tile, rank, nb, w0, h0, n);
@@ -433,7 +447,20 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
       const int tchunk = ((h - hl) / TILE_H * p.tiles_w + (w - wl) / TILE_W) * 2 + half;
       for (int c0 = 0; c0 < p.block_n; c0 += 32) {
         const int col = nb * p.block_n + c0;
-        if (p.stats || col + 32 > p.Ncols) {
+        if (p.tma_store && col >= p.Ncols) {
+          // chunk past the last output column (Ncols % 32 == 0 here): nothing to compute, but a first half waiting in
+          // the staging buffer still has to leave
+          if (c0 & 32) {
+            const uint32_t buf = stg_s + ((p.st_bufs == 2 && (job & 1u)) ? (uint32_t)STG_BYTES : 0u);
+            ptx::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              ptx::tma_store_4d_s(&tmY, buf, col - 32, w, h, n);
+              ptx::bulk_commit();
+            }
+            ++job;
+          }
+        } else if (p.stats || col + 32 > p.Ncols) {
           epi_finish(eo, t_addr + (uint32_t)c0, col, valid, pix, n, h, w, ad, c0 >> 5);
         } else {
           uint32_t r[32];
@@ -450,7 +477,29 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
             case 6: epi_math<false, true, true>(r, p.bias, p.scale, p.relu, col, ad, out); break;
             default: epi_math<true, true, true>(r, p.bias, p.scale, p.relu, col, ad, out); break;
           }
-          if (valid) {
+          if (p.tma_store) {
+            const bool first = (c0 & 32) == 0;
+            const uint32_t buf = row_s + ((p.st_bufs == 2 && (job & 1u)) ? (uint32_t)STG_BYTES : 0u);
+            if (first) {   // the store that last read this buffer has drained it
+              if (lane == 0) {
+                if (p.st_bufs == 2) ptx::bulk_wait_read<1>(); else ptx::bulk_wait_read<0>();
+              }
+              __syncwarp();
+            }
+            const uint32_t pb = first ? 0u : 4u;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) ptx::st_shared_v4(buf + (((pb + (uint32_t)g) ^ sx) << 4), out[g]);
+            if (!first || c0 + 32 >= p.block_n) {
+              ptx::fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {   // lane 0 is the box origin: pixel (h0 + 4 lg, w0 + 8 half); columns past Ncols, pixels past
+                                 // the image and the tile of a pair's idle CTA (n >= N) are clipped by the tensor map
+                ptx::tma_store_4d_s(&tmY, buf - (uint32_t)lane * 128u, first ? col : col - 32, w, h, n);
+                ptx::bulk_commit();
+              }
+              ++job;
+            }
+          } else if (valid) {
             uint4* dst = reinterpret_cast<uint4*>(yrow + col);
             dst[0] = out[0]; dst[1] = out[1]; dst[2] = out[2]; dst[3] = out[3];
           }
@@ -512,6 +561,7 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
       }
       nb = nb2; n = n2; h = h2; w = w2; valid = valid2; pix = pix2;
     }
+    if (p.tma_store && lane == 0) ptx::bulk_wait_read<0>();   // shared memory stays allocated until the last box is read
     if (p.stats) {
       // every tile of this CTA has the same column block (grid % n_blocks == 0): flush the warp's accumulators
       const int nbf = blockIdx.x % p.n_blocks;
@@ -541,15 +591,15 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                  const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
-                 const __grid_constant__ HParams p) {
-  conv_halo_body<false>(tmA0, tmB0, tmA1, tmB1, p);
+                 const __grid_constant__ CUtensorMap tmY, const __grid_constant__ HParams p) {
+  conv_halo_body<false>(tmA0, tmB0, tmA1, tmB1, tmY, p);
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 conv_halo_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                       const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
-                      const __grid_constant__ HParams p) {
-  conv_halo_body<true>(tmA0, tmB0, tmA1, tmB1, p);
+                      const __grid_constant__ CUtensorMap tmY, const __grid_constant__ HParams p) {
+  conv_halo_body<true>(tmA0, tmB0, tmA1, tmB1, tmY, p);
 }
 
 }  // namespace
@@ -610,7 +660,22 @@ int rbu_conv_halo_launch(const rbu_conv_gemm_args* a, cudaStream_t stream) {
   const int b_bytes = (pair ? p.block_n / 2 : p.block_n) * 128;     // one tap's weight tile in ONE CTA's shared memory
   p.tps = p.block_n <= 128 ? 3 : 1;
   p.a_stages = 2;
-  p.b_stages = (SMEM_LIMIT - 2048 - p.a_stages * A_HALO_BYTES) / (b_bytes * p.tps);
+  // Staged epilogue (TMA stores) when the output is whole 32-column chunks and the staging buffers (8 warps x 4 KB, two per
+  // warp if the weight ring keeps >= 3 stages) fit; RBU_NO_TMA_STORE=1 forces the per-thread stores.
+  static int no_tma_store = -1;
+  if (no_tma_store < 0) no_tma_store = getenv("RBU_NO_TMA_STORE") ? 1 : 0;
+  const bool can_stage = !no_tma_store && !a->stats && a->Ncols % 32 == 0 && ((uintptr_t)a->y & 15) == 0 && a->y_ld % 8 == 0;
+  const int ring_room = SMEM_LIMIT - 2048 - p.a_stages * A_HALO_BYTES;
+  p.tma_store = 0;
+  p.st_bufs = 0;
+  if (can_stage) {
+    for (int bufs = 2; bufs >= 1 && !p.tma_store; --bufs)
+      if ((ring_room - 8 * bufs * STG_BYTES) / (b_bytes * p.tps) >= (bufs == 2 ? 3 : 2)) {
+        p.tma_store = 1;
+        p.st_bufs = bufs;
+      }
+  }
+  p.b_stages = (ring_room - 8 * p.st_bufs * STG_BYTES) / (b_bytes * p.tps);
   if (p.b_stages > MAX_B_STAGES) p.b_stages = MAX_B_STAGES;
   {
     // resident weights: one 3x3 segment, one column block, whole operand <= the shared memory left beside 2-3 A stages
@@ -620,6 +685,9 @@ int rbu_conv_halo_launch(const rbu_conv_gemm_args* a, cudaStream_t stream) {
     if (!no_res && a->nseg == 1 && a->seg[0].taps == 9 && p.n_blocks == 1 && a->seg[0].C % BLOCK_K == 0) {
       const int as = 2;   // a third stage does not help (pair 64->64: 759 vs 918 TFLOP/s)
       if (wbytes + as * A_HALO_BYTES <= SMEM_LIMIT - 2048) {
+        const long room = SMEM_LIMIT - 2048 - wbytes - as * A_HALO_BYTES;
+        p.st_bufs = can_stage ? (room >= 16 * STG_BYTES ? 2 : (room >= 8 * STG_BYTES ? 1 : 0)) : 0;
+        p.tma_store = p.st_bufs > 0;
         p.resident = 1;
         p.a_stages = as;
         p.tps = 1;
@@ -666,7 +734,16 @@ int rbu_conv_halo_launch(const rbu_conv_gemm_args* a, cudaStream_t stream) {
     tmA[1] = tmA[0];
     tmB[1] = tmB[0];
   }
-  const int smem_bytes = p.a_stages * A_HALO_BYTES + p.b_stages * b_bytes * p.tps + 1024 + 512;
+  CUtensorMap tmY;
+  memset(&tmY, 0, sizeof(tmY));
+  if (p.tma_store) {
+    const uint64_t dims[4] = {(uint64_t)a->Ncols, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->N};
+    const uint64_t str[3] = {(uint64_t)a->y_ld * 2, (uint64_t)a->y_ld * 2 * a->W, (uint64_t)a->y_ld * 2 * a->W * a->H};
+    const uint32_t box[4] = {64, HALF_W, 4, 1};
+    const int rc = rbu_encode_tmap_bf16(&tmY, a->y, 4, dims, str, box);
+    if (rc) return rc;
+  }
+  const int smem_bytes = p.a_stages * A_HALO_BYTES + p.b_stages * b_bytes * p.tps + 8 * p.st_bufs * STG_BYTES + 1024 + 512;
   static std::atomic<unsigned long long> attr_set{0};      // one bit per device ordinal
   if (rbu_first_use_on_device(&attr_set))
     RBU_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
@@ -676,7 +753,7 @@ int rbu_conv_halo_launch(const rbu_conv_gemm_args* a, cudaStream_t stream) {
       RBU_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     const int pairs = rbu_num_sms() / 2;
     const int gridp = 2 * (p.total_tiles < pairs ? p.total_tiles : pairs);
-    conv_halo_pair_kernel<<<gridp, NUM_THREADS, smem_bytes, stream>>>(tmA[0], tmB[0], tmA[1], tmB[1], p);
+    conv_halo_pair_kernel<<<gridp, NUM_THREADS, smem_bytes, stream>>>(tmA[0], tmB[0], tmA[1], tmB[1], tmY, p);
     RBU_CHECK_LAUNCH();
     return RBU_OK;
   }
@@ -686,7 +763,7 @@ int rbu_conv_halo_launch(const rbu_conv_gemm_args* a, cudaStream_t stream) {
                   "rbu_conv_gemm: output statistics are not supported for this shape");
     RBU_CHECK_CUDA(cudaMemsetAsync(a->stats, 0, rbu_conv_stats_floats(a->Ncols) * sizeof(float), stream));
   }
-  conv_halo_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(tmA[0], tmB[0], tmA[1], tmB[1], p);
+  conv_halo_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(tmA[0], tmB[0], tmA[1], tmB[1], tmY, p);
   RBU_CHECK_LAUNCH();
   return RBU_OK;
 }

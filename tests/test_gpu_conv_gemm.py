@@ -180,10 +180,11 @@ def test_invalid_arguments_raise():
         ops.conv_gemm(1, 4, 4, [(ops.View(x), w, 1, 1, False)], 60, ops.View(y))   # Ncols % 8
 
 
-@pytest.mark.parametrize("switch", ["RBU_CONV_PAIR", "RBU_CONV_NOPAIR"])
+@pytest.mark.parametrize("switch", ["RBU_CONV_PAIR", "RBU_CONV_NOPAIR", "RBU_NO_TMA_STORE"])
 def test_halo_kernel_forced_variants(switch):
-    """The library picks the single-CTA or the CTA-pair 3x3 kernel by shape; the switches are read once per process, so
-    the 3x3 cases, the data-gradient and the two-segment case are repeated in a child process with each variant forced."""
+    """The library picks the single-CTA or the CTA-pair 3x3 kernel by shape and stages its outputs for TMA stores when
+    the buffers fit; the switches are read once per process, so the 3x3 cases, the data-gradient and the two-segment case
+    are repeated in a child process with each variant forced (pair everywhere / never / per-thread stores)."""
     import os
     import subprocess
     import sys
