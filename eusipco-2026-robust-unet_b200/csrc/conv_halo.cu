@@ -38,8 +38,12 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int TILE_W = 16, TILE_H = 16, HALF_W = 8;
-constexpr int HALO_W = 24, HALO_H = 18;               // 24 column slots (18 used): row pitch 3072 B = 3 swizzle atoms
-constexpr int A_HALO_BYTES = HALO_H * HALO_W * 128;   // 55296
+#ifndef RBU_HALO_W
+#define RBU_HALO_W 24
+#endif
+constexpr int HALO_W = RBU_HALO_W, HALO_H = 18;       // halo row pitch in pixel slots (18 used)
+constexpr int A_HALO_TX = HALO_H * HALO_W * 128;      // bytes one halo box delivers
+constexpr int A_HALO_BYTES = (A_HALO_TX + 1023) & ~1023;   // stage stride (1024-aligned swizzle phase)
 constexpr int A_PLAIN_BYTES = TILE_H * TILE_W * 128;  // 32768
 constexpr int NUM_THREADS = 320;   // TMA warp, MMA warp, 8 epilogue warps
 constexpr int MAX_B_STAGES = 8;
@@ -220,7 +224,7 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
         tile_coords<PAIR>(p, ia.tile, rank, nb, w0, h0, n);
         const bool halo = p.taps[ia.seg] == 9;
         ptx::mbar_wait_backoff(&emptyA[s], ph ^ 1);
-        if (rank == 0) ptx::mbar_arrive_expect_tx(&fullA[s], txm * (halo ? A_HALO_BYTES : A_PLAIN_BYTES));
+        if (rank == 0) ptx::mbar_arrive_expect_tx(&fullA[s], txm * (halo ? A_HALO_TX : A_PLAIN_BYTES));
         const CUtensorMap* mA = ia.seg ? &tmA1 : &tmA0;
         if (halo)
           load_4d<PAIR>(smA + s * A_HALO_BYTES, mA, &fullA[s], ia.kc * BLOCK_K, w0 - 1, h0 - 1, n);
