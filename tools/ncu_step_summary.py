@@ -56,6 +56,33 @@ def main():
         us = a["us"] or 1.0
         print(f"| {name[:60]} | {int(a['n'])} | {a['us']:.0f} | {100 * a['us'] / total:.1f}% | " +
               " | ".join(f"{a[k] / us:.1f}" for k in keys) + f" | {a['bytes'] / 1e6:.0f} | {int(a['regs'])} |")
+    if "--traffic" in sys.argv:
+        # profiles/traffic.json: per GEMM class DRAM bytes per launch and time-weighted tensor-pipe activity (bench.py reads it
+        # for roofline.traffic)
+        import json
+        import os
+        source = sys.argv[sys.argv.index("--traffic") + 1]
+        cls = {"conv_halo_pair_kernel": "conv3x3", "conv_halo_kernel": "conv3x3", "conv_gemm_kernel": "conv_small",
+               "wgrad_halo_kernel": "wgrad_gemm", "wgrad_halo2_kernel": "wgrad_gemm", "wgrad_pair_kernel": "wgrad_gemm",
+               "wgrad_gemm_kernel": "wgrad_gemm"}
+        out = {}
+        for name, a in agg.items():
+            c = cls.get(name.replace("<unnamed>::", ""))
+            if c is None:
+                continue
+            o = out.setdefault(c, {"launches": 0, "bytes": 0.0, "us": 0.0, "tp_us": 0.0})
+            o["launches"] += int(a["n"])
+            o["bytes"] += a["bytes"]
+            o["us"] += a["us"]
+            o["tp_us"] += a["tensor%"]
+        res = {c: {"dram_bytes_per_launch": o["bytes"] / o["launches"], "launches": o["launches"], "source": source,
+                   "tensor_pipe_active_pct": o["tp_us"] / o["us"]} for c, o in out.items()}
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        with open(os.path.join(root, "profiles", "traffic.json"), "w") as f:
+            json.dump(res, f, indent=1)
+        print("\n| class | launches | DRAM MB / launch | time-weighted tensor pipe % |\n|---|---|---|---|")
+        for c, r in res.items():
+            print(f"| {c} | {r['launches']} | {r['dram_bytes_per_launch'] / 1e6:.1f} | {r['tensor_pipe_active_pct']:.1f} |")
     if "--launches" in sys.argv:
         print("\n## launches in order\n")
         for d in step:
