@@ -449,21 +449,73 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
       // statistics chunk of this half-tile inside its image
       const int chunks_img = p.tiles_w * p.tiles_h * 2;
       const int tchunk = ((h - hl) / TILE_H * p.tiles_w + (w - wl) / TILE_W) * 2 + half;
+      // tile statistics, second half: the four lane-group warps of this half-tile meet at a named barrier and warp lg == 0
+      // writes one row per statistic for the 32 columns from col32 -- the [n][chunk][4][C] layout rbu_bn_stats' second
+      // stage consumes
+      auto combine_and_write = [&](const float* xb, int col32) {
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+        if (lg == 0 && (!PAIR || n < p.N)) {
+          float acc[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[q] = xb[q * 32 + lane];
+#pragma unroll
+          for (int g2 = 1; g2 < 4; ++g2) {
+            acc[0] += xb[(g2 * 4 + 0) * 32 + lane];
+            acc[1] += xb[(g2 * 4 + 1) * 32 + lane];
+            acc[2] = fmaxf(acc[2], xb[(g2 * 4 + 2) * 32 + lane]);
+            acc[3] = fminf(acc[3], xb[(g2 * 4 + 3) * 32 + lane]);
+          }
+          float* dstp = p.tile_stats + (((long long)n * chunks_img + tchunk) * 4) * p.Ncols + col32 + lane;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) dstp[(long long)q * p.Ncols] = acc[q];
+        }
+      };
+      // staged job (64 columns from jcol, or 32 for a trailing / clipped half) complete in this warp's buffer: hand the box
+      // to the TMA store engine, then read the tile statistics off the staged bf16 values -- lane = channel pair, one
+      // conflict-free 4-byte shared-memory load per pixel row instead of 31 shuffles per statistic and 32 columns
+      auto finish_job = [&](int jcol, int chunks32) {
+        const uint32_t jb = stg_s + ((p.st_bufs == 2 && (job & 1u)) ? (uint32_t)STG_BYTES : 0u);
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {   // lane 0 is the box origin: pixel (h0 + 4 lg, w0 + 8 half); columns past Ncols, pixels past the
+                           // image and the tile of a pair's idle CTA (n >= N) are clipped by the tensor map
+          ptx::tma_store_4d_s(&tmY, jb, jcol, w, h, n);
+          ptx::bulk_commit();
+        }
+        ++job;
+        if (p.tile_stats) {
+          const unsigned rowmask = __ballot_sync(0xffffffffu, valid);    // lane r owns pixel row r of the box
+          const uint32_t coff = ((uint32_t)lane & 3u) << 2, cch = (uint32_t)lane >> 2;
+          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f, mx0 = -INFINITY, mx1 = -INFINITY, mn0 = INFINITY, mn1 = INFINITY;
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) {
+            const uint32_t v2 = ptx::ld_shared_b32(jb + (uint32_t)rr * 128u + ((cch ^ ((uint32_t)rr & 7u)) << 4) + coff);
+            if ((rowmask >> rr) & 1u) {
+              const float f0 = __uint_as_float(v2 << 16), f1 = __uint_as_float(v2 & 0xffff0000u);
+              s0 += f0; q0 += f0 * f0; mx0 = fmaxf(mx0, f0); mn0 = fminf(mn0, f0);
+              s1 += f1; q1 += f1 * f1; mx1 = fmaxf(mx1, f1); mn1 = fminf(mn1, f1);
+            }
+          }
+          for (int rd = 0; rd < chunks32; ++rd) {     // lanes 0-15 hold columns 0-31 of the job, lanes 16-31 columns 32-63
+            float* xb = stat_smem + ((jc & 1) * 2 + half) * (4 * 4 * 32);     // [parity][half][lg][q][32]
+            ++jc;
+            if ((lane >> 4) == rd) {
+              float* xw = xb + lg * (4 * 32) + 2 * (lane & 15);
+              *reinterpret_cast<float2*>(xw) = make_float2(s0, s1);
+              *reinterpret_cast<float2*>(xw + 32) = make_float2(q0, q1);
+              *reinterpret_cast<float2*>(xw + 64) = make_float2(mx0, mx1);
+              *reinterpret_cast<float2*>(xw + 96) = make_float2(mn0, mn1);
+            }
+            combine_and_write(xb, jcol + 32 * rd);
+          }
+        }
+      };
       for (int c0 = 0; c0 < p.block_n; c0 += 32) {
         const int col = nb * p.block_n + c0;
         if (p.tma_store && col >= p.Ncols) {
           // chunk past the last output column (Ncols % 32 == 0 here): nothing to compute, but a first half waiting in
           // the staging buffer still has to leave
-          if (c0 & 32) {
-            const uint32_t buf = stg_s + ((p.st_bufs == 2 && (job & 1u)) ? (uint32_t)STG_BYTES : 0u);
-            ptx::fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-              ptx::tma_store_4d_s(&tmY, buf, col - 32, w, h, n);
-              ptx::bulk_commit();
-            }
-            ++job;
-          }
+          if (c0 & 32) finish_job(col - 32, 1);
         } else if (p.stats || col + 32 > p.Ncols) {
           epi_finish(eo, t_addr + (uint32_t)c0, col, valid, pix, n, h, w, ad, c0 >> 5);
         } else {
@@ -493,24 +545,15 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
             const uint32_t pb = first ? 0u : 4u;
 #pragma unroll
             for (int g = 0; g < 4; ++g) ptx::st_shared_v4(buf + (((pb + (uint32_t)g) ^ sx) << 4), out[g]);
-            if (!first || c0 + 32 >= p.block_n) {
-              ptx::fence_proxy_async();
-              __syncwarp();
-              if (lane == 0) {   // lane 0 is the box origin: pixel (h0 + 4 lg, w0 + 8 half); columns past Ncols, pixels past
-                                 // the image and the tile of a pair's idle CTA (n >= N) are clipped by the tensor map
-                ptx::tma_store_4d_s(&tmY, buf - (uint32_t)lane * 128u, first ? col : col - 32, w, h, n);
-                ptx::bulk_commit();
-              }
-              ++job;
-            }
+            if (!first) finish_job(col - 32, 2);
+            else if (c0 + 32 >= p.block_n) finish_job(col, 1);
           } else if (valid) {
             uint4* dst = reinterpret_cast<uint4*>(yrow + col);
             dst[0] = out[0]; dst[1] = out[1]; dst[2] = out[2]; dst[3] = out[3];
           }
-          if (p.tile_stats) {
-            // per-image statistics of the stored values: the warp reduces its 32 pixels per column (lane l ends up with
-            // column l), the four lane-group warps of this half-tile exchange through shared memory and warp lg == 0
-            // writes one row per statistic -- in the [n][chunk][4][C] layout rbu_bn_stats' second stage consumes
+          if (p.tile_stats && !p.tma_store) {
+            // per-thread-store path: the warp reduces its 32 pixels per column with shuffles (lane l ends up with column l),
+            // then the same exchange as the staged path
             float rv[32], tmp[32];
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
@@ -535,22 +578,7 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
             ++jc;
 #pragma unroll
             for (int q = 0; q < 4; ++q) xb[(lg * 4 + q) * 32 + lane] = red[q];
-            asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
-            if (lg == 0 && (!PAIR || n < p.N)) {
-              float acc[4];
-#pragma unroll
-              for (int q = 0; q < 4; ++q) acc[q] = xb[q * 32 + lane];
-#pragma unroll
-              for (int g2 = 1; g2 < 4; ++g2) {
-                acc[0] += xb[(g2 * 4 + 0) * 32 + lane];
-                acc[1] += xb[(g2 * 4 + 1) * 32 + lane];
-                acc[2] = fmaxf(acc[2], xb[(g2 * 4 + 2) * 32 + lane]);
-                acc[3] = fminf(acc[3], xb[(g2 * 4 + 3) * 32 + lane]);
-              }
-              float* dstp = p.tile_stats + (((long long)n * chunks_img + tchunk) * 4) * p.Ncols + col + lane;
-#pragma unroll
-              for (int q = 0; q < 4; ++q) dstp[(long long)q * p.Ncols] = acc[q];
-            }
+            combine_and_write(xb, col);
           }
         }
         if (c0 + 32 < p.block_n)

@@ -78,6 +78,11 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
   return v;
 }
+__device__ __forceinline__ uint32_t ld_shared_b32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
 // same, addressed by a 32-bit shared address (no generic->shared conversion in hot loops)
 __device__ __forceinline__ uint32_t mbar_try_wait_s(uint32_t bar, uint32_t parity) {
   uint32_t ok;

@@ -195,7 +195,7 @@ def test_base64_against_reference_golden(golden_dir, name):
     lref = float(g["loss_train"])
     rep.rows.append(("loss vs reference golden", abs(loss.item() - lref) / lref, 1.25 * abs(la - lref) / lref + 5e-3))
     grads = dict(model.named_parameters())
-    dn, an, dh, ah = [], [], [], []
+    dn, an, dh, ah, vec = [], [], [], [], []
     for i, n in enumerate(names):
         s_ = g["grad_summary"][i]          # [norm, sum, first 8 values] of the reference gradient
         if n.endswith(".bias") and any(t in n for t in ZERO_GRAD_BIASES):
@@ -206,6 +206,7 @@ def test_base64_against_reference_golden(golden_dir, name):
         # the part of the reference gradient the fixture carries: its norm and its leading values
         dn.append(abs(got.norm().item() - s_[0]) / (s_[0] + 1e-30))
         an.append(abs(ga[n].double().norm().item() - s_[0]) / (s_[0] + 1e-30))
+        vec.append(got.numel() >= 8)
         if got.numel() >= 1024:
             rep.rows.append((f"{n} |grad| vs golden (autocast {an[-1]:.2e})", dn[-1], 1.5 * an[-1] + 0.15))
         scale = s_[0] / got.numel() ** 0.5 * k ** 0.5 + 1e-30          # expected norm of k entries
@@ -213,7 +214,14 @@ def test_base64_against_reference_golden(golden_dir, name):
         ah.append(((ga[n].double().flatten()[:k] - head).norm() / scale).item())
     rms = lambda v: float(np.sqrt(np.mean(np.square(v))))          # noqa: E731
     med = lambda v: float(np.median(v))                            # noqa: E731
-    rep.rows.append((f"RMS |grad| deviation over {len(dn)} tensors (autocast {rms(an):.2e})", rms(dn), 1.25 * rms(an) + 0.02))
+    # The RMS runs over the tensors with at least 8 elements: the 1-element gradients (the psi BatchNorms of the attention
+    # gates, |g| ~ 1e-4 = a sum of cancelling terms) move by 1-4x their own size between any two bf16 executions -- torch's
+    # autocast run included, and this library with or without the fused statistics -- and one of them would decide an RMS
+    # over 157 tensors; they stay in the two medians below.
+    dnv = [d for d, v in zip(dn, vec) if v]
+    anv = [a for a, v in zip(an, vec) if v]
+    rep.rows.append((f"RMS |grad| deviation over {len(dnv)} tensors of >= 8 elements (autocast {rms(anv):.2e})", rms(dnv),
+                     1.25 * rms(anv) + 0.02))
     rep.rows.append((f"median |grad| deviation (autocast {med(an):.2e})", med(dn), 1.25 * med(an) + 5e-3))
     rep.rows.append((f"median deviation of grad[:8] (autocast {med(ah):.2e})", med(dh), 1.25 * med(ah) + 0.02))
     model.load_state_dict(sd)
