@@ -68,12 +68,13 @@ class Engine:
         # Per-image statistics (sum, sum of squares, max, min per half-tile) from the 3x3 halo kernel's epilogue: BatchNorm
         # batch statistics and ChannelAttention's pooled inputs without re-reading the conv output.  Measured on B200: in
         # the training step (batch 64, 256^2) the 18 statistics passes it replaces cost 1.34 ms, the longer epilogues 0.4 ms
-        # and the reduction of the partials 0.35 ms.  Used from 128 output channels up (at 64 channels, K = 576, the longer
-        # epilogue costs what the saved pass gains) and in training mode only (inference at 1024^2, round 2: statistics
-        # pass -1.9 ms, convolutions +1.7 ms -- no gain).
+        # and the reduction of the partials 0.35 ms.  Since the statistics are read off the staged outputs (round 2: half the
+        # epilogue cost) they are used from 64 output channels up -- 64->64 at 256^2: +0.059 ms in the convolution against a
+        # 0.115-0.151 ms statistics pass, step -0.2 to -0.4 ms (tools/tile_stats_ab.py) -- and in training mode only
+        # (inference at 1024^2, round 2: statistics pass -1.9 ms, convolutions +1.7 ms -- no gain).
         self.fuse_tile_stats = True
         self.tile_stats_eval = False
-        self.tile_stats_min_c = 128
+        self.tile_stats_min_c = 64
         self._ws = None
         self._defer_counters = False     # whole-model forward: the 39 num_batches_tracked increments become one launch
         self._pending_counters = []

@@ -31,6 +31,7 @@ from oracle import robust_unet_ref as R
 
 pytestmark = pytest.mark.gpu
 
+NOISE_DOMINATED = 0.25     # rel-L2 of torch's own bf16-autocast gradient against fp32 from which a tensor is judged in a group
 ZERO_GRAD_BIASES = ("bottleneck.1.conv", "W_g.0.bias", "W_x.0.bias", "psi.0.bias")
 DEV = "cuda:0"
 
@@ -100,7 +101,7 @@ def _train_case(tag, nc, B, S, w_dice, init):
     rep.check(f"{tag}: probs vs fp32 oracle (autocast yardstick {ya:.2e})", p.detach(), pf, 1.25 * ya + 2e-3)
     rep.rows.append((f"{tag}: loss vs fp32 oracle (autocast {abs(la - lf) / abs(lf):.2e})", abs(loss.item() - lf) / abs(lf),
                      1.25 * abs(la - lf) / abs(lf) + 5e-3))
-    dev_f, ac_f, small_dev, small_ac = [], [], [], []
+    dev_f, ac_f, small_dev, small_ac, noisy_dev, noisy_ac = [], [], [], [], [], []
     dots = n1 = n2 = dots_a = n1a = 0.0
     worst = []
     for n, prm in model.named_parameters():
@@ -115,8 +116,14 @@ def _train_case(tag, nc, B, S, w_dice, init):
         ac_f.append(e_ac)
         nf = gf[n].double().norm().item() + 1e-30
         worst.append((e_dev / (e_ac + 1e-3), n, e_dev, e_ac, got.double().norm().item() / nf, ga[n].double().norm().item() / nf))
-        if got.numel() >= 1024:
+        if got.numel() >= 1024 and e_ac < NOISE_DOMINATED:
             rep.rows.append((f"{n} grad vs fp32 (autocast {e_ac:.2e})", e_dev, 1.25 * e_ac + 0.05))
+        elif got.numel() >= 1024:
+            # torch's own bf16 run is >= 25 % off the fp32 gradient on this tensor (ChannelAttention's fc weights behind the
+            # arg-max of AdaptiveMaxPool, the 7x7 SpatialAttention kernels): one tensor is one draw of that noise, any
+            # perturbation of the summation order moves it by its own size -- judged as a group below
+            noisy_dev.append(e_dev)
+            noisy_ac.append(e_ac)
         else:
             small_dev.append(e_dev)
             small_ac.append(e_ac)
@@ -130,6 +137,9 @@ def _train_case(tag, nc, B, S, w_dice, init):
     rep.rows.append((f"{tag}: RMS grad deviation vs fp32 (autocast {rms(ac_f):.2e})", rms(dev_f), 1.25 * rms(ac_f) + 1e-3))
     rep.rows.append((f"{tag}: RMS deviation of the {len(small_dev)} tensors < 1024 elements (autocast {rms(small_ac):.2e})",
                      rms(small_dev), 1.25 * rms(small_ac) + 0.02))
+    if noisy_dev:
+        rep.rows.append((f"{tag}: RMS deviation of the {len(noisy_dev)} noise-dominated tensors (autocast {rms(noisy_ac):.2e})",
+                         rms(noisy_dev), 1.25 * rms(noisy_ac) + 0.05))
     rep.rows.append((f"{tag}: 1 - cosine(all grads, fp32) (autocast {1 - cos_a:.2e})", 1 - cos, max(0.02, 1.25 * (1 - cos_a))))
     if init == "reference":
         assert cos >= 0.98, cos                      # the product configuration: absolute bar
@@ -195,7 +205,7 @@ def test_base64_against_reference_golden(golden_dir, name):
     lref = float(g["loss_train"])
     rep.rows.append(("loss vs reference golden", abs(loss.item() - lref) / lref, 1.25 * abs(la - lref) / lref + 5e-3))
     grads = dict(model.named_parameters())
-    dn, an, dh, ah, vec = [], [], [], [], []
+    dn, an, dh, ah, vec, ndn, nan_ = [], [], [], [], [], [], []
     for i, n in enumerate(names):
         s_ = g["grad_summary"][i]          # [norm, sum, first 8 values] of the reference gradient
         if n.endswith(".bias") and any(t in n for t in ZERO_GRAD_BIASES):
@@ -207,8 +217,11 @@ def test_base64_against_reference_golden(golden_dir, name):
         dn.append(abs(got.norm().item() - s_[0]) / (s_[0] + 1e-30))
         an.append(abs(ga[n].double().norm().item() - s_[0]) / (s_[0] + 1e-30))
         vec.append(got.numel() >= 8)
-        if got.numel() >= 1024:
+        if got.numel() >= 1024 and an[-1] < 0.1:
             rep.rows.append((f"{n} |grad| vs golden (autocast {an[-1]:.2e})", dn[-1], 1.5 * an[-1] + 0.15))
+        elif got.numel() >= 1024:     # the norm itself is >= 10 % off under torch's bf16 autocast: judged as a group
+            ndn.append(dn[-1])
+            nan_.append(an[-1])
         scale = s_[0] / got.numel() ** 0.5 * k ** 0.5 + 1e-30          # expected norm of k entries
         dh.append(((got[:k] - head).norm() / scale).item())
         ah.append(((ga[n].double().flatten()[:k] - head).norm() / scale).item())
@@ -222,6 +235,9 @@ def test_base64_against_reference_golden(golden_dir, name):
     anv = [a for a, v in zip(an, vec) if v]
     rep.rows.append((f"RMS |grad| deviation over {len(dnv)} tensors of >= 8 elements (autocast {rms(anv):.2e})", rms(dnv),
                      1.25 * rms(anv) + 0.02))
+    if ndn:
+        rep.rows.append((f"RMS |grad| deviation of the {len(ndn)} noise-dominated large tensors (autocast {rms(nan_):.2e})",
+                         rms(ndn), 1.5 * rms(nan_) + 0.15))
     rep.rows.append((f"median |grad| deviation (autocast {med(an):.2e})", med(dn), 1.25 * med(an) + 5e-3))
     rep.rows.append((f"median deviation of grad[:8] (autocast {med(ah):.2e})", med(dh), 1.25 * med(ah) + 0.02))
     model.load_state_dict(sd)

@@ -32,7 +32,7 @@ def main():
     dev = torch.device("cuda:0")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     B = 64
-    for name, S, ci, co in [("64->128 @128", 128, 64, 128), ("128->128 @128", 128, 128, 128), ("256->128 @128", 128, 256, 128),
+    for name, S, ci, co in [("64->64 @256", 256, 64, 64), ("128->64 @256", 256, 128, 64), ("64->128 @128", 128, 64, 128), ("128->128 @128", 128, 128, 128), ("256->128 @128", 128, 256, 128),
                             ("256->256 @64", 64, 256, 256), ("512->512 @32", 32, 512, 512), ("1024->1024 @16", 16, 1024, 1024)]:
         x = ops.View(torch.randn((B, S, S, ci), device=dev).to(torch.bfloat16))
         y = ops.View(torch.empty((B, S, S, co), dtype=torch.bfloat16, device=dev))
@@ -55,13 +55,14 @@ def main():
         loss.backward()
         opt.step()
 
-    for rnd in range(2):
-        for fuse in (True, False):
+    for rnd in range(3):
+        for fuse, min_c in ((True, 128), (True, 64), (False, 128)):
             model.engine.fuse_tile_stats = fuse
+            model.engine.tile_stats_min_c = min_c
             for _ in range(3):
                 step()
             t = timed(step, reps, flush)
-            print(f"step  tile statistics {'on ' if fuse else 'off'}: {t:7.3f} ms", flush=True)
+            print(f"step  tile statistics {'on ' if fuse else 'off'} (from {min_c} channels): {t:7.3f} ms", flush=True)
 
 
 if __name__ == "__main__":
