@@ -61,10 +61,12 @@ class Engine:
         # Weight gradients on a side stream (see wgrad()).  RBU_NO_OVERLAP=1 keeps them on the compute stream: used by the
         # profiling tools, which need per-kernel times that are not inflated by a co-running kernel.
         self.overlap_wgrad = os.environ.get("RBU_NO_OVERLAP") is None
-        # BatchNorm batch statistics fused into the generic convolution's epilogue (rbu_conv_gemm stats=...): one pass over
-        # the activations less, but the warp-transpose reduction slows the epilogue-sensitive small-N GEMMs by about as
-        # much (measured on B200: 44.9 vs 45.0 ms/step) -- off; kept as an attribute because the parity tests exercise it.
-        self.fuse_bn_stats = False
+        # BatchNorm batch statistics of the 1x1 (shortcut, attention-gate, stem, dilated-block) convolutions from the generic
+        # kernel's staged epilogue (rbu_conv_gemm stats=...) instead of a separate pass over the stored tensor.  Round 1's
+        # warp-transpose reduction cost as much as the pass it saved (44.9 vs 45.0 ms/step); since the statistics are read
+        # off the staged outputs (lane = channel pair, register accumulators for the life of the CTA) they are on.
+        # RBU_NO_FUSE_BN=1 restores the separate passes (A/B runs).
+        self.fuse_bn_stats = os.environ.get("RBU_NO_FUSE_BN") is None
         # Per-image statistics (sum, sum of squares, max, min per half-tile) from the 3x3 halo kernel's epilogue: BatchNorm
         # batch statistics and ChannelAttention's pooled inputs without re-reading the conv output.  Measured on B200: in
         # the training step (batch 64, 256^2) the 18 statistics passes it replaces cost 1.34 ms, the longer epilogues 0.4 ms
@@ -419,22 +421,27 @@ class Engine:
             if fuse:
                 bn1 = self.bn_from_conv(st12, 2 * C, 0, C, P, blk.bn1)
                 bns = self.bn_from_conv(st12, 2 * C, C, C, P, blk.shortcut[1])
+                self._bump(blk.bn1)
+                self._bump(blk.shortcut[1])
         else:
             folded = not training and not self._saving   # inference: BN1 + ReLU ride in conv1's epilogue, no y1
             y1 = None if folded else self.new(N, H, W, C, dev)
-            st1 = self.conv_stats_buf(C, dev) if fuse else None
+            # conv1 is a 3x3 convolution: per-tile statistics from the halo kernel where it runs them, else the per-CTA ones
+            use_ts1 = training and not folded and self.tile_stats_ok(H, W, C)
+            st1 = self.conv_stats_buf(C, dev) if (fuse and not use_ts1) else None
             if folded:
                 bn1 = self.bn_eval_affine(blk.bn1, x)
                 a1 = self.new(N, H, W, C, dev)
                 conv_gemm(N, H, W, [(x, self.pack(blk.conv1.weight, 0), 9, 1, False)], C, a1, scale=bn1["scale"],
                           bias=bn1["shift"], relu=C)
             else:
-                ts1 = self.tile_stats_buf(N, H, W, C, dev) if (training and not fuse and self.tile_stats_ok(H, W, C)) else None
+                ts1 = self.tile_stats_buf(N, H, W, C, dev) if use_ts1 else None
                 conv_gemm(N, H, W, [(x, self.pack(blk.conv1.weight, 0), 9, 1, False)], C, y1, stats=st1, tile_stats=ts1)
                 if ts1 is not None:
                     bn1 = self.bn_stats_tiles(ts1, N, H, W, C, blk.bn1, training)
-            if fuse:
+            if st1 is not None:
                 bn1 = self.bn_from_conv(st1, C, 0, C, P, blk.bn1)
+                self._bump(blk.bn1)
             ys = None
             if proj:
                 ys = self.new(N, H, W, C, dev)
@@ -442,10 +449,8 @@ class Engine:
                 conv_gemm(N, H, W, [(x, self.pack(blk.shortcut[0].weight, 0), 1, 0, False)], C, ys, stats=sts)
                 if fuse:
                     bns = self.bn_from_conv(sts, C, 0, C, P, blk.shortcut[1])
-        if fuse:
-            for b_ in ((blk.bn1, blk.shortcut[1]) if proj else (blk.bn1,)):
-                self._bump(b_)
-        elif y1 is not None and bn1 is None:
+                    self._bump(blk.shortcut[1])
+        if y1 is not None and bn1 is None:
             bn1 = self.bn_stats(y1, N, HW, blk.bn1, training)
         drop = self.drop_mask(name, N, C, blk.dropout.p, dev) if training and blk.dropout.p > 0 else None
         if y1 is not None:

@@ -200,3 +200,34 @@ def test_halo_kernel_forced_variants(switch):
                        cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert " passed" in r.stdout
+
+
+@pytest.mark.parametrize("shape", [
+    # N, H, W, Cin, Ncols, bias
+    (3, 32, 32, 64, 64, False),      # shortcut-like
+    (2, 24, 40, 32, 128, False),     # ragged tile edges (W, H not multiples of the 16 x 8 pixel tile), stem-like 128 columns
+    (5, 8, 8, 128, 32, True),        # tiny images: a tile spans two images; one 32-column job
+    (2, 16, 16, 256, 512, True),     # two column blocks of 256
+    (70, 4, 4, 64, 96, False),       # 16-pixel images, 8 per tile, odd number of 32-column chunks
+])
+def test_conv_epilogue_statistics(shape):
+    """rbu_conv_gemm(stats=...) of the generic kernel (staged epilogue: statistics read off the staged outputs): the rows of
+    per-(CTA, warp) partial sums add up to the column sums / sums of squares of the stored bf16 output."""
+    from rbunet import _lib, ops
+    N, H, W, Cin, Ncols, use_bias = shape
+    dev = torch.device("cuda:0")
+    x = _rand((N, Cin, H, W), 21)
+    w = _rand((Ncols, Cin, 1, 1), 22, scale=(1.0 / Cin) ** 0.5)
+    bias = _rand((Ncols,), 23).to(dev) if use_bias else None
+    xbuf = _nhwc_buffer(x, Cin, 0, dev)
+    y = torch.zeros((N, H, W, Ncols), dtype=torch.bfloat16, device=dev)
+    st = torch.full((_lib.lib().rbu_conv_stats_floats(Ncols),), 7.0, dtype=torch.float32, device=dev)
+    ops.conv_gemm(N, H, W, [(ops.View(xbuf), ops.pack_weight(w.to(dev).contiguous(), 0), 1, 0, False)], Ncols, ops.View(y),
+                  bias=bias, stats=st)
+    torch.cuda.synchronize()
+    got = st.view(-1, 2, Ncols).double().sum(0).cpu()
+    yf = y.double().reshape(-1, Ncols)
+    ref = torch.stack([yf.sum(0), (yf * yf).sum(0)]).cpu()
+    assert _rel_l2(got[0], ref[0]) < 1e-5 and _rel_l2(got[1], ref[1]) < 1e-5, (_rel_l2(got[0], ref[0]), _rel_l2(got[1], ref[1]))
+    yref = F.conv2d(x.to(torch.bfloat16).float(), w.to(torch.bfloat16).float(), bias.cpu() if use_bias else None)
+    assert _rel_l2(y.float().cpu().permute(0, 3, 1, 2), yref) < 4e-3

@@ -130,7 +130,12 @@ def test_train_step_matches_oracle(golden_dir, name):
         agg["dev_q"].append(rel_l2(got, gq[n]))
         agg["q2_q"].append(rel_l2(gq2[n], gq[n]))
         if got.numel() >= 64:          # per-tensor bar on real tensors; scalars / tiny vectors only enter the RMS
-            rep.rows.append((n + " grad vs fp32 oracle", agg["dev_f"][-1], 4.0 * agg["q_f"][-1] + 0.25))
+            # yardstick: the bf16-storage oracle's own distance from fp32, or -- where it is larger -- how far that oracle's
+            # gradient moves under a 1e-6 perturbation of the input (down2.1.ca.fc.0.weight of the 32 x 32 case: 0.135 from
+            # fp32 but 0.73 under the perturbation: behind the arg-max of AdaptiveMaxPool2d on 8 x 8 maps the tensor is one
+            # draw of rounding noise, and reordering an fp32 BatchNorm sum redraws it)
+            rep.rows.append((n + " grad vs fp32 oracle", agg["dev_f"][-1],
+                             4.0 * max(agg["q_f"][-1], agg["q2_q"][-1]) + 0.25))
         dots += (got.double() * gf[n].double()).sum().item()
         n1 += got.double().pow(2).sum().item()
         n2 += gf[n].double().pow(2).sum().item()
