@@ -47,7 +47,7 @@ struct KParams {
   int relu;
   const bf16* addend;
   long long addend_ld;
-  float* stats;   // [8*SMs][2][Ncols] (rows 4*CTA + lane group) column sum / sum of squares of the stored output, or NULL
+  float* stats;   // [SMs][2][Ncols] (one row per CTA) column sum / sum of squares of the stored output, or NULL
   // staged epilogue (TMA stores): see the epilogue branch of the kernel
   int b_resident;         // 1: this CTA's whole weight operand (all k-blocks of its column block) is loaded once
   int tma_store;          // 1: outputs leave through the y tensor map, 0: per-thread 16-byte stores
@@ -386,16 +386,29 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
       if (lane == 0) ptx::bulk_wait_read<0>();
       if (p.stats) {
-        // one row per epilogue warp: [2][Ncols] sums / sums of squares of this CTA's column block (grid % n_blocks == 0)
-        const int nbf = blockIdx.x % p.n_blocks;
-        float* row_out = p.stats + (long long)(blockIdx.x * 8 + ew) * 2 * p.Ncols;
+        // The eight epilogue warps park their accumulators in their (drained) staging buffers -- [job][lane] x (s0, s1, q0,
+        // q1) -- and after a named barrier thread (J, lane) of the first four warps adds the eight up in warp order: ONE row
+        // [2][Ncols] per CTA for this CTA's column block (grid % n_blocks == 0).
+        __syncwarp();                        // lane 0 has seen the last store drain this warp's buffers
 #pragma unroll
-        for (int J = 0; J < 4; ++J) {
-          const int col = nbf * p.block_n + J * 64 + 2 * lane;
-          if (J * 64 < p.block_n && col < p.Ncols) {
-            *reinterpret_cast<float2*>(row_out + col) = make_float2(sacc[J][0], sacc[J][1]);
-            *reinterpret_cast<float2*>(row_out + p.Ncols + col) = make_float2(sacc[J][2], sacc[J][3]);
+        for (int J = 0; J < 4; ++J)
+          ptx::st_shared_v4(stg_s + (uint32_t)((J * 32 + lane) * 16),
+                            make_uint4(__float_as_uint(sacc[J][0]), __float_as_uint(sacc[J][1]), __float_as_uint(sacc[J][2]),
+                                       __float_as_uint(sacc[J][3])));
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+        const int J = ew;                    // warps 0..3 of the epilogue flush job index J = ew
+        const int nbf = blockIdx.x % p.n_blocks;
+        const int col = nbf * p.block_n + J * 64 + 2 * lane;
+        if (J < 4 && J * 64 < p.block_n && col < p.Ncols) {
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+          const uint32_t base0 = ptx::smem_u32(stg_base) + (uint32_t)((J * 32 + lane) * 16);
+          for (int w8 = 0; w8 < 8; ++w8) {
+            const uint4 v = ptx::ld_shared_v4(base0 + (uint32_t)(w8 * 2 * STG_BYTES));
+            a0 += __uint_as_float(v.x); a1 += __uint_as_float(v.y); a2 += __uint_as_float(v.z); a3 += __uint_as_float(v.w);
           }
+          float* row_out = p.stats + (long long)blockIdx.x * 2 * p.Ncols;
+          *reinterpret_cast<float2*>(row_out + col) = make_float2(a0, a1);
+          *reinterpret_cast<float2*>(row_out + p.Ncols + col) = make_float2(a2, a3);
         }
       }
     }
@@ -462,16 +475,24 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       nb = nb2; n = n2; h = h2; w = w2; valid = valid2; pix = pix2;
     }
     if (p.stats) {
-      // every tile of this CTA has the same column block (grid % n_blocks == 0): flush the warp's accumulators
+      // every tile of this CTA has the same column block (grid % n_blocks == 0).  Warp (lg, half) holds chunk j = columns
+      // half * 32 + 64 j; the four lane-group warps of a half are added up in lg order by warp (lg = j, half) and the CTA
+      // writes ONE row.
+      asm volatile("bar.sync 3, 256;" ::: "memory");
       const int nbf = blockIdx.x % p.n_blocks;
-      float* row_out = p.stats + (long long)(blockIdx.x * 4 + lg) * 2 * p.Ncols;
-      for (int c0 = half * 32, j = 0; c0 < p.block_n; c0 += 64, ++j) {
-        const int col = nbf * p.block_n + c0 + lane;
-        if (col < p.Ncols) {
-          const float2 v = reinterpret_cast<const float2*>(eo.stat_acc)[j * 32 + lane];
-          row_out[col] = v.x;
-          row_out[p.Ncols + col] = v.y;
+      const int j = lg;
+      const int c0 = half * 32 + 64 * j;
+      const int col = nbf * p.block_n + c0 + lane;
+      if (c0 < p.block_n && col < p.Ncols) {
+        float2 acc = make_float2(0.f, 0.f);
+        for (int g4 = 0; g4 < 4; ++g4) {
+          const float2 v = reinterpret_cast<const float2*>(stat_smem + (half * 4 + g4) * (EPI_STAT_CHUNKS * 64))[j * 32 + lane];
+          acc.x += v.x;
+          acc.y += v.y;
         }
+        float* row_out = p.stats + (long long)blockIdx.x * 2 * p.Ncols;
+        row_out[col] = acc.x;
+        row_out[p.Ncols + col] = acc.y;
       }
     }
   }
@@ -495,12 +516,13 @@ extern "C" size_t rbu_conv_tile_stats_floats(int N, int H, int W, int Ncols) {
   return (size_t)N * rbu_conv_tile_stats_chunks(H, W) * 4 * Ncols;
 }
 
-// rows: (CTA, lane group) for the generic kernel, (CTA, half-tile, lane group) for the halo kernel; unused rows stay zero
-extern "C" size_t rbu_conv_stats_floats(int Ncols) { return (size_t)8 * rbu_num_sms() * 2 * Ncols; }
+// one row [2][Ncols] per CTA (its epilogue warps' partial sums added up in warp order); rows of SMs the grid does not reach
+// and columns outside a CTA's column block stay zero
+extern "C" size_t rbu_conv_stats_floats(int Ncols) { return (size_t)rbu_num_sms() * 2 * Ncols; }
 
 // BatchNorm affine from the per-(CTA, lane group) partial sums written by rbu_conv_gemm(stats != NULL):
-// block = 32 channels x 32 lanes over the 8*SMs rows (lane sums combined in lane order -> deterministic; 37 dependent-free
-// loads per thread instead of 148: with 8 lanes the kernel took ~39 us per BatchNorm, 0.86 ms per training step).
+// block = 32 channels x 32 lanes over the one-row-per-CTA partials (lane sums combined in lane order -> deterministic).
+// History: 8 rows per CTA read by 8 lanes took ~39 us per BatchNorm = 0.86 ms per training step.
 namespace {
 constexpr int FIN_LANES = 32;
 __global__ void __launch_bounds__(32 * FIN_LANES)
@@ -551,7 +573,7 @@ extern "C" int rbu_bn_finalize_partials(const float* part, int Ncols, int col_of
   RBU_CHECK_ARG(part && gamma && beta && scale && shift && Ncols > 0 && C > 0 && col_off >= 0 && col_off + C <= Ncols &&
                     count > 0, "rbu_bn_finalize_partials: bad arguments");
   bn_finalize_partials_kernel<<<rbu_cdiv(C, 32), 32 * FIN_LANES, 0, (cudaStream_t)stream_>>>(
-      part, 8 * rbu_num_sms(), Ncols, col_off, C, (double)count, 1, gamma, beta, running_mean, running_var, momentum, eps,
+      part, rbu_num_sms(), Ncols, col_off, C, (double)count, 1, gamma, beta, running_mean, running_var, momentum, eps,
       scale, shift, mean_out, rstd_out);
   RBU_CHECK_LAUNCH();
   return RBU_OK;
@@ -747,7 +769,7 @@ extern "C" int rbu_conv_gemm(const rbu_conv_gemm_args* a, void* stream_) {
                   "rbu_conv_gemm: output statistics are not supported for this shape");
     // staged epilogue with one column block: every warp of every CTA writes its whole row, only the rows of the SMs the grid
     // does not reach need zeros
-    const size_t row_floats = (size_t)2 * a->Ncols, written = (p.tma_store && p.n_blocks == 1) ? (size_t)8 * grid : 0;
+    const size_t row_floats = (size_t)2 * a->Ncols, written = (p.tma_store && p.n_blocks == 1) ? (size_t)grid : 0;
     const size_t total = rbu_conv_stats_floats(a->Ncols);
     if (written * row_floats < total)
       RBU_CHECK_CUDA(cudaMemsetAsync(a->stats + written * row_floats, 0, (total - written * row_floats) * sizeof(float), stream));

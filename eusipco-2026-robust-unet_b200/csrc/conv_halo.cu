@@ -76,7 +76,7 @@ struct HParams {
   const bf16* addend;
   long long addend_ld;
   float* tile_stats;   // [N][tiles_h*tiles_w*2][4][Ncols]: per image and half-tile column sum / sum of squares / max / min
-  float* stats;   // [8*SMs][2][Ncols] per-(CTA, half-tile, lane group) column sum / sum of squares of the stored output, or NULL
+  float* stats;   // [SMs][2][Ncols] (one row per CTA) column sum / sum of squares of the stored output, or NULL
 };
 
 // Enumerates the (tile, segment, 64-channel slab) sequence of this CTA; producer and MMA issuer walk it in lockstep.
@@ -595,16 +595,22 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
     }
     if (p.tma_store && lane == 0) ptx::bulk_wait_read<0>();   // shared memory stays allocated until the last box is read
     if (p.stats) {
-      // every tile of this CTA has the same column block (grid % n_blocks == 0): flush the warp's accumulators
+      // every tile of this CTA has the same column block (grid % n_blocks == 0): the eight epilogue warps' shared-memory
+      // accumulators are added up in warp order and leave as ONE row per CTA (warp j flushes the 32-column chunk j)
+      asm volatile("bar.sync 3, 256;" ::: "memory");
       const int nbf = blockIdx.x % p.n_blocks;
-      float* row_out = p.stats + (long long)((blockIdx.x * 2 + half) * 4 + lg) * 2 * p.Ncols;
-      for (int c0 = 0, j = 0; c0 < p.block_n; c0 += 32, ++j) {
-        const int col = nbf * p.block_n + c0 + lane;
-        if (col < p.Ncols) {
-          const float2 v = reinterpret_cast<const float2*>(eo.stat_acc)[j * 32 + lane];
-          row_out[col] = v.x;
-          row_out[p.Ncols + col] = v.y;
+      const int j = warp - 2;
+      const int col = nbf * p.block_n + j * 32 + lane;
+      if (j * 32 < p.block_n && col < p.Ncols) {
+        float2 acc = make_float2(0.f, 0.f);
+        for (int w8 = 0; w8 < 8; ++w8) {
+          const float2 v = reinterpret_cast<const float2*>(stat_smem + w8 * (EPI_STAT_CHUNKS * 64))[j * 32 + lane];
+          acc.x += v.x;
+          acc.y += v.y;
         }
+        float* row_out = p.stats + (long long)blockIdx.x * 2 * p.Ncols;
+        row_out[col] = acc.x;
+        row_out[p.Ncols + col] = acc.y;
       }
     }
   }

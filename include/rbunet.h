@@ -93,7 +93,7 @@ typedef struct {
   int64_t addend_ld;
   const float* scale;       /* optional fp32 [Cout]: y = scale*acc + bias (eval-mode BatchNorm folded into the conv) */
   int relu;                 /* ReLU after scale / bias / addend on output channels [0, relu) (0: none)         */
-  float* stats;             /* optional: rbu_conv_stats_floats(Ncols) floats receiving per-(CTA, epilogue warp) */
+  float* stats;             /* optional: rbu_conv_stats_floats(Ncols) floats receiving one row per CTA of      */
                             /* partial sum / sum of squares per output column of the STORED (bf16) result --  */
                             /* the BatchNorm batch statistics, fused into the epilogue (scatter=0 only)        */
   float* tile_stats;        /* optional (3x3 dilation-1 convs on >= 16x16 images, Ncols % 32 == 0):            */
