@@ -415,6 +415,11 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
     const uint32_t row_s = stg_s + (uint32_t)lane * 128u;
     const uint32_t sx = (uint32_t)lane & 7u;
     uint32_t job = 0;     // stores issued by this warp (staging buffer parity)
+    // per-CTA BatchNorm statistics on the staged path (p.stats): sum / sum of squares per channel pair (lane) and 64-column
+    // job, kept in registers for the life of the CTA -- all its tiles share one column block
+    float sacc[4][4];
+#pragma unroll
+    for (int J = 0; J < 4; ++J) sacc[J][0] = sacc[J][1] = sacc[J][2] = sacc[J][3] = 0.f;
     auto locate = [&](int tile, int& nb, bool& valid, long long& pix, int& n, int& h, int& w) {
       int w0, h0;
       const bool ok = tile_coords<PAIR>(p, tile, rank, nb, w0, h0, n);
@@ -509,6 +514,24 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
             combine_and_write(xb, jcol + 32 * rd);
           }
         }
+        if (p.stats) {
+          const unsigned rowmask = __ballot_sync(0xffffffffu, valid);
+          const uint32_t ja = jb + (((uint32_t)lane & 3u) << 2), cch = (uint32_t)lane >> 2;
+          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) {
+            const uint32_t v2 = ptx::ld_shared_b32(ja + (uint32_t)rr * 128u + ((cch ^ ((uint32_t)rr & 7u)) << 4));
+            if ((rowmask >> rr) & 1u) {
+              const float f0 = __uint_as_float(v2 << 16), f1 = __uint_as_float(v2 & 0xffff0000u);
+              s0 += f0; q0 += f0 * f0;
+              s1 += f1; q1 += f1 * f1;
+            }
+          }
+          const int jj = (jcol - nb * p.block_n) >> 6;
+#pragma unroll
+          for (int J = 0; J < 4; ++J)
+            if (J == jj) { sacc[J][0] += s0; sacc[J][1] += s1; sacc[J][2] += q0; sacc[J][3] += q1; }
+        }
       };
       for (int c0 = 0; c0 < p.block_n; c0 += 32) {
         const int col = nb * p.block_n + c0;
@@ -516,7 +539,7 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
           // chunk past the last output column (Ncols % 32 == 0 here): nothing to compute, but a first half waiting in
           // the staging buffer still has to leave
           if (c0 & 32) finish_job(col - 32, 1);
-        } else if (p.stats || col + 32 > p.Ncols) {
+        } else if ((p.stats && !p.tma_store) || col + 32 > p.Ncols) {
           epi_finish(eo, t_addr + (uint32_t)c0, col, valid, pix, n, h, w, ad, c0 >> 5);
         } else {
           uint32_t r[32];
@@ -594,11 +617,36 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
       nb = nb2; n = n2; h = h2; w = w2; valid = valid2; pix = pix2;
     }
     if (p.tma_store && lane == 0) ptx::bulk_wait_read<0>();   // shared memory stays allocated until the last box is read
-    if (p.stats) {
-      // every tile of this CTA has the same column block (grid % n_blocks == 0): the eight epilogue warps' shared-memory
-      // accumulators are added up in warp order and leave as ONE row per CTA (warp j flushes the 32-column chunk j)
+    if (p.stats && p.tma_store) {
+      // every tile of this CTA (pair) has the same column block: the eight epilogue warps park their register accumulators
+      // in their drained staging buffers -- [job][lane] x (s0, s1, q0, q1) -- and warp J adds the eight up in warp order:
+      // ONE row [2][Ncols] per CTA
+      __syncwarp();
+#pragma unroll
+      for (int J = 0; J < 4; ++J)
+        ptx::st_shared_v4(stg_s + (uint32_t)((J * 32 + lane) * 16),
+                          make_uint4(__float_as_uint(sacc[J][0]), __float_as_uint(sacc[J][1]), __float_as_uint(sacc[J][2]),
+                                     __float_as_uint(sacc[J][3])));
       asm volatile("bar.sync 3, 256;" ::: "memory");
-      const int nbf = blockIdx.x % p.n_blocks;
+      const int J = warp - 2;
+      const int nbf = cta0 % p.n_blocks;
+      const int col = nbf * p.block_n + J * 64 + 2 * lane;
+      if (J < 4 && J * 64 < p.block_n && col < p.Ncols) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        const uint32_t base0 = ptx::smem_u32(stg_base) + (uint32_t)((J * 32 + lane) * 16);
+        for (int w8 = 0; w8 < 8; ++w8) {
+          const uint4 v = ptx::ld_shared_v4(base0 + (uint32_t)(w8 * p.st_bufs * STG_BYTES));
+          a0 += __uint_as_float(v.x); a1 += __uint_as_float(v.y); a2 += __uint_as_float(v.z); a3 += __uint_as_float(v.w);
+        }
+        float* row_out = p.stats + (long long)blockIdx.x * 2 * p.Ncols;
+        *reinterpret_cast<float2*>(row_out + col) = make_float2(a0, a1);
+        *reinterpret_cast<float2*>(row_out + p.Ncols + col) = make_float2(a2, a3);
+      }
+    } else if (p.stats) {
+      // per-thread-store path: the eight epilogue warps' shared-memory accumulators are added up in warp order and leave as
+      // ONE row per CTA (warp j flushes the 32-column chunk j)
+      asm volatile("bar.sync 3, 256;" ::: "memory");
+      const int nbf = cta0 % p.n_blocks;
       const int j = warp - 2;
       const int col = nbf * p.block_n + j * 32 + lane;
       if (j * 32 < p.block_n && col < p.Ncols) {
@@ -646,7 +694,11 @@ conv_halo_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
 // 16 x 16 pixels, no gather / scatter), else 0.
 int rbu_conv_halo_supported(const rbu_conv_gemm_args* a) {
   if (a->scatter || a->H < TILE_H || a->W < TILE_W) return 0;
-  if (a->stats && a->Ncols > 32 * EPI_STAT_CHUNKS) return 0;   // per-warp statistics accumulators cover 128 columns
+  // per-CTA statistics: register accumulators on the staged path (any width that is whole 32-column chunks), shared-memory
+  // accumulators covering 128 columns on the per-thread path
+  if (a->stats && a->Ncols > 32 * EPI_STAT_CHUNKS &&
+      (a->Ncols % 32 != 0 || getenv("RBU_NO_TMA_STORE") || getenv("RBU_CONV_NOPAIR")))
+    return 0;
   int any3x3 = 0;
   for (int s = 0; s < a->nseg; ++s) {
     const rbu_gemm_operand& o = a->seg[s];
@@ -693,8 +745,8 @@ int rbu_conv_halo_launch(const rbu_conv_gemm_args* a, cudaStream_t stream) {
   const bool single_resident = !getenv("RBU_NO_RESIDENT") && a->nseg == 1 && a->seg[0].taps == 9 && p.n_blocks == 1 &&
                                a->seg[0].C % BLOCK_K == 0 &&
                                (long)(a->seg[0].C / BLOCK_K) * 9 * p.block_n * 128 + 2 * A_HALO_BYTES <= SMEM_LIMIT - 2048;
-  const bool pair = pair_mode && (pair_mode == 2 || !single_resident) && !a->stats && p.block_n % 32 == 0 &&
-                    rbu_num_sms() >= 2;
+  const bool pair = pair_mode && (pair_mode == 2 || !single_resident) && p.block_n % 32 == 0 && rbu_num_sms() >= 2 &&
+                    (!a->stats || p.n_blocks <= rbu_num_sms() / 2);
   const int b_bytes = (pair ? p.block_n / 2 : p.block_n) * 128;     // one tap's weight tile in ONE CTA's shared memory
   p.tps = p.block_n <= 128 ? 3 : 1;
   p.a_stages = 2;
@@ -702,7 +754,7 @@ int rbu_conv_halo_launch(const rbu_conv_gemm_args* a, cudaStream_t stream) {
   // warp if the weight ring keeps >= 3 stages) fit; RBU_NO_TMA_STORE=1 forces the per-thread stores.
   static int no_tma_store = -1;
   if (no_tma_store < 0) no_tma_store = getenv("RBU_NO_TMA_STORE") ? 1 : 0;
-  const bool can_stage = !no_tma_store && !a->stats && a->Ncols % 32 == 0 && ((uintptr_t)a->y & 15) == 0 && a->y_ld % 8 == 0;
+  const bool can_stage = !no_tma_store && a->Ncols % 32 == 0 && ((uintptr_t)a->y & 15) == 0 && a->y_ld % 8 == 0;
   const int ring_room = SMEM_LIMIT - 2048 - p.a_stages * A_HALO_BYTES;
   p.tma_store = 0;
   p.st_bufs = 0;
@@ -789,17 +841,31 @@ int rbu_conv_halo_launch(const rbu_conv_gemm_args* a, cudaStream_t stream) {
     static std::atomic<unsigned long long> attr_pair{0};
     if (rbu_first_use_on_device(&attr_pair))
       RBU_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    const int pairs = rbu_num_sms() / 2;
-    const int gridp = 2 * (p.total_tiles < pairs ? p.total_tiles : pairs);
+    int pairs = rbu_num_sms() / 2;
+    if (pairs > p.total_tiles) pairs = p.total_tiles;
+    if (a->stats) {
+      pairs = pairs / p.n_blocks * p.n_blocks;     // every pair keeps one column block: work unit stride % n_blocks == 0
+      RBU_CHECK_ARG(pairs > 0 && (p.tma_store || p.block_n <= 32 * EPI_STAT_CHUNKS) && ((uintptr_t)a->stats & 15) == 0,
+                    "rbu_conv_gemm: output statistics are not supported for this shape");
+      const size_t row_floats = (size_t)2 * a->Ncols, written = (p.tma_store && p.n_blocks == 1) ? (size_t)2 * pairs : 0;
+      const size_t total = rbu_conv_stats_floats(a->Ncols);
+      if (written * row_floats < total)
+        RBU_CHECK_CUDA(cudaMemsetAsync(a->stats + written * row_floats, 0, (total - written * row_floats) * sizeof(float), stream));
+    }
+    const int gridp = 2 * pairs;
     conv_halo_pair_kernel<<<gridp, NUM_THREADS, smem_bytes, stream>>>(tmA[0], tmB[0], tmA[1], tmB[1], tmY, p);
     RBU_CHECK_LAUNCH();
     return RBU_OK;
   }
-  const int grid = p.total_tiles < rbu_num_sms() ? p.total_tiles : rbu_num_sms();
+  int grid = p.total_tiles < rbu_num_sms() ? p.total_tiles : rbu_num_sms();
   if (a->stats) {
-    RBU_CHECK_ARG(p.block_n <= 32 * EPI_STAT_CHUNKS && grid % p.n_blocks == 0 && ((uintptr_t)a->stats & 15) == 0,
+    grid = grid / p.n_blocks * p.n_blocks;         // every CTA keeps one column block
+    RBU_CHECK_ARG(grid > 0 && (p.tma_store || p.block_n <= 32 * EPI_STAT_CHUNKS) && ((uintptr_t)a->stats & 15) == 0,
                   "rbu_conv_gemm: output statistics are not supported for this shape");
-    RBU_CHECK_CUDA(cudaMemsetAsync(a->stats, 0, rbu_conv_stats_floats(a->Ncols) * sizeof(float), stream));
+    const size_t row_floats = (size_t)2 * a->Ncols, written = (p.tma_store && p.n_blocks == 1) ? (size_t)grid : 0;
+    const size_t total = rbu_conv_stats_floats(a->Ncols);
+    if (written * row_floats < total)
+      RBU_CHECK_CUDA(cudaMemsetAsync(a->stats + written * row_floats, 0, (total - written * row_floats) * sizeof(float), stream));
   }
   conv_halo_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(tmA[0], tmB[0], tmA[1], tmB[1], tmY, p);
   RBU_CHECK_LAUNCH();

@@ -426,9 +426,10 @@ class Engine:
         else:
             folded = not training and not self._saving   # inference: BN1 + ReLU ride in conv1's epilogue, no y1
             y1 = None if folded else self.new(N, H, W, C, dev)
-            # conv1 is a 3x3 convolution: per-tile statistics from the halo kernel where it runs them, else the per-CTA ones
-            use_ts1 = training and not folded and self.tile_stats_ok(H, W, C)
-            st1 = self.conv_stats_buf(C, dev) if (fuse and not use_ts1) else None
+            # bn1 needs the batch statistics only (no per-image pooling): per-CTA register accumulators in the convolution's
+            # epilogue (no per-tile exchange, no second stage over tiles); per-tile statistics when those are switched off
+            use_ts1 = training and not folded and not fuse and self.tile_stats_ok(H, W, C)
+            st1 = self.conv_stats_buf(C, dev) if fuse else None
             if folded:
                 bn1 = self.bn_eval_affine(blk.bn1, x)
                 a1 = self.new(N, H, W, C, dev)

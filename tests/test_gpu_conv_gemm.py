@@ -195,7 +195,7 @@ def test_halo_kernel_forced_variants(switch):
     env.pop("RBU_CONV_NOPAIR", None)
     env[switch] = "1"
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-m", "gpu", "-x",
-                        "-k", "3x3 or dgrad or two_segment", "-p", "no:cacheprovider"],
+                        "-k", "3x3 or dgrad or two_segment or statistics", "-p", "no:cacheprovider"],
                        env=env, capture_output=True, text=True, timeout=600,
                        cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
@@ -230,4 +230,35 @@ def test_conv_epilogue_statistics(shape):
     ref = torch.stack([yf.sum(0), (yf * yf).sum(0)]).cpu()
     assert _rel_l2(got[0], ref[0]) < 1e-5 and _rel_l2(got[1], ref[1]) < 1e-5, (_rel_l2(got[0], ref[0]), _rel_l2(got[1], ref[1]))
     yref = F.conv2d(x.to(torch.bfloat16).float(), w.to(torch.bfloat16).float(), bias.cpu() if use_bias else None)
+    assert _rel_l2(y.float().cpu().permute(0, 3, 1, 2), yref) < 4e-3
+
+
+@pytest.mark.parametrize("shape", [
+    # N, H, W, Cin, Ncols
+    (2, 32, 48, 64, 128),      # CTA pairs, one column block, 12 tiles
+    (3, 16, 48, 128, 256),     # two column blocks, odd number of spatial tiles (idle CTA in the last pair)
+    (1, 40, 56, 64, 96),       # ragged tile edges, 96 columns (trailing 32-column job)
+    (2, 16, 16, 256, 1024),    # one-tile images, 256-column blocks, four column blocks
+    (2, 32, 32, 64, 64),       # single-CTA kernel (resident 64 -> 64)
+    (2, 32, 32, 128, 512),     # four column blocks of 128
+])
+def test_halo_epilogue_statistics(shape):
+    """rbu_conv_gemm(stats=...) on the 3x3 halo kernels (staged epilogue, single CTA and CTA pairs): the one-row-per-CTA partial
+    sums add up to the column sums / sums of squares of the stored bf16 output."""
+    from rbunet import _lib, ops
+    N, H, W, Cin, Ncols = shape
+    dev = torch.device("cuda:0")
+    x = _rand((N, Cin, H, W), 31)
+    w = _rand((Ncols, Cin, 3, 3), 32, scale=(1.0 / (9 * Cin)) ** 0.5)
+    xbuf = _nhwc_buffer(x, Cin, 0, dev)
+    y = torch.zeros((N, H, W, Ncols), dtype=torch.bfloat16, device=dev)
+    st = torch.full((_lib.lib().rbu_conv_stats_floats(Ncols),), 7.0, dtype=torch.float32, device=dev)
+    ops.conv_gemm(N, H, W, [(ops.View(xbuf), ops.pack_weight(w.to(dev).contiguous(), 0), 9, 1, False)], Ncols, ops.View(y),
+                  stats=st)
+    torch.cuda.synchronize()
+    got = st.view(-1, 2, Ncols).double().sum(0).cpu()
+    yf = y.double().reshape(-1, Ncols)
+    ref = torch.stack([yf.sum(0), (yf * yf).sum(0)]).cpu()
+    assert _rel_l2(got[0], ref[0]) < 1e-5 and _rel_l2(got[1], ref[1]) < 1e-5, (_rel_l2(got[0], ref[0]), _rel_l2(got[1], ref[1]))
+    yref = F.conv2d(x.to(torch.bfloat16).float(), w.to(torch.bfloat16).float(), padding=1)
     assert _rel_l2(y.float().cpu().permute(0, 3, 1, 2), yref) < 4e-3
