@@ -688,6 +688,16 @@ conv_halo_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
   conv_halo_body<true>(tmA0, tmB0, tmA1, tmB1, tmY, p);
 }
 
+// debug switches, read once per process
+struct Switches {
+  int no_pair, force_pair, no_resident, no_tma_store;
+};
+const Switches& switches() {
+  static const Switches sw = {getenv("RBU_CONV_NOPAIR") ? 1 : 0, getenv("RBU_CONV_PAIR") ? 1 : 0,
+                              getenv("RBU_NO_RESIDENT") ? 1 : 0, getenv("RBU_NO_TMA_STORE") ? 1 : 0};
+  return sw;
+}
+
 }  // namespace
 
 // Returns 1 if the halo kernel can run these arguments (3x3 dilation-1 and 1x1 segments on images of at least
@@ -697,7 +707,7 @@ int rbu_conv_halo_supported(const rbu_conv_gemm_args* a) {
   // per-CTA statistics: register accumulators on the staged path (any width that is whole 32-column chunks), shared-memory
   // accumulators covering 128 columns on the per-thread path
   if (a->stats && a->Ncols > 32 * EPI_STAT_CHUNKS &&
-      (a->Ncols % 32 != 0 || getenv("RBU_NO_TMA_STORE") || getenv("RBU_CONV_NOPAIR")))
+      (a->Ncols % 32 != 0 || switches().no_tma_store || switches().no_pair))
     return 0;
   int any3x3 = 0;
   for (int s = 0; s < a->nseg; ++s) {
@@ -740,9 +750,8 @@ int rbu_conv_halo_launch(const rbu_conv_gemm_args* a, cudaStream_t stream) {
   // TFLOP/s), with the per-CTA output statistics (unused by the engine), or for column blocks whose halves are not whole
   // 8-row swizzle groups.  RBU_CONV_NOPAIR=1 selects the single-CTA kernel everywhere (A/B runs), RBU_CONV_PAIR=1 the
   // pair kernel wherever it can run.
-  static int pair_mode = -1;     // 0 never, 1 by shape, 2 always
-  if (pair_mode < 0) pair_mode = getenv("RBU_CONV_NOPAIR") ? 0 : (getenv("RBU_CONV_PAIR") ? 2 : 1);
-  const bool single_resident = !getenv("RBU_NO_RESIDENT") && a->nseg == 1 && a->seg[0].taps == 9 && p.n_blocks == 1 &&
+  const int pair_mode = switches().no_pair ? 0 : (switches().force_pair ? 2 : 1);     // 0 never, 1 by shape, 2 always
+  const bool single_resident = !switches().no_resident && a->nseg == 1 && a->seg[0].taps == 9 && p.n_blocks == 1 &&
                                a->seg[0].C % BLOCK_K == 0 &&
                                (long)(a->seg[0].C / BLOCK_K) * 9 * p.block_n * 128 + 2 * A_HALO_BYTES <= SMEM_LIMIT - 2048;
   const bool pair = pair_mode && (pair_mode == 2 || !single_resident) && p.block_n % 32 == 0 && rbu_num_sms() >= 2 &&
@@ -752,9 +761,7 @@ int rbu_conv_halo_launch(const rbu_conv_gemm_args* a, cudaStream_t stream) {
   p.a_stages = 2;
   // Staged epilogue (TMA stores) when the output is whole 32-column chunks and the staging buffers (8 warps x 4 KB, two per
   // warp if the weight ring keeps >= 3 stages) fit; RBU_NO_TMA_STORE=1 forces the per-thread stores.
-  static int no_tma_store = -1;
-  if (no_tma_store < 0) no_tma_store = getenv("RBU_NO_TMA_STORE") ? 1 : 0;
-  const bool can_stage = !no_tma_store && a->Ncols % 32 == 0 && ((uintptr_t)a->y & 15) == 0 && a->y_ld % 8 == 0;
+  const bool can_stage = !switches().no_tma_store && a->Ncols % 32 == 0 && ((uintptr_t)a->y & 15) == 0 && a->y_ld % 8 == 0;
   const int ring_room = SMEM_LIMIT - 2048 - p.a_stages * A_HALO_BYTES;
   p.tma_store = 0;
   p.st_bufs = 0;
@@ -769,8 +776,7 @@ int rbu_conv_halo_launch(const rbu_conv_gemm_args* a, cudaStream_t stream) {
   if (p.b_stages > MAX_B_STAGES) p.b_stages = MAX_B_STAGES;
   {
     // resident weights: one 3x3 segment, one column block, whole operand <= the shared memory left beside 2-3 A stages
-    static int no_res = -1;
-    if (no_res < 0) no_res = getenv("RBU_NO_RESIDENT") ? 1 : 0;
+    const int no_res = switches().no_resident;
     const long wbytes = (long)(a->seg[0].C / BLOCK_K) * 9 * b_bytes;
     if (!no_res && a->nseg == 1 && a->seg[0].taps == 9 && p.n_blocks == 1 && a->seg[0].C % BLOCK_K == 0) {
       const int as = 2;   // a third stage does not help (pair 64->64: 759 vs 918 TFLOP/s)
