@@ -276,3 +276,67 @@ def test_dropout_masks_follow_the_dropout2d_rng_stream():
         want = drop(torch.ones((N, C, 2, 2), device=dev))[:, :, 0, 0]          # the reference module itself
         got = S[key]["drop"]
         assert torch.equal(got, want), name
+
+
+# ----------------------------------------------------------------------------------------------- sa_reduce, directly
+@pytest.mark.parametrize("C,H,W", [(32, 19, 23), (64, 67, 61), (128, 40, 33), (256, 19, 23), (512, 17, 16), (1024, 9, 11)])
+def test_sa_reduce_values_and_first_maximum_bookkeeping(C, H, W):
+    """rbu_sa_reduce alone, at every lane layout the dispatch picks (one, two, four and eight channel groups per lane),
+    on a channel slice of a wider buffer and pixel counts that are no multiple of a block's pixels:
+    * per-pixel mean / max over channels of A2g*y2 + B2g (Main_Final.py:113-115) against float64;
+    * the arg-max channel: channel j + C/2 duplicates channel j exactly, so every pixel has an exact tie and torch.max's
+      lowest-index rule demands an index below C/2 that attains the maximum;
+    * nc_arg[n,c] = FIRST pixel whose stored value equals tv[n,c] (AdaptiveMaxPool2d's routing, Main_Final.py:99), with
+      coarse values (ties the rule), a signed-zero target, and an absent target (slot stays at its initial value);
+    * the inference form (no arg-max outputs) returns the same values."""
+    from rbunet._lib import call, stream_ptr
+    from ctypes import c_void_p
+    dev = torch.device(DEV)
+    N, HW = 3, H * W
+    g = torch.Generator().manual_seed(C + H)
+    y = torch.round(torch.randn((N, C, H, W), generator=g) * 4) / 4          # multiples of 0.25: bf16-exact, many ties
+    y[:, 1] = -y[:, 1].abs()
+    y[:, 1][y[:, 1] == 0] = -0.0                                               # channel 1: <= 0 with negative zeros
+    y[:, C // 2:] = y[:, :C // 2]
+    a = torch.randn((N, C), generator=g)
+    b = torch.randn((N, C), generator=g)
+    a[:, C // 2:], b[:, C // 2:] = a[:, :C // 2], b[:, :C // 2]
+    flat = y.flatten(2)                                                        # [N, C, HW]
+    tv = torch.where(a >= 0, flat.max(2).values, flat.min(2).values)
+    tv[:, 1] = 0.0                                                             # +0 target, -0 stored
+    tv[:, 2] = 1000.0                                                          # never attained
+    want_arg = torch.full((N, C), 0x7fffffff, dtype=torch.int32)
+    for n in range(N):
+        for c in range(C):
+            hit = (flat[n, c] == tv[n, c]).nonzero()
+            if len(hit):
+                want_arg[n, c] = int(hit[0])
+    assert (want_arg[:, 1] != 0x7fffffff).all() and (want_arg[:, 2] == 0x7fffffff).all()
+    c64 = a.double()[:, :, None] * flat.double() + b.double()[:, :, None]      # [N, C, HW]
+    want_avg, want_max = c64.mean(1), c64.max(1).values
+
+    yv = to_view(y, dev, ld=C + 16, off=8, fill=99.0)
+    p = lambda t: c_void_p(t.data_ptr())
+    a_d, b_d, tv_d = a.to(dev), b.to(dev), tv.to(dev)
+    for with_arg in (True, False):
+        s = torch.full((N * HW, 2), float("nan"), device=dev)
+        amax = torch.full((N * HW,), -1, dtype=torch.int32, device=dev)
+        nc_arg = torch.full((N, C), 0x7fffffff, dtype=torch.int32, device=dev)
+        call("rbu_sa_reduce", c_void_p(yv.ptr), yv.ld, N * HW, HW, C, p(a_d), p(b_d), p(tv_d) if with_arg else None,
+             p(nc_arg) if with_arg else None, p(s), p(amax) if with_arg else None, stream_ptr())
+        torch.cuda.synchronize()
+        s_h = s.cpu().reshape(N, HW, 2).double()
+        assert torch.allclose(s_h[..., 0], want_avg, rtol=0, atol=1e-5 * float(c64.abs().max())), (C, with_arg)
+        assert torch.allclose(s_h[..., 1], want_max, rtol=0, atol=1e-6 * float(c64.abs().max())), (C, with_arg)
+        if not with_arg:
+            assert (amax == -1).all()
+            continue
+        am = amax.cpu().reshape(N, HW).long()
+        assert (am >= 0).all() and (am < C // 2).all(), "exact ties go to the lowest channel"
+        picked = c64.gather(1, am[:, None, :]).squeeze(1)
+        assert (picked >= want_max - 1e-6 * float(c64.abs().max())).all()
+        # below the picked channel nothing attains the maximum (fp32 arithmetic of the device: c = fma(a, y, b))
+        c32 = torch.addcmul(b[:, :, None], a[:, :, None], flat)
+        lower = torch.arange(C)[None, :, None] < am[:, None, :]
+        assert not (lower & (c32 > s.cpu().reshape(N, HW, 2)[..., 1][:, None, :] + 1e-6 * float(c64.abs().max()))).any()
+        assert torch.equal(nc_arg.cpu(), want_arg), (C, (nc_arg.cpu() != want_arg).nonzero()[:5])
