@@ -184,6 +184,22 @@ rb_bwd1_kernel(const bf16* __restrict__ dout, long dout_ld, const bf16* __restri
   for (int it = 0; it < iters; ++it) {
     bf16x8 rg[U], ro[U], ry[U], rs[U];
     bool act[U];
+    // The four vectors of the NEXT iteration are prefetched into L2 while this one's are in flight (no registers held):
+    // the kernel is latency-bound at two resident blocks per SM (ncu: 25 % warps active, 5 warps per issue on the long
+    // scoreboard).  Same-box A/B, two alternations: 2.15 / 2.07 -> 1.93 / 1.97 ms per step.  The same prefetch made
+    // rb_bwd3 (+3 %) and rb_bwd2 (+11 %) slower and left bn_bwd_apply / ag_bwd2 / ag_bwd3 unchanged, so only this kernel has it
+    // (profiles/r02_i_ab_prefetch.txt).
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int pl = p0 + ((it + 1) * U + u) * rows + row;
+      if (row < rows && pl < p1) {
+        const long p = (long)n * HW + pl;
+        prefetch_l2(dout + p * dout_ld + cg * 8);
+        prefetch_l2(out + p * out_ld + cg * 8);
+        prefetch_l2(y2 + p * y2_ld + cg * 8);
+        if (ys) prefetch_l2(ys + p * ys_ld + cg * 8);
+      }
+    }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int pl = p0 + (it * U + u) * rows + row;

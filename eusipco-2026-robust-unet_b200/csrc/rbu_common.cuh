@@ -79,6 +79,8 @@ __device__ __forceinline__ bf16x8 ld_bf16x8_stream(const bf16* p) {
   *reinterpret_cast<uint4*>(&r) = u;
   return r;
 }
+// Pull the line behind `p` into L2 without tying up a register (see rb_bwd1_kernel).
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void st_bf16x8(bf16* p, const bf16x8& v) {
   *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(&v);
 }

@@ -12,11 +12,11 @@ for v in "$@"; do
   env $envs python bench.py --steps ${AB_STEPS:-10} --warmup ${AB_WARMUP:-4} ${AB_ARGS:-} --no-extras --no-cpu-baseline --no-eager-baseline \
       > "$out" 2> gpurun_out/${prefix}_${i}.err || echo "variant '$v' FAILED rc=$?"
   python - "$out" "$v" <<'P'
-import json, sys
+import json, os, sys
 try:
     d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
     kc = d.get("kernel_classes", {})
-    pick = {k: kc[k]["ms"] for k in ("rbu_sa_reduce", "wgrad_gemm", "conv3x3") if k in kc}
+    pick = {k: kc[k]["ms"] for k in (os.environ.get("AB_KERNELS") or "rbu_sa_reduce,wgrad_gemm,conv3x3").split(",") if k in kc}
     print(f"{sys.argv[2]:28s} {d['ms_per_step']:8.3f} ms/step  {d['value']:8.1f} {d['unit']}  hbm_kernels {d.get('hbm_kernels', {}).get('ms')} ms frac {d.get('hbm_kernels', {}).get('hbm_frac')}  {pick}")
 except Exception as e:
     print(sys.argv[2], "unreadable:", e)
