@@ -409,6 +409,93 @@ sa_reduce_kernel(const bf16* __restrict__ y2, long ld, int HW, int C, const floa
   }
 }
 
+// Training form for C >= 64: the per-(image, channel) coefficients and the packed arg-max targets live in shared memory (a
+// block works on one image), so a lane can own FOUR channel groups without 100 registers of coefficients: TPP = C/32 lanes
+// per pixel instead of C/8 -- two fewer combination rounds per pixel and the rounds, the guards and the store are paid once
+// per four vectors.  Same arithmetic and visiting order as sa_reduce_kernel (channels ascending within a lane, strict >;
+// across lanes the lower channel wins a tie).
+template <int TPP>
+__global__ void __launch_bounds__(NT, 3)
+sa_reduce_arg_kernel(const bf16* __restrict__ y2, long ld, int HW, int C, const float* __restrict__ A2g,
+                     const float* __restrict__ B2g, const float* __restrict__ tv, int* __restrict__ nc_arg,
+                     float2* __restrict__ s_out, int* __restrict__ amax_out) {
+  constexpr int K = 4, U = 2, SLOTS = NT / TPP;
+  extern __shared__ float4 sa_smem[];
+  float* const sa = reinterpret_cast<float*>(sa_smem);       // [C] A2g[n]
+  float* const sb = sa + C;                                  // [C] B2g[n]
+  bf16* const st = reinterpret_cast<bf16*>(sb + C);          // [C] tv[n], exact in bf16 (extremes of stored bf16 values)
+  const int n = blockIdx.y;
+  const float* __restrict__ const tv_n = tv + (long)n * C;
+  for (int c = threadIdx.x; c < C; c += NT) {
+    sa[c] = A2g[(long)n * C + c];
+    sb[c] = B2g[(long)n * C + c];
+    st[c] = __float2bfloat16_rn(tv_n[c]);
+  }
+  __syncthreads();
+  const int li = threadIdx.x % TPP;
+  const int slot = threadIdx.x / TPP;
+  const float invC = 1.f / (float)C;
+  const long step_u = (long)SLOTS * ld;
+  const long step_it = (long)gridDim.x * (SLOTS * U) * ld;
+  const bf16* ptr = y2 + ((long)n * HW + (long)blockIdx.x * (SLOTS * U) + slot) * ld + li * 8;
+  float2* __restrict__ const s_n = s_out + (long)n * HW;
+  int* __restrict__ const amax_n = amax_out + (long)n * HW;
+  int* __restrict__ const arg_n = nc_arg + (long)n * C;
+  for (int pb = blockIdx.x * (SLOTS * U); pb < HW; pb += gridDim.x * (SLOTS * U), ptr += step_it) {
+    bf16x8 raw[U][K];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int pp = pb + u * SLOTS + slot;
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+        if (pp < HW) raw[u][k] = ld_bf16x8(ptr + u * step_u + k * (TPP * 8));
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int pp = pb + u * SLOTS + slot;
+      float sum = 0.f, best = -INFINITY;
+      int bi = 0x7fffffff;
+      if (pp < HW) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const int cg = li + k * TPP;
+          const float4 a0 = *reinterpret_cast<const float4*>(sa + cg * 8), a1 = *reinterpret_cast<const float4*>(sa + cg * 8 + 4);
+          const float4 b0 = *reinterpret_cast<const float4*>(sb + cg * 8), b1 = *reinterpret_cast<const float4*>(sb + cg * 8 + 4);
+          const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+          const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          const bf16x8 tp = *reinterpret_cast<const bf16x8*>(st + cg * 8);
+          float v[8];
+          unpack8(raw[u][k], v);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float c = a[e] * v[e] + b[e];
+            sum += c;
+            if (c > best) { best = c; bi = cg * 8 + e; }
+          }
+          const bool miss = (__hne2_mask(raw[u][k].v[0], tp.v[0]) & __hne2_mask(raw[u][k].v[1], tp.v[1]) &
+                             __hne2_mask(raw[u][k].v[2], tp.v[2]) & __hne2_mask(raw[u][k].v[3], tp.v[3])) == 0xffffffffu;
+          if (!miss) {                      // rare: the exact comparison against the fp32 targets
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              if (v[e] == tv_n[cg * 8 + e]) atomicMin(arg_n + cg * 8 + e, pp);
+          }
+        }
+      }
+#pragma unroll
+      for (int o = TPP / 2; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+      }
+      if (li == 0 && pp < HW) {
+        s_n[pp] = make_float2(sum * invC, best);
+        amax_n[pp] = bi;
+      }
+    }
+  }
+}
+
 // g_s = sigmoid(conv7x7([s_avg, s_max]))  (Main_Final.py:109,116-117); weight layout [1][2][7][7].
 // Shared-memory tiled stencil: a block computes a 32 x 8 tile of one image from its 38 x 14 halo (zero padded).
 // A block computes a 32 x 16 tile from its 38 x 22 halo; a thread owns four horizontally adjacent pixels, so one 10-wide
@@ -972,6 +1059,19 @@ extern "C" int rbu_sa_reduce(const void* y2, int64_t ld, int64_t P, int HW, int 
   // (shuffles, stores) is paid once per two vectors (3.41 -> 3.11 ms at 32 x 1024^2, same-box A/B).  The training form
   // keeps one group per lane there: 94 registers instead of 74 cost a resident block per SM (0.83 against 0.79 ms per step).
   if (!arg && K == 1 && G >= 8) { tpp = G >= 32 ? 16 : G / 2; K = 2; }
+  // Training form from 64 channels up: coefficients in shared memory, four channel groups per lane (same-box A/B against
+  // the register form below, two alternations: 0.796 / 0.790 -> 0.712 / 0.700 ms per step; profiles/r02_l_ab_sa_smem.txt)
+  if (arg && G >= 8 && G <= 128) {
+    const int t4 = G / 4;                                               // lanes per pixel, four channel groups each
+    const dim3 grid4((unsigned)rbu_stream_blocks(HW, NT / t4 * 2, N), (unsigned)N);
+    const size_t smem = (size_t)C * 10;
+#define LAUNCH4(T)                                                                                                           \
+  sa_reduce_arg_kernel<T><<<grid4, NT, smem, st>>>((const bf16*)y2, ld, HW, C, A2g, B2g, tv, nc_arg, (float2*)s_out, amax_out)
+    if (t4 == 2) LAUNCH4(2); else if (t4 == 4) LAUNCH4(4); else if (t4 == 8) LAUNCH4(8); else if (t4 == 16) LAUNCH4(16); else LAUNCH4(32);
+#undef LAUNCH4
+    RBU_CHECK_LAUNCH();
+    return RBU_OK;
+  }
   const int U = K == 1 ? 4 : (K == 2 ? 2 : 1);
   const int per_block = NT / tpp * U;
   const long blocks = rbu_stream_blocks(HW, per_block, N);
