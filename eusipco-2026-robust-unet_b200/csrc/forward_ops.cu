@@ -1056,8 +1056,8 @@ extern "C" int rbu_sa_reduce(const void* y2, int64_t ld, int64_t P, int HW, int 
   int tpp = G >= 32 ? 32 : (G < 4 ? 4 : G);
   int K = G > 32 ? G / 32 : 1;
   // Inference form: two channel groups per lane from 64 channels up, so that the per-pixel combination across lanes
-  // (shuffles, stores) is paid once per two vectors (3.41 -> 3.11 ms at 32 x 1024^2, same-box A/B).  The training form
-  // keeps one group per lane there: 94 registers instead of 74 cost a resident block per SM (0.83 against 0.79 ms per step).
+  // (shuffles, stores) is paid once per two vectors (3.41 -> 3.11 ms at 32 x 1024^2, same-box A/B).  With the arg-max
+  // bookkeeping the same layout needs 94 registers instead of 74, costs a resident block per SM and loses (0.83 / 0.79 ms).
   if (!arg && K == 1 && G >= 8) { tpp = G >= 32 ? 16 : G / 2; K = 2; }
   // Training form from 64 channels up: coefficients in shared memory, four channel groups per lane (same-box A/B against
   // the register form below, two alternations: 0.796 / 0.790 -> 0.712 / 0.700 ms per step; profiles/r02_l_ab_sa_smem.txt)
