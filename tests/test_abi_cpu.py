@@ -79,3 +79,24 @@ def test_bench_product_arm_does_not_import_the_oracle():
     src = open(os.path.join(ROOT, "bench.py")).read()
     own = src[src.index("class Env"):src.index("def load_reference_module")]
     assert "oracle" not in own
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) on a tiny sample: one JSON line with the
+    contract's keys, `impl: reference`, a cpu_baseline describing the run and an e2e record with zero copy bytes.  It
+    runs the staged reference (`baseline/_ref`, kind "reference") when build() has staged it, else the oracle port."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                        "--size", "32"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, r.stdout[-2000:]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "train_images_per_sec" and d["unit"] == "img/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0
